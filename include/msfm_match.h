@@ -1,0 +1,163 @@
+/*
+ * msfm_match.h — C ABI of the B200-native pairwise SIFT-128 matcher (drop-in for MetricSfM's matching hot path).
+ *
+ * Plain C, plain pointers and sizes; no C++/torch/OpenCV types cross this boundary.  Every entry point returns an
+ * msfm_status and never aborts or throws (the reference's cudaSift `safeCall` exit(-1)s on error,
+ * SfM/thirdparty/cudasift/include/cudaSift/utils.h:17-23 — deliberately not imitated).
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/SfM):
+ *   seam S1  flann_build_index / flann_find_nearest_neighbors_index(k=2) / flann_free_index as called at
+ *            src/graph/fine_matching_graph.cc:81,99,101 and src/slam_gps.cc:447,463,549
+ *              -> msfm_upload_f32 / msfm_upload_u8 (build, once per image), msfm_knn2 (query), msfm_release (free)
+ *   seam S2  FeatureMatching::KNNMatchingWithGeoVerify(kp1, kp2, int* id, float* dis, matches)
+ *            src/feature/feature_matching.h:57-58, feature_matching.cpp:477-501 (caller-supplied kNN arrays)
+ *              -> msfm_knn2 fills exactly those id/dis arrays ([2*Nquery], (nn0,nn1) interleaved, squared L2)
+ *   seam S3  bool Matcher(vector<KeyPoint>&, Mat&, vector<KeyPoint>&, Mat&, vector<pair<int,int>>&)
+ *            src/feature/feature_matching.h:33-35 (KNNMatching), feature_matching_cuda_sift.h:34-36 (Run)
+ *              -> msfm_match_pairs with n_pairs = 1 (host shim: metricsfm_b200/host/feature_matching_b200.h)
+ *   batch    the OpenMP partner loop + serial ratio loop of FineMatchingGraph::BuildMatchGraph
+ *            src/graph/fine_matching_graph.cc:87-133
+ *              -> msfm_match_pairs over the whole candidate pair list (ratio 0.85 "all" + ratio_good 0.6 flags)
+ *   declared GPU matchers (no call sites, semantic precedent):
+ *            cudaSift::MatchSiftData  thirdparty/cudasift/include/cudaSift/sift.h:97
+ *            SiftMatchGPU::SetDescriptors/GetSiftMatch(max_match, buf, distmax, ratiomax, mutual_best_match)
+ *            thirdparty/siftgpu/include/siftgpu/SiftGPU.h:297-308  -> msfm_params.{max_dist_sq, ratio, mutual}
+ *
+ * MATCH-SPEC: reference set R (M x 128), query set Q (N x 128), u8 rows.
+ *   d(q,j) = sum_k (Q[q,k]-R[j,k])^2 exactly in int32; nn0 = argmin_j d (lowest j on ties);
+ *   nn1 = argmin_{j != nn0} d (lowest j on ties); ids[2q..2q+1] = (nn0,nn1); dists[2q..] = ((float)d0,(float)d1);
+ *   accept iff (float)d0/(float)d1 < ratio (IEEE fp32 divide, strict; NaN => reject), and, when mutual,
+ *   argmin_q' d(q',nn0) == q (lowest q' on ties); a pair with M < min_keypoints or N < min_keypoints is rejected
+ *   as a whole (ok = 0, no matches), like feature_matching.cpp:30-33.  Missing neighbours: id = -1, dist = +inf.
+ */
+#ifndef MSFM_MATCH_H_
+#define MSFM_MATCH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSFM_DIM 128              /* descriptor length (SIFT-128), bytes per packed row */
+#define MSFM_ABI_VERSION 1
+#define MSFM_MAX_ROWS_PER_IMAGE 1000000 /* idx_max_per_image, src/basic_structs.h:171 */
+
+typedef enum msfm_status {
+    MSFM_OK = 0,
+    MSFM_ERR_INVALID_ARG = 1,   /* null pointer, negative size, bad id */
+    MSFM_ERR_CUDA = 2,          /* a CUDA runtime/driver call failed; see msfm_last_error */
+    MSFM_ERR_OUT_OF_MEMORY = 3, /* host or device allocation failed */
+    MSFM_ERR_NOT_FOUND = 4,     /* image id not uploaded */
+    MSFM_ERR_CAPACITY = 5,      /* descriptor arena, image table or caller output buffer too small */
+    MSFM_ERR_UNSUPPORTED = 6,   /* device is not sm_100 (no fallback path exists by design) */
+    MSFM_ERR_EXISTS = 7         /* image id already uploaded (release it first) */
+} msfm_status;
+
+typedef struct msfm_ctx msfm_ctx;
+
+typedef struct msfm_config {
+    int32_t device;          /* CUDA ordinal */
+    int32_t max_images;      /* image ids are 0 .. max_images-1 */
+    int64_t arena_rows;      /* total packed-descriptor rows the table can hold (each image is padded to 128 rows) */
+    /* Optional caller-owned device memory for the packed table (e.g. tensors a collective library fills during
+     * multi-GPU replication).  Both NULL => the library allocates.  desc: arena_rows*128 bytes, 1024-byte aligned;
+     * norms: arena_rows uint32. */
+    void *external_desc_arena;
+    void *external_norm_arena;
+    int32_t reserved[4];     /* must be zero */
+} msfm_config;
+
+typedef struct msfm_params {
+    float ratio;           /* accept iff d0/d1 < ratio (strict, fp32).  Callers: 0.5 feature_matching.cpp:27;
+                              0.85 / 0.6 fine_matching_graph.cc:42-43; 0.7 feature_matching_essential.cpp:31 */
+    float ratio_good;      /* > 0: also flag matches with d0/d1 < ratio_good (fine_matching_graph.cc:118-123) */
+    float max_dist_sq;     /* > 0: also require (float)d0 < max_dist_sq (SiftGPU distmax analogue); 0 = off */
+    int32_t mutual;        /* 1: keep (q,nn0) only if q is also the best query of reference row nn0 */
+    int32_t min_keypoints; /* pairs with fewer rows on either side are rejected; reference value 20 */
+    int32_t orientation;   /* 0: emit (ref_index, query_index)  fine_matching_graph.cc:121,127
+                              1: emit (query_index, ref_index)  feature_matching.cpp:60-61 */
+} msfm_params;
+
+/* One candidate pair: the kNN index is "built" on image `ref`, rows of image `query` are the queries
+ * (fine_matching_graph.cc: ref = idx1, query = idx2; feature_matching.cpp:35-44: ref = image 2, query = image 1). */
+typedef struct msfm_pair {
+    int32_t ref;
+    int32_t query;
+} msfm_pair;
+
+/* Caller-provided output of msfm_match_pairs.  matches[offsets[p] .. offsets[p+1]) belong to pair p, ascending query
+ * index.  Capacity needed is at most sum over pairs of query rows (one match per query row). */
+typedef struct msfm_result {
+    int64_t *offsets;        /* [n_pairs + 1] */
+    int32_t *ok;             /* [n_pairs] 1 = matched, 0 = rejected by the min_keypoints gate */
+    int32_t (*matches)[2];   /* [match_capacity][2] */
+    uint8_t *good;           /* [match_capacity] or NULL; 1 iff the match also passes ratio_good */
+    int64_t match_capacity;
+} msfm_result;
+
+/* Device-side timing of the last msfm_match_pairs / msfm_knn2 call on a context (CUDA events on the library's own
+ * stream).  kernel_ms covers only launches of the dominant matching kernel. */
+typedef struct msfm_timing {
+    float total_ms;          /* first enqueue -> last result byte landed in host memory */
+    float match_kernel_ms;   /* sum over launches of the tcgen05 matching kernel */
+    float finalize_ms;       /* ratio / mutual / compaction kernels */
+    float d2h_ms;            /* result copies device -> host */
+    int32_t match_launches;  /* number of launches of the matching kernel */
+    int32_t total_launches;  /* all kernels launched by the call */
+    int64_t d2h_bytes;
+    int64_t int8_ops;        /* algorithmic work: sum over matched pairs of 2*M*N*128 */
+} msfm_timing;
+
+int32_t msfm_abi_version(void);
+const char *msfm_status_string(msfm_status s);
+
+msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out);
+msfm_status msfm_destroy(msfm_ctx *ctx);
+/* Last error text of this context (valid until the next call on it); never NULL. */
+const char *msfm_last_error(const msfm_ctx *ctx);
+
+/* ---- descriptor packer: once per image (replaces the per-idx1 flann_build_index) ------------------------------- */
+/* u8 rows, row_stride_bytes >= 128.  The library copies; the caller may free `desc` on return. */
+msfm_status msfm_upload_u8(msfm_ctx *ctx, int32_t image_id, const uint8_t *desc, int32_t rows, int64_t row_stride_bytes);
+/* float rows (cv::Mat CV_32FC1 rows x 128, database.cc:368-370): q = min(255, max(0, rint(x*scale))).
+ * scale = 1 for 512-scaled VLSIFT rows (feature_extractor_vl_sift.cpp:201-203), 512 for unit-norm rows
+ * (feature_extractor_cuda_sift.cpp:75-80). */
+msfm_status msfm_upload_f32(msfm_ctx *ctx, int32_t image_id, const float *desc, int32_t rows, int64_t row_stride_floats,
+                            float scale);
+/* Reserve table space for an image whose packed rows + norms are written by someone else (a collective during
+ * multi-GPU replication) at the returned row offset of the arenas.  Pad rows/norms are initialised here. */
+msfm_status msfm_reserve(msfm_ctx *ctx, int32_t image_id, int32_t rows, int64_t *row_offset);
+msfm_status msfm_release(msfm_ctx *ctx, int32_t image_id);
+msfm_status msfm_release_all(msfm_ctx *ctx);
+msfm_status msfm_image_info(const msfm_ctx *ctx, int32_t image_id, int32_t *rows, int64_t *row_offset);
+/* Device addresses of the packed table (for collectives / inspection). */
+msfm_status msfm_table_ptrs(const msfm_ctx *ctx, void **desc_arena, void **norm_arena, int64_t *arena_rows,
+                            int64_t *rows_used);
+/* Copy an image's packed u8 rows / uint32 squared norms back to the host (tests, debugging). */
+msfm_status msfm_download_packed(msfm_ctx *ctx, int32_t image_id, uint8_t *desc_out, uint32_t *norms_out);
+
+/* ---- kNN query in FLANN layout (seams S1/S2) ------------------------------------------------------------------- */
+/* ids[2*Nq], dists[2*Nq] host buffers, Nq = rows of image `query_id`.  No min_keypoints gate (FLANN has none). */
+msfm_status msfm_knn2(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_t *ids, float *dists);
+/* Per reference row j of ref_id: best query row (lowest index on ties) and its squared distance. */
+msfm_status msfm_colbest(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_t *best_query, float *best_dist);
+
+/* ---- batched pair matching (the fast path; replaces the OMP partner loop + ratio loop) ------------------------- */
+msfm_status msfm_match_pairs(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const msfm_params *params,
+                             msfm_result *out);
+/* Same work with results left in HBM (no device->host copy): used to time the device-resident path.  n_matches_total
+ * (optional) receives the total match count (one 8-byte read-back). */
+msfm_status msfm_match_pairs_resident(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const msfm_params *params,
+                                      int64_t *n_matches_total);
+
+msfm_status msfm_last_timing(const msfm_ctx *ctx, msfm_timing *out);
+
+/* ---- GPU-side cross-check kernel (CUDA cores, dp4a); used by the tests to localise faults, never by the fast path */
+msfm_status msfm_knn2_crosscheck(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_t *ids, float *dists);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSFM_MATCH_H_ */

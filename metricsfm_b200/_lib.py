@@ -1,0 +1,94 @@
+"""ctypes binding of include/msfm_match.h.  Loading fails loudly when the CUDA library has not been built —
+there is no CPU or PyTorch fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_f32p = C.POINTER(C.c_float)
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+
+MSFM_OK = 0
+STATUS_NAMES = {
+    0: "MSFM_OK", 1: "MSFM_ERR_INVALID_ARG", 2: "MSFM_ERR_CUDA", 3: "MSFM_ERR_OUT_OF_MEMORY", 4: "MSFM_ERR_NOT_FOUND",
+    5: "MSFM_ERR_CAPACITY", 6: "MSFM_ERR_UNSUPPORTED", 7: "MSFM_ERR_EXISTS",
+}
+
+# Every symbol include/msfm_match.h declares (tests/test_abi.py checks the two lists against each other).
+EXPORTED_SYMBOLS = [
+    "msfm_abi_version", "msfm_status_string", "msfm_create", "msfm_destroy", "msfm_last_error", "msfm_upload_u8",
+    "msfm_upload_f32", "msfm_reserve", "msfm_release", "msfm_release_all", "msfm_image_info", "msfm_table_ptrs",
+    "msfm_download_packed", "msfm_knn2", "msfm_colbest", "msfm_match_pairs", "msfm_match_pairs_resident",
+    "msfm_last_timing", "msfm_knn2_crosscheck",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_images", C.c_int32), ("arena_rows", C.c_int64),
+                ("external_desc_arena", C.c_void_p), ("external_norm_arena", C.c_void_p), ("reserved", C.c_int32 * 4)]
+
+
+class Params(C.Structure):
+    _fields_ = [("ratio", C.c_float), ("ratio_good", C.c_float), ("max_dist_sq", C.c_float), ("mutual", C.c_int32),
+                ("min_keypoints", C.c_int32), ("orientation", C.c_int32)]
+
+
+class Pair(C.Structure):
+    _fields_ = [("ref", C.c_int32), ("query", C.c_int32)]
+
+
+class Result(C.Structure):
+    _fields_ = [("offsets", _i64p), ("ok", _i32p), ("matches", C.c_void_p), ("good", _u8p), ("match_capacity", C.c_int64)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("total_ms", C.c_float), ("match_kernel_ms", C.c_float), ("finalize_ms", C.c_float), ("d2h_ms", C.c_float),
+                ("match_launches", C.c_int32), ("total_launches", C.c_int32), ("d2h_bytes", C.c_int64), ("int8_ops", C.c_int64)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree CUDA library; raise if it is missing (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA extension has not been built (run `python -m metricsfm_b200.build`). "
+            "metricsfm_b200 has no CPU fallback by design.")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.msfm_abi_version.restype = C.c_int32
+    L.msfm_status_string.restype = C.c_char_p
+    L.msfm_status_string.argtypes = [C.c_int]
+    L.msfm_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.msfm_destroy.argtypes = [vp]
+    L.msfm_last_error.restype = C.c_char_p
+    L.msfm_last_error.argtypes = [vp]
+    L.msfm_upload_u8.argtypes = [vp, C.c_int32, vp, C.c_int32, C.c_int64]
+    L.msfm_upload_f32.argtypes = [vp, C.c_int32, vp, C.c_int32, C.c_int64, C.c_float]
+    L.msfm_reserve.argtypes = [vp, C.c_int32, C.c_int32, _i64p]
+    L.msfm_release.argtypes = [vp, C.c_int32]
+    L.msfm_release_all.argtypes = [vp]
+    L.msfm_image_info.argtypes = [vp, C.c_int32, _i32p, _i64p]
+    L.msfm_table_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), _i64p, _i64p]
+    L.msfm_download_packed.argtypes = [vp, C.c_int32, vp, vp]
+    L.msfm_knn2.argtypes = [vp, C.c_int32, C.c_int32, vp, vp]
+    L.msfm_colbest.argtypes = [vp, C.c_int32, C.c_int32, vp, vp]
+    L.msfm_match_pairs.argtypes = [vp, vp, C.c_int64, C.POINTER(Params), C.POINTER(Result)]
+    L.msfm_match_pairs_resident.argtypes = [vp, vp, C.c_int64, C.POINTER(Params), _i64p]
+    L.msfm_last_timing.argtypes = [vp, C.POINTER(Timing)]
+    L.msfm_knn2_crosscheck.argtypes = [vp, C.c_int32, C.c_int32, vp, vp]
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(L, name)
+        if name not in ("msfm_abi_version", "msfm_status_string", "msfm_last_error"):
+            fn.restype = C.c_int
+    _lib = L
+    return L

@@ -1,0 +1,251 @@
+// aux_kernels.cuh — the small HBM-bound kernels around the matching kernel:
+//   * descriptor packer (north_star subsystem 1): f32/u8 rows -> 128-byte u8 rows + uint32 squared norms
+//   * finalize: ratio test (+ max-dist gate, + mutual check) and ordered per-pair compaction
+//   * offsets scan + tight gather of the per-pair match lists
+//   * a CUDA-core dp4a brute-force kNN used only by tests as a GPU-side cross-check
+#pragma once
+#include <cstdint>
+#include <climits>
+#include <cuda_runtime.h>
+
+#include "match_kernel.cuh"
+
+namespace msfm {
+
+// ------------------------------------------------------------------------------------------------ packer
+// One warp per row; lane l owns bytes 4l..4l+3.  rows_padded - rows pad rows get zero bytes and kNormPad norms.
+// Quantisation rule (mirrored by oracle_quantize_f32): q = min(255, max(0, rint(x * scale))), NaN -> 0.
+__global__ void pack_f32_kernel(const float *__restrict__ src, int64_t src_stride_floats, int rows, int rows_padded,
+                                float scale, uint8_t *__restrict__ dst, uint32_t *__restrict__ norms) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows_padded; r += gridDim.x * warps_per_block) {
+        uint32_t packed = 0, nrm = kNormPad;
+        if (r < rows) {
+            const float *s = src + (int64_t)r * src_stride_floats + lane * 4;
+            const float f[4] = {s[0], s[1], s[2], s[3]};
+            uint32_t acc = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float x = rintf(f[k] * scale);
+                if (!(x > 0.0f)) x = 0.0f;
+                if (x > 255.0f) x = 255.0f;
+                const uint32_t qv = (uint32_t)x;
+                packed |= qv << (8 * k);
+                acc += qv * qv;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+            nrm = acc;
+        }
+        reinterpret_cast<uint32_t *>(dst + (int64_t)r * kDim)[lane] = packed;
+        if (lane == 0) norms[r] = nrm;
+    }
+}
+
+__global__ void pack_u8_kernel(const uint8_t *__restrict__ src, int64_t src_stride_bytes, int rows, int rows_padded,
+                               uint8_t *__restrict__ dst, uint32_t *__restrict__ norms) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows_padded; r += gridDim.x * warps_per_block) {
+        uint32_t packed = 0, nrm = kNormPad;
+        if (r < rows) {
+            const uint8_t *s8 = src + (int64_t)r * src_stride_bytes + lane * 4;
+            packed = (uint32_t)s8[0] | ((uint32_t)s8[1] << 8) | ((uint32_t)s8[2] << 16) | ((uint32_t)s8[3] << 24);
+            uint32_t acc = __dp4a(packed, packed, 0u);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+            nrm = acc;
+        }
+        reinterpret_cast<uint32_t *>(dst + (int64_t)r * kDim)[lane] = packed;
+        if (lane == 0) norms[r] = nrm;
+    }
+}
+
+// Pad rows of a reserved (externally filled) image.
+__global__ void init_pad_kernel(int rows, int rows_padded, uint8_t *__restrict__ dst, uint32_t *__restrict__ norms) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int r = rows + blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows_padded; r += gridDim.x * warps_per_block) {
+        reinterpret_cast<uint32_t *>(dst + (int64_t)r * kDim)[lane] = 0u;
+        if (lane == 0) norms[r] = kNormPad;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ finalize
+struct FinalizeParams {
+    const PairDesc *pairs;
+    const int4 *knn;                    // per-batch kNN scratch
+    const unsigned long long *colbest;  // per-batch column-best scratch (unused when !mutual)
+    int2 *matches;                      // per-batch scratch; pair p writes its list from row knn_off
+    uint8_t *good;                      // same indexing
+    int32_t *counts;                    // [n_pairs]
+    float ratio, ratio_good, max_dist_sq;
+    int32_t mutual, orientation;
+};
+
+// One CTA per pair.  Rows are scanned in ascending query order, 1024 at a time, and kept matches are written in
+// that order (the order of fine_matching_graph.cc:116-133 / feature_matching.cpp:56-64).
+__global__ void __launch_bounds__(1024) finalize_kernel(const FinalizeParams fp) {
+    __shared__ int warp_excl[32];
+    __shared__ int chunk_total;
+    const PairDesc pd = fp.pairs[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int running = 0;
+    for (int base = 0; base < pd.qry_rows; base += blockDim.x) {
+        const int q = base + threadIdx.x;
+        bool keep = false, is_good = false;
+        int nn0 = -1;
+        if (q < pd.qry_rows) {
+            const int4 k = fp.knn[pd.knn_off + q];
+            if (k.x >= 0 && k.y >= 0) {
+                const float d0 = (float)k.z, d1 = (float)k.w;
+                const float r = __fdiv_rn(d0, d1);  // IEEE divide; 0/0 = NaN fails every comparison
+                keep = r < fp.ratio;
+                if (fp.max_dist_sq > 0.0f) keep = keep && (d0 < fp.max_dist_sq);
+                if (keep && fp.mutual) {
+                    const unsigned long long cb = fp.colbest[pd.col_off + k.x];
+                    keep = (uint32_t)(cb & 0xFFFFFFFFull) == (uint32_t)q;
+                }
+                is_good = keep && fp.ratio_good > 0.0f && r < fp.ratio_good;
+                nn0 = k.x;
+            }
+        }
+        const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
+        const int prefix = __popc(ballot & ((1u << lane) - 1u));
+        if (lane == 0) warp_excl[warp] = __popc(ballot);
+        __syncthreads();
+        if (warp == 0) {
+            const int v = (lane < nwarps) ? warp_excl[lane] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            warp_excl[lane] = incl - v;
+            if (lane == 31) chunk_total = incl;
+        }
+        __syncthreads();
+        if (keep) {
+            const int64_t pos = pd.knn_off + running + warp_excl[warp] + prefix;
+            int2 m;
+            if (fp.orientation == 0) { m.x = nn0; m.y = q; } else { m.x = q; m.y = nn0; }
+            fp.matches[pos] = m;
+            if (fp.good) fp.good[pos] = is_good ? 1 : 0;
+        }
+        running += chunk_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) fp.counts[blockIdx.x] = running;
+}
+
+// Exclusive scan of the per-pair counts into int64 offsets[n+1]; single CTA (n is a per-batch pair count).
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t *__restrict__ counts, int n, int64_t *__restrict__ offsets) {
+    __shared__ long long warp_excl[32];
+    __shared__ long long chunk_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long running = 0;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const long long v = (i < n) ? counts[i] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_excl[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const long long w = warp_excl[lane];
+            long long wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_excl[lane] = wi - w;
+            if (lane == 31) chunk_total = wi;
+        }
+        __syncthreads();
+        if (i < n) offsets[i] = running + warp_excl[warp] + incl - v;
+        running += chunk_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[n] = running;
+}
+
+// Copy each pair's list from its scratch segment to the tight output.
+__global__ void gather_matches_kernel(const PairDesc *__restrict__ pairs, const int32_t *__restrict__ counts,
+                                      const int64_t *__restrict__ offsets, const int2 *__restrict__ matches,
+                                      const uint8_t *__restrict__ good, int2 *__restrict__ out_matches,
+                                      uint8_t *__restrict__ out_good) {
+    const PairDesc pd = pairs[blockIdx.x];
+    const int n = counts[blockIdx.x];
+    const int64_t dst = offsets[blockIdx.x];
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        out_matches[dst + k] = matches[pd.knn_off + k];
+        if (out_good) out_good[dst + k] = good[pd.knn_off + k];
+    }
+}
+
+// kNN scratch {id0,id1,d0,d1} -> FLANN layout ids[2q..], dists[2q..] (float), one pair.
+__global__ void knn_to_flann_kernel(const int4 *__restrict__ knn, int rows, int32_t *__restrict__ ids, float *__restrict__ dists) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= rows) return;
+    const int4 k = knn[q];
+    ids[2 * q] = k.x;
+    ids[2 * q + 1] = k.y;
+    dists[2 * q] = k.x >= 0 ? (float)k.z : __int_as_float(0x7f800000);
+    dists[2 * q + 1] = k.y >= 0 ? (float)k.w : __int_as_float(0x7f800000);
+}
+
+__global__ void colbest_unpack_kernel(const unsigned long long *__restrict__ cb, int rows, int32_t *__restrict__ best,
+                                      float *__restrict__ dist) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= rows) return;
+    const unsigned long long v = cb[j];
+    const bool has = v != ~0ull;
+    best[j] = has ? (int32_t)(uint32_t)(v & 0xFFFFFFFFull) : -1;
+    dist[j] = has ? (float)(uint32_t)(v >> 32) : __int_as_float(0x7f800000);
+}
+
+// ------------------------------------------------------------------------------------------------ cross-check
+// CUDA-core brute force (dp4a): thread = query row, loops over all reference rows (warp-uniform broadcast loads).
+// Test-only GPU cross-check of the tcgen05 path; exact int32, lowest index on ties.
+__global__ void crosscheck_knn2_kernel(const uint8_t *__restrict__ ref, const uint32_t *__restrict__ ref_norms, int M,
+                                       const uint8_t *__restrict__ qry, const uint32_t *__restrict__ qry_norms, int N,
+                                       int4 *__restrict__ knn) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= N) return;
+    uint32_t a[32];
+    const uint4 *qa = reinterpret_cast<const uint4 *>(qry + (int64_t)q * kDim);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint4 v = qa[k];
+        a[4 * k] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
+    }
+    const int na = (int)qry_norms[q];
+    int d0 = INT_MAX, d1 = INT_MAX, i0 = -1, i1 = -1;
+    for (int j = 0; j < M; ++j) {
+        const uint4 *rb = reinterpret_cast<const uint4 *>(ref + (int64_t)j * kDim);
+        uint32_t dot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint4 v = __ldg(rb + k);
+            dot = __dp4a(a[4 * k], v.x, dot);
+            dot = __dp4a(a[4 * k + 1], v.y, dot);
+            dot = __dp4a(a[4 * k + 2], v.z, dot);
+            dot = __dp4a(a[4 * k + 3], v.w, dot);
+        }
+        const int d = na + (int)__ldg(ref_norms + j) - 2 * (int)dot;
+        if (d < d1) {
+            if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = j; }
+            else { d1 = d; i1 = j; }
+        }
+    }
+    knn[q] = make_int4(i0, i1, i0 >= 0 ? d0 : INT_MAX, i1 >= 0 ? d1 : INT_MAX);
+}
+
+}  // namespace msfm

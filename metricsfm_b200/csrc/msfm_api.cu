@@ -1,0 +1,764 @@
+// msfm_api.cu — implementation of the C ABI declared in include/msfm_match.h.
+//
+// Host side of the B200-native matcher: the packed descriptor table (HBM arena + per-image TMA tensor maps), the
+// per-batch work-list builder / pair scheduler for one GPU, and the launch sequence
+//   match_pairs_kernel (tcgen05)  ->  finalize_kernel  ->  scan_counts_kernel  ->  gather_matches_kernel  ->  D2H.
+// There is deliberately no CPU or non-sm_100 fallback: msfm_create fails with MSFM_ERR_UNSUPPORTED elsewhere.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/msfm_match.h"
+#include "aux_kernels.cuh"
+#include "match_kernel.cuh"
+
+namespace {
+
+using msfm::kAlignRows;
+using msfm::kDim;
+using msfm::PairDesc;
+using msfm::WorkItem;
+
+// Kernel configuration of this build.
+constexpr int kStrips = 2;
+constexpr int kTileN = 128;
+constexpr int kStages = 4;
+using KCfg = msfm::MatchKernelCfg<kStrips, kTileN, kStages>;
+constexpr int kItemRows = kStrips * msfm::kStripRows;
+
+// Per-batch scratch bounds (rows).  16 Mi query rows -> 256 MiB kNN scratch + 128 MiB match scratch.
+constexpr int64_t kBatchMaxQueryRows = 16ll << 20;
+constexpr int64_t kBatchMaxRefRows = 16ll << 20;
+constexpr int64_t kBatchMaxPairs = 16384;
+
+struct DeviceBuf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct ImageSlot {
+    bool present = false;
+    int32_t rows = 0;
+    int32_t rows_padded = 0;
+    int64_t off = 0;
+};
+
+struct Extent {
+    int64_t off, rows;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct msfm_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    int32_t max_images = 0;
+    int64_t arena_rows = 0;
+    int64_t rows_high_water = 0;  // bump pointer
+    std::vector<Extent> free_list;
+    uint8_t *desc = nullptr;
+    uint32_t *norms = nullptr;
+    bool own_arena = false;
+    CUtensorMap *d_maps = nullptr;
+    std::vector<ImageSlot> images;
+    EncodeTiledFn encode = nullptr;
+
+    DeviceBuf staging, knn, colbest, matches, good, counts, offsets, pairdesc, items, tight_matches, tight_good;
+    void *h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_f1 = nullptr;
+
+    msfm_timing timing{};
+    std::string err;
+    std::mutex mu;
+};
+
+namespace {
+
+msfm_status fail(msfm_ctx *ctx, msfm_status st, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return st;
+}
+
+#define MSFM_CUDA(ctx, call)                                                                                   \
+    do {                                                                                                       \
+        cudaError_t e__ = (call);                                                                              \
+        if (e__ != cudaSuccess)                                                                                \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? MSFM_ERR_OUT_OF_MEMORY : MSFM_ERR_CUDA,         \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);          \
+    } while (0)
+
+msfm_status ensure(msfm_ctx *ctx, DeviceBuf &b, size_t bytes) {
+    if (b.bytes >= bytes && b.ptr) return MSFM_OK;
+    if (b.ptr) {
+        MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        MSFM_CUDA(ctx, cudaFree(b.ptr));
+        b.ptr = nullptr;
+        b.bytes = 0;
+    }
+    size_t want = std::max<size_t>(bytes, 256);
+    MSFM_CUDA(ctx, cudaMalloc(&b.ptr, want));
+    b.bytes = want;
+    return MSFM_OK;
+}
+
+msfm_status ensure_pinned(msfm_ctx *ctx, size_t bytes) {
+    if (ctx->h_pinned_bytes >= bytes) return MSFM_OK;
+    if (ctx->h_pinned) {
+        MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        MSFM_CUDA(ctx, cudaFreeHost(ctx->h_pinned));
+        ctx->h_pinned = nullptr;
+        ctx->h_pinned_bytes = 0;
+    }
+    MSFM_CUDA(ctx, cudaMallocHost(&ctx->h_pinned, bytes));
+    ctx->h_pinned_bytes = bytes;
+    return MSFM_OK;
+}
+
+int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// First-fit over the free list, else bump.  Extents are multiples of kAlignRows.
+bool arena_alloc(msfm_ctx *ctx, int64_t rows_padded, int64_t *off) {
+    for (size_t i = 0; i < ctx->free_list.size(); ++i) {
+        Extent &e = ctx->free_list[i];
+        if (e.rows >= rows_padded) {
+            *off = e.off;
+            e.off += rows_padded;
+            e.rows -= rows_padded;
+            if (e.rows == 0) ctx->free_list.erase(ctx->free_list.begin() + i);
+            return true;
+        }
+    }
+    if (ctx->rows_high_water + rows_padded > ctx->arena_rows) return false;
+    *off = ctx->rows_high_water;
+    ctx->rows_high_water += rows_padded;
+    return true;
+}
+
+void arena_free(msfm_ctx *ctx, int64_t off, int64_t rows_padded) {
+    if (rows_padded <= 0) return;
+    ctx->free_list.push_back({off, rows_padded});
+    std::sort(ctx->free_list.begin(), ctx->free_list.end(), [](const Extent &a, const Extent &b) { return a.off < b.off; });
+    std::vector<Extent> merged;
+    for (const Extent &e : ctx->free_list) {
+        if (!merged.empty() && merged.back().off + merged.back().rows == e.off) merged.back().rows += e.rows;
+        else merged.push_back(e);
+    }
+    if (!merged.empty() && merged.back().off + merged.back().rows == ctx->rows_high_water) {
+        ctx->rows_high_water = merged.back().off;
+        merged.pop_back();
+    }
+    ctx->free_list.swap(merged);
+}
+
+// One 2-D tensor map per image: inner dim 128 bytes, outer dim = exact row count, so that TMA zero-fills rows past
+// the image end (ragged sizes need no masking of the operands).
+msfm_status write_tensor_map(msfm_ctx *ctx, int32_t image_id, int64_t off, int32_t rows) {
+    CUtensorMap m;
+    memset(&m, 0, sizeof m);
+    cuuint64_t dims[2] = {(cuuint64_t)kDim, (cuuint64_t)std::max(rows, 1)};
+    cuuint64_t strides[1] = {(cuuint64_t)kDim};
+    cuuint32_t box[2] = {(cuuint32_t)kDim, 128u};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = ctx->encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ctx->desc + off * kDim, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, MSFM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_maps + image_id, &m, sizeof m, cudaMemcpyHostToDevice, ctx->stream));
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `m` lives on this stack frame
+    return MSFM_OK;
+}
+
+msfm_status check_image_id(msfm_ctx *ctx, int32_t id, bool must_exist) {
+    if (id < 0 || id >= ctx->max_images) return fail(ctx, MSFM_ERR_INVALID_ARG, "image id %d outside [0, %d)", id, ctx->max_images);
+    if (must_exist && !ctx->images[id].present) return fail(ctx, MSFM_ERR_NOT_FOUND, "image id %d has not been uploaded", id);
+    return MSFM_OK;
+}
+
+msfm_status reserve_locked(msfm_ctx *ctx, int32_t image_id, int32_t rows, int64_t *row_offset) {
+    msfm_status st = check_image_id(ctx, image_id, false);
+    if (st != MSFM_OK) return st;
+    if (rows < 0 || rows > MSFM_MAX_ROWS_PER_IMAGE) return fail(ctx, MSFM_ERR_INVALID_ARG, "rows %d outside [0, %d]", rows, MSFM_MAX_ROWS_PER_IMAGE);
+    if (ctx->images[image_id].present) return fail(ctx, MSFM_ERR_EXISTS, "image id %d already uploaded", image_id);
+    const int64_t padded = round_up(std::max(rows, 1), kAlignRows);
+    int64_t off = 0;
+    if (!arena_alloc(ctx, padded, &off))
+        return fail(ctx, MSFM_ERR_CAPACITY, "descriptor arena full: need %lld rows, %lld of %lld in use", (long long)padded,
+                    (long long)ctx->rows_high_water, (long long)ctx->arena_rows);
+    ImageSlot &s = ctx->images[image_id];
+    s.present = true;
+    s.rows = rows;
+    s.rows_padded = (int32_t)padded;
+    s.off = off;
+    st = write_tensor_map(ctx, image_id, off, rows);
+    if (st != MSFM_OK) {
+        s.present = false;
+        arena_free(ctx, off, padded);
+        return st;
+    }
+    if (row_offset) *row_offset = off;
+    return MSFM_OK;
+}
+
+struct BatchPlan {
+    std::vector<PairDesc> pairs;     // device pair descriptors (only pairs passing the gate)
+    std::vector<int64_t> src_index;  // index into the caller's pair list
+    std::vector<WorkItem> items;
+    int64_t query_rows = 0, ref_rows = 0;
+    int64_t ops = 0;
+};
+
+msfm_status launch_match_kernel(msfm_ctx *ctx, const BatchPlan &plan, bool want_colbest) {
+    msfm::MatchKernelParams kp;
+    kp.maps = ctx->d_maps;
+    kp.norms = ctx->norms;
+    kp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
+    kp.items = static_cast<const WorkItem *>(ctx->items.ptr);
+    kp.n_items = (int32_t)plan.items.size();
+    kp.want_colbest = want_colbest ? 1 : 0;
+    kp.knn = static_cast<int4 *>(ctx->knn.ptr);
+    kp.colbest = static_cast<unsigned long long *>(ctx->colbest.ptr);
+    const int grid = std::max(1, std::min<int>(ctx->num_sms, kp.n_items));
+    msfm::match_pairs_kernel<kStrips, kTileN, kStages><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
+    MSFM_CUDA(ctx, cudaGetLastError());
+    return MSFM_OK;
+}
+
+// Upload the plan, run the matching kernel (timed), leave {knn, colbest} in scratch.
+msfm_status run_match_stage(msfm_ctx *ctx, const BatchPlan &plan, bool want_colbest) {
+    msfm_status st;
+    const size_t pd_bytes = plan.pairs.size() * sizeof(PairDesc);
+    const size_t it_bytes = plan.items.size() * sizeof(WorkItem);
+    if ((st = ensure(ctx, ctx->pairdesc, pd_bytes)) != MSFM_OK) return st;
+    if ((st = ensure(ctx, ctx->items, it_bytes)) != MSFM_OK) return st;
+    if ((st = ensure(ctx, ctx->knn, (size_t)plan.query_rows * sizeof(int4))) != MSFM_OK) return st;
+    if ((st = ensure(ctx, ctx->colbest, (size_t)std::max<int64_t>(plan.ref_rows, 1) * 8)) != MSFM_OK) return st;
+    if ((st = ensure_pinned(ctx, pd_bytes + it_bytes + 64)) != MSFM_OK) return st;
+    // the pinned staging area is reused per batch: the previous batch has been synchronised by its D2H
+    memcpy(ctx->h_pinned, plan.pairs.data(), pd_bytes);
+    memcpy(static_cast<char *>(ctx->h_pinned) + pd_bytes, plan.items.data(), it_bytes);
+    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->pairdesc.ptr, ctx->h_pinned, pd_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->items.ptr, static_cast<char *>(ctx->h_pinned) + pd_bytes, it_bytes, cudaMemcpyHostToDevice,
+                                   ctx->stream));
+    if (want_colbest) MSFM_CUDA(ctx, cudaMemsetAsync(ctx->colbest.ptr, 0xFF, (size_t)plan.ref_rows * 8, ctx->stream));
+    MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
+    if ((st = launch_match_kernel(ctx, plan, want_colbest)) != MSFM_OK) return st;
+    MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
+    ctx->timing.match_launches += 1;
+    ctx->timing.total_launches += 1;
+    ctx->timing.int8_ops += plan.ops;
+    return MSFM_OK;
+}
+
+void plan_add_pair(msfm_ctx *ctx, BatchPlan &plan, int64_t src, int32_t ref, int32_t qry) {
+    const ImageSlot &r = ctx->images[ref], &q = ctx->images[qry];
+    PairDesc pd;
+    pd.ref_img = ref;
+    pd.qry_img = qry;
+    pd.ref_rows = r.rows;
+    pd.qry_rows = q.rows;
+    pd.ref_off = r.off;
+    pd.qry_off = q.off;
+    pd.knn_off = plan.query_rows;
+    pd.col_off = plan.ref_rows;
+    const int32_t pidx = (int32_t)plan.pairs.size();
+    plan.pairs.push_back(pd);
+    plan.src_index.push_back(src);
+    if (r.rows > 0)
+        for (int32_t row0 = 0; row0 < q.rows; row0 += kItemRows) plan.items.push_back({pidx, row0});
+    plan.query_rows += q.rows;
+    plan.ref_rows += r.rows;
+    plan.ops += 2ll * r.rows * q.rows * kDim;
+}
+
+msfm_status accumulate_kernel_time(msfm_ctx *ctx) {
+    float ms = 0.f;
+    MSFM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1));
+    ctx->timing.match_kernel_ms += ms;
+    return MSFM_OK;
+}
+
+// kNN of a single pair into scratch (no gate).  Caller holds the lock.
+msfm_status knn_single(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, bool want_colbest, BatchPlan &plan) {
+    msfm_status st;
+    if ((st = check_image_id(ctx, ref_id, true)) != MSFM_OK) return st;
+    if ((st = check_image_id(ctx, query_id, true)) != MSFM_OK) return st;
+    plan_add_pair(ctx, plan, 0, ref_id, query_id);
+    ctx->timing = msfm_timing{};
+    MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
+    if (plan.query_rows == 0) return MSFM_OK;
+    if (plan.items.empty()) {
+        // no reference rows: every neighbour is absent
+        if ((st = ensure(ctx, ctx->knn, (size_t)plan.query_rows * sizeof(int4))) != MSFM_OK) return st;
+        std::vector<int4> none((size_t)plan.query_rows, make_int4(-1, -1, INT_MAX, INT_MAX));
+        MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->knn.ptr, none.data(), none.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+        MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return MSFM_OK;
+    }
+    return run_match_stage(ctx, plan, want_colbest);
+}
+
+msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const msfm_params *params, msfm_result *out,
+                             bool resident, int64_t *n_matches_total) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (n_pairs < 0 || (n_pairs > 0 && !pairs) || !params) return fail(ctx, MSFM_ERR_INVALID_ARG, "null pair list / params or negative n_pairs");
+    if (!resident && (!out || !out->offsets || !out->ok || (!out->matches && out->match_capacity > 0)))
+        return fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_result needs offsets, ok and matches buffers");
+    if (!(params->ratio > 0.0f)) return fail(ctx, MSFM_ERR_INVALID_ARG, "ratio must be > 0");
+    msfm_status st;
+    for (int64_t i = 0; i < n_pairs; ++i) {
+        if ((st = check_image_id(ctx, pairs[i].ref, true)) != MSFM_OK) return st;
+        if ((st = check_image_id(ctx, pairs[i].query, true)) != MSFM_OK) return st;
+    }
+    ctx->timing = msfm_timing{};
+    MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
+    const bool want_good = params->ratio_good > 0.0f && (resident || out->good);
+    int64_t written = 0;  // matches written to the caller so far
+    int64_t total = 0;
+    if (!resident) out->offsets[0] = 0;
+
+    int64_t next = 0;
+    while (next < n_pairs) {
+        // ---- carve the next batch
+        BatchPlan plan;
+        const int64_t first = next;
+        while (next < n_pairs && (int64_t)plan.pairs.size() < kBatchMaxPairs) {
+            const ImageSlot &r = ctx->images[pairs[next].ref], &q = ctx->images[pairs[next].query];
+            const bool gated = r.rows < params->min_keypoints || q.rows < params->min_keypoints;
+            if (!gated) {
+                if (!plan.pairs.empty() &&
+                    (plan.query_rows + q.rows > kBatchMaxQueryRows || plan.ref_rows + r.rows > kBatchMaxRefRows))
+                    break;
+                plan_add_pair(ctx, plan, next, pairs[next].ref, pairs[next].query);
+            }
+            ++next;
+        }
+        const int64_t last = next;
+        const int nb = (int)plan.pairs.size();
+        std::vector<int64_t> batch_offsets;
+        if (nb > 0 && plan.query_rows > 0) {
+            if (!plan.items.empty()) {
+                if ((st = run_match_stage(ctx, plan, params->mutual != 0)) != MSFM_OK) return st;
+            } else {
+                if ((st = ensure(ctx, ctx->pairdesc, nb * sizeof(PairDesc))) != MSFM_OK) return st;
+                if ((st = ensure(ctx, ctx->knn, (size_t)plan.query_rows * sizeof(int4))) != MSFM_OK) return st;
+                MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->pairdesc.ptr, plan.pairs.data(), nb * sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream));
+                MSFM_CUDA(ctx, cudaMemsetAsync(ctx->knn.ptr, 0xFF, (size_t)plan.query_rows * sizeof(int4), ctx->stream));
+                MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            }
+            // ---- ratio / mutual / compaction
+            if ((st = ensure(ctx, ctx->matches, (size_t)plan.query_rows * sizeof(int2))) != MSFM_OK) return st;
+            if (want_good && (st = ensure(ctx, ctx->good, (size_t)plan.query_rows)) != MSFM_OK) return st;
+            if ((st = ensure(ctx, ctx->counts, (size_t)nb * 4)) != MSFM_OK) return st;
+            if ((st = ensure(ctx, ctx->offsets, (size_t)(nb + 1) * 8)) != MSFM_OK) return st;
+            if ((st = ensure(ctx, ctx->tight_matches, (size_t)plan.query_rows * sizeof(int2))) != MSFM_OK) return st;
+            if (want_good && (st = ensure(ctx, ctx->tight_good, (size_t)plan.query_rows)) != MSFM_OK) return st;
+            msfm::FinalizeParams fp;
+            fp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
+            fp.knn = static_cast<const int4 *>(ctx->knn.ptr);
+            fp.colbest = static_cast<const unsigned long long *>(ctx->colbest.ptr);
+            fp.matches = static_cast<int2 *>(ctx->matches.ptr);
+            fp.good = want_good ? static_cast<uint8_t *>(ctx->good.ptr) : nullptr;
+            fp.counts = static_cast<int32_t *>(ctx->counts.ptr);
+            fp.ratio = params->ratio;
+            fp.ratio_good = params->ratio_good;
+            fp.max_dist_sq = params->max_dist_sq;
+            fp.mutual = params->mutual != 0;
+            fp.orientation = params->orientation;
+            msfm::finalize_kernel<<<nb, 1024, 0, ctx->stream>>>(fp);
+            msfm::scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(fp.counts, nb, static_cast<int64_t *>(ctx->offsets.ptr));
+            msfm::gather_matches_kernel<<<nb, 256, 0, ctx->stream>>>(
+                fp.pairs, fp.counts, static_cast<const int64_t *>(ctx->offsets.ptr), fp.matches, fp.good,
+                static_cast<int2 *>(ctx->tight_matches.ptr), want_good ? static_cast<uint8_t *>(ctx->tight_good.ptr) : nullptr);
+            MSFM_CUDA(ctx, cudaGetLastError());
+            MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_f1, ctx->stream));
+            ctx->timing.total_launches += 3;
+            // ---- results
+            batch_offsets.resize(nb + 1);
+            MSFM_CUDA(ctx, cudaMemcpyAsync(batch_offsets.data(), ctx->offsets.ptr, (size_t)(nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->timing.d2h_bytes += (nb + 1) * 8;
+            if (!plan.items.empty() && (st = accumulate_kernel_time(ctx)) != MSFM_OK) return st;
+            {
+                float ms = 0.f;
+                if (!plan.items.empty()) {
+                    MSFM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_k1, ctx->ev_f1));
+                    ctx->timing.finalize_ms += ms;
+                }
+            }
+            const int64_t bt = batch_offsets[nb];
+            total += bt;
+            if (!resident && bt > 0) {
+                if (written + bt > out->match_capacity)
+                    return fail(ctx, MSFM_ERR_CAPACITY, "match buffer too small: need at least %lld entries, capacity %lld",
+                                (long long)(written + bt), (long long)out->match_capacity);
+                cudaEvent_t d0 = ctx->ev_k0, d1 = ctx->ev_k1;  // reuse as D2H brackets (kernel time already read)
+                MSFM_CUDA(ctx, cudaEventRecord(d0, ctx->stream));
+                MSFM_CUDA(ctx, cudaMemcpyAsync(out->matches + written, ctx->tight_matches.ptr, (size_t)bt * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
+                if (out->good) {
+                    if (want_good) MSFM_CUDA(ctx, cudaMemcpyAsync(out->good + written, ctx->tight_good.ptr, (size_t)bt, cudaMemcpyDeviceToHost, ctx->stream));
+                    else memset(out->good + written, 0, (size_t)bt);
+                }
+                MSFM_CUDA(ctx, cudaEventRecord(d1, ctx->stream));
+                MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                float ms = 0.f;
+                MSFM_CUDA(ctx, cudaEventElapsedTime(&ms, d0, d1));
+                ctx->timing.d2h_ms += ms;
+                ctx->timing.d2h_bytes += bt * (int64_t)(sizeof(int2) + (out->good && want_good ? 1 : 0));
+            }
+        }
+        // ---- host bookkeeping for pairs [first, last)
+        if (!resident) {
+            size_t k = 0;
+            for (int64_t i = first; i < last; ++i) {
+                if (k < plan.src_index.size() && plan.src_index[k] == i) {
+                    const int64_t cnt = batch_offsets.empty() ? 0 : batch_offsets[k + 1] - batch_offsets[k];
+                    out->ok[i] = 1;
+                    out->offsets[i + 1] = out->offsets[i] + cnt;
+                    ++k;
+                } else {
+                    out->ok[i] = 0;
+                    out->offsets[i + 1] = out->offsets[i];
+                }
+            }
+            written = out->offsets[last];
+        }
+    }
+    MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
+    MSFM_CUDA(ctx, cudaEventSynchronize(ctx->ev_end));
+    MSFM_CUDA(ctx, cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev_begin, ctx->ev_end));
+    if (n_matches_total) *n_matches_total = total;
+    return MSFM_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+int32_t msfm_abi_version(void) { return MSFM_ABI_VERSION; }
+
+const char *msfm_status_string(msfm_status s) {
+    switch (s) {
+        case MSFM_OK: return "ok";
+        case MSFM_ERR_INVALID_ARG: return "invalid argument";
+        case MSFM_ERR_CUDA: return "CUDA error";
+        case MSFM_ERR_OUT_OF_MEMORY: return "out of memory";
+        case MSFM_ERR_NOT_FOUND: return "image not uploaded";
+        case MSFM_ERR_CAPACITY: return "capacity exceeded";
+        case MSFM_ERR_UNSUPPORTED: return "unsupported device (sm_100 required)";
+        case MSFM_ERR_EXISTS: return "image already uploaded";
+    }
+    return "unknown status";
+}
+
+const char *msfm_last_error(const msfm_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
+    if (!cfg || !out) return MSFM_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (cfg->max_images <= 0 || cfg->arena_rows <= 0) return MSFM_ERR_INVALID_ARG;
+    if ((cfg->external_desc_arena == nullptr) != (cfg->external_norm_arena == nullptr)) return MSFM_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return MSFM_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return MSFM_ERR_CUDA;
+    if (prop.major != 10) return MSFM_ERR_UNSUPPORTED;  // tcgen05/TMEM path only; no fallback by design
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return MSFM_ERR_CUDA;
+
+    msfm_ctx *ctx = new (std::nothrow) msfm_ctx();
+    if (!ctx) return MSFM_ERR_OUT_OF_MEMORY;
+    ctx->device = cfg->device;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->max_images = cfg->max_images;
+    ctx->arena_rows = round_up(cfg->arena_rows, kAlignRows);
+    ctx->images.resize(cfg->max_images);
+
+    auto bail = [&](msfm_status st) {
+        msfm_destroy(ctx);
+        return st;
+    };
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return bail(MSFM_ERR_CUDA);
+    ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MSFM_ERR_CUDA);
+    cudaEvent_t *evs[] = {&ctx->ev_begin, &ctx->ev_end, &ctx->ev_k0, &ctx->ev_k1, &ctx->ev_f1};
+    for (cudaEvent_t *e : evs)
+        if (cudaEventCreate(e) != cudaSuccess) return bail(MSFM_ERR_CUDA);
+    if (cfg->external_desc_arena) {
+        if (reinterpret_cast<uintptr_t>(cfg->external_desc_arena) % 1024 != 0) return bail(MSFM_ERR_INVALID_ARG);
+        ctx->desc = static_cast<uint8_t *>(cfg->external_desc_arena);
+        ctx->norms = static_cast<uint32_t *>(cfg->external_norm_arena);
+        ctx->arena_rows = cfg->arena_rows / kAlignRows * kAlignRows;
+        ctx->own_arena = false;
+    } else {
+        if (cudaMalloc(&ctx->desc, (size_t)ctx->arena_rows * kDim) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
+        if (cudaMalloc(&ctx->norms, (size_t)ctx->arena_rows * 4) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
+        ctx->own_arena = true;
+    }
+    if (cudaMalloc(&ctx->d_maps, (size_t)ctx->max_images * sizeof(CUtensorMap)) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
+    if (cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             KCfg::kSmemAlloc) != cudaSuccess)
+        return bail(MSFM_ERR_CUDA);
+    *out = ctx;
+    return MSFM_OK;
+}
+
+msfm_status msfm_destroy(msfm_ctx *ctx) {
+    if (!ctx) return MSFM_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DeviceBuf *bufs[] = {&ctx->staging, &ctx->knn, &ctx->colbest, &ctx->matches, &ctx->good, &ctx->counts, &ctx->offsets,
+                         &ctx->pairdesc, &ctx->items, &ctx->tight_matches, &ctx->tight_good};
+    for (DeviceBuf *b : bufs)
+        if (b->ptr) cudaFree(b->ptr);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->own_arena) {
+        if (ctx->desc) cudaFree(ctx->desc);
+        if (ctx->norms) cudaFree(ctx->norms);
+    }
+    if (ctx->d_maps) cudaFree(ctx->d_maps);
+    cudaEvent_t evs[] = {ctx->ev_begin, ctx->ev_end, ctx->ev_k0, ctx->ev_k1, ctx->ev_f1};
+    for (cudaEvent_t e : evs)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return MSFM_OK;
+}
+
+msfm_status msfm_reserve(msfm_ctx *ctx, int32_t image_id, int32_t rows, int64_t *row_offset) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    int64_t off = 0;
+    msfm_status st = reserve_locked(ctx, image_id, rows, &off);
+    if (st != MSFM_OK) return st;
+    const ImageSlot &s = ctx->images[image_id];
+    if (s.rows_padded > s.rows) {
+        msfm::init_pad_kernel<<<8, 256, 0, ctx->stream>>>(s.rows, s.rows_padded, ctx->desc + off * kDim, ctx->norms + off);
+        MSFM_CUDA(ctx, cudaGetLastError());
+        MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (row_offset) *row_offset = off;
+    return MSFM_OK;
+}
+
+msfm_status msfm_upload_u8(msfm_ctx *ctx, int32_t image_id, const uint8_t *desc, int32_t rows, int64_t row_stride_bytes) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if ((rows > 0 && !desc) || row_stride_bytes < kDim) return fail(ctx, MSFM_ERR_INVALID_ARG, "null descriptors or stride < 128 bytes");
+    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    int64_t off = 0;
+    msfm_status st = reserve_locked(ctx, image_id, rows, &off);
+    if (st != MSFM_OK) return st;
+    const ImageSlot &s = ctx->images[image_id];
+    const size_t bytes = rows > 0 ? (size_t)(rows - 1) * row_stride_bytes + kDim : 0;
+    if ((st = ensure(ctx, ctx->staging, bytes)) != MSFM_OK) return st;
+    if (bytes) MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->staging.ptr, desc, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const int blocks = std::max(1, std::min(4 * ctx->num_sms, (s.rows_padded + 7) / 8));
+    msfm::pack_u8_kernel<<<blocks, 256, 0, ctx->stream>>>(static_cast<const uint8_t *>(ctx->staging.ptr), row_stride_bytes, rows,
+                                                         s.rows_padded, ctx->desc + off * kDim, ctx->norms + off);
+    MSFM_CUDA(ctx, cudaGetLastError());
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller may free `desc` on return
+    return MSFM_OK;
+}
+
+msfm_status msfm_upload_f32(msfm_ctx *ctx, int32_t image_id, const float *desc, int32_t rows, int64_t row_stride_floats, float scale) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if ((rows > 0 && !desc) || row_stride_floats < kDim || !(scale > 0.0f))
+        return fail(ctx, MSFM_ERR_INVALID_ARG, "null descriptors, stride < 128 floats or scale <= 0");
+    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    int64_t off = 0;
+    msfm_status st = reserve_locked(ctx, image_id, rows, &off);
+    if (st != MSFM_OK) return st;
+    const ImageSlot &s = ctx->images[image_id];
+    const size_t bytes = rows > 0 ? ((size_t)(rows - 1) * row_stride_floats + kDim) * sizeof(float) : 0;
+    if ((st = ensure(ctx, ctx->staging, bytes)) != MSFM_OK) return st;
+    if (bytes) MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->staging.ptr, desc, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const int blocks = std::max(1, std::min(4 * ctx->num_sms, (s.rows_padded + 7) / 8));
+    msfm::pack_f32_kernel<<<blocks, 256, 0, ctx->stream>>>(static_cast<const float *>(ctx->staging.ptr), row_stride_floats, rows,
+                                                          s.rows_padded, scale, ctx->desc + off * kDim, ctx->norms + off);
+    MSFM_CUDA(ctx, cudaGetLastError());
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MSFM_OK;
+}
+
+msfm_status msfm_release(msfm_ctx *ctx, int32_t image_id) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    msfm_status st = check_image_id(ctx, image_id, true);
+    if (st != MSFM_OK) return st;
+    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ImageSlot &s = ctx->images[image_id];
+    arena_free(ctx, s.off, s.rows_padded);
+    s = ImageSlot{};
+    return MSFM_OK;
+}
+
+msfm_status msfm_release_all(msfm_ctx *ctx) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (ImageSlot &s : ctx->images) s = ImageSlot{};
+    ctx->free_list.clear();
+    ctx->rows_high_water = 0;
+    return MSFM_OK;
+}
+
+msfm_status msfm_image_info(const msfm_ctx *ctx_c, int32_t image_id, int32_t *rows, int64_t *row_offset) {
+    msfm_ctx *ctx = const_cast<msfm_ctx *>(ctx_c);
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    msfm_status st = check_image_id(ctx, image_id, true);
+    if (st != MSFM_OK) return st;
+    if (rows) *rows = ctx->images[image_id].rows;
+    if (row_offset) *row_offset = ctx->images[image_id].off;
+    return MSFM_OK;
+}
+
+msfm_status msfm_table_ptrs(const msfm_ctx *ctx, void **desc_arena, void **norm_arena, int64_t *arena_rows, int64_t *rows_used) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    if (desc_arena) *desc_arena = ctx->desc;
+    if (norm_arena) *norm_arena = ctx->norms;
+    if (arena_rows) *arena_rows = ctx->arena_rows;
+    if (rows_used) *rows_used = ctx->rows_high_water;
+    return MSFM_OK;
+}
+
+msfm_status msfm_download_packed(msfm_ctx *ctx, int32_t image_id, uint8_t *desc_out, uint32_t *norms_out) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    msfm_status st = check_image_id(ctx, image_id, true);
+    if (st != MSFM_OK) return st;
+    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const ImageSlot &s = ctx->images[image_id];
+    if (desc_out && s.rows) MSFM_CUDA(ctx, cudaMemcpyAsync(desc_out, ctx->desc + s.off * kDim, (size_t)s.rows * kDim, cudaMemcpyDeviceToHost, ctx->stream));
+    if (norms_out && s.rows) MSFM_CUDA(ctx, cudaMemcpyAsync(norms_out, ctx->norms + s.off, (size_t)s.rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MSFM_OK;
+}
+
+msfm_status msfm_knn2(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_t *ids, float *dists) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!ids || !dists) return fail(ctx, MSFM_ERR_INVALID_ARG, "null output buffer");
+    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    BatchPlan plan;
+    msfm_status st = knn_single(ctx, ref_id, query_id, false, plan);
+    if (st != MSFM_OK) return st;
+    const int n = (int)plan.query_rows;
+    if (n == 0) return MSFM_OK;
+    if ((st = ensure(ctx, ctx->tight_matches, (size_t)n * 8)) != MSFM_OK) return st;
+    if ((st = ensure(ctx, ctx->matches, (size_t)n * 8)) != MSFM_OK) return st;
+    int32_t *d_ids = static_cast<int32_t *>(ctx->tight_matches.ptr);
+    float *d_dists = static_cast<float *>(ctx->matches.ptr);
+    msfm::knn_to_flann_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const int4 *>(ctx->knn.ptr), n, d_ids, d_dists);
+    MSFM_CUDA(ctx, cudaGetLastError());
+    ctx->timing.total_launches += 1;
+    MSFM_CUDA(ctx, cudaMemcpyAsync(ids, d_ids, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MSFM_CUDA(ctx, cudaMemcpyAsync(dists, d_dists, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->timing.d2h_bytes = (int64_t)n * 16;
+    if (!plan.items.empty() && (st = accumulate_kernel_time(ctx)) != MSFM_OK) return st;
+    MSFM_CUDA(ctx, cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev_begin, ctx->ev_end));
+    return MSFM_OK;
+}
+
+msfm_status msfm_colbest(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_t *best_query, float *best_dist) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!best_query || !best_dist) return fail(ctx, MSFM_ERR_INVALID_ARG, "null output buffer");
+    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    BatchPlan plan;
+    msfm_status st = knn_single(ctx, ref_id, query_id, true, plan);
+    if (st != MSFM_OK) return st;
+    const int m = (int)plan.ref_rows;
+    if (m == 0) return MSFM_OK;
+    if (plan.items.empty()) {  // no query rows: nobody is best
+        for (int j = 0; j < m; ++j) { best_query[j] = -1; best_dist[j] = __builtin_inff(); }
+        return MSFM_OK;
+    }
+    if ((st = ensure(ctx, ctx->tight_matches, (size_t)m * 4)) != MSFM_OK) return st;
+    if ((st = ensure(ctx, ctx->matches, (size_t)m * 4)) != MSFM_OK) return st;
+    int32_t *d_best = static_cast<int32_t *>(ctx->tight_matches.ptr);
+    float *d_dist = static_cast<float *>(ctx->matches.ptr);
+    msfm::colbest_unpack_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const unsigned long long *>(ctx->colbest.ptr), m, d_best, d_dist);
+    MSFM_CUDA(ctx, cudaGetLastError());
+    MSFM_CUDA(ctx, cudaMemcpyAsync(best_query, d_best, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MSFM_CUDA(ctx, cudaMemcpyAsync(best_dist, d_dist, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((st = accumulate_kernel_time(ctx)) != MSFM_OK) return st;
+    return MSFM_OK;
+}
+
+msfm_status msfm_match_pairs(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const msfm_params *params, msfm_result *out) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return MSFM_ERR_CUDA;
+    return match_pairs_impl(ctx, pairs, n_pairs, params, out, false, nullptr);
+}
+
+msfm_status msfm_match_pairs_resident(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const msfm_params *params,
+                                      int64_t *n_matches_total) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return MSFM_ERR_CUDA;
+    return match_pairs_impl(ctx, pairs, n_pairs, params, nullptr, true, n_matches_total);
+}
+
+msfm_status msfm_last_timing(const msfm_ctx *ctx, msfm_timing *out) {
+    if (!ctx || !out) return MSFM_ERR_INVALID_ARG;
+    *out = ctx->timing;
+    return MSFM_OK;
+}
+
+msfm_status msfm_knn2_crosscheck(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_t *ids, float *dists) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!ids || !dists) return fail(ctx, MSFM_ERR_INVALID_ARG, "null output buffer");
+    msfm_status st;
+    if ((st = check_image_id(ctx, ref_id, true)) != MSFM_OK) return st;
+    if ((st = check_image_id(ctx, query_id, true)) != MSFM_OK) return st;
+    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const ImageSlot &r = ctx->images[ref_id], &q = ctx->images[query_id];
+    const int n = q.rows;
+    if (n == 0) return MSFM_OK;
+    if ((st = ensure(ctx, ctx->knn, (size_t)n * sizeof(int4))) != MSFM_OK) return st;
+    if ((st = ensure(ctx, ctx->tight_matches, (size_t)n * 8)) != MSFM_OK) return st;
+    if ((st = ensure(ctx, ctx->matches, (size_t)n * 8)) != MSFM_OK) return st;
+    msfm::crosscheck_knn2_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->desc + r.off * kDim, ctx->norms + r.off, r.rows,
+                                                                         ctx->desc + q.off * kDim, ctx->norms + q.off, n,
+                                                                         static_cast<int4 *>(ctx->knn.ptr));
+    int32_t *d_ids = static_cast<int32_t *>(ctx->tight_matches.ptr);
+    float *d_dists = static_cast<float *>(ctx->matches.ptr);
+    msfm::knn_to_flann_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const int4 *>(ctx->knn.ptr), n, d_ids, d_dists);
+    MSFM_CUDA(ctx, cudaGetLastError());
+    MSFM_CUDA(ctx, cudaMemcpyAsync(ids, d_ids, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MSFM_CUDA(ctx, cudaMemcpyAsync(dists, d_dists, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MSFM_OK;
+}
+
+}  // extern "C"

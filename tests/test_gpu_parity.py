@@ -1,0 +1,237 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs, against the committed golden vectors of the reference engine, and through size-independent
+properties at full size.  Bar: bit-exact ids, distances and match lists (integer regime)."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES
+from metricsfm_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RATIOS = {"r50": 0.5, "r60": 0.6, "r85": 0.85}
+
+
+@pytest.fixture(scope="module")
+def matcher(native_lib):
+    from metricsfm_b200.matcher import Matcher
+    m = Matcher(device=0, max_images=256, arena_rows=1 << 20)
+    yield m
+    m.close()
+
+
+def _upload_pair(matcher, ref, qry):
+    matcher.release_all()
+    matcher.upload(0, ref)
+    matcher.upload(1, qry)
+
+
+def _check_knn(oracle_mod, matcher, ref, qry):
+    ids, dists = matcher.knn2(0, 1)
+    oids, odists = oracle_mod.knn2_u8(ref, qry)
+    np.testing.assert_array_equal(dists, odists)
+    np.testing.assert_array_equal(ids, oids)
+    return ids, dists
+
+
+def test_packer_roundtrip_and_norms(matcher, golden):
+    g = golden["basic"]
+    _upload_pair(matcher, g["ref"], g["qry"])
+    d, n = matcher.download_packed(0)
+    np.testing.assert_array_equal(d, g["ref"])
+    np.testing.assert_array_equal(n, (g["ref"].astype(np.int64) ** 2).sum(1).astype(np.uint32))
+    # float upload: integer-valued floats at scale 1, unit-norm floats at scale 512 (quantiser golden)
+    matcher.release_all()
+    matcher.upload(0, g["ref"].astype(np.float32), scale=1.0)
+    np.testing.assert_array_equal(matcher.download_packed(0)[0], g["ref"])
+    fu = golden["float_unit"]
+    matcher.upload(1, fu["unit"], scale=512.0)
+    np.testing.assert_array_equal(matcher.download_packed(1)[0], fu["q512"])
+    # strided rows (a cv::Mat ROI): every other row of a larger buffer
+    big = np.zeros((2 * g["qry"].shape[0], 128), np.uint8)
+    big[::2] = g["qry"]
+    matcher.upload(2, big[::2])
+    np.testing.assert_array_equal(matcher.download_packed(2)[0], g["qry"])
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_golden_reference_vectors(matcher, golden, case):
+    g = golden[case]
+    _upload_pair(matcher, g["ref"], g["qry"])
+    ids, dists = matcher.knn2(0, 1)
+    np.testing.assert_array_equal(dists, g["fm_dists"])
+    np.testing.assert_array_equal(ids, g["fm_ids"])
+    for tag, th in RATIOS.items():
+        ok, pairs = matcher.MatchAgainstIndex(0, 1, th_ratio=th, th_reject=20)
+        exp = g["fm_pairs_" + tag]
+        if exp.shape[0] == 1 and exp[0, 0] == -7:
+            assert not ok and len(pairs) == 0
+        else:
+            assert ok
+            np.testing.assert_array_equal(pairs, exp)
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (1, 40), (2, 2), (19, 20), (20, 20), (21, 127), (127, 128), (128, 129), (129, 255),
+                                 (256, 256), (257, 513), (1000, 300), (300, 1000), (2049, 777)])
+def test_knn2_ragged_sizes(oracle_mod, matcher, m, n):
+    rng = np.random.default_rng(m * 7919 + n)
+    ref = rng.integers(0, 256, size=(m, 128), dtype=np.uint8)
+    qry = rng.integers(0, 256, size=(n, 128), dtype=np.uint8)
+    _upload_pair(matcher, ref, qry)
+    _check_knn(oracle_mod, matcher, ref, qry)
+    cb, cd = matcher.colbest(0, 1)
+    ob, od = oracle_mod.colbest_u8(ref, qry)
+    np.testing.assert_array_equal(cd, od)
+    np.testing.assert_array_equal(cb, ob)
+
+
+def test_ties_duplicates_extremes(oracle_mod, matcher):
+    rng = np.random.default_rng(77)
+    ref = rng.integers(0, 4, size=(700, 128), dtype=np.uint8)   # tiny value range: masses of exact ties
+    qry = rng.integers(0, 4, size=(515, 128), dtype=np.uint8)
+    ref[100:110] = ref[5]
+    ref[300] = 0
+    ref[301] = 255
+    qry[7] = ref[5]
+    qry[8] = ref[5]
+    qry[9] = 255
+    qry[10] = 0
+    _upload_pair(matcher, ref, qry)
+    _check_knn(oracle_mod, matcher, ref, qry)
+    cb, cd = matcher.colbest(0, 1)
+    ob, od = oracle_mod.colbest_u8(ref, qry)
+    np.testing.assert_array_equal(cd, od)
+    np.testing.assert_array_equal(cb, ob)
+    # worst-case magnitudes: all-255 vs all-0 rows give d = 128*255^2
+    ref2 = np.zeros((40, 128), np.uint8)
+    qry2 = np.full((33, 128), 255, np.uint8)
+    ref2[3] = 255
+    _upload_pair(matcher, ref2, qry2)
+    ids, dists = _check_knn(oracle_mod, matcher, ref2, qry2)
+    assert dists[0, 0] == 0 and dists[0, 1] == 128 * 255 * 255 and ids[0, 0] == 3 and ids[0, 1] == 0
+
+
+def test_crosscheck_kernel_agrees(oracle_mod, matcher):
+    col = synth.Collection(900, seed=31)
+    ref, qry = col.image_u8(0, 900), col.image_u8(1, 650)
+    _upload_pair(matcher, ref, qry)
+    ids, dists = matcher.knn2(0, 1)
+    cids, cdists = matcher.knn2_crosscheck(0, 1)
+    np.testing.assert_array_equal(ids, cids)
+    np.testing.assert_array_equal(dists, cdists)
+
+
+@pytest.mark.parametrize("mutual", [False, True])
+@pytest.mark.parametrize("orientation", [0, 1])
+def test_match_pairs_batch_vs_oracle(oracle_mod, matcher, mutual, orientation):
+    col = synth.Collection(1100, seed=41)
+    rows = [1100, 980, 513, 19, 256, 1024, 0, 37]
+    imgs = [col.image_u8(i, r) for i, r in enumerate(rows)]
+    matcher.release_all()
+    for i, d in enumerate(imgs):
+        matcher.upload(i, d)
+    pairs = [(0, 1), (1, 0), (0, 2), (2, 5), (3, 0), (0, 3), (4, 5), (5, 4), (6, 0), (0, 6), (7, 2), (1, 1)]
+    res = matcher.match_pairs(pairs, 0.85, ratio_good=0.6, mutual=mutual, orientation=orientation)
+    assert res.offsets[0] == 0 and res.offsets[-1] == len(res.matches)
+    for p, (r, q) in enumerate(pairs):
+        exp = oracle_mod.match_pair_u8(imgs[r], imgs[q], 0.85, mutual=mutual, orientation=orientation, ratio_good=0.6)
+        assert bool(res.ok[p]) == exp["ok"], (p, r, q)
+        np.testing.assert_array_equal(res.pair(p), exp["pairs"], err_msg=f"pair {p} = ({r},{q})")
+        np.testing.assert_array_equal(res.pair_good(p), exp["good"], err_msg=f"pair {p} = ({r},{q})")
+    total = matcher.match_pairs_resident(pairs, 0.85, ratio_good=0.6, mutual=mutual, orientation=orientation)
+    assert total == len(res.matches)
+
+
+def test_reference_shaped_entry_points(oracle_mod, matcher):
+    col = synth.Collection(800, seed=43)
+    d1, d2 = col.image_u8(0, 800), col.image_u8(1, 700)
+    _upload_pair(matcher, d1, d2)
+    ok, m = matcher.KNNMatching(0, 1)  # index on image 2, queries = image 1, (i1, i2) ascending i1
+    exp = oracle_mod.match_pair_u8(d2, d1, 0.5, orientation=1)
+    assert ok
+    np.testing.assert_array_equal(m, exp["pairs"])
+    assert (np.diff(m[:, 0]) > 0).all()
+
+
+def test_max_dist_gate(oracle_mod, matcher):
+    col = synth.Collection(600, seed=47)
+    a, b = col.image_u8(0, 600), col.image_u8(1, 600)
+    _upload_pair(matcher, a, b)
+    res = matcher.match_pairs([(0, 1)], 0.85, max_dist_sq=40000.0)
+    exp = oracle_mod.match_pair_u8(a, b, 0.85, max_dist_sq=40000.0)
+    np.testing.assert_array_equal(res.pair(0), exp["pairs"])
+
+
+def test_error_paths(matcher):
+    from metricsfm_b200.matcher import MsfmError
+    matcher.release_all()
+    matcher.upload(0, np.zeros((30, 128), np.uint8))
+    with pytest.raises(MsfmError) as e:
+        matcher.knn2(0, 5)
+    assert e.value.status == 4
+    with pytest.raises(MsfmError) as e:
+        matcher.upload(0, np.zeros((30, 128), np.uint8))
+    assert e.value.status == 7
+    with pytest.raises(MsfmError) as e:
+        matcher.upload(100000, np.zeros((30, 128), np.uint8))
+    assert e.value.status == 1
+    matcher.upload(1, np.zeros((30, 128), np.uint8))
+    with pytest.raises(MsfmError) as e:
+        matcher.match_pairs([(0, 9)], 0.6)
+    assert e.value.status == 4
+    with pytest.raises(MsfmError) as e:   # caller buffer too small for the matches -> capacity error, not overflow
+        rng = np.random.default_rng(5)
+        matcher.upload(2, rng.integers(0, 256, size=(64, 128), dtype=np.uint8))
+        matcher.upload(3, rng.integers(0, 256, size=(64, 128), dtype=np.uint8))
+        matcher.match_pairs([(2, 3)], 0.99, capacity=1)
+    assert e.value.status == 5
+    matcher.release(0)
+    matcher.upload(0, np.ones((40, 128), np.uint8))  # slot and arena space are reusable after release
+    assert matcher.image_info(0)[0] == 40
+
+
+def test_full_size_8k_pair_vs_oracle(oracle_mod, matcher):
+    """BASELINE config #1: 2 x 8192 x 128, one pair — the oracle still finishes in seconds here."""
+    col = synth.Collection(8192, seed=1)
+    a, b = col.image_u8(0), col.image_u8(1)
+    _upload_pair(matcher, a, b)
+    ids, dists = _check_knn(oracle_mod, matcher, a, b)
+    for mutual in (False, True):
+        res = matcher.match_pairs([(0, 1)], 0.6, mutual=mutual)
+        exp = oracle_mod.match_pair_u8(a, b, 0.6, mutual=mutual)
+        np.testing.assert_array_equal(res.pair(0), exp["pairs"])
+    assert len(res.matches) > 50  # the synthetic pair has real correspondences
+
+
+def test_full_size_properties_20k(oracle_mod, matcher):
+    """Config #3 shape (20 000 rows, ragged): properties that need no full oracle pass."""
+    col = synth.Collection(20000, seed=2)
+    a, b = col.image_u8(0), col.image_u8(1)
+    _upload_pair(matcher, a, b)
+    ids, dists = matcher.knn2(0, 1)
+    # (1) self-consistency: recompute the two reported distances exactly on the host
+    qa = b.astype(np.int64)
+    for col_i in (0, 1):
+        ref_rows = a[ids[:, col_i]].astype(np.int64)
+        np.testing.assert_array_equal(((qa - ref_rows) ** 2).sum(1).astype(np.float32), dists[:, col_i])
+    assert (dists[:, 0] <= dists[:, 1]).all() and (ids[:, 0] != ids[:, 1]).all()
+    # (2) optimality on a random sample of query rows against the oracle
+    rng = np.random.default_rng(3)
+    sample = np.sort(rng.choice(20000, size=256, replace=False))
+    oids, odists = oracle_mod.knn2_u8(a, b[sample])
+    np.testing.assert_array_equal(ids[sample], oids)
+    np.testing.assert_array_equal(dists[sample], odists)
+    # (3) symmetry: the column-best of (a,b) equals the row-best of the swapped problem
+    cb, cd = matcher.colbest(0, 1)
+    sids, sdists = matcher.knn2(1, 0)
+    np.testing.assert_array_equal(cb, sids[:, 0])
+    np.testing.assert_array_equal(cd, sdists[:, 0])
+    # (4) mutual matches are a subset of one-way matches and are one-to-one
+    one = matcher.match_pairs([(0, 1)], 0.85).pair(0)
+    mut = matcher.match_pairs([(0, 1)], 0.85, mutual=True).pair(0)
+    assert {tuple(p) for p in mut} <= {tuple(p) for p in one}
+    assert len(np.unique(mut[:, 0])) == len(mut) and (np.diff(mut[:, 1]) > 0).all()
+    # (5) idempotence
+    ids2, dists2 = matcher.knn2(0, 1)
+    np.testing.assert_array_equal(ids, ids2)
+    np.testing.assert_array_equal(dists, dists2)
