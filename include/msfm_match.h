@@ -153,6 +153,9 @@ msfm_status msfm_match_pairs_resident(msfm_ctx *ctx, const msfm_pair *pairs, int
                                       int64_t *n_matches_total);
 
 msfm_status msfm_last_timing(const msfm_ctx *ctx, msfm_timing *out);
+/* The CUDA stream (cudaStream_t) every kernel and copy of this context is enqueued on, so a host harness can record
+ * its own events around calls (bench.py) or order foreign work (a collective filling the table) against it. */
+msfm_status msfm_get_stream(const msfm_ctx *ctx, void **cuda_stream);
 
 /* ---- GPU-side cross-check kernel (CUDA cores, dp4a); used by the tests to localise faults, never by the fast path */
 msfm_status msfm_knn2_crosscheck(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_t *ids, float *dists);

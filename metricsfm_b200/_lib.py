@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "msfm_abi_version", "msfm_status_string", "msfm_create", "msfm_destroy", "msfm_last_error", "msfm_upload_u8",
     "msfm_upload_f32", "msfm_reserve", "msfm_release", "msfm_release_all", "msfm_image_info", "msfm_table_ptrs",
     "msfm_download_packed", "msfm_knn2", "msfm_colbest", "msfm_match_pairs", "msfm_match_pairs_resident",
-    "msfm_last_timing", "msfm_knn2_crosscheck",
+    "msfm_last_timing", "msfm_get_stream", "msfm_knn2_crosscheck",
 ]
 
 
@@ -85,6 +85,7 @@ def load() -> C.CDLL:
     L.msfm_match_pairs.argtypes = [vp, vp, C.c_int64, C.POINTER(Params), C.POINTER(Result)]
     L.msfm_match_pairs_resident.argtypes = [vp, vp, C.c_int64, C.POINTER(Params), _i64p]
     L.msfm_last_timing.argtypes = [vp, C.POINTER(Timing)]
+    L.msfm_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.msfm_knn2_crosscheck.argtypes = [vp, C.c_int32, C.c_int32, vp, vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)

@@ -734,6 +734,12 @@ msfm_status msfm_last_timing(const msfm_ctx *ctx, msfm_timing *out) {
     return MSFM_OK;
 }
 
+msfm_status msfm_get_stream(const msfm_ctx *ctx, void **cuda_stream) {
+    if (!ctx || !cuda_stream) return MSFM_ERR_INVALID_ARG;
+    *cuda_stream = static_cast<void *>(ctx->stream);
+    return MSFM_OK;
+}
+
 msfm_status msfm_knn2_crosscheck(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_t *ids, float *dists) {
     if (!ctx) return MSFM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);

@@ -216,6 +216,12 @@ class Matcher:
         self._check(self._L.msfm_match_pairs_resident(self._h, pa.ctypes.data, pa.shape[0], C.byref(prm), C.byref(total)))
         return total.value
 
+    def cuda_stream(self) -> int:
+        """Raw cudaStream_t of this context (wrap with torch.cuda.ExternalStream to record events on it)."""
+        s = C.c_void_p()
+        self._check(self._L.msfm_get_stream(self._h, C.byref(s)))
+        return s.value or 0
+
     def timing(self) -> dict:
         t = Timing()
         self._check(self._L.msfm_last_timing(self._h, C.byref(t)))
