@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-pairs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mutual", type=int, default=1, help="1 = ratio + mutual cross-check (headline), 0 = ratio only")
     return ap.parse_args()
 
 
@@ -225,7 +226,7 @@ def run_native(args):
         return n_local * rows * 128
 
     stage_table()
-    kw = dict(ratio_good=RATIO_GOOD, mutual=True, min_keypoints=20, orientation=0)
+    kw = dict(ratio_good=RATIO_GOOD, mutual=bool(args.mutual), min_keypoints=20, orientation=0)
     flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -322,7 +323,7 @@ def run_native(args):
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"exhaustive matching of {n_local} web images x {rows} SIFT-128 descriptors ({len(base)} pairs) per GPU "
-                                   f"(BASELINE config #2); 2-NN + ratio {RATIO_ALL}/{RATIO_GOOD} + mutual cross-check",
+                                   f"(BASELINE config #2); 2-NN + ratio {RATIO_ALL}/{RATIO_GOOD}" + (" + mutual cross-check" if args.mutual else " (no mutual check)"),
                        "pairs_per_step_all_gpus": int(len(pairs)), "parallelism": f"pair-sharded x{world}, table replicated",
                        "l2": "flushed between timed steps (256 MiB write)", "matches_per_step_rank0": int(n_matches)},
             "roofline": {"bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TFLOP/s", "frac": achieved_tops / peak_tops,

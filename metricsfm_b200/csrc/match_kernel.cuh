@@ -54,7 +54,7 @@ struct MatchKernelParams {
     const PairDesc *pairs;
     const WorkItem *items;
     int32_t n_items;
-    int32_t want_colbest;         // 0: skip the per-reference-row reduction
+    unsigned long long *stats;    // optional debug counter (slow-path group visits); null in production
     int4 *knn;                    // [sum qry_rows] {id0, id1, d0, d1}; id = -1 / d = INT_MAX when absent
     unsigned long long *colbest;  // [sum ref_rows] (d << 32 | query row), initialised to ~0
 };
@@ -82,7 +82,7 @@ struct MatchKernelCfg {
     static_assert(kAlignRows % TILE_N == 0, "image padding must cover whole reference tiles");
 };
 
-template <int STRIPS, int TILE_N, int STAGES>
+template <int STRIPS, int TILE_N, int STAGES, bool COLBEST>
 __global__ void __launch_bounds__(MatchKernelCfg<STRIPS, TILE_N, STAGES>::kThreads, 1)
 match_pairs_kernel(const MatchKernelParams p) {
     using Cfg = MatchKernelCfg<STRIPS, TILE_N, STAGES>;
@@ -185,10 +185,17 @@ match_pairs_kernel(const MatchKernelParams p) {
         }
     } else {
         // =========================================================== epilogue (thread = query row)
+        // Scores s = 2*acc - ||r||^2 (maximise; d = ||q||^2 - s).  Fast path: the running maximum of the RAW accumulators of
+        // a group of 8 columns is compared with T = floor((S1 + min||r||^2 over the tile) / 2): if no lane of the warp
+        // exceeds it, no column of the group can enter any lane's top-2 (2*acc - nb_j <= 2*acc - nbmin <= S1) and the group
+        // costs ~0.7 instructions per element.  Otherwise the group is re-scanned exactly (slow path).  Ties never displace
+        // (strict >) and columns are visited in ascending order, hence lowest-index tie-breaking.
         const int strip = warp >> 2;
         const int quarter = warp & 3;
         const int row_local = strip * kStripRows + quarter * 32 + lane;
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + strip * TILE_N;
+        constexpr int kChunks = TILE_N / 32;
+        constexpr int kAbsent = -0x20000000;  // scores below this are pad columns / "no neighbour"
         uint32_t g = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const WorkItem wi = p.items[item];
@@ -198,37 +205,71 @@ match_pairs_kernel(const MatchKernelParams p) {
             const uint32_t na = valid ? p.norms[pd.qry_off + q] : 0u;
             // column key = (na + 2^23 - 2 acc) * 32 + lane  (29 bits); invalid rows sit above every valid key
             const uint32_t kcol = valid ? (((na + (1u << 23)) << 5) | (uint32_t)lane) : ((1u << 29) | (uint32_t)lane);
-            int v0 = INT_MAX, v1 = INT_MAX, i0 = -1, i1 = -1;
+            // rows past the image end hold zeros; park their state where nothing can trigger the slow path
+            int S0 = valid ? INT_MIN : 0x20000000, S1 = S0, J0 = -1, J1 = -1;
             const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
             for (int t = 0; t < ntiles; ++t, ++g) {
                 const uint32_t buf = g & 1;
                 const uint32_t ns = g % Cfg::kNormSlots;
                 ptx::mbar_wait(&n_full[ns], (g / Cfg::kNormSlots) & 1);
+                const uint32_t *nb = sNorm + ns * TILE_N;
+                uint32_t nbmin = nb[lane];
+#pragma unroll
+                for (int k = 1; k < TILE_N / 32; ++k) nbmin = min(nbmin, nb[lane + 32 * k]);
+                nbmin = __reduce_min_sync(0xFFFFFFFFu, nbmin);
+                int T = (S1 + (int)nbmin) >> 1;
                 ptx::mbar_wait(&t_full[buf], (g >> 1) & 1);
                 ptx::tc_fence_after();
-                const uint32_t *nb = sNorm + ns * TILE_N;
-#pragma unroll 1
-                for (int c = 0; c < TILE_N / 32; ++c) {
-                    uint32_t acc[32];
-                    ptx::tmem_ld_32x32b_x32(lane_taddr + buf * (STRIPS * TILE_N) + c * 32, acc);
-                    ptx::tmem_ld_wait();
-                    const int jbase = t * TILE_N + c * 32;
-                    uint32_t mycol = 0xFFFFFFFFu;
+                const uint32_t tile_taddr = lane_taddr + buf * (STRIPS * TILE_N);
+                uint32_t acc[2][32];
+                ptx::tmem_ld_32x32b_x32(tile_taddr, acc[0]);
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) {
-                        const int a = (int)acc[k];
-                        const int v = (int)nb[c * 32 + k] - 2 * a;
-                        if (v < v1) {
-                            if (v < v0) { v1 = v0; i1 = i0; v0 = v; i0 = jbase + k; }
-                            else { v1 = v; i1 = jbase + k; }
+                for (int c = 0; c < kChunks; ++c) {
+                    ptx::tmem_ld_wait();
+                    if (c + 1 < kChunks) {
+                        ptx::tmem_ld_32x32b_x32(tile_taddr + (c + 1) * 32, acc[(c + 1) & 1]);
+                    } else {
+                        // every TMEM read of this buffer has landed in registers: hand it back to the MMA warp early
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&t_empty[buf]);
+                    }
+                    const uint32_t(&a)[32] = acc[c & 1];
+                    const int jbase = t * TILE_N + c * 32;
+                    int m[4];
+#pragma unroll
+                    for (int gq = 0; gq < 4; ++gq) {
+                        const int m1 = __vimax3_s32((int)a[8 * gq], (int)a[8 * gq + 1], (int)a[8 * gq + 2]);
+                        const int m2 = __vimax3_s32((int)a[8 * gq + 3], (int)a[8 * gq + 4], (int)a[8 * gq + 5]);
+                        m[gq] = __vimax3_s32((int)a[8 * gq + 6], (int)a[8 * gq + 7], max(m1, m2));
+                    }
+                    const int mall = max(max(m[0], m[1]), max(m[2], m[3]));
+                    if (__any_sync(0xFFFFFFFFu, mall > T)) {
+#pragma unroll
+                        for (int gq = 0; gq < 4; ++gq) {
+                            if (__any_sync(0xFFFFFFFFu, m[gq] > T)) {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    const int sc = 2 * (int)a[8 * gq + k] - (int)nb[c * 32 + 8 * gq + k];
+                                    const int j = jbase + 8 * gq + k;
+                                    if (sc > S1) {
+                                        if (sc > S0) { S1 = S0; J1 = J0; S0 = sc; J0 = j; }
+                                        else { S1 = sc; J1 = j; }
+                                    }
+                                }
+                                T = (S1 + (int)nbmin) >> 1;
+                                if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
+                            }
                         }
-                        if (p.want_colbest) {
-                            const uint32_t key = kcol - 64u * (uint32_t)a;
+                    }
+                    if (COLBEST) {
+                        uint32_t mycol = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) {
+                            const uint32_t key = kcol - 64u * a[k];
                             const uint32_t r = __reduce_min_sync(0xFFFFFFFFu, key);
                             if (lane == k) mycol = r;
                         }
-                    }
-                    if (p.want_colbest) {
                         const int j = jbase + lane;
                         if (j < pd.ref_rows && mycol < (1u << 29)) {
                             const uint32_t d = (mycol >> 5) - (1u << 23) + nb[c * 32 + lane];
@@ -239,16 +280,13 @@ match_pairs_kernel(const MatchKernelParams p) {
                         }
                     }
                 }
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&t_empty[buf]);
             }
             if (valid) {
                 int4 out;
-                out.x = (v0 < (int)kNormPad) ? i0 : -1;
-                out.y = (v1 < (int)kNormPad) ? i1 : -1;
-                out.z = (v0 < (int)kNormPad) ? v0 + (int)na : INT_MAX;
-                out.w = (v1 < (int)kNormPad) ? v1 + (int)na : INT_MAX;
+                out.x = (S0 > kAbsent) ? J0 : -1;
+                out.y = (S1 > kAbsent) ? J1 : -1;
+                out.z = (S0 > kAbsent) ? (int)na - S0 : INT_MAX;
+                out.w = (S1 > kAbsent) ? (int)na - S1 : INT_MAX;
                 p.knn[pd.knn_off + q] = out;
             }
         }

@@ -233,11 +233,14 @@ msfm_status launch_match_kernel(msfm_ctx *ctx, const BatchPlan &plan, bool want_
     kp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
     kp.items = static_cast<const WorkItem *>(ctx->items.ptr);
     kp.n_items = (int32_t)plan.items.size();
-    kp.want_colbest = want_colbest ? 1 : 0;
+    kp.stats = nullptr;
     kp.knn = static_cast<int4 *>(ctx->knn.ptr);
     kp.colbest = static_cast<unsigned long long *>(ctx->colbest.ptr);
     const int grid = std::max(1, std::min<int>(ctx->num_sms, kp.n_items));
-    msfm::match_pairs_kernel<kStrips, kTileN, kStages><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
+    if (want_colbest)
+        msfm::match_pairs_kernel<kStrips, kTileN, kStages, true><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
+    else
+        msfm::match_pairs_kernel<kStrips, kTileN, kStages, false><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
     MSFM_CUDA(ctx, cudaGetLastError());
     return MSFM_OK;
 }
@@ -517,7 +520,9 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
         ctx->own_arena = true;
     }
     if (cudaMalloc(&ctx->d_maps, (size_t)ctx->max_images * sizeof(CUtensorMap)) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
-    if (cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             KCfg::kSmemAlloc) != cudaSuccess ||
+        cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              KCfg::kSmemAlloc) != cudaSuccess)
         return bail(MSFM_ERR_CUDA);
     *out = ctx;
