@@ -34,6 +34,7 @@ constexpr int kDim = 128;                 // bytes per packed descriptor row
 constexpr int kStripRows = 128;           // MMA M
 constexpr uint32_t kNormPad = 0x3FFFFFFFu; // ||r||^2 stored for pad rows: never wins a minimum
 constexpr int kAlignRows = 256;           // every image starts on / is padded to a multiple of this many rows
+constexpr int kBoxRows = 64;              // rows per TMA box (strips and reference tiles are loaded as 64-row boxes)
 
 struct PairDesc {
     int32_t ref_img, qry_img;  // tensor-map slots
@@ -49,12 +50,13 @@ struct WorkItem {
 };
 
 struct MatchKernelParams {
-    const CUtensorMap *maps;      // [max_images] one 2-D map per image: {128 B, rows}, box {128 B, 128 rows}, SW128
+    const CUtensorMap *maps;      // [max_images] one 2-D map per image: {128 B, rows}, box {128 B, kBoxRows rows}, SW128
     const uint32_t *norms;        // arena of squared norms (pad rows = kNormPad)
     const PairDesc *pairs;
     const WorkItem *items;
     int32_t n_items;
     unsigned long long *stats;    // optional debug counter (slow-path group visits); null in production
+    uint32_t debug_flags;         // bit 0: skip the exact slow path (timing experiments only; results are wrong)
     int4 *knn;                    // [sum qry_rows] {id0, id1, d0, d1}; id = -1 / d = INT_MAX when absent
     unsigned long long *colbest;  // [sum ref_rows] (d << 32 | query row), initialised to ~0
 };
@@ -63,7 +65,10 @@ template <int STRIPS, int TILE_N, int STAGES>
 struct MatchKernelCfg {
     static constexpr int kEpiWarps = 4 * STRIPS;
     static constexpr int kThreads = (kEpiWarps + 2) * 32;
-    static constexpr int kNormSlots = STAGES + 2;
+    // The producer may refill a norm slot once the MMA that shares its B stage has completed; that MMA was issued after
+    // the epilogue released the TMEM buffer two tiles earlier, and the release happens one chunk before the epilogue
+    // stops reading that tile's norms: STAGES + 3 slots can therefore never be overrun.
+    static constexpr int kNormSlots = STAGES + 3;
     static constexpr int kTmemBufs = 2;
     static constexpr int kTmemCols = kTmemBufs * STRIPS * TILE_N;
     static constexpr int kABytes = STRIPS * kStripRows * kDim;  // one A buffer
@@ -78,7 +83,8 @@ struct MatchKernelCfg {
     static constexpr int kSmemAlloc = kSmemBytes + 1024;  // slack for manual 1024-byte alignment
     static_assert(kTmemCols == 32 || kTmemCols == 64 || kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512,
                   "TMEM allocation must be a power of two in [32, 512] columns");
-    static_assert(TILE_N % 128 == 0 && TILE_N <= 256, "reference tile is loaded as 128-row TMA boxes; UMMA N <= 256");
+    static_assert(TILE_N % kBoxRows == 0 && TILE_N <= 256, "reference tile is loaded as 64-row TMA boxes; UMMA N <= 256");
+    static_assert(kThreads <= 1024, "too many warps");
     static_assert(kAlignRows % TILE_N == 0, "image padding must cover whole reference tiles");
 };
 
@@ -131,17 +137,18 @@ match_pairs_kernel(const MatchKernelParams p) {
                 ptx::mbar_wait(&a_empty[abuf], ((a >> 1) & 1) ^ 1);
                 ptx::mbar_arrive_expect_tx(&a_full[abuf], Cfg::kABytes);
 #pragma unroll
-                for (int s = 0; s < STRIPS; ++s)
-                    ptx::tma_load_2d(sA + abuf * Cfg::kABytes + s * kStripRows * kDim, qmap, &a_full[abuf], 0,
-                                     wi.row0 + s * kStripRows);
+                for (int s = 0; s < STRIPS * kStripRows / kBoxRows; ++s)
+                    ptx::tma_load_2d(sA + abuf * Cfg::kABytes + s * kBoxRows * kDim, qmap, &a_full[abuf], 0,
+                                     wi.row0 + s * kBoxRows);
                 const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
                 for (int t = 0; t < ntiles; ++t, ++g) {
                     const uint32_t st = g % STAGES;
                     ptx::mbar_wait(&b_empty[st], ((g / STAGES) & 1) ^ 1);
                     ptx::mbar_arrive_expect_tx(&b_full[st], Cfg::kBBytes);
 #pragma unroll
-                    for (int h = 0; h < TILE_N / 128; ++h)
-                        ptx::tma_load_2d(sB + st * Cfg::kBBytes + h * 128 * kDim, rmap, &b_full[st], 0, t * TILE_N + h * 128);
+                    for (int h = 0; h < TILE_N / kBoxRows; ++h)
+                        ptx::tma_load_2d(sB + st * Cfg::kBBytes + h * kBoxRows * kDim, rmap, &b_full[st], 0,
+                                         t * TILE_N + h * kBoxRows);
                     const uint32_t ns = g % Cfg::kNormSlots;
                     ptx::mbar_arrive_expect_tx(&n_full[ns], TILE_N * 4);
                     ptx::bulk_load_1d(sNorm + ns * TILE_N, p.norms + pd.ref_off + (int64_t)t * TILE_N, TILE_N * 4, &n_full[ns]);
@@ -244,20 +251,23 @@ match_pairs_kernel(const MatchKernelParams p) {
                         m[gq] = __vimax3_s32((int)a[8 * gq + 6], (int)a[8 * gq + 7], max(m1, m2));
                     }
                     const int mall = max(max(m[0], m[1]), max(m[2], m[3]));
-                    if (__any_sync(0xFFFFFFFFu, mall > T)) {
+                    if (__any_sync(0xFFFFFFFFu, mall > T) && !(p.debug_flags & 1u)) {
 #pragma unroll
                         for (int gq = 0; gq < 4; ++gq) {
                             if (__any_sync(0xFFFFFFFFu, m[gq] > T)) {
 #pragma unroll
                                 for (int k = 0; k < 8; ++k) {
-                                    const int sc = 2 * (int)a[8 * gq + k] - (int)nb[c * 32 + 8 * gq + k];
-                                    const int j = jbase + 8 * gq + k;
-                                    if (sc > S1) {
-                                        if (sc > S0) { S1 = S0; J1 = J0; S0 = sc; J0 = j; }
-                                        else { S1 = sc; J1 = j; }
+                                    // only columns that can still beat some lane's second best are scored exactly
+                                    if (__any_sync(0xFFFFFFFFu, (int)a[8 * gq + k] > T)) {
+                                        const int sc = 2 * (int)a[8 * gq + k] - (int)nb[c * 32 + 8 * gq + k];
+                                        const int j = jbase + 8 * gq + k;
+                                        if (sc > S1) {
+                                            if (sc > S0) { S1 = S0; J1 = J0; S0 = sc; J0 = j; }
+                                            else { S1 = sc; J1 = j; }
+                                        }
+                                        T = (S1 + (int)nbmin) >> 1;
                                     }
                                 }
-                                T = (S1 + (int)nbmin) >> 1;
                                 if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
                             }
                         }

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -28,9 +29,9 @@ using msfm::PairDesc;
 using msfm::WorkItem;
 
 // Kernel configuration of this build.
-constexpr int kStrips = 2;
-constexpr int kTileN = 128;
-constexpr int kStages = 4;
+constexpr int kStrips = 4;
+constexpr int kTileN = 64;
+constexpr int kStages = 6;
 using KCfg = msfm::MatchKernelCfg<kStrips, kTileN, kStages>;
 constexpr int kItemRows = kStrips * msfm::kStripRows;
 
@@ -82,6 +83,7 @@ struct msfm_ctx {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_f1 = nullptr;
 
     msfm_timing timing{};
+    uint32_t debug_flags = 0;  // MSFM_DEBUG_FLAGS environment variable (timing experiments)
     std::string err;
     std::mutex mu;
 };
@@ -176,7 +178,7 @@ msfm_status write_tensor_map(msfm_ctx *ctx, int32_t image_id, int64_t off, int32
     memset(&m, 0, sizeof m);
     cuuint64_t dims[2] = {(cuuint64_t)kDim, (cuuint64_t)std::max(rows, 1)};
     cuuint64_t strides[1] = {(cuuint64_t)kDim};
-    cuuint32_t box[2] = {(cuuint32_t)kDim, 128u};
+    cuuint32_t box[2] = {(cuuint32_t)kDim, (cuuint32_t)msfm::kBoxRows};
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r = ctx->encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ctx->desc + off * kDim, dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -234,6 +236,7 @@ msfm_status launch_match_kernel(msfm_ctx *ctx, const BatchPlan &plan, bool want_
     kp.items = static_cast<const WorkItem *>(ctx->items.ptr);
     kp.n_items = (int32_t)plan.items.size();
     kp.stats = nullptr;
+    kp.debug_flags = ctx->debug_flags;
     kp.knn = static_cast<int4 *>(ctx->knn.ptr);
     kp.colbest = static_cast<unsigned long long *>(ctx->colbest.ptr);
     const int grid = std::max(1, std::min<int>(ctx->num_sms, kp.n_items));
@@ -495,6 +498,7 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
     ctx->max_images = cfg->max_images;
     ctx->arena_rows = round_up(cfg->arena_rows, kAlignRows);
     ctx->images.resize(cfg->max_images);
+    if (const char *dbg = getenv("MSFM_DEBUG_FLAGS")) ctx->debug_flags = (uint32_t)strtoul(dbg, nullptr, 0);
 
     auto bail = [&](msfm_status st) {
         msfm_destroy(ctx);

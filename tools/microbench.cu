@@ -159,13 +159,18 @@ int main() {
     {   // (1) MMA
         const int iters = 20000;
         auto k1 = mma_rate_kernel<256, 1>; auto k2 = mma_rate_kernel<128, 2>; auto k3 = mma_rate_kernel<128, 1>;
-        const int smem = 3 * 128 * 128 + 256 * 128 + 2048;
+        auto k4 = mma_rate_kernel<64, 4>; auto k5 = mma_rate_kernel<64, 2>;
+        const int smem = 4 * 128 * 128 + 256 * 128 + 2048;
+        CK(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(k5, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CK(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         run("mma i8 M128 N256 (1 strip)", [&] { k1<<<sms, 128, smem>>>(iters, d_cycles); }, sms, d_cycles, 2.0 * 128 * 256 * 128 * iters, "op");
         run("mma i8 M128 N128 x2 strips", [&] { k2<<<sms, 128, smem>>>(iters, d_cycles); }, sms, d_cycles, 2.0 * 2 * 128 * 128 * 128 * iters, "op");
         run("mma i8 M128 N128 (1 strip)", [&] { k3<<<sms, 128, smem>>>(iters, d_cycles); }, sms, d_cycles, 2.0 * 128 * 128 * 128 * iters, "op");
+        run("mma i8 M128 N64 x4 strips", [&] { k4<<<sms, 128, smem>>>(iters, d_cycles); }, sms, d_cycles, 2.0 * 4 * 128 * 64 * 128 * iters, "op");
+        run("mma i8 M128 N64 x2 strips", [&] { k5<<<sms, 128, smem>>>(iters, d_cycles); }, sms, d_cycles, 2.0 * 2 * 128 * 64 * 128 * iters, "op");
         run("mma i8 M128 N256, 1 SM only", [&] { k1<<<1, 128, smem>>>(iters, d_cycles); }, 1, d_cycles, 2.0 * 128 * 256 * 128 * iters, "op");
     }
     {   // (2) LDTM
