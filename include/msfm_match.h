@@ -63,7 +63,7 @@ typedef struct msfm_config {
     int64_t arena_rows;      /* total packed-descriptor rows the table can hold (each image is padded to 128 rows) */
     /* Optional caller-owned device memory for the packed table (e.g. tensors a collective library fills during
      * multi-GPU replication).  Both NULL => the library allocates.  desc: arena_rows*128 bytes, 1024-byte aligned;
-     * norms: arena_rows uint32. */
+     * norms: arena_rows 32-bit words (an opaque per-row side table derived from the squared norms). */
     void *external_desc_arena;
     void *external_norm_arena;
     int32_t reserved[4];     /* must be zero */

@@ -14,9 +14,10 @@ namespace msfm {
 
 // ------------------------------------------------------------------------------------------------ packer
 // One warp per row; lane l owns bytes 4l..4l+3.  rows_padded - rows pad rows get zero bytes and kNormPad norms.
+// The side table stores column keys, ckey = -8*||row||^2 + (7 - row%8) (see match_kernel.cuh), not raw norms.
 // Quantisation rule (mirrored by oracle_quantize_f32): q = min(255, max(0, rint(x * scale))), NaN -> 0.
 __global__ void pack_f32_kernel(const float *__restrict__ src, int64_t src_stride_floats, int rows, int rows_padded,
-                                float scale, uint8_t *__restrict__ dst, uint32_t *__restrict__ norms) {
+                                float scale, uint8_t *__restrict__ dst, int32_t *__restrict__ ckeys) {
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows_padded; r += gridDim.x * warps_per_block) {
@@ -39,12 +40,12 @@ __global__ void pack_f32_kernel(const float *__restrict__ src, int64_t src_strid
             nrm = acc;
         }
         reinterpret_cast<uint32_t *>(dst + (int64_t)r * kDim)[lane] = packed;
-        if (lane == 0) norms[r] = nrm;
+        if (lane == 0) ckeys[r] = make_ckey(nrm, r);
     }
 }
 
 __global__ void pack_u8_kernel(const uint8_t *__restrict__ src, int64_t src_stride_bytes, int rows, int rows_padded,
-                               uint8_t *__restrict__ dst, uint32_t *__restrict__ norms) {
+                               uint8_t *__restrict__ dst, int32_t *__restrict__ ckeys) {
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows_padded; r += gridDim.x * warps_per_block) {
@@ -58,17 +59,17 @@ __global__ void pack_u8_kernel(const uint8_t *__restrict__ src, int64_t src_stri
             nrm = acc;
         }
         reinterpret_cast<uint32_t *>(dst + (int64_t)r * kDim)[lane] = packed;
-        if (lane == 0) norms[r] = nrm;
+        if (lane == 0) ckeys[r] = make_ckey(nrm, r);
     }
 }
 
 // Pad rows of a reserved (externally filled) image.
-__global__ void init_pad_kernel(int rows, int rows_padded, uint8_t *__restrict__ dst, uint32_t *__restrict__ norms) {
+__global__ void init_pad_kernel(int rows, int rows_padded, uint8_t *__restrict__ dst, int32_t *__restrict__ ckeys) {
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     for (int r = rows + blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows_padded; r += gridDim.x * warps_per_block) {
         reinterpret_cast<uint32_t *>(dst + (int64_t)r * kDim)[lane] = 0u;
-        if (lane == 0) norms[r] = kNormPad;
+        if (lane == 0) ckeys[r] = make_ckey(kNormPad, r);
     }
 }
 
@@ -214,8 +215,8 @@ __global__ void colbest_unpack_kernel(const unsigned long long *__restrict__ cb,
 // ------------------------------------------------------------------------------------------------ cross-check
 // CUDA-core brute force (dp4a): thread = query row, loops over all reference rows (warp-uniform broadcast loads).
 // Test-only GPU cross-check of the tcgen05 path; exact int32, lowest index on ties.
-__global__ void crosscheck_knn2_kernel(const uint8_t *__restrict__ ref, const uint32_t *__restrict__ ref_norms, int M,
-                                       const uint8_t *__restrict__ qry, const uint32_t *__restrict__ qry_norms, int N,
+__global__ void crosscheck_knn2_kernel(const uint8_t *__restrict__ ref, const int32_t *__restrict__ ref_ckeys, int M,
+                                       const uint8_t *__restrict__ qry, const int32_t *__restrict__ qry_ckeys, int N,
                                        int4 *__restrict__ knn) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= N) return;
@@ -226,7 +227,7 @@ __global__ void crosscheck_knn2_kernel(const uint8_t *__restrict__ ref, const ui
         const uint4 v = qa[k];
         a[4 * k] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
     }
-    const int na = (int)qry_norms[q];
+    const int na = ckey_to_norm(qry_ckeys[q]);
     int d0 = INT_MAX, d1 = INT_MAX, i0 = -1, i1 = -1;
     for (int j = 0; j < M; ++j) {
         const uint4 *rb = reinterpret_cast<const uint4 *>(ref + (int64_t)j * kDim);
@@ -239,7 +240,7 @@ __global__ void crosscheck_knn2_kernel(const uint8_t *__restrict__ ref, const ui
             dot = __dp4a(a[4 * k + 2], v.z, dot);
             dot = __dp4a(a[4 * k + 3], v.w, dot);
         }
-        const int d = na + (int)__ldg(ref_norms + j) - 2 * (int)dot;
+        const int d = na + ckey_to_norm(__ldg(ref_ckeys + j)) - 2 * (int)dot;
         if (d < d1) {
             if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = j; }
             else { d1 = d; i1 = j; }

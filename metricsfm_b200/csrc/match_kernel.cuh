@@ -1,9 +1,9 @@
 // match_kernel.cuh — the hot path: persistent, warp-specialised sm_100a kernel that, for a list of
-// (pair, query-strip) work items, computes the u8 x u8 -> s32 Gram tile on the 5th-gen tensor cores
+// (pair, query-strip-group) work items, computes the u8 x u8 -> s32 Gram tile on the 5th-gen tensor cores
 // (tcgen05.mma.kind::i8, operands TMA-staged in 128B-swizzled shared memory, accumulators in TMEM) and reduces it
 // in a fused epilogue to
 //   * per query row: exact top-2 of d = ||q||^2 + ||r||^2 - 2 q.r  (lowest reference index on ties), and
-//   * per reference row: the best query row (lowest query index on ties; global u64 atomicMin),
+//   * (COLBEST) per reference row: the best query row (lowest query index on ties; global u64 atomicMin),
 // so the N x M distance matrix never leaves the SM.
 //
 // Replaces the arithmetic of flann_find_nearest_neighbors_index(k=2) at
@@ -15,11 +15,12 @@
 //   warp  4*STRIPS         TMA producer (one elected lane)
 //   warp  4*STRIPS+1       TMEM allocator + MMA issuer (one elected lane)
 // Pipelines (all mbarrier based):
-//   A ring (2 deep)   : query strips of a work item, STRIPS x [128 rows x 128 B]
-//   B ring (STAGES)   : reference tiles [TILE_N rows x 128 B]
-//   norm ring         : ||r||^2 of the tile's reference rows (no empty barrier: STAGES+2 slots cannot be
-//                       overrun because the producer is throttled by B-empty, which trails TMEM-empty)
-//   TMEM ring (2 deep): STRIPS x TILE_N int32 accumulator columns per buffer
+//   A ring (2 deep)     : query strips of a work item, STRIPS x [128 rows x 128 B]
+//   B ring (STAGES)     : reference tiles [TILE_N rows x 128 B]
+//   column-key ring     : ckey_j = -8*||r_j||^2 + (7 - j%8) of the tile's reference rows (no empty barrier needed,
+//                         see MatchKernelCfg::kKeySlots)
+//   TMEM                : one TILE_N-column int32 accumulator block PER STRIP with its own full/empty barrier pair,
+//                         so the four warps of a strip run their epilogue while the MMA warp refills other strips
 #pragma once
 #include <cstdint>
 #include <climits>
@@ -30,11 +31,19 @@
 
 namespace msfm {
 
-constexpr int kDim = 128;                 // bytes per packed descriptor row
-constexpr int kStripRows = 128;           // MMA M
-constexpr uint32_t kNormPad = 0x3FFFFFFFu; // ||r||^2 stored for pad rows: never wins a minimum
-constexpr int kAlignRows = 256;           // every image starts on / is padded to a multiple of this many rows
-constexpr int kBoxRows = 64;              // rows per TMA box (strips and reference tiles are loaded as 64-row boxes)
+constexpr int kDim = 128;        // bytes per packed descriptor row
+constexpr int kStripRows = 128;  // MMA M
+constexpr int kAlignRows = 256;  // every image starts on / is padded to a multiple of this many rows
+constexpr int kBoxRows = 64;     // rows per TMA box (strips and reference tiles are loaded as 64-row boxes)
+
+// Per-row side table ("column keys").  For row j with squared norm nb:  ckey = -8*nb + (7 - j%8).
+//   * exact packed score key of element (q, j):  16*acc + ckey = 8*(2*acc - nb) + (7 - j%8)
+//     (max key = best score, then lowest column inside a group of 8)
+//   * nb = (7 - ckey) >> 3
+// Pad rows carry kNormPad so that they lose against every real column.
+constexpr uint32_t kNormPad = 0x0FFFFFF0u;
+__host__ __device__ constexpr int32_t make_ckey(uint32_t nb, int j) { return -8 * (int32_t)nb + (7 - (j & 7)); }
+__host__ __device__ constexpr int32_t ckey_to_norm(int32_t ckey) { return (7 - ckey) >> 3; }
 
 struct PairDesc {
     int32_t ref_img, qry_img;  // tensor-map slots
@@ -51,12 +60,12 @@ struct WorkItem {
 
 struct MatchKernelParams {
     const CUtensorMap *maps;      // [max_images] one 2-D map per image: {128 B, rows}, box {128 B, kBoxRows rows}, SW128
-    const uint32_t *norms;        // arena of squared norms (pad rows = kNormPad)
+    const int32_t *ckeys;         // arena of column keys (see make_ckey)
     const PairDesc *pairs;
     const WorkItem *items;
     int32_t n_items;
-    unsigned long long *stats;    // optional debug counter (slow-path group visits); null in production
     uint32_t debug_flags;         // bit 0: skip the exact slow path (timing experiments only; results are wrong)
+    unsigned long long *stats;    // optional debug counter (slow-path group visits); null in production
     int4 *knn;                    // [sum qry_rows] {id0, id1, d0, d1}; id = -1 / d = INT_MAX when absent
     unsigned long long *colbest;  // [sum ref_rows] (d << 32 | query row), initialised to ~0
 };
@@ -65,28 +74,52 @@ template <int STRIPS, int TILE_N, int STAGES>
 struct MatchKernelCfg {
     static constexpr int kEpiWarps = 4 * STRIPS;
     static constexpr int kThreads = (kEpiWarps + 2) * 32;
-    // The producer may refill a norm slot once the MMA that shares its B stage has completed; that MMA was issued after
-    // the epilogue released the TMEM buffer two tiles earlier, and the release happens one chunk before the epilogue
-    // stops reading that tile's norms: STAGES + 3 slots can therefore never be overrun.
-    static constexpr int kNormSlots = STAGES + 3;
-    static constexpr int kTmemBufs = 2;
-    static constexpr int kTmemCols = kTmemBufs * STRIPS * TILE_N;
+    // The producer may refill a key slot once the MMAs that share its B stage have completed; those were issued after
+    // every strip's epilogue released its accumulator of the previous tile, which happens one chunk before the
+    // epilogue stops reading that tile's keys: tiles <= t-STAGES-2 are done when tile t is loaded.  +1 for margin.
+    static constexpr int kKeySlots = STAGES + 3;
+    static constexpr int kTmemCols = STRIPS * TILE_N;
     static constexpr int kABytes = STRIPS * kStripRows * kDim;  // one A buffer
     static constexpr int kBBytes = TILE_N * kDim;               // one B stage
     static constexpr int kSmemA = 0;
     static constexpr int kSmemB = kSmemA + 2 * kABytes;
-    static constexpr int kSmemNorm = kSmemB + STAGES * kBBytes;
-    static constexpr int kSmemBar = kSmemNorm + kNormSlots * TILE_N * 4;
-    static constexpr int kNumBars = 2 + 2 + STAGES + STAGES + kNormSlots + 2 + 2;
+    static constexpr int kSmemKey = kSmemB + STAGES * kBBytes;
+    static constexpr int kSmemBar = kSmemKey + kKeySlots * TILE_N * 4;
+    static constexpr int kNumBars = 2 + 2 + STAGES + STAGES + kKeySlots + STRIPS + STRIPS;
     static constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
     static constexpr int kSmemBytes = kSmemTmemPtr + 16;
     static constexpr int kSmemAlloc = kSmemBytes + 1024;  // slack for manual 1024-byte alignment
     static_assert(kTmemCols == 32 || kTmemCols == 64 || kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512,
                   "TMEM allocation must be a power of two in [32, 512] columns");
     static_assert(TILE_N % kBoxRows == 0 && TILE_N <= 256, "reference tile is loaded as 64-row TMA boxes; UMMA N <= 256");
-    static_assert(kThreads <= 1024, "too many warps");
     static_assert(kAlignRows % TILE_N == 0, "image padding must cover whole reference tiles");
+    static_assert(kThreads <= 1024, "too many warps");
+    static_assert(kSmemAlloc <= 227 * 1024, "shared memory budget");
 };
+
+// Top-2 (largest, second largest) of eight distinct keys: 17 min/max operations, depth 4, no branches.
+__device__ __forceinline__ void top2_of8(const int (&k)[8], int &g0, int &g1) {
+    const int h0 = max(k[0], k[1]), l0 = min(k[0], k[1]);
+    const int h1 = max(k[2], k[3]), l1 = min(k[2], k[3]);
+    const int h2 = max(k[4], k[5]), l2 = min(k[4], k[5]);
+    const int h3 = max(k[6], k[7]), l3 = min(k[6], k[7]);
+    const int H0 = max(h0, h1), L0 = __vimax3_s32(min(h0, h1), l0, l1);
+    const int H1 = max(h2, h3), L1 = __vimax3_s32(min(h2, h3), l2, l3);
+    g0 = max(H0, H1);
+    g1 = __vimax3_s32(min(H0, H1), L0, L1);
+}
+
+// Merge a group's two best (score, column) candidates a >= b into the running (S0,J0) >= (S1,J1).  Candidates come
+// from higher column indices than anything in the running state, so they must beat it strictly.
+__device__ __forceinline__ void merge_top2(int sa, int ja, int sb, int jb, int &S0, int &J0, int &S1, int &J1) {
+    const bool t0 = sa > S0, t1 = sa > S1, u = sb > S0;
+    const int x1s = u ? sb : S0, x1j = u ? jb : J0;    // second place when a takes first
+    const int y1s = t1 ? sa : S1, y1j = t1 ? ja : J1;  // second place when a does not
+    S1 = t0 ? x1s : y1s;
+    J1 = t0 ? x1j : y1j;
+    S0 = t0 ? sa : S0;
+    J0 = t0 ? ja : J0;
+}
 
 template <int STRIPS, int TILE_N, int STAGES, bool COLBEST>
 __global__ void __launch_bounds__(MatchKernelCfg<STRIPS, TILE_N, STAGES>::kThreads, 1)
@@ -97,15 +130,15 @@ match_pairs_kernel(const MatchKernelParams p) {
 
     uint8_t *sA = smem + Cfg::kSmemA;
     uint8_t *sB = smem + Cfg::kSmemB;
-    uint32_t *sNorm = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemNorm);
+    int32_t *sKey = reinterpret_cast<int32_t *>(smem + Cfg::kSmemKey);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
-    uint64_t *a_full = bars;                       // [2]
-    uint64_t *a_empty = a_full + 2;                // [2]
-    uint64_t *b_full = a_empty + 2;                // [STAGES]
-    uint64_t *b_empty = b_full + STAGES;           // [STAGES]
-    uint64_t *n_full = b_empty + STAGES;           // [kNormSlots]
-    uint64_t *t_full = n_full + Cfg::kNormSlots;   // [2]
-    uint64_t *t_empty = t_full + 2;                // [2]
+    uint64_t *a_full = bars;                     // [2]
+    uint64_t *a_empty = a_full + 2;              // [2]
+    uint64_t *b_full = a_empty + 2;              // [STAGES]
+    uint64_t *b_empty = b_full + STAGES;         // [STAGES]
+    uint64_t *k_full = b_empty + STAGES;         // [kKeySlots]
+    uint64_t *t_full = k_full + Cfg::kKeySlots;  // [STRIPS]
+    uint64_t *t_empty = t_full + STRIPS;         // [STRIPS]
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
 
     const int warp = threadIdx.x >> 5;
@@ -114,8 +147,8 @@ match_pairs_kernel(const MatchKernelParams p) {
     if (warp == Cfg::kEpiWarps && lane == 0) {
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < Cfg::kNormSlots; ++i) ptx::mbar_init(&n_full[i], 1);
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], Cfg::kEpiWarps); }
+        for (int i = 0; i < Cfg::kKeySlots; ++i) ptx::mbar_init(&k_full[i], 1);
+        for (int i = 0; i < STRIPS; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 4); }
         ptx::fence_mbar_init();
     }
     if (warp == Cfg::kEpiWarps + 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
@@ -149,9 +182,9 @@ match_pairs_kernel(const MatchKernelParams p) {
                     for (int h = 0; h < TILE_N / kBoxRows; ++h)
                         ptx::tma_load_2d(sB + st * Cfg::kBBytes + h * kBoxRows * kDim, rmap, &b_full[st], 0,
                                          t * TILE_N + h * kBoxRows);
-                    const uint32_t ns = g % Cfg::kNormSlots;
-                    ptx::mbar_arrive_expect_tx(&n_full[ns], TILE_N * 4);
-                    ptx::bulk_load_1d(sNorm + ns * TILE_N, p.norms + pd.ref_off + (int64_t)t * TILE_N, TILE_N * 4, &n_full[ns]);
+                    const uint32_t ks = g % Cfg::kKeySlots;
+                    ptx::mbar_arrive_expect_tx(&k_full[ks], TILE_N * 4);
+                    ptx::bulk_load_1d(sKey + ks * TILE_N, p.ckeys + pd.ref_off + (int64_t)t * TILE_N, TILE_N * 4, &k_full[ks]);
                 }
             }
         }
@@ -169,65 +202,63 @@ match_pairs_kernel(const MatchKernelParams p) {
                 const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
                 for (int t = 0; t < ntiles; ++t, ++g) {
                     const uint32_t st = g % STAGES;
-                    const uint32_t buf = g & 1;
                     ptx::mbar_wait(&b_full[st], (g / STAGES) & 1);
-                    ptx::mbar_wait(&t_empty[buf], ((g >> 1) & 1) ^ 1);
-                    ptx::tc_fence_after();
                     const uint32_t b_addr = ptx::smem_u32(sB + st * Cfg::kBBytes);
 #pragma unroll
                     for (int s = 0; s < STRIPS; ++s) {
-                        const uint32_t d_tmem = tmem_base + buf * (STRIPS * TILE_N) + s * TILE_N;
+                        ptx::mbar_wait(&t_empty[s], (g & 1) ^ 1);  // strip s has drained its previous tile
+                        ptx::tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + s * TILE_N;
 #pragma unroll
                         for (int k = 0; k < kDim / 32; ++k) {
                             const uint64_t da = ptx::make_smem_desc_sw128(a_addr + s * kStripRows * kDim + k * 32);
                             const uint64_t db = ptx::make_smem_desc_sw128(b_addr + k * 32);
                             ptx::mma_i8_ss(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
                         }
+                        ptx::mma_commit(&t_full[s]);  // this strip's accumulators are ready
                     }
-                    ptx::mma_commit(&b_empty[st]);  // B stage reusable once these MMAs have read it
-                    ptx::mma_commit(&t_full[buf]);  // accumulators ready for the epilogue
+                    ptx::mma_commit(&b_empty[st]);    // B stage reusable once every strip's MMAs have read it
                 }
-                ptx::mma_commit(&a_empty[abuf]);    // A buffer reusable
+                ptx::mma_commit(&a_empty[abuf]);      // A buffer reusable
             }
         }
     } else {
         // =========================================================== epilogue (thread = query row)
-        // Scores s = 2*acc - ||r||^2 (maximise; d = ||q||^2 - s).  Fast path: the running maximum of the RAW accumulators of
-        // a group of 8 columns is compared with T = floor((S1 + min||r||^2 over the tile) / 2): if no lane of the warp
-        // exceeds it, no column of the group can enter any lane's top-2 (2*acc - nb_j <= 2*acc - nbmin <= S1) and the group
-        // costs ~0.7 instructions per element.  Otherwise the group is re-scanned exactly (slow path).  Ties never displace
-        // (strict >) and columns are visited in ascending order, hence lowest-index tie-breaking.
+        // Scores s = 2*acc - ||r||^2 (maximise; d = ||q||^2 - s).  Fast path: the maximum of the RAW accumulators of a
+        // group of 8 columns is compared with T = floor((S1 + min||r||^2 over the tile) / 2): if no lane of the warp
+        // exceeds it, no column of the group can enter any lane's top-2 (2*acc - nb_j <= 2*acc - nbmin <= S1) and the
+        // group costs ~0.5 instructions per element.  Otherwise the group is scored exactly with packed keys
+        // (branch-free top-2-of-8 network + merge).  Ties never displace (strict >) and columns are visited in
+        // ascending order, hence lowest-index tie-breaking.
         const int strip = warp >> 2;
         const int quarter = warp & 3;
         const int row_local = strip * kStripRows + quarter * 32 + lane;
-        const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + strip * TILE_N;
+        const uint32_t tile_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + strip * TILE_N;
         constexpr int kChunks = TILE_N / 32;
-        constexpr int kAbsent = -0x20000000;  // scores below this are pad columns / "no neighbour"
+        constexpr int kAbsent = -0x08000000;  // scores below this are pad columns / "no neighbour"
         uint32_t g = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const WorkItem wi = p.items[item];
             const PairDesc pd = p.pairs[wi.pair];
             const int q = wi.row0 + row_local;
             const bool valid = q < pd.qry_rows;
-            const uint32_t na = valid ? p.norms[pd.qry_off + q] : 0u;
+            const int na = valid ? ckey_to_norm(p.ckeys[pd.qry_off + q]) : 0;
             // column key = (na + 2^23 - 2 acc) * 32 + lane  (29 bits); invalid rows sit above every valid key
-            const uint32_t kcol = valid ? (((na + (1u << 23)) << 5) | (uint32_t)lane) : ((1u << 29) | (uint32_t)lane);
+            const uint32_t kcol = valid ? ((((uint32_t)na + (1u << 23)) << 5) | (uint32_t)lane) : ((1u << 29) | (uint32_t)lane);
             // rows past the image end hold zeros; park their state where nothing can trigger the slow path
             int S0 = valid ? INT_MIN : 0x20000000, S1 = S0, J0 = -1, J1 = -1;
             const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
             for (int t = 0; t < ntiles; ++t, ++g) {
-                const uint32_t buf = g & 1;
-                const uint32_t ns = g % Cfg::kNormSlots;
-                ptx::mbar_wait(&n_full[ns], (g / Cfg::kNormSlots) & 1);
-                const uint32_t *nb = sNorm + ns * TILE_N;
-                uint32_t nbmin = nb[lane];
+                const uint32_t ks = g % Cfg::kKeySlots;
+                ptx::mbar_wait(&k_full[ks], (g / Cfg::kKeySlots) & 1);
+                const int32_t *ck = sKey + ks * TILE_N;
+                int ckmax = ck[lane];
 #pragma unroll
-                for (int k = 1; k < TILE_N / 32; ++k) nbmin = min(nbmin, nb[lane + 32 * k]);
-                nbmin = __reduce_min_sync(0xFFFFFFFFu, nbmin);
-                int T = (S1 + (int)nbmin) >> 1;
-                ptx::mbar_wait(&t_full[buf], (g >> 1) & 1);
+                for (int k = 1; k < TILE_N / 32; ++k) ckmax = max(ckmax, ck[lane + 32 * k]);
+                const int nbmin = ckey_to_norm(__reduce_max_sync(0xFFFFFFFFu, ckmax));
+                int T = (S1 + nbmin) >> 1;
+                ptx::mbar_wait(&t_full[strip], g & 1);
                 ptx::tc_fence_after();
-                const uint32_t tile_taddr = lane_taddr + buf * (STRIPS * TILE_N);
                 uint32_t acc[2][32];
                 ptx::tmem_ld_32x32b_x32(tile_taddr, acc[0]);
 #pragma unroll
@@ -236,10 +267,10 @@ match_pairs_kernel(const MatchKernelParams p) {
                     if (c + 1 < kChunks) {
                         ptx::tmem_ld_32x32b_x32(tile_taddr + (c + 1) * 32, acc[(c + 1) & 1]);
                     } else {
-                        // every TMEM read of this buffer has landed in registers: hand it back to the MMA warp early
+                        // every TMEM read of this strip's accumulator has landed in registers: hand it back early
                         ptx::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&t_empty[buf]);
+                        if (lane == 0) ptx::mbar_arrive(&t_empty[strip]);
                     }
                     const uint32_t(&a)[32] = acc[c & 1];
                     const int jbase = t * TILE_N + c * 32;
@@ -255,19 +286,17 @@ match_pairs_kernel(const MatchKernelParams p) {
 #pragma unroll
                         for (int gq = 0; gq < 4; ++gq) {
                             if (__any_sync(0xFFFFFFFFu, m[gq] > T)) {
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) {
-                                    // only columns that can still beat some lane's second best are scored exactly
-                                    if (__any_sync(0xFFFFFFFFu, (int)a[8 * gq + k] > T)) {
-                                        const int sc = 2 * (int)a[8 * gq + k] - (int)nb[c * 32 + 8 * gq + k];
-                                        const int j = jbase + 8 * gq + k;
-                                        if (sc > S1) {
-                                            if (sc > S0) { S1 = S0; J1 = J0; S0 = sc; J0 = j; }
-                                            else { S1 = sc; J1 = j; }
-                                        }
-                                        T = (S1 + (int)nbmin) >> 1;
-                                    }
-                                }
+                                const int4 c0 = *reinterpret_cast<const int4 *>(ck + c * 32 + 8 * gq);
+                                const int4 c1 = *reinterpret_cast<const int4 *>(ck + c * 32 + 8 * gq + 4);
+                                const int key[8] = {16 * (int)a[8 * gq + 0] + c0.x, 16 * (int)a[8 * gq + 1] + c0.y,
+                                                    16 * (int)a[8 * gq + 2] + c0.z, 16 * (int)a[8 * gq + 3] + c0.w,
+                                                    16 * (int)a[8 * gq + 4] + c1.x, 16 * (int)a[8 * gq + 5] + c1.y,
+                                                    16 * (int)a[8 * gq + 6] + c1.z, 16 * (int)a[8 * gq + 7] + c1.w};
+                                int g0, g1;
+                                top2_of8(key, g0, g1);
+                                const int jb8 = jbase + 8 * gq;
+                                merge_top2(g0 >> 3, jb8 + ((g0 & 7) ^ 7), g1 >> 3, jb8 + ((g1 & 7) ^ 7), S0, J0, S1, J1);
+                                T = (S1 + nbmin) >> 1;
                                 if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
                             }
                         }
@@ -282,7 +311,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                         }
                         const int j = jbase + lane;
                         if (j < pd.ref_rows && mycol < (1u << 29)) {
-                            const uint32_t d = (mycol >> 5) - (1u << 23) + nb[c * 32 + lane];
+                            const uint32_t d = (mycol >> 5) - (1u << 23) + (uint32_t)ckey_to_norm(ck[c * 32 + lane]);
                             const uint32_t qsrc = (uint32_t)(wi.row0 + strip * kStripRows + quarter * 32) + (mycol & 31u);
                             const unsigned long long val = ((unsigned long long)d << 32) | qsrc;
                             unsigned long long *dst = p.colbest + pd.col_off + j;
@@ -295,8 +324,8 @@ match_pairs_kernel(const MatchKernelParams p) {
                 int4 out;
                 out.x = (S0 > kAbsent) ? J0 : -1;
                 out.y = (S1 > kAbsent) ? J1 : -1;
-                out.z = (S0 > kAbsent) ? (int)na - S0 : INT_MAX;
-                out.w = (S1 > kAbsent) ? (int)na - S1 : INT_MAX;
+                out.z = (S0 > kAbsent) ? na - S0 : INT_MAX;
+                out.w = (S1 > kAbsent) ? na - S1 : INT_MAX;
                 p.knn[pd.knn_off + q] = out;
             }
         }

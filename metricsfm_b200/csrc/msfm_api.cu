@@ -30,8 +30,8 @@ using msfm::WorkItem;
 
 // Kernel configuration of this build.
 constexpr int kStrips = 4;
-constexpr int kTileN = 64;
-constexpr int kStages = 6;
+constexpr int kTileN = 128;
+constexpr int kStages = 4;
 using KCfg = msfm::MatchKernelCfg<kStrips, kTileN, kStages>;
 constexpr int kItemRows = kStrips * msfm::kStripRows;
 
@@ -71,7 +71,7 @@ struct msfm_ctx {
     int64_t rows_high_water = 0;  // bump pointer
     std::vector<Extent> free_list;
     uint8_t *desc = nullptr;
-    uint32_t *norms = nullptr;
+    int32_t *norms = nullptr;  // column-key arena: ckey = -8*||row||^2 + (7 - row%8), see match_kernel.cuh
     bool own_arena = false;
     CUtensorMap *d_maps = nullptr;
     std::vector<ImageSlot> images;
@@ -231,7 +231,7 @@ struct BatchPlan {
 msfm_status launch_match_kernel(msfm_ctx *ctx, const BatchPlan &plan, bool want_colbest) {
     msfm::MatchKernelParams kp;
     kp.maps = ctx->d_maps;
-    kp.norms = ctx->norms;
+    kp.ckeys = ctx->norms;
     kp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
     kp.items = static_cast<const WorkItem *>(ctx->items.ptr);
     kp.n_items = (int32_t)plan.items.size();
@@ -515,7 +515,7 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
     if (cfg->external_desc_arena) {
         if (reinterpret_cast<uintptr_t>(cfg->external_desc_arena) % 1024 != 0) return bail(MSFM_ERR_INVALID_ARG);
         ctx->desc = static_cast<uint8_t *>(cfg->external_desc_arena);
-        ctx->norms = static_cast<uint32_t *>(cfg->external_norm_arena);
+        ctx->norms = static_cast<int32_t *>(cfg->external_norm_arena);
         ctx->arena_rows = cfg->arena_rows / kAlignRows * kAlignRows;
         ctx->own_arena = false;
     } else {
@@ -667,6 +667,8 @@ msfm_status msfm_download_packed(msfm_ctx *ctx, int32_t image_id, uint8_t *desc_
     if (desc_out && s.rows) MSFM_CUDA(ctx, cudaMemcpyAsync(desc_out, ctx->desc + s.off * kDim, (size_t)s.rows * kDim, cudaMemcpyDeviceToHost, ctx->stream));
     if (norms_out && s.rows) MSFM_CUDA(ctx, cudaMemcpyAsync(norms_out, ctx->norms + s.off, (size_t)s.rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
     MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (norms_out)  // the table stores column keys; hand back plain squared norms
+        for (int32_t r = 0; r < s.rows; ++r) norms_out[r] = (uint32_t)msfm::ckey_to_norm((int32_t)norms_out[r]);
     return MSFM_OK;
 }
 
