@@ -77,7 +77,6 @@ __global__ void init_pad_kernel(int rows, int rows_padded, uint8_t *__restrict__
 struct FinalizeParams {
     const PairDesc *pairs;
     const int4 *knn;                    // per-batch kNN scratch
-    const unsigned long long *colbest;  // per-batch column-best scratch (unused when !mutual)
     int2 *matches;                      // per-batch scratch; pair p writes its list from row knn_off
     uint8_t *good;                      // same indexing
     int32_t *counts;                    // [n_pairs]
@@ -104,10 +103,8 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const FinalizeParams fp)
                 const float r = __fdiv_rn(d0, d1);  // IEEE divide; 0/0 = NaN fails every comparison
                 keep = r < fp.ratio;
                 if (fp.max_dist_sq > 0.0f) keep = keep && (d0 < fp.max_dist_sq);
-                if (keep && fp.mutual) {
-                    const unsigned long long cb = fp.colbest[pd.col_off + k.x];
-                    keep = (uint32_t)(cb & 0xFFFFFFFFull) == (uint32_t)q;
-                }
+                if (keep && fp.mutual)  // the twin's row nn0 holds the best query of reference row nn0 (lowest index on ties)
+                    keep = fp.knn[pd.rev_off + k.x].x == q;
                 is_good = keep && fp.ratio_good > 0.0f && r < fp.ratio_good;
                 nn0 = k.x;
             }
@@ -202,14 +199,13 @@ __global__ void knn_to_flann_kernel(const int4 *__restrict__ knn, int rows, int3
     dists[2 * q + 1] = k.y >= 0 ? (float)k.w : __int_as_float(0x7f800000);
 }
 
-__global__ void colbest_unpack_kernel(const unsigned long long *__restrict__ cb, int rows, int32_t *__restrict__ best,
-                                      float *__restrict__ dist) {
+// Nearest neighbour only (used for the "best query of each reference row" query).
+__global__ void knn_best_kernel(const int4 *__restrict__ knn, int rows, int32_t *__restrict__ best, float *__restrict__ dist) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= rows) return;
-    const unsigned long long v = cb[j];
-    const bool has = v != ~0ull;
-    best[j] = has ? (int32_t)(uint32_t)(v & 0xFFFFFFFFull) : -1;
-    dist[j] = has ? (float)(uint32_t)(v >> 32) : __int_as_float(0x7f800000);
+    const int4 k = knn[j];
+    best[j] = k.x;
+    dist[j] = k.x >= 0 ? (float)k.z : __int_as_float(0x7f800000);
 }
 
 // ------------------------------------------------------------------------------------------------ cross-check

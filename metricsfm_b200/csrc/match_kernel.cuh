@@ -2,9 +2,9 @@
 // (pair, query-strip-group) work items, computes the u8 x u8 -> s32 Gram tile on the 5th-gen tensor cores
 // (tcgen05.mma.kind::i8, operands TMA-staged in 128B-swizzled shared memory, accumulators in TMEM) and reduces it
 // in a fused epilogue to
-//   * per query row: exact top-2 of d = ||q||^2 + ||r||^2 - 2 q.r  (lowest reference index on ties), and
-//   * (COLBEST) per reference row: the best query row (lowest query index on ties; global u64 atomicMin),
-// so the N x M distance matrix never leaves the SM.
+//   * per query row: exact top-2 of d = ||q||^2 + ||r||^2 - 2 q.r  (lowest reference index on ties),
+// so the N x M distance matrix never leaves the SM.  The mutual cross-check ("best query of a reference row") is the
+// same reduction with the roles of the two images swapped; the host schedules those items into the same launch.
 //
 // Replaces the arithmetic of flann_find_nearest_neighbors_index(k=2) at
 // /root/reference/SfM/src/graph/fine_matching_graph.cc:99 (and slam_gps.cc:463, feature_matching.cpp:44,336,409)
@@ -50,7 +50,7 @@ struct PairDesc {
     int32_t ref_rows, qry_rows;
     int64_t ref_off, qry_off;  // first row in the arenas
     int64_t knn_off;           // first row of this pair in the per-batch kNN scratch
-    int64_t col_off;           // first row of this pair in the per-batch column-best scratch
+    int64_t rev_off;           // first row of the role-swapped twin of this pair in the kNN scratch (-1: none)
 };
 
 struct WorkItem {
@@ -67,7 +67,6 @@ struct MatchKernelParams {
     uint32_t debug_flags;         // bit 0: skip the exact slow path (timing experiments only; results are wrong)
     unsigned long long *stats;    // optional debug counter (slow-path group visits); null in production
     int4 *knn;                    // [sum qry_rows] {id0, id1, d0, d1}; id = -1 / d = INT_MAX when absent
-    unsigned long long *colbest;  // [sum ref_rows] (d << 32 | query row), initialised to ~0
 };
 
 template <int STRIPS, int TILE_N, int STAGES>
@@ -121,7 +120,7 @@ __device__ __forceinline__ void merge_top2(int sa, int ja, int sb, int jb, int &
     J0 = t0 ? ja : J0;
 }
 
-template <int STRIPS, int TILE_N, int STAGES, bool COLBEST>
+template <int STRIPS, int TILE_N, int STAGES>
 __global__ void __launch_bounds__(MatchKernelCfg<STRIPS, TILE_N, STAGES>::kThreads, 1)
 match_pairs_kernel(const MatchKernelParams p) {
     using Cfg = MatchKernelCfg<STRIPS, TILE_N, STAGES>;
@@ -167,7 +166,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                 const CUtensorMap *qmap = p.maps + pd.qry_img;
                 const CUtensorMap *rmap = p.maps + pd.ref_img;
                 const uint32_t abuf = a & 1;
-                ptx::mbar_wait(&a_empty[abuf], ((a >> 1) & 1) ^ 1);
+                ptx::mbar_wait_backoff(&a_empty[abuf], ((a >> 1) & 1) ^ 1);
                 ptx::mbar_arrive_expect_tx(&a_full[abuf], Cfg::kABytes);
 #pragma unroll
                 for (int s = 0; s < STRIPS * kStripRows / kBoxRows; ++s)
@@ -176,7 +175,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                 const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
                 for (int t = 0; t < ntiles; ++t, ++g) {
                     const uint32_t st = g % STAGES;
-                    ptx::mbar_wait(&b_empty[st], ((g / STAGES) & 1) ^ 1);
+                    ptx::mbar_wait_backoff(&b_empty[st], ((g / STAGES) & 1) ^ 1);
                     ptx::mbar_arrive_expect_tx(&b_full[st], Cfg::kBBytes);
 #pragma unroll
                     for (int h = 0; h < TILE_N / kBoxRows; ++h)
@@ -197,16 +196,16 @@ match_pairs_kernel(const MatchKernelParams p) {
                 const WorkItem wi = p.items[item];
                 const PairDesc pd = p.pairs[wi.pair];
                 const uint32_t abuf = a & 1;
-                ptx::mbar_wait(&a_full[abuf], (a >> 1) & 1);
+                ptx::mbar_wait_backoff(&a_full[abuf], (a >> 1) & 1);
                 const uint32_t a_addr = ptx::smem_u32(sA + abuf * Cfg::kABytes);
                 const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
                 for (int t = 0; t < ntiles; ++t, ++g) {
                     const uint32_t st = g % STAGES;
-                    ptx::mbar_wait(&b_full[st], (g / STAGES) & 1);
+                    ptx::mbar_wait_backoff(&b_full[st], (g / STAGES) & 1);
                     const uint32_t b_addr = ptx::smem_u32(sB + st * Cfg::kBBytes);
 #pragma unroll
                     for (int s = 0; s < STRIPS; ++s) {
-                        ptx::mbar_wait(&t_empty[s], (g & 1) ^ 1);  // strip s has drained its previous tile
+                        ptx::mbar_wait_backoff(&t_empty[s], (g & 1) ^ 1);  // strip s has drained its previous tile
                         ptx::tc_fence_after();
                         const uint32_t d_tmem = tmem_base + s * TILE_N;
 #pragma unroll
@@ -224,18 +223,21 @@ match_pairs_kernel(const MatchKernelParams p) {
         }
     } else {
         // =========================================================== epilogue (thread = query row)
-        // Scores s = 2*acc - ||r||^2 (maximise; d = ||q||^2 - s).  Fast path: the maximum of the RAW accumulators of a
-        // group of 8 columns is compared with T = floor((S1 + min||r||^2 over the tile) / 2): if no lane of the warp
-        // exceeds it, no column of the group can enter any lane's top-2 (2*acc - nb_j <= 2*acc - nbmin <= S1) and the
-        // group costs ~0.5 instructions per element.  Otherwise the group is scored exactly with packed keys
-        // (branch-free top-2-of-8 network + merge).  Ties never displace (strict >) and columns are visited in
-        // ascending order, hence lowest-index tie-breaking.
+        // Scores s = 2*acc - ||r||^2 (maximise; d = ||q||^2 - s).
+        // Phase 1 (filter): stream the strip's accumulator tile through registers once and keep only the maximum RAW
+        //   accumulator of every group of 8 columns; a group is flagged when that maximum exceeds
+        //   T = floor((S1 + min||r||^2 over the tile) / 2) in any lane of the warp.  An unflagged group cannot enter any
+        //   lane's top-2 (2*acc - nb_j <= 2*acc - nbmin <= S1) and costs ~0.45 instructions per element.
+        // Phase 2 (exact): flagged groups (a few per tile) are re-read from TMEM and scored exactly with packed keys
+        //   (branch-free top-2-of-8 network + merge), in ascending column order.  Ties never displace (strict >), hence
+        //   lowest-index tie-breaking.  Then the accumulator is handed back to the MMA warp.
         const int strip = warp >> 2;
         const int quarter = warp & 3;
         const int row_local = strip * kStripRows + quarter * 32 + lane;
         const uint32_t tile_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + strip * TILE_N;
         constexpr int kChunks = TILE_N / 32;
         constexpr int kAbsent = -0x08000000;  // scores below this are pad columns / "no neighbour"
+        static_assert(kChunks * 4 <= 32, "one flag bit per group of 8 columns");
         uint32_t g = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const WorkItem wi = p.items[item];
@@ -243,9 +245,7 @@ match_pairs_kernel(const MatchKernelParams p) {
             const int q = wi.row0 + row_local;
             const bool valid = q < pd.qry_rows;
             const int na = valid ? ckey_to_norm(p.ckeys[pd.qry_off + q]) : 0;
-            // column key = (na + 2^23 - 2 acc) * 32 + lane  (29 bits); invalid rows sit above every valid key
-            const uint32_t kcol = valid ? ((((uint32_t)na + (1u << 23)) << 5) | (uint32_t)lane) : ((1u << 29) | (uint32_t)lane);
-            // rows past the image end hold zeros; park their state where nothing can trigger the slow path
+            // rows past the image end hold zeros; park their state where nothing can flag a group
             int S0 = valid ? INT_MIN : 0x20000000, S1 = S0, J0 = -1, J1 = -1;
             const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
             for (int t = 0; t < ntiles; ++t, ++g) {
@@ -256,69 +256,49 @@ match_pairs_kernel(const MatchKernelParams p) {
 #pragma unroll
                 for (int k = 1; k < TILE_N / 32; ++k) ckmax = max(ckmax, ck[lane + 32 * k]);
                 const int nbmin = ckey_to_norm(__reduce_max_sync(0xFFFFFFFFu, ckmax));
-                int T = (S1 + nbmin) >> 1;
+                const int T = (S1 + nbmin) >> 1;
                 ptx::mbar_wait(&t_full[strip], g & 1);
                 ptx::tc_fence_after();
-                uint32_t acc[2][32];
-                ptx::tmem_ld_32x32b_x32(tile_taddr, acc[0]);
+                // ---- phase 1
+                uint32_t acc[2][16];
+                uint32_t flags = 0;
+                ptx::tmem_ld_32x32b_x16(tile_taddr, acc[0]);
 #pragma unroll
-                for (int c = 0; c < kChunks; ++c) {
+                for (int c = 0; c < 2 * kChunks; ++c) {
                     ptx::tmem_ld_wait();
-                    if (c + 1 < kChunks) {
-                        ptx::tmem_ld_32x32b_x32(tile_taddr + (c + 1) * 32, acc[(c + 1) & 1]);
-                    } else {
-                        // every TMEM read of this strip's accumulator has landed in registers: hand it back early
-                        ptx::tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&t_empty[strip]);
-                    }
-                    const uint32_t(&a)[32] = acc[c & 1];
-                    const int jbase = t * TILE_N + c * 32;
-                    int m[4];
+                    if (c + 1 < 2 * kChunks) ptx::tmem_ld_32x32b_x16(tile_taddr + (c + 1) * 16, acc[(c + 1) & 1]);
+                    const uint32_t(&a)[16] = acc[c & 1];
 #pragma unroll
-                    for (int gq = 0; gq < 4; ++gq) {
+                    for (int gq = 0; gq < 2; ++gq) {
                         const int m1 = __vimax3_s32((int)a[8 * gq], (int)a[8 * gq + 1], (int)a[8 * gq + 2]);
                         const int m2 = __vimax3_s32((int)a[8 * gq + 3], (int)a[8 * gq + 4], (int)a[8 * gq + 5]);
-                        m[gq] = __vimax3_s32((int)a[8 * gq + 6], (int)a[8 * gq + 7], max(m1, m2));
-                    }
-                    const int mall = max(max(m[0], m[1]), max(m[2], m[3]));
-                    if (__any_sync(0xFFFFFFFFu, mall > T) && !(p.debug_flags & 1u)) {
-#pragma unroll
-                        for (int gq = 0; gq < 4; ++gq) {
-                            if (__any_sync(0xFFFFFFFFu, m[gq] > T)) {
-                                const int4 c0 = *reinterpret_cast<const int4 *>(ck + c * 32 + 8 * gq);
-                                const int4 c1 = *reinterpret_cast<const int4 *>(ck + c * 32 + 8 * gq + 4);
-                                const int key[8] = {16 * (int)a[8 * gq + 0] + c0.x, 16 * (int)a[8 * gq + 1] + c0.y,
-                                                    16 * (int)a[8 * gq + 2] + c0.z, 16 * (int)a[8 * gq + 3] + c0.w,
-                                                    16 * (int)a[8 * gq + 4] + c1.x, 16 * (int)a[8 * gq + 5] + c1.y,
-                                                    16 * (int)a[8 * gq + 6] + c1.z, 16 * (int)a[8 * gq + 7] + c1.w};
-                                int g0, g1;
-                                top2_of8(key, g0, g1);
-                                const int jb8 = jbase + 8 * gq;
-                                merge_top2(g0 >> 3, jb8 + ((g0 & 7) ^ 7), g1 >> 3, jb8 + ((g1 & 7) ^ 7), S0, J0, S1, J1);
-                                T = (S1 + nbmin) >> 1;
-                                if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
-                            }
-                        }
-                    }
-                    if (COLBEST) {
-                        uint32_t mycol = 0xFFFFFFFFu;
-#pragma unroll
-                        for (int k = 0; k < 32; ++k) {
-                            const uint32_t key = kcol - 64u * a[k];
-                            const uint32_t r = __reduce_min_sync(0xFFFFFFFFu, key);
-                            if (lane == k) mycol = r;
-                        }
-                        const int j = jbase + lane;
-                        if (j < pd.ref_rows && mycol < (1u << 29)) {
-                            const uint32_t d = (mycol >> 5) - (1u << 23) + (uint32_t)ckey_to_norm(ck[c * 32 + lane]);
-                            const uint32_t qsrc = (uint32_t)(wi.row0 + strip * kStripRows + quarter * 32) + (mycol & 31u);
-                            const unsigned long long val = ((unsigned long long)d << 32) | qsrc;
-                            unsigned long long *dst = p.colbest + pd.col_off + j;
-                            if (val < *reinterpret_cast<volatile unsigned long long *>(dst)) atomicMin(dst, val);
-                        }
+                        const int m = __vimax3_s32((int)a[8 * gq + 6], (int)a[8 * gq + 7], max(m1, m2));
+                        if (m > T) flags |= 1u << (2 * c + gq);
                     }
                 }
+                uint32_t todo = __reduce_or_sync(0xFFFFFFFFu, flags);
+                if (p.debug_flags & 1u) todo = 0;
+                // ---- phase 2
+                while (todo) {
+                    const int grp = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    uint32_t b[8];
+                    ptx::tmem_ld_32x32b_x8(tile_taddr + grp * 8, b);
+                    const int4 c0 = *reinterpret_cast<const int4 *>(ck + grp * 8);
+                    const int4 c1 = *reinterpret_cast<const int4 *>(ck + grp * 8 + 4);
+                    ptx::tmem_ld_wait();
+                    const int key[8] = {16 * (int)b[0] + c0.x, 16 * (int)b[1] + c0.y, 16 * (int)b[2] + c0.z, 16 * (int)b[3] + c0.w,
+                                        16 * (int)b[4] + c1.x, 16 * (int)b[5] + c1.y, 16 * (int)b[6] + c1.z, 16 * (int)b[7] + c1.w};
+                    int g0, g1;
+                    top2_of8(key, g0, g1);
+                    const int jb8 = t * TILE_N + grp * 8;
+                    merge_top2(g0 >> 3, jb8 + ((g0 & 7) ^ 7), g1 >> 3, jb8 + ((g1 & 7) ^ 7), S0, J0, S1, J1);
+                    if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
+                }
+                // every TMEM read of this strip's accumulator has landed in registers: hand it back
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&t_empty[strip]);
             }
             if (valid) {
                 int4 out;

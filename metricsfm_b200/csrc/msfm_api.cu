@@ -37,7 +37,7 @@ constexpr int kItemRows = kStrips * msfm::kStripRows;
 
 // Per-batch scratch bounds (rows).  16 Mi query rows -> 256 MiB kNN scratch + 128 MiB match scratch.
 constexpr int64_t kBatchMaxQueryRows = 16ll << 20;
-constexpr int64_t kBatchMaxRefRows = 16ll << 20;
+constexpr int64_t kBatchMaxRefRows = 16ll << 20;  // twin kNN rows (mutual cross-check)
 constexpr int64_t kBatchMaxPairs = 16384;
 
 struct DeviceBuf {
@@ -77,7 +77,7 @@ struct msfm_ctx {
     std::vector<ImageSlot> images;
     EncodeTiledFn encode = nullptr;
 
-    DeviceBuf staging, knn, colbest, matches, good, counts, offsets, pairdesc, items, tight_matches, tight_good;
+    DeviceBuf staging, knn, matches, good, counts, offsets, pairdesc, items, tight_matches, tight_good;
     void *h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_f1 = nullptr;
@@ -221,14 +221,18 @@ msfm_status reserve_locked(msfm_ctx *ctx, int32_t image_id, int32_t rows, int64_
 }
 
 struct BatchPlan {
-    std::vector<PairDesc> pairs;     // device pair descriptors (only pairs passing the gate)
+    std::vector<PairDesc> pairs;     // forward pair descriptors (only pairs passing the gate)
+    std::vector<PairDesc> twins;     // role-swapped twins (mutual cross-check), appended after `pairs` on the device
     std::vector<int64_t> src_index;  // index into the caller's pair list
-    std::vector<WorkItem> items;
-    int64_t query_rows = 0, ref_rows = 0;
+    std::vector<WorkItem> items;     // twin items carry pair = -1 - twin index until finish_plan()
+    int64_t query_rows = 0;          // forward kNN rows (= match scratch rows)
+    int64_t twin_rows = 0;           // kNN rows of the twins
     int64_t ops = 0;
+    bool has_empty = false;          // some pair has no work items: its kNN rows must read "absent"
+    int64_t knn_rows() const { return query_rows + twin_rows; }
 };
 
-msfm_status launch_match_kernel(msfm_ctx *ctx, const BatchPlan &plan, bool want_colbest) {
+msfm_status launch_match_kernel(msfm_ctx *ctx, const BatchPlan &plan) {
     msfm::MatchKernelParams kp;
     kp.maps = ctx->d_maps;
     kp.ckeys = ctx->norms;
@@ -238,35 +242,43 @@ msfm_status launch_match_kernel(msfm_ctx *ctx, const BatchPlan &plan, bool want_
     kp.stats = nullptr;
     kp.debug_flags = ctx->debug_flags;
     kp.knn = static_cast<int4 *>(ctx->knn.ptr);
-    kp.colbest = static_cast<unsigned long long *>(ctx->colbest.ptr);
     const int grid = std::max(1, std::min<int>(ctx->num_sms, kp.n_items));
-    if (want_colbest)
-        msfm::match_pairs_kernel<kStrips, kTileN, kStages, true><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
-    else
-        msfm::match_pairs_kernel<kStrips, kTileN, kStages, false><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
+    msfm::match_pairs_kernel<kStrips, kTileN, kStages><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
     MSFM_CUDA(ctx, cudaGetLastError());
     return MSFM_OK;
 }
 
-// Upload the plan, run the matching kernel (timed), leave {knn, colbest} in scratch.
-msfm_status run_match_stage(msfm_ctx *ctx, const BatchPlan &plan, bool want_colbest) {
+// Resolve the forward <-> twin cross references once the batch is complete.
+void finish_plan(BatchPlan &plan) {
+    const int32_t nb = (int32_t)plan.pairs.size();
+    for (PairDesc &t : plan.twins) t.knn_off += plan.query_rows;
+    for (PairDesc &f : plan.pairs)
+        if (f.rev_off >= 0) f.rev_off += plan.query_rows;
+    for (WorkItem &w : plan.items)
+        if (w.pair < 0) w.pair = nb + (-1 - w.pair);
+}
+
+// Upload the plan, run the matching kernel (timed), leave the kNN rows in scratch.
+msfm_status run_match_stage(msfm_ctx *ctx, const BatchPlan &plan) {
     msfm_status st;
-    const size_t pd_bytes = plan.pairs.size() * sizeof(PairDesc);
+    const size_t fw_bytes = plan.pairs.size() * sizeof(PairDesc);
+    const size_t tw_bytes = plan.twins.size() * sizeof(PairDesc);
+    const size_t pd_bytes = fw_bytes + tw_bytes;
     const size_t it_bytes = plan.items.size() * sizeof(WorkItem);
     if ((st = ensure(ctx, ctx->pairdesc, pd_bytes)) != MSFM_OK) return st;
     if ((st = ensure(ctx, ctx->items, it_bytes)) != MSFM_OK) return st;
-    if ((st = ensure(ctx, ctx->knn, (size_t)plan.query_rows * sizeof(int4))) != MSFM_OK) return st;
-    if ((st = ensure(ctx, ctx->colbest, (size_t)std::max<int64_t>(plan.ref_rows, 1) * 8)) != MSFM_OK) return st;
+    if ((st = ensure(ctx, ctx->knn, (size_t)plan.knn_rows() * sizeof(int4))) != MSFM_OK) return st;
     if ((st = ensure_pinned(ctx, pd_bytes + it_bytes + 64)) != MSFM_OK) return st;
     // the pinned staging area is reused per batch: the previous batch has been synchronised by its D2H
-    memcpy(ctx->h_pinned, plan.pairs.data(), pd_bytes);
-    memcpy(static_cast<char *>(ctx->h_pinned) + pd_bytes, plan.items.data(), it_bytes);
-    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->pairdesc.ptr, ctx->h_pinned, pd_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->items.ptr, static_cast<char *>(ctx->h_pinned) + pd_bytes, it_bytes, cudaMemcpyHostToDevice,
-                                   ctx->stream));
-    if (want_colbest) MSFM_CUDA(ctx, cudaMemsetAsync(ctx->colbest.ptr, 0xFF, (size_t)plan.ref_rows * 8, ctx->stream));
+    char *hp = static_cast<char *>(ctx->h_pinned);
+    memcpy(hp, plan.pairs.data(), fw_bytes);
+    if (tw_bytes) memcpy(hp + fw_bytes, plan.twins.data(), tw_bytes);
+    memcpy(hp + pd_bytes, plan.items.data(), it_bytes);
+    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->pairdesc.ptr, hp, pd_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->items.ptr, hp + pd_bytes, it_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (plan.has_empty) MSFM_CUDA(ctx, cudaMemsetAsync(ctx->knn.ptr, 0xFF, (size_t)plan.knn_rows() * sizeof(int4), ctx->stream));
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
-    if ((st = launch_match_kernel(ctx, plan, want_colbest)) != MSFM_OK) return st;
+    if ((st = launch_match_kernel(ctx, plan)) != MSFM_OK) return st;
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
     ctx->timing.match_launches += 1;
     ctx->timing.total_launches += 1;
@@ -274,7 +286,9 @@ msfm_status run_match_stage(msfm_ctx *ctx, const BatchPlan &plan, bool want_colb
     return MSFM_OK;
 }
 
-void plan_add_pair(msfm_ctx *ctx, BatchPlan &plan, int64_t src, int32_t ref, int32_t qry) {
+// Adds pair (ref, qry) and, for the mutual cross-check, its role-swapped twin (best query of every reference row =
+// nearest neighbour of that row among the query rows).
+void plan_add_pair(msfm_ctx *ctx, BatchPlan &plan, int64_t src, int32_t ref, int32_t qry, bool mutual) {
     const ImageSlot &r = ctx->images[ref], &q = ctx->images[qry];
     PairDesc pd;
     pd.ref_img = ref;
@@ -284,14 +298,31 @@ void plan_add_pair(msfm_ctx *ctx, BatchPlan &plan, int64_t src, int32_t ref, int
     pd.ref_off = r.off;
     pd.qry_off = q.off;
     pd.knn_off = plan.query_rows;
-    pd.col_off = plan.ref_rows;
+    pd.rev_off = mutual ? plan.twin_rows : -1;
     const int32_t pidx = (int32_t)plan.pairs.size();
     plan.pairs.push_back(pd);
     plan.src_index.push_back(src);
-    if (r.rows > 0)
+    const bool work = r.rows > 0 && q.rows > 0;
+    if (!work) plan.has_empty = true;
+    if (work)
         for (int32_t row0 = 0; row0 < q.rows; row0 += kItemRows) plan.items.push_back({pidx, row0});
     plan.query_rows += q.rows;
-    plan.ref_rows += r.rows;
+    if (mutual) {
+        PairDesc tw;
+        tw.ref_img = qry;
+        tw.qry_img = ref;
+        tw.ref_rows = q.rows;
+        tw.qry_rows = r.rows;
+        tw.ref_off = q.off;
+        tw.qry_off = r.off;
+        tw.knn_off = plan.twin_rows;
+        tw.rev_off = -1;
+        const int32_t tidx = (int32_t)plan.twins.size();
+        plan.twins.push_back(tw);
+        if (work)
+            for (int32_t row0 = 0; row0 < r.rows; row0 += kItemRows) plan.items.push_back({-1 - tidx, row0});
+        plan.twin_rows += r.rows;
+    }
     plan.ops += 2ll * r.rows * q.rows * kDim;
 }
 
@@ -303,11 +334,12 @@ msfm_status accumulate_kernel_time(msfm_ctx *ctx) {
 }
 
 // kNN of a single pair into scratch (no gate).  Caller holds the lock.
-msfm_status knn_single(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, bool want_colbest, BatchPlan &plan) {
+msfm_status knn_single(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, BatchPlan &plan) {
     msfm_status st;
     if ((st = check_image_id(ctx, ref_id, true)) != MSFM_OK) return st;
     if ((st = check_image_id(ctx, query_id, true)) != MSFM_OK) return st;
-    plan_add_pair(ctx, plan, 0, ref_id, query_id);
+    plan_add_pair(ctx, plan, 0, ref_id, query_id, false);
+    finish_plan(plan);
     ctx->timing = msfm_timing{};
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
     if (plan.query_rows == 0) return MSFM_OK;
@@ -319,7 +351,7 @@ msfm_status knn_single(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, bool wan
         MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return MSFM_OK;
     }
-    return run_match_stage(ctx, plan, want_colbest);
+    return run_match_stage(ctx, plan);
 }
 
 msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const msfm_params *params, msfm_result *out,
@@ -352,23 +384,24 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             const bool gated = r.rows < params->min_keypoints || q.rows < params->min_keypoints;
             if (!gated) {
                 if (!plan.pairs.empty() &&
-                    (plan.query_rows + q.rows > kBatchMaxQueryRows || plan.ref_rows + r.rows > kBatchMaxRefRows))
+                    (plan.query_rows + q.rows > kBatchMaxQueryRows || plan.twin_rows + r.rows > kBatchMaxRefRows))
                     break;
-                plan_add_pair(ctx, plan, next, pairs[next].ref, pairs[next].query);
+                plan_add_pair(ctx, plan, next, pairs[next].ref, pairs[next].query, params->mutual != 0);
             }
             ++next;
         }
         const int64_t last = next;
+        finish_plan(plan);
         const int nb = (int)plan.pairs.size();
         std::vector<int64_t> batch_offsets;
         if (nb > 0 && plan.query_rows > 0) {
             if (!plan.items.empty()) {
-                if ((st = run_match_stage(ctx, plan, params->mutual != 0)) != MSFM_OK) return st;
+                if ((st = run_match_stage(ctx, plan)) != MSFM_OK) return st;
             } else {
                 if ((st = ensure(ctx, ctx->pairdesc, nb * sizeof(PairDesc))) != MSFM_OK) return st;
-                if ((st = ensure(ctx, ctx->knn, (size_t)plan.query_rows * sizeof(int4))) != MSFM_OK) return st;
+                if ((st = ensure(ctx, ctx->knn, (size_t)plan.knn_rows() * sizeof(int4))) != MSFM_OK) return st;
                 MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->pairdesc.ptr, plan.pairs.data(), nb * sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream));
-                MSFM_CUDA(ctx, cudaMemsetAsync(ctx->knn.ptr, 0xFF, (size_t)plan.query_rows * sizeof(int4), ctx->stream));
+                MSFM_CUDA(ctx, cudaMemsetAsync(ctx->knn.ptr, 0xFF, (size_t)plan.knn_rows() * sizeof(int4), ctx->stream));
                 MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             }
             // ---- ratio / mutual / compaction
@@ -381,7 +414,6 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             msfm::FinalizeParams fp;
             fp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
             fp.knn = static_cast<const int4 *>(ctx->knn.ptr);
-            fp.colbest = static_cast<const unsigned long long *>(ctx->colbest.ptr);
             fp.matches = static_cast<int2 *>(ctx->matches.ptr);
             fp.good = want_good ? static_cast<uint8_t *>(ctx->good.ptr) : nullptr;
             fp.counts = static_cast<int32_t *>(ctx->counts.ptr);
@@ -524,9 +556,7 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
         ctx->own_arena = true;
     }
     if (cudaMalloc(&ctx->d_maps, (size_t)ctx->max_images * sizeof(CUtensorMap)) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
-    if (cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             KCfg::kSmemAlloc) != cudaSuccess ||
-        cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              KCfg::kSmemAlloc) != cudaSuccess)
         return bail(MSFM_ERR_CUDA);
     *out = ctx;
@@ -537,7 +567,7 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
     if (!ctx) return MSFM_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DeviceBuf *bufs[] = {&ctx->staging, &ctx->knn, &ctx->colbest, &ctx->matches, &ctx->good, &ctx->counts, &ctx->offsets,
+    DeviceBuf *bufs[] = {&ctx->staging, &ctx->knn, &ctx->matches, &ctx->good, &ctx->counts, &ctx->offsets,
                          &ctx->pairdesc, &ctx->items, &ctx->tight_matches, &ctx->tight_good};
     for (DeviceBuf *b : bufs)
         if (b->ptr) cudaFree(b->ptr);
@@ -678,7 +708,7 @@ msfm_status msfm_knn2(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_t *
     if (!ids || !dists) return fail(ctx, MSFM_ERR_INVALID_ARG, "null output buffer");
     MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
     BatchPlan plan;
-    msfm_status st = knn_single(ctx, ref_id, query_id, false, plan);
+    msfm_status st = knn_single(ctx, ref_id, query_id, plan);
     if (st != MSFM_OK) return st;
     const int n = (int)plan.query_rows;
     if (n == 0) return MSFM_OK;
@@ -704,25 +734,22 @@ msfm_status msfm_colbest(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (!best_query || !best_dist) return fail(ctx, MSFM_ERR_INVALID_ARG, "null output buffer");
     MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    // best query of every reference row = nearest neighbour of that row among the query rows (roles swapped)
     BatchPlan plan;
-    msfm_status st = knn_single(ctx, ref_id, query_id, true, plan);
+    msfm_status st = knn_single(ctx, query_id, ref_id, plan);
     if (st != MSFM_OK) return st;
-    const int m = (int)plan.ref_rows;
+    const int m = (int)plan.query_rows;
     if (m == 0) return MSFM_OK;
-    if (plan.items.empty()) {  // no query rows: nobody is best
-        for (int j = 0; j < m; ++j) { best_query[j] = -1; best_dist[j] = __builtin_inff(); }
-        return MSFM_OK;
-    }
     if ((st = ensure(ctx, ctx->tight_matches, (size_t)m * 4)) != MSFM_OK) return st;
     if ((st = ensure(ctx, ctx->matches, (size_t)m * 4)) != MSFM_OK) return st;
     int32_t *d_best = static_cast<int32_t *>(ctx->tight_matches.ptr);
     float *d_dist = static_cast<float *>(ctx->matches.ptr);
-    msfm::colbest_unpack_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const unsigned long long *>(ctx->colbest.ptr), m, d_best, d_dist);
+    msfm::knn_best_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const int4 *>(ctx->knn.ptr), m, d_best, d_dist);
     MSFM_CUDA(ctx, cudaGetLastError());
     MSFM_CUDA(ctx, cudaMemcpyAsync(best_query, d_best, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
     MSFM_CUDA(ctx, cudaMemcpyAsync(best_dist, d_dist, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
     MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if ((st = accumulate_kernel_time(ctx)) != MSFM_OK) return st;
+    if (!plan.items.empty() && (st = accumulate_kernel_time(ctx)) != MSFM_OK) return st;
     return MSFM_OK;
 }
 
