@@ -73,6 +73,37 @@ __global__ void init_pad_kernel(int rows, int rows_padded, uint8_t *__restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------------ kNN shares
+// The matching kernel leaves `nshare` partial results per query row (one per column share).  Each is sorted
+// (d0,id0) <= (d1,id1); absent entries are (INT_MAX, -1).  The row's result is the two smallest (d, id) pairs.
+__device__ __forceinline__ bool knn_less(int da, int ia, int db, int ib) { return da < db || (da == db && ia < ib); }
+__device__ __forceinline__ int4 load_knn_share(const int4 *__restrict__ knn, int64_t idx) {
+    int4 v = knn[idx];
+    if (v.x < 0) v.z = INT_MAX;  // rows of work-less pairs are memset to -1
+    if (v.y < 0) v.w = INT_MAX;
+    return v;
+}
+__device__ __forceinline__ int4 merge_knn_shares(const int4 *__restrict__ knn, int64_t row, int nshare) {
+    int4 r = load_knn_share(knn, row * nshare);
+    for (int s = 1; s < nshare; ++s) {
+        const int4 o = load_knn_share(knn, row * nshare + s);
+        int4 m;
+        if (knn_less(o.z, o.x, r.z, r.x)) {  // o first
+            m.x = o.x; m.z = o.z;
+            const bool o2 = knn_less(o.w, o.y, r.z, r.x);
+            m.y = o2 ? o.y : r.x; m.w = o2 ? o.w : r.z;
+        } else {
+            m.x = r.x; m.z = r.z;
+            const bool r2 = knn_less(r.w, r.y, o.z, o.x);
+            m.y = r2 ? r.y : o.x; m.w = r2 ? r.w : o.z;
+        }
+        r = m;
+    }
+    if (r.z == INT_MAX) r.x = -1;
+    if (r.w == INT_MAX) r.y = -1;
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------ finalize
 struct FinalizeParams {
     const PairDesc *pairs;
@@ -82,6 +113,7 @@ struct FinalizeParams {
     int32_t *counts;                    // [n_pairs]
     float ratio, ratio_good, max_dist_sq;
     int32_t mutual, orientation;
+    int32_t nshare;                     // column shares per kNN row (MatchKernelCfg CSPLIT)
 };
 
 // One CTA per pair.  Rows are scanned in ascending query order, 1024 at a time, and kept matches are written in
@@ -97,14 +129,14 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const FinalizeParams fp)
         bool keep = false, is_good = false;
         int nn0 = -1;
         if (q < pd.qry_rows) {
-            const int4 k = fp.knn[pd.knn_off + q];
+            const int4 k = merge_knn_shares(fp.knn, pd.knn_off + q, fp.nshare);
             if (k.x >= 0 && k.y >= 0) {
                 const float d0 = (float)k.z, d1 = (float)k.w;
                 const float r = __fdiv_rn(d0, d1);  // IEEE divide; 0/0 = NaN fails every comparison
                 keep = r < fp.ratio;
                 if (fp.max_dist_sq > 0.0f) keep = keep && (d0 < fp.max_dist_sq);
                 if (keep && fp.mutual)  // the twin's row nn0 holds the best query of reference row nn0 (lowest index on ties)
-                    keep = fp.knn[pd.rev_off + k.x].x == q;
+                    keep = merge_knn_shares(fp.knn, pd.rev_off + k.x, fp.nshare).x == q;
                 is_good = keep && fp.ratio_good > 0.0f && r < fp.ratio_good;
                 nn0 = k.x;
             }
@@ -189,10 +221,11 @@ __global__ void gather_matches_kernel(const PairDesc *__restrict__ pairs, const 
 }
 
 // kNN scratch {id0,id1,d0,d1} -> FLANN layout ids[2q..], dists[2q..] (float), one pair.
-__global__ void knn_to_flann_kernel(const int4 *__restrict__ knn, int rows, int32_t *__restrict__ ids, float *__restrict__ dists) {
+__global__ void knn_to_flann_kernel(const int4 *__restrict__ knn, int rows, int nshare, int32_t *__restrict__ ids,
+                                    float *__restrict__ dists) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= rows) return;
-    const int4 k = knn[q];
+    const int4 k = merge_knn_shares(knn, q, nshare);
     ids[2 * q] = k.x;
     ids[2 * q + 1] = k.y;
     dists[2 * q] = k.x >= 0 ? (float)k.z : __int_as_float(0x7f800000);
@@ -200,10 +233,11 @@ __global__ void knn_to_flann_kernel(const int4 *__restrict__ knn, int rows, int3
 }
 
 // Nearest neighbour only (used for the "best query of each reference row" query).
-__global__ void knn_best_kernel(const int4 *__restrict__ knn, int rows, int32_t *__restrict__ best, float *__restrict__ dist) {
+__global__ void knn_best_kernel(const int4 *__restrict__ knn, int rows, int nshare, int32_t *__restrict__ best,
+                                float *__restrict__ dist) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= rows) return;
-    const int4 k = knn[j];
+    const int4 k = merge_knn_shares(knn, j, nshare);
     best[j] = k.x;
     dist[j] = k.x >= 0 ? (float)k.z : __int_as_float(0x7f800000);
 }

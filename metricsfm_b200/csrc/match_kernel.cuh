@@ -10,17 +10,18 @@
 // /root/reference/SfM/src/graph/fine_matching_graph.cc:99 (and slam_gps.cc:463, feature_matching.cpp:44,336,409)
 // with the brute-force/mutual-best semantics of the declared GPU matchers (SiftGPU.h:303-308, cudaSift sift.h:97).
 //
-// Roles per CTA ((4*STRIPS + 2) warps, one CTA per SM, persistent over work items):
-//   warps 0 .. 4*STRIPS-1  epilogue: warp w owns TMEM lanes 32*(w%4).. of query strip w/4 (thread = query row)
-//   warp  4*STRIPS         TMA producer (one elected lane)
-//   warp  4*STRIPS+1       TMEM allocator + MMA issuer (one elected lane)
+// Roles per CTA ((4*STRIPS*CSPLIT + 2) warps, one CTA per SM, persistent over work items):
+//   epilogue warps  warp w owns TMEM lanes 32*(w%4).. of query strip (w/4)%STRIPS and the column share w/(4*STRIPS)
+//                   of every tile (thread = query row x column share)
+//   next warp       TMA producer (one elected lane)
+//   last warp       TMEM allocator + MMA issuer (one elected lane)
 // Pipelines (all mbarrier based):
 //   A ring (2 deep)     : query strips of a work item, STRIPS x [128 rows x 128 B]
 //   B ring (STAGES)     : reference tiles [TILE_N rows x 128 B]
 //   column-key ring     : ckey_j = -8*||r_j||^2 + (7 - j%8) of the tile's reference rows (no empty barrier needed,
 //                         see MatchKernelCfg::kKeySlots)
-//   TMEM                : one TILE_N-column int32 accumulator block PER STRIP with its own full/empty barrier pair,
-//                         so the four warps of a strip run their epilogue while the MMA warp refills other strips
+//   TMEM                : TBUFS x STRIPS accumulator blocks of TILE_N int32 columns, each with its own full/empty
+//                         barrier pair, so the MMA of tile t+1 runs under the epilogue of tile t
 #pragma once
 #include <cstdint>
 #include <climits>
@@ -66,25 +67,30 @@ struct MatchKernelParams {
     int32_t n_items;
     uint32_t debug_flags;         // bit 0: skip the exact slow path (timing experiments only; results are wrong)
     unsigned long long *stats;    // optional debug counter (slow-path group visits); null in production
-    int4 *knn;                    // [sum qry_rows] {id0, id1, d0, d1}; id = -1 / d = INT_MAX when absent
+    int4 *knn;                    // [sum qry_rows][CSPLIT] partial {id0, id1, d0, d1} per column share; id = -1 /
+                                  // d = INT_MAX when absent; consumers merge the shares with merge_knn_shares()
 };
 
-template <int STRIPS, int TILE_N, int STAGES>
+template <int STRIPS, int TILE_N, int STAGES, int CSPLIT, int TBUFS>
 struct MatchKernelCfg {
-    static constexpr int kEpiWarps = 4 * STRIPS;
+    // CSPLIT warps share one (strip, 32-row quarter) and split the tile's columns between them; TBUFS accumulator
+    // buffers per strip let the MMA of tile t+1 run under the epilogue of tile t.
+    static constexpr int kEpiWarps = 4 * STRIPS * CSPLIT;
     static constexpr int kThreads = (kEpiWarps + 2) * 32;
+    static constexpr int kColsPerWarp = TILE_N / CSPLIT;
     // The producer may refill a key slot once the MMAs that share its B stage have completed; those were issued after
-    // every strip's epilogue released its accumulator of the previous tile, which happens one chunk before the
-    // epilogue stops reading that tile's keys: tiles <= t-STAGES-2 are done when tile t is loaded.  +1 for margin.
-    static constexpr int kKeySlots = STAGES + 3;
-    static constexpr int kTmemCols = STRIPS * TILE_N;
+    // every epilogue warp released the accumulator buffer TBUFS tiles earlier, i.e. after it finished reading that
+    // tile's keys: tiles <= t-STAGES-TBUFS are done when tile t is loaded.  +1 for margin.
+    static constexpr int kKeySlots = STAGES + TBUFS + 1;
+    static constexpr int kTmemCols = TBUFS * STRIPS * TILE_N;
     static constexpr int kABytes = STRIPS * kStripRows * kDim;  // one A buffer
     static constexpr int kBBytes = TILE_N * kDim;               // one B stage
     static constexpr int kSmemA = 0;
     static constexpr int kSmemB = kSmemA + 2 * kABytes;
     static constexpr int kSmemKey = kSmemB + STAGES * kBBytes;
-    static constexpr int kSmemBar = kSmemKey + kKeySlots * TILE_N * 4;
-    static constexpr int kNumBars = 2 + 2 + STAGES + STAGES + kKeySlots + STRIPS + STRIPS;
+    static constexpr int kSmemShare = kSmemKey + kKeySlots * TILE_N * 4;       // [STRIPS*128 rows][CSPLIT] u64
+    static constexpr int kSmemBar = kSmemShare + STRIPS * kStripRows * CSPLIT * 8;
+    static constexpr int kNumBars = 2 + 2 + STAGES + STAGES + kKeySlots + 2 * TBUFS * STRIPS;
     static constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
     static constexpr int kSmemBytes = kSmemTmemPtr + 16;
     static constexpr int kSmemAlloc = kSmemBytes + 1024;  // slack for manual 1024-byte alignment
@@ -92,6 +98,8 @@ struct MatchKernelCfg {
                   "TMEM allocation must be a power of two in [32, 512] columns");
     static_assert(TILE_N % kBoxRows == 0 && TILE_N <= 256, "reference tile is loaded as 64-row TMA boxes; UMMA N <= 256");
     static_assert(kAlignRows % TILE_N == 0, "image padding must cover whole reference tiles");
+    static_assert(CSPLIT == 1 || CSPLIT == 2, "one or two warps per (strip, quarter)");
+    static_assert(kColsPerWarp % 16 == 0 && kColsPerWarp / 8 <= 32, "one flag bit per group of 8 columns");
     static_assert(kThreads <= 1024, "too many warps");
     static_assert(kSmemAlloc <= 227 * 1024, "shared memory budget");
 };
@@ -120,24 +128,25 @@ __device__ __forceinline__ void merge_top2(int sa, int ja, int sb, int jb, int &
     J0 = t0 ? ja : J0;
 }
 
-template <int STRIPS, int TILE_N, int STAGES>
-__global__ void __launch_bounds__(MatchKernelCfg<STRIPS, TILE_N, STAGES>::kThreads, 1)
+template <int STRIPS, int TILE_N, int STAGES, int CSPLIT, int TBUFS>
+__global__ void __launch_bounds__(MatchKernelCfg<STRIPS, TILE_N, STAGES, CSPLIT, TBUFS>::kThreads, 1)
 match_pairs_kernel(const MatchKernelParams p) {
-    using Cfg = MatchKernelCfg<STRIPS, TILE_N, STAGES>;
+    using Cfg = MatchKernelCfg<STRIPS, TILE_N, STAGES, CSPLIT, TBUFS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
     uint8_t *sA = smem + Cfg::kSmemA;
     uint8_t *sB = smem + Cfg::kSmemB;
     int32_t *sKey = reinterpret_cast<int32_t *>(smem + Cfg::kSmemKey);
+    unsigned long long *sShare = reinterpret_cast<unsigned long long *>(smem + Cfg::kSmemShare);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
-    uint64_t *a_full = bars;                     // [2]
-    uint64_t *a_empty = a_full + 2;              // [2]
-    uint64_t *b_full = a_empty + 2;              // [STAGES]
-    uint64_t *b_empty = b_full + STAGES;         // [STAGES]
-    uint64_t *k_full = b_empty + STAGES;         // [kKeySlots]
-    uint64_t *t_full = k_full + Cfg::kKeySlots;  // [STRIPS]
-    uint64_t *t_empty = t_full + STRIPS;         // [STRIPS]
+    uint64_t *a_full = bars;                         // [2]
+    uint64_t *a_empty = a_full + 2;                  // [2]
+    uint64_t *b_full = a_empty + 2;                  // [STAGES]
+    uint64_t *b_empty = b_full + STAGES;             // [STAGES]
+    uint64_t *k_full = b_empty + STAGES;             // [kKeySlots]
+    uint64_t *t_full = k_full + Cfg::kKeySlots;      // [TBUFS][STRIPS]
+    uint64_t *t_empty = t_full + TBUFS * STRIPS;     // [TBUFS][STRIPS]
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
 
     const int warp = threadIdx.x >> 5;
@@ -147,10 +156,12 @@ match_pairs_kernel(const MatchKernelParams p) {
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < Cfg::kKeySlots; ++i) ptx::mbar_init(&k_full[i], 1);
-        for (int i = 0; i < STRIPS; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 4); }
+        for (int i = 0; i < TBUFS * STRIPS; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 4 * CSPLIT); }
         ptx::fence_mbar_init();
     }
     if (warp == Cfg::kEpiWarps + 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+    if (warp < Cfg::kEpiWarps)  // threshold-sharing slots start out "no information"
+        for (int i = threadIdx.x; i < STRIPS * kStripRows * CSPLIT; i += Cfg::kEpiWarps * 32) sShare[i] = ~0ull;
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -201,20 +212,22 @@ match_pairs_kernel(const MatchKernelParams p) {
                 const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
                 for (int t = 0; t < ntiles; ++t, ++g) {
                     const uint32_t st = g % STAGES;
+                    const uint32_t buf = g % TBUFS;
+                    const uint32_t tph = (g / TBUFS) & 1;
                     ptx::mbar_wait_backoff(&b_full[st], (g / STAGES) & 1);
                     const uint32_t b_addr = ptx::smem_u32(sB + st * Cfg::kBBytes);
 #pragma unroll
                     for (int s = 0; s < STRIPS; ++s) {
-                        ptx::mbar_wait_backoff(&t_empty[s], (g & 1) ^ 1);  // strip s has drained its previous tile
+                        ptx::mbar_wait_backoff(&t_empty[buf * STRIPS + s], tph ^ 1);  // accumulator drained by the epilogue
                         ptx::tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + s * TILE_N;
+                        const uint32_t d_tmem = tmem_base + (buf * STRIPS + s) * TILE_N;
 #pragma unroll
                         for (int k = 0; k < kDim / 32; ++k) {
                             const uint64_t da = ptx::make_smem_desc_sw128(a_addr + s * kStripRows * kDim + k * 32);
                             const uint64_t db = ptx::make_smem_desc_sw128(b_addr + k * 32);
                             ptx::mma_i8_ss(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
                         }
-                        ptx::mma_commit(&t_full[s]);  // this strip's accumulators are ready
+                        ptx::mma_commit(&t_full[buf * STRIPS + s]);  // this strip's accumulators are ready
                     }
                     ptx::mma_commit(&b_empty[st]);    // B stage reusable once every strip's MMAs have read it
                 }
@@ -222,24 +235,31 @@ match_pairs_kernel(const MatchKernelParams p) {
             }
         }
     } else {
-        // =========================================================== epilogue (thread = query row)
+        // =========================================================== epilogue (thread = query row x column share)
         // Scores s = 2*acc - ||r||^2 (maximise; d = ||q||^2 - s).
-        // Phase 1 (filter): stream the strip's accumulator tile through registers once and keep only the maximum RAW
-        //   accumulator of every group of 8 columns; a group is flagged when that maximum exceeds
-        //   T = floor((S1 + min||r||^2 over the tile) / 2) in any lane of the warp.  An unflagged group cannot enter any
-        //   lane's top-2 (2*acc - nb_j <= 2*acc - nbmin <= S1) and costs ~0.45 instructions per element.
+        // Phase 1 (filter): stream this warp's share of the strip's accumulator tile through registers once and keep
+        //   only the maximum RAW accumulator of every group of 8 columns; a group is flagged when that maximum exceeds
+        //   T = floor((theta + min||r||^2 over the share) / 2) in any lane.  theta is a lower bound of the row's final
+        //   second-best score, so an unflagged group cannot enter the row's top-2
+        //   (2*acc - nb_j <= 2*acc - nbmin <= theta) and costs ~0.45 instructions per element.
         // Phase 2 (exact): flagged groups (a few per tile) are re-read from TMEM and scored exactly with packed keys
-        //   (branch-free top-2-of-8 network + merge), in ascending column order.  Ties never displace (strict >), hence
-        //   lowest-index tie-breaking.  Then the accumulator is handed back to the MMA warp.
-        const int strip = warp >> 2;
+        //   (branch-free top-2-of-8 network + merge), in ascending column order; ties never displace (strict >), hence
+        //   lowest-index tie-breaking inside a share.  Then the accumulator is handed back to the MMA warp.
+        // Column shares (CSPLIT = 2): the two threads of a row keep independent top-2 states over their own columns
+        //   (merged by the consumer kernels) but publish their second-best score; theta = max(own S1, partner S1 - 1).
+        //   The "- 1" keeps every element that merely TIES the partner's second best in play, because the partner's
+        //   columns may lie to the right of it; elements strictly below two known scores can never reach the top-2.
+        const int share = warp / (4 * STRIPS);
+        const int strip = (warp >> 2) % STRIPS;
         const int quarter = warp & 3;
         const int row_local = strip * kStripRows + quarter * 32 + lane;
-        const uint32_t tile_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + strip * TILE_N;
-        constexpr int kChunks = TILE_N / 32;
+        const uint32_t warp_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + strip * TILE_N + share * Cfg::kColsPerWarp;
+        constexpr int kCols = Cfg::kColsPerWarp;
         constexpr int kAbsent = -0x08000000;  // scores below this are pad columns / "no neighbour"
-        static_assert(kChunks * 4 <= 32, "one flag bit per group of 8 columns");
-        uint32_t g = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        unsigned long long *my_slot = sShare + row_local * CSPLIT + share;
+        const unsigned long long *peer_slot = sShare + row_local * CSPLIT + (share ^ (CSPLIT - 1));
+        uint32_t g = 0, a = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++a) {
             const WorkItem wi = p.items[item];
             const PairDesc pd = p.pairs[wi.pair];
             const int q = wi.row0 + row_local;
@@ -250,29 +270,37 @@ match_pairs_kernel(const MatchKernelParams p) {
             const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
             for (int t = 0; t < ntiles; ++t, ++g) {
                 const uint32_t ks = g % Cfg::kKeySlots;
+                const uint32_t buf = g % TBUFS;
                 ptx::mbar_wait(&k_full[ks], (g / Cfg::kKeySlots) & 1);
-                const int32_t *ck = sKey + ks * TILE_N;
+                const int32_t *ck = sKey + ks * TILE_N + share * kCols;
                 int ckmax = ck[lane];
 #pragma unroll
-                for (int k = 1; k < TILE_N / 32; ++k) ckmax = max(ckmax, ck[lane + 32 * k]);
+                for (int k = 1; k < kCols / 32; ++k) ckmax = max(ckmax, ck[lane + 32 * k]);
                 const int nbmin = ckey_to_norm(__reduce_max_sync(0xFFFFFFFFu, ckmax));
-                const int T = (S1 + nbmin) >> 1;
-                ptx::mbar_wait(&t_full[strip], g & 1);
+                int theta = S1;
+                if (CSPLIT > 1) {
+                    const unsigned long long peer = *reinterpret_cast<const volatile unsigned long long *>(peer_slot);
+                    const int ps1 = (int)(uint32_t)peer;
+                    if ((uint32_t)(peer >> 32) == a && ps1 > INT_MIN) theta = max(theta, ps1 - 1);
+                }
+                const int T = (theta + nbmin) >> 1;
+                ptx::mbar_wait(&t_full[buf * STRIPS + strip], (g / TBUFS) & 1);
                 ptx::tc_fence_after();
+                const uint32_t tile_taddr = warp_taddr + buf * (STRIPS * TILE_N);
                 // ---- phase 1
                 uint32_t acc[2][16];
                 uint32_t flags = 0;
                 ptx::tmem_ld_32x32b_x16(tile_taddr, acc[0]);
 #pragma unroll
-                for (int c = 0; c < 2 * kChunks; ++c) {
+                for (int c = 0; c < kCols / 16; ++c) {
                     ptx::tmem_ld_wait();
-                    if (c + 1 < 2 * kChunks) ptx::tmem_ld_32x32b_x16(tile_taddr + (c + 1) * 16, acc[(c + 1) & 1]);
-                    const uint32_t(&a)[16] = acc[c & 1];
+                    if (c + 1 < kCols / 16) ptx::tmem_ld_32x32b_x16(tile_taddr + (c + 1) * 16, acc[(c + 1) & 1]);
+                    const uint32_t(&v)[16] = acc[c & 1];
 #pragma unroll
                     for (int gq = 0; gq < 2; ++gq) {
-                        const int m1 = __vimax3_s32((int)a[8 * gq], (int)a[8 * gq + 1], (int)a[8 * gq + 2]);
-                        const int m2 = __vimax3_s32((int)a[8 * gq + 3], (int)a[8 * gq + 4], (int)a[8 * gq + 5]);
-                        const int m = __vimax3_s32((int)a[8 * gq + 6], (int)a[8 * gq + 7], max(m1, m2));
+                        const int m1 = __vimax3_s32((int)v[8 * gq], (int)v[8 * gq + 1], (int)v[8 * gq + 2]);
+                        const int m2 = __vimax3_s32((int)v[8 * gq + 3], (int)v[8 * gq + 4], (int)v[8 * gq + 5]);
+                        const int m = __vimax3_s32((int)v[8 * gq + 6], (int)v[8 * gq + 7], max(m1, m2));
                         if (m > T) flags |= 1u << (2 * c + gq);
                     }
                 }
@@ -291,14 +319,15 @@ match_pairs_kernel(const MatchKernelParams p) {
                                         16 * (int)b[4] + c1.x, 16 * (int)b[5] + c1.y, 16 * (int)b[6] + c1.z, 16 * (int)b[7] + c1.w};
                     int g0, g1;
                     top2_of8(key, g0, g1);
-                    const int jb8 = t * TILE_N + grp * 8;
+                    const int jb8 = t * TILE_N + share * kCols + grp * 8;
                     merge_top2(g0 >> 3, jb8 + ((g0 & 7) ^ 7), g1 >> 3, jb8 + ((g1 & 7) ^ 7), S0, J0, S1, J1);
                     if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
                 }
-                // every TMEM read of this strip's accumulator has landed in registers: hand it back
+                // every TMEM read of this accumulator share has landed in registers: hand it back
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&t_empty[strip]);
+                if (lane == 0) ptx::mbar_arrive(&t_empty[buf * STRIPS + strip]);
+                if (CSPLIT > 1) *reinterpret_cast<volatile unsigned long long *>(my_slot) = ((unsigned long long)a << 32) | (uint32_t)S1;
             }
             if (valid) {
                 int4 out;
@@ -306,7 +335,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                 out.y = (S1 > kAbsent) ? J1 : -1;
                 out.z = (S0 > kAbsent) ? na - S0 : INT_MAX;
                 out.w = (S1 > kAbsent) ? na - S1 : INT_MAX;
-                p.knn[pd.knn_off + q] = out;
+                p.knn[(pd.knn_off + q) * CSPLIT + share] = out;
             }
         }
     }

@@ -29,10 +29,12 @@ using msfm::PairDesc;
 using msfm::WorkItem;
 
 // Kernel configuration of this build.
-constexpr int kStrips = 4;
-constexpr int kTileN = 128;
-constexpr int kStages = 4;
-using KCfg = msfm::MatchKernelCfg<kStrips, kTileN, kStages>;
+constexpr int kStrips = 2;   // query strips (128 rows each) per work item
+constexpr int kTileN = 128;  // reference rows per tile (UMMA N)
+constexpr int kStages = 6;   // B-tile ring depth
+constexpr int kCsplit = 2;   // epilogue warps per (strip, quarter): column shares
+constexpr int kTbufs = 2;    // TMEM accumulator buffers per strip
+using KCfg = msfm::MatchKernelCfg<kStrips, kTileN, kStages, kCsplit, kTbufs>;
 constexpr int kItemRows = kStrips * msfm::kStripRows;
 
 // Per-batch scratch bounds (rows).  16 Mi query rows -> 256 MiB kNN scratch + 128 MiB match scratch.
@@ -243,7 +245,7 @@ msfm_status launch_match_kernel(msfm_ctx *ctx, const BatchPlan &plan) {
     kp.debug_flags = ctx->debug_flags;
     kp.knn = static_cast<int4 *>(ctx->knn.ptr);
     const int grid = std::max(1, std::min<int>(ctx->num_sms, kp.n_items));
-    msfm::match_pairs_kernel<kStrips, kTileN, kStages><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
+    msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
     MSFM_CUDA(ctx, cudaGetLastError());
     return MSFM_OK;
 }
@@ -267,7 +269,7 @@ msfm_status run_match_stage(msfm_ctx *ctx, const BatchPlan &plan) {
     const size_t it_bytes = plan.items.size() * sizeof(WorkItem);
     if ((st = ensure(ctx, ctx->pairdesc, pd_bytes)) != MSFM_OK) return st;
     if ((st = ensure(ctx, ctx->items, it_bytes)) != MSFM_OK) return st;
-    if ((st = ensure(ctx, ctx->knn, (size_t)plan.knn_rows() * sizeof(int4))) != MSFM_OK) return st;
+    if ((st = ensure(ctx, ctx->knn, (size_t)plan.knn_rows() * kCsplit * sizeof(int4))) != MSFM_OK) return st;
     if ((st = ensure_pinned(ctx, pd_bytes + it_bytes + 64)) != MSFM_OK) return st;
     // the pinned staging area is reused per batch: the previous batch has been synchronised by its D2H
     char *hp = static_cast<char *>(ctx->h_pinned);
@@ -276,7 +278,7 @@ msfm_status run_match_stage(msfm_ctx *ctx, const BatchPlan &plan) {
     memcpy(hp + pd_bytes, plan.items.data(), it_bytes);
     MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->pairdesc.ptr, hp, pd_bytes, cudaMemcpyHostToDevice, ctx->stream));
     MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->items.ptr, hp + pd_bytes, it_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    if (plan.has_empty) MSFM_CUDA(ctx, cudaMemsetAsync(ctx->knn.ptr, 0xFF, (size_t)plan.knn_rows() * sizeof(int4), ctx->stream));
+    if (plan.has_empty) MSFM_CUDA(ctx, cudaMemsetAsync(ctx->knn.ptr, 0xFF, (size_t)plan.knn_rows() * kCsplit * sizeof(int4), ctx->stream));
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
     if ((st = launch_match_kernel(ctx, plan)) != MSFM_OK) return st;
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
@@ -345,8 +347,8 @@ msfm_status knn_single(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, BatchPla
     if (plan.query_rows == 0) return MSFM_OK;
     if (plan.items.empty()) {
         // no reference rows: every neighbour is absent
-        if ((st = ensure(ctx, ctx->knn, (size_t)plan.query_rows * sizeof(int4))) != MSFM_OK) return st;
-        std::vector<int4> none((size_t)plan.query_rows, make_int4(-1, -1, INT_MAX, INT_MAX));
+        if ((st = ensure(ctx, ctx->knn, (size_t)plan.query_rows * kCsplit * sizeof(int4))) != MSFM_OK) return st;
+        std::vector<int4> none((size_t)plan.query_rows * kCsplit, make_int4(-1, -1, INT_MAX, INT_MAX));
         MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->knn.ptr, none.data(), none.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
         MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return MSFM_OK;
@@ -399,9 +401,9 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
                 if ((st = run_match_stage(ctx, plan)) != MSFM_OK) return st;
             } else {
                 if ((st = ensure(ctx, ctx->pairdesc, nb * sizeof(PairDesc))) != MSFM_OK) return st;
-                if ((st = ensure(ctx, ctx->knn, (size_t)plan.knn_rows() * sizeof(int4))) != MSFM_OK) return st;
+                if ((st = ensure(ctx, ctx->knn, (size_t)plan.knn_rows() * kCsplit * sizeof(int4))) != MSFM_OK) return st;
                 MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->pairdesc.ptr, plan.pairs.data(), nb * sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream));
-                MSFM_CUDA(ctx, cudaMemsetAsync(ctx->knn.ptr, 0xFF, (size_t)plan.knn_rows() * sizeof(int4), ctx->stream));
+                MSFM_CUDA(ctx, cudaMemsetAsync(ctx->knn.ptr, 0xFF, (size_t)plan.knn_rows() * kCsplit * sizeof(int4), ctx->stream));
                 MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             }
             // ---- ratio / mutual / compaction
@@ -422,6 +424,7 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             fp.max_dist_sq = params->max_dist_sq;
             fp.mutual = params->mutual != 0;
             fp.orientation = params->orientation;
+            fp.nshare = kCsplit;
             msfm::finalize_kernel<<<nb, 1024, 0, ctx->stream>>>(fp);
             msfm::scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(fp.counts, nb, static_cast<int64_t *>(ctx->offsets.ptr));
             msfm::gather_matches_kernel<<<nb, 256, 0, ctx->stream>>>(
@@ -556,7 +559,7 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
         ctx->own_arena = true;
     }
     if (cudaMalloc(&ctx->d_maps, (size_t)ctx->max_images * sizeof(CUtensorMap)) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
-    if (cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              KCfg::kSmemAlloc) != cudaSuccess)
         return bail(MSFM_ERR_CUDA);
     *out = ctx;
@@ -716,7 +719,7 @@ msfm_status msfm_knn2(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_t *
     if ((st = ensure(ctx, ctx->matches, (size_t)n * 8)) != MSFM_OK) return st;
     int32_t *d_ids = static_cast<int32_t *>(ctx->tight_matches.ptr);
     float *d_dists = static_cast<float *>(ctx->matches.ptr);
-    msfm::knn_to_flann_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const int4 *>(ctx->knn.ptr), n, d_ids, d_dists);
+    msfm::knn_to_flann_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const int4 *>(ctx->knn.ptr), n, kCsplit, d_ids, d_dists);
     MSFM_CUDA(ctx, cudaGetLastError());
     ctx->timing.total_launches += 1;
     MSFM_CUDA(ctx, cudaMemcpyAsync(ids, d_ids, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -744,7 +747,7 @@ msfm_status msfm_colbest(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_
     if ((st = ensure(ctx, ctx->matches, (size_t)m * 4)) != MSFM_OK) return st;
     int32_t *d_best = static_cast<int32_t *>(ctx->tight_matches.ptr);
     float *d_dist = static_cast<float *>(ctx->matches.ptr);
-    msfm::knn_best_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const int4 *>(ctx->knn.ptr), m, d_best, d_dist);
+    msfm::knn_best_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const int4 *>(ctx->knn.ptr), m, kCsplit, d_best, d_dist);
     MSFM_CUDA(ctx, cudaGetLastError());
     MSFM_CUDA(ctx, cudaMemcpyAsync(best_query, d_best, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
     MSFM_CUDA(ctx, cudaMemcpyAsync(best_dist, d_dist, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -797,7 +800,7 @@ msfm_status msfm_knn2_crosscheck(msfm_ctx *ctx, int32_t ref_id, int32_t query_id
                                                                          static_cast<int4 *>(ctx->knn.ptr));
     int32_t *d_ids = static_cast<int32_t *>(ctx->tight_matches.ptr);
     float *d_dists = static_cast<float *>(ctx->matches.ptr);
-    msfm::knn_to_flann_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const int4 *>(ctx->knn.ptr), n, d_ids, d_dists);
+    msfm::knn_to_flann_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const int4 *>(ctx->knn.ptr), n, 1, d_ids, d_dists);
     MSFM_CUDA(ctx, cudaGetLastError());
     MSFM_CUDA(ctx, cudaMemcpyAsync(ids, d_ids, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     MSFM_CUDA(ctx, cudaMemcpyAsync(dists, d_dists, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
