@@ -79,9 +79,10 @@ struct MatchKernelCfg {
     static constexpr int kThreads = (kEpiWarps + 2) * 32;
     static constexpr int kColsPerWarp = TILE_N / CSPLIT;
     // The producer may refill a key slot once the MMAs that share its B stage have completed; those were issued after
-    // every epilogue warp released the accumulator buffer TBUFS tiles earlier, i.e. after it finished reading that
-    // tile's keys: tiles <= t-STAGES-TBUFS are done when tile t is loaded.  +1 for margin.
-    static constexpr int kKeySlots = STAGES + TBUFS + 1;
+    // every epilogue warp released the accumulator buffer TBUFS tiles earlier; a warp releases a buffer before it has
+    // finished reading that tile's keys, but it must finish before it can release the next one:
+    // tiles <= t-STAGES-TBUFS-1 are done when tile t is loaded.  +1 for margin.
+    static constexpr int kKeySlots = STAGES + TBUFS + 2;
     static constexpr int kTmemCols = TBUFS * STRIPS * TILE_N;
     static constexpr int kABytes = STRIPS * kStripRows * kDim;  // one A buffer
     static constexpr int kBBytes = TILE_N * kDim;               // one B stage
@@ -234,7 +235,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                 ptx::mma_commit(&a_empty[abuf]);      // A buffer reusable
             }
         }
-    } else {
+    } else if (warp < Cfg::kEpiWarps) {
         // =========================================================== epilogue (thread = query row x column share)
         // Scores s = 2*acc - ||r||^2 (maximise; d = ||q||^2 - s).
         // Phase 1 (filter): stream this warp's share of the strip's accumulator tile through registers once and keep
@@ -271,6 +272,14 @@ match_pairs_kernel(const MatchKernelParams p) {
             for (int t = 0; t < ntiles; ++t, ++g) {
                 const uint32_t ks = g % Cfg::kKeySlots;
                 const uint32_t buf = g % TBUFS;
+                // ---- pull this warp's whole share of the accumulator tile into registers and release TMEM at once
+                ptx::mbar_wait(&t_full[buf * STRIPS + strip], (g / TBUFS) & 1);
+                ptx::tc_fence_after();
+                const uint32_t tile_taddr = warp_taddr + buf * (STRIPS * TILE_N);
+                uint32_t acc[kCols / 16][16];
+#pragma unroll
+                for (int c = 0; c < kCols / 16; ++c) ptx::tmem_ld_32x32b_x16(tile_taddr + c * 16, acc[c]);
+                // ---- while the loads fly: column keys of the tile, smallest reference norm, pruning threshold
                 ptx::mbar_wait(&k_full[ks], (g / Cfg::kKeySlots) & 1);
                 const int32_t *ck = sKey + ks * TILE_N + share * kCols;
                 int ckmax = ck[lane];
@@ -284,50 +293,42 @@ match_pairs_kernel(const MatchKernelParams p) {
                     if ((uint32_t)(peer >> 32) == a && ps1 > INT_MIN) theta = max(theta, ps1 - 1);
                 }
                 const int T = (theta + nbmin) >> 1;
-                ptx::mbar_wait(&t_full[buf * STRIPS + strip], (g / TBUFS) & 1);
-                ptx::tc_fence_after();
-                const uint32_t tile_taddr = warp_taddr + buf * (STRIPS * TILE_N);
-                // ---- phase 1
-                uint32_t acc[2][16];
-                uint32_t flags = 0;
-                ptx::tmem_ld_32x32b_x16(tile_taddr, acc[0]);
-#pragma unroll
-                for (int c = 0; c < kCols / 16; ++c) {
-                    ptx::tmem_ld_wait();
-                    if (c + 1 < kCols / 16) ptx::tmem_ld_32x32b_x16(tile_taddr + (c + 1) * 16, acc[(c + 1) & 1]);
-                    const uint32_t(&v)[16] = acc[c & 1];
-#pragma unroll
-                    for (int gq = 0; gq < 2; ++gq) {
-                        const int m1 = __vimax3_s32((int)v[8 * gq], (int)v[8 * gq + 1], (int)v[8 * gq + 2]);
-                        const int m2 = __vimax3_s32((int)v[8 * gq + 3], (int)v[8 * gq + 4], (int)v[8 * gq + 5]);
-                        const int m = __vimax3_s32((int)v[8 * gq + 6], (int)v[8 * gq + 7], max(m1, m2));
-                        if (m > T) flags |= 1u << (2 * c + gq);
-                    }
-                }
-                uint32_t todo = __reduce_or_sync(0xFFFFFFFFu, flags);
-                if (p.debug_flags & 1u) todo = 0;
-                // ---- phase 2
-                while (todo) {
-                    const int grp = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    uint32_t b[8];
-                    ptx::tmem_ld_32x32b_x8(tile_taddr + grp * 8, b);
-                    const int4 c0 = *reinterpret_cast<const int4 *>(ck + grp * 8);
-                    const int4 c1 = *reinterpret_cast<const int4 *>(ck + grp * 8 + 4);
-                    ptx::tmem_ld_wait();
-                    const int key[8] = {16 * (int)b[0] + c0.x, 16 * (int)b[1] + c0.y, 16 * (int)b[2] + c0.z, 16 * (int)b[3] + c0.w,
-                                        16 * (int)b[4] + c1.x, 16 * (int)b[5] + c1.y, 16 * (int)b[6] + c1.z, 16 * (int)b[7] + c1.w};
-                    int g0, g1;
-                    top2_of8(key, g0, g1);
-                    const int jb8 = t * TILE_N + share * kCols + grp * 8;
-                    merge_top2(g0 >> 3, jb8 + ((g0 & 7) ^ 7), g1 >> 3, jb8 + ((g1 & 7) ^ 7), S0, J0, S1, J1);
-                    if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
-                }
-                // every TMEM read of this accumulator share has landed in registers: hand it back
+                ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&t_empty[buf * STRIPS + strip]);
-                if (CSPLIT > 1) *reinterpret_cast<volatile unsigned long long *>(my_slot) = ((unsigned long long)a << 32) | (uint32_t)S1;
+                // ---- phase 1: flag groups of 8 columns whose raw maximum can still matter
+                uint32_t flags = 0;
+#pragma unroll
+                for (int gq = 0; gq < kCols / 8; ++gq) {
+                    const uint32_t *v = &acc[gq / 2][8 * (gq & 1)];
+                    const int m1 = __vimax3_s32((int)v[0], (int)v[1], (int)v[2]);
+                    const int m2 = __vimax3_s32((int)v[3], (int)v[4], (int)v[5]);
+                    const int m = __vimax3_s32((int)v[6], (int)v[7], max(m1, m2));
+                    if (m > T) flags |= 1u << gq;
+                }
+                uint32_t todo = __reduce_or_sync(0xFFFFFFFFu, flags);
+                if (p.debug_flags & 1u) todo = 0;
+                // ---- phase 2: exact scoring of the flagged groups straight from the registers
+                if (todo) {
+#pragma unroll
+                    for (int gq = 0; gq < kCols / 8; ++gq) {
+                        if (todo & (1u << gq)) {
+                            const uint32_t *v = &acc[gq / 2][8 * (gq & 1)];
+                            const int4 c0 = *reinterpret_cast<const int4 *>(ck + gq * 8);
+                            const int4 c1 = *reinterpret_cast<const int4 *>(ck + gq * 8 + 4);
+                            const int key[8] = {16 * (int)v[0] + c0.x, 16 * (int)v[1] + c0.y, 16 * (int)v[2] + c0.z,
+                                                16 * (int)v[3] + c0.w, 16 * (int)v[4] + c1.x, 16 * (int)v[5] + c1.y,
+                                                16 * (int)v[6] + c1.z, 16 * (int)v[7] + c1.w};
+                            int g0, g1;
+                            top2_of8(key, g0, g1);
+                            const int jb8 = t * TILE_N + share * kCols + gq * 8;
+                            merge_top2(g0 >> 3, jb8 + ((g0 & 7) ^ 7), g1 >> 3, jb8 + ((g1 & 7) ^ 7), S0, J0, S1, J1);
+                            if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
+                        }
+                    }
+                    if (CSPLIT > 1) *reinterpret_cast<volatile unsigned long long *>(my_slot) = ((unsigned long long)a << 32) | (uint32_t)S1;
+                }
             }
             if (valid) {
                 int4 out;

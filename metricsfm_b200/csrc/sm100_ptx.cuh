@@ -59,6 +59,12 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity
     while (!mbar_try_wait(bar, parity)) __nanosleep(20);
 }
 
+// Register re-balancing between warpgroups (4 consecutive, 4-aligned warps execute it together).
+template <uint32_t kRegs>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <uint32_t kRegs>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tensormap(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
