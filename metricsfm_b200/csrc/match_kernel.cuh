@@ -65,7 +65,8 @@ struct MatchKernelParams {
     const PairDesc *pairs;
     const WorkItem *items;
     int32_t n_items;
-    uint32_t debug_flags;         // bit 0: skip the exact slow path (timing experiments only; results are wrong)
+    uint32_t debug_flags;         // timing experiments only (results are wrong): 1 = skip the exact phase,
+                                  // 2 = no epilogue work at all, 4 = TMEM loads + hand-back only
     unsigned long long *stats;    // optional debug counter (slow-path group visits); null in production
     int4 *knn;                    // [sum qry_rows][CSPLIT] partial {id0, id1, d0, d1} per column share; id = -1 /
                                   // d = INT_MAX when absent; consumers merge the shares with merge_knn_shares()
@@ -129,12 +130,13 @@ __device__ __forceinline__ void merge_top2(int sa, int ja, int sb, int jb, int &
     J0 = t0 ? ja : J0;
 }
 
-template <int STRIPS, int TILE_N, int STAGES, int CSPLIT, int TBUFS>
+template <int STRIPS, int TILE_N, int STAGES, int CSPLIT, int TBUFS, bool DEBUG>
 __global__ void __launch_bounds__(MatchKernelCfg<STRIPS, TILE_N, STAGES, CSPLIT, TBUFS>::kThreads, 1)
 match_pairs_kernel(const MatchKernelParams p) {
     using Cfg = MatchKernelCfg<STRIPS, TILE_N, STAGES, CSPLIT, TBUFS>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // No static shared memory is declared, so the dynamic window starts at shared offset 0 (1024-byte aligned, as
+    // the 128B-swizzled operand tiles require); checked once below.
+    extern __shared__ __align__(1024) uint8_t smem[];
 
     uint8_t *sA = smem + Cfg::kSmemA;
     uint8_t *sB = smem + Cfg::kSmemB;
@@ -152,6 +154,7 @@ match_pairs_kernel(const MatchKernelParams p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
 
     if (warp == Cfg::kEpiWarps && lane == 0) {
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
@@ -161,7 +164,7 @@ match_pairs_kernel(const MatchKernelParams p) {
         ptx::fence_mbar_init();
     }
     if (warp == Cfg::kEpiWarps + 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
-    if (warp < Cfg::kEpiWarps)  // threshold-sharing slots start out "no information"
+    if (warp < Cfg::kEpiWarps)  // threshold-sharing slots {score, item tag} start out "no information"
         for (int i = threadIdx.x; i < STRIPS * kStripRows * CSPLIT; i += Cfg::kEpiWarps * 32) sShare[i] = ~0ull;
     ptx::tc_fence_before();
     __syncthreads();
@@ -257,9 +260,15 @@ match_pairs_kernel(const MatchKernelParams p) {
         const uint32_t warp_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + strip * TILE_N + share * Cfg::kColsPerWarp;
         constexpr int kCols = Cfg::kColsPerWarp;
         constexpr int kAbsent = -0x08000000;  // scores below this are pad columns / "no neighbour"
-        unsigned long long *my_slot = sShare + row_local * CSPLIT + share;
-        const unsigned long long *peer_slot = sShare + row_local * CSPLIT + (share ^ (CSPLIT - 1));
-        uint32_t g = 0, a = 0;
+        // everything the tile loop touches in shared memory, as 32-bit shared addresses
+        const uint32_t my_slot = ptx::smem_u32(sShare + row_local * CSPLIT + share);
+        const uint32_t peer_slot = ptx::smem_u32(sShare + row_local * CSPLIT + (share ^ (CSPLIT - 1)));
+        const uint32_t key_base = ptx::smem_u32(sKey) + share * kCols * 4;
+        const uint32_t k_full_base = ptx::smem_u32(k_full);
+        const uint32_t t_full_base = ptx::smem_u32(t_full + strip);
+        const uint32_t t_empty_base = ptx::smem_u32(t_empty + strip);
+        // ring positions are carried incrementally (no divisions in the tile loop)
+        uint32_t ks = 0, k_phase = 0, buf = 0, t_phase = 0, a = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++a) {
             const WorkItem wi = p.items[item];
             const PairDesc pd = p.pairs[wi.pair];
@@ -269,66 +278,68 @@ match_pairs_kernel(const MatchKernelParams p) {
             // rows past the image end hold zeros; park their state where nothing can flag a group
             int S0 = valid ? INT_MIN : 0x20000000, S1 = S0, J0 = -1, J1 = -1;
             const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
-            for (int t = 0; t < ntiles; ++t, ++g) {
-                const uint32_t ks = g % Cfg::kKeySlots;
-                const uint32_t buf = g % TBUFS;
+            int jtile = share * kCols;  // first column of this warp's share in the current tile
+            for (int t = 0; t < ntiles; ++t, jtile += TILE_N) {
                 // ---- pull this warp's whole share of the accumulator tile into registers and release TMEM at once
-                ptx::mbar_wait(&t_full[buf * STRIPS + strip], (g / TBUFS) & 1);
+                ptx::mbar_wait_a(t_full_base + buf * (STRIPS * 8), t_phase);
                 ptx::tc_fence_after();
                 const uint32_t tile_taddr = warp_taddr + buf * (STRIPS * TILE_N);
                 uint32_t acc[kCols / 16][16];
 #pragma unroll
                 for (int c = 0; c < kCols / 16; ++c) ptx::tmem_ld_32x32b_x16(tile_taddr + c * 16, acc[c]);
                 // ---- while the loads fly: column keys of the tile, smallest reference norm, pruning threshold
-                ptx::mbar_wait(&k_full[ks], (g / Cfg::kKeySlots) & 1);
-                const int32_t *ck = sKey + ks * TILE_N + share * kCols;
-                int ckmax = ck[lane];
+                ptx::mbar_wait_a(k_full_base + ks * 8, k_phase);
+                const uint32_t ck = key_base + ks * (TILE_N * 4);
+                int ckmax = ptx::lds_s32(ck + lane * 4);
 #pragma unroll
-                for (int k = 1; k < kCols / 32; ++k) ckmax = max(ckmax, ck[lane + 32 * k]);
+                for (int k = 1; k < kCols / 32; ++k) ckmax = max(ckmax, ptx::lds_s32(ck + (lane + 32 * k) * 4));
                 const int nbmin = ckey_to_norm(__reduce_max_sync(0xFFFFFFFFu, ckmax));
                 int theta = S1;
                 if (CSPLIT > 1) {
-                    const unsigned long long peer = *reinterpret_cast<const volatile unsigned long long *>(peer_slot);
-                    const int ps1 = (int)(uint32_t)peer;
-                    if ((uint32_t)(peer >> 32) == a && ps1 > INT_MIN) theta = max(theta, ps1 - 1);
+                    const uint2 peer = ptx::lds_v2_volatile(peer_slot);  // {second-best score, item tag}
+                    if (peer.y == a && (int)peer.x > INT_MIN) theta = max(theta, (int)peer.x - 1);
                 }
                 const int T = (theta + nbmin) >> 1;
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&t_empty[buf * STRIPS + strip]);
-                // ---- phase 1: flag groups of 8 columns whose raw maximum can still matter
-                uint32_t flags = 0;
-#pragma unroll
-                for (int gq = 0; gq < kCols / 8; ++gq) {
-                    const uint32_t *v = &acc[gq / 2][8 * (gq & 1)];
-                    const int m1 = __vimax3_s32((int)v[0], (int)v[1], (int)v[2]);
-                    const int m2 = __vimax3_s32((int)v[3], (int)v[4], (int)v[5]);
-                    const int m = __vimax3_s32((int)v[6], (int)v[7], max(m1, m2));
-                    if (m > T) flags |= 1u << gq;
-                }
-                uint32_t todo = __reduce_or_sync(0xFFFFFFFFu, flags);
-                if (p.debug_flags & 1u) todo = 0;
-                // ---- phase 2: exact scoring of the flagged groups straight from the registers
-                if (todo) {
+                if (lane == 0) ptx::mbar_arrive_a(t_empty_base + buf * (STRIPS * 8));
+                if (DEBUG && (p.debug_flags & 6u)) {  // experiments: 2/4 = TMEM loads + hand-back only
+                    if (acc[0][0] == 0x7fffffffu) S1 = 0;
+                } else {
+                    // ---- phase 1: which groups of 8 columns can still matter to some lane?
+                    bool hot[kCols / 8];
 #pragma unroll
                     for (int gq = 0; gq < kCols / 8; ++gq) {
-                        if (todo & (1u << gq)) {
+                        const uint32_t *v = &acc[gq / 2][8 * (gq & 1)];
+                        const int m1 = __vimax3_s32((int)v[0], (int)v[1], (int)v[2]);
+                        const int m2 = __vimax3_s32((int)v[3], (int)v[4], (int)v[5]);
+                        const int m3 = __vimax3_s32((int)v[6], (int)v[7], m1);
+                        hot[gq] = __any_sync(0xFFFFFFFFu, max(m2, m3) > T);
+                    }
+                    // ---- phase 2: exact scoring of the hot groups straight from the registers
+                    bool touched = false;
+#pragma unroll
+                    for (int gq = 0; gq < kCols / 8; ++gq) {
+                        if (hot[gq] && !(DEBUG && (p.debug_flags & 1u))) {
                             const uint32_t *v = &acc[gq / 2][8 * (gq & 1)];
-                            const int4 c0 = *reinterpret_cast<const int4 *>(ck + gq * 8);
-                            const int4 c1 = *reinterpret_cast<const int4 *>(ck + gq * 8 + 4);
+                            const int4 c0 = ptx::lds_v4(ck + gq * 32);
+                            const int4 c1 = ptx::lds_v4(ck + gq * 32 + 16);
                             const int key[8] = {16 * (int)v[0] + c0.x, 16 * (int)v[1] + c0.y, 16 * (int)v[2] + c0.z,
                                                 16 * (int)v[3] + c0.w, 16 * (int)v[4] + c1.x, 16 * (int)v[5] + c1.y,
                                                 16 * (int)v[6] + c1.z, 16 * (int)v[7] + c1.w};
                             int g0, g1;
                             top2_of8(key, g0, g1);
-                            const int jb8 = t * TILE_N + share * kCols + gq * 8;
+                            const int jb8 = jtile + gq * 8;
                             merge_top2(g0 >> 3, jb8 + ((g0 & 7) ^ 7), g1 >> 3, jb8 + ((g1 & 7) ^ 7), S0, J0, S1, J1);
-                            if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
+                            touched = true;
+                            if (DEBUG && p.stats && lane == 0) atomicAdd(p.stats, 1ull);
                         }
                     }
-                    if (CSPLIT > 1) *reinterpret_cast<volatile unsigned long long *>(my_slot) = ((unsigned long long)a << 32) | (uint32_t)S1;
+                    if (CSPLIT > 1 && touched) ptx::sts_v2_volatile(my_slot, (uint32_t)S1, a);
                 }
+                if (++ks == Cfg::kKeySlots) { ks = 0; k_phase ^= 1; }
+                if (++buf == TBUFS) { buf = 0; t_phase ^= 1; }
             }
             if (valid) {
                 int4 out;

@@ -245,7 +245,10 @@ msfm_status launch_match_kernel(msfm_ctx *ctx, const BatchPlan &plan) {
     kp.debug_flags = ctx->debug_flags;
     kp.knn = static_cast<int4 *>(ctx->knn.ptr);
     const int grid = std::max(1, std::min<int>(ctx->num_sms, kp.n_items));
-    msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
+    if (ctx->debug_flags)
+        msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, true><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
+    else
+        msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, false><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
     MSFM_CUDA(ctx, cudaGetLastError());
     return MSFM_OK;
 }
@@ -559,8 +562,10 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
         ctx->own_arena = true;
     }
     if (cudaMalloc(&ctx->d_maps, (size_t)ctx->max_images * sizeof(CUtensorMap)) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
-    if (cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             KCfg::kSmemAlloc) != cudaSuccess)
+    if (cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::kSmemAlloc) != cudaSuccess ||
+        cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::kSmemAlloc) != cudaSuccess)
         return bail(MSFM_ERR_CUDA);
     *out = ctx;
     return MSFM_OK;

@@ -25,6 +25,47 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---------------------------------------------------------------- shared-memory access by 32-bit shared address
+// (keeps the compiler from falling back to generic LD/ST with 64-bit address arithmetic)
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int4 lds_v4(uint32_t addr) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_v2_volatile(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_v2_volatile(uint32_t addr, uint32_t x, uint32_t y) {
+    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+
+// ---------------------------------------------------------------- mbarrier (by 32-bit shared address)
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait_a(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

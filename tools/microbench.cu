@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) ldtm_rate_kernel(int iters, uns
 }
 
 // ------------------------------------------------------------------ (3) ALU op rates
-enum Op { OP_IMAD = 0, OP_IADD3, OP_VIADDMIN, OP_VIMIN3, OP_MIN, OP_REDUX, OP_LOP3, OP_ISETP_SEL, OP_FFMA, OP_IMAD_MIN, OP_SHFL, OP_LDS };
+enum Op { OP_MIX_MAX3_IMAD = 100, OP_MIX_MAX3_VIADDMAX, OP_MIX_MAX_VIADDMAX, OP_MIX_MAX3_FFMA, OP_VIADDMAX_ONLY, OP_MAX_ONLY, OP_IMAD = 0, OP_IADD3, OP_VIADDMIN, OP_VIMIN3, OP_MIN, OP_REDUX, OP_LOP3, OP_ISETP_SEL, OP_FFMA, OP_IMAD_MIN, OP_SHFL, OP_LDS };
 template <int OP>
 __global__ void __launch_bounds__(512, 1) alu_rate_kernel(int iters, unsigned long long *cycles, int *sink, int seed) {
     __shared__ int sm[1024];
@@ -123,6 +123,13 @@ __global__ void __launch_bounds__(512, 1) alu_rate_kernel(int iters, unsigned lo
             if (OP == OP_IMAD_MIN) x[i] = min(x[i], (x[(i + 1) & 7] & 0xffff) * c + d);
             if (OP == OP_SHFL) x[i] = __shfl_xor_sync(0xFFFFFFFFu, x[i], 1) + i;
             if (OP == OP_LDS) x[i] = sm[(x[i] + i) & 1023];
+            // pipe co-issue probes: even chains run one op type, odd chains another
+            if (OP == OP_MIX_MAX3_IMAD) { if (i & 1) x[i] = x[i] * c + d; else x[i] = __vimax3_s32(x[i], c + i, d); }
+            if (OP == OP_MIX_MAX3_VIADDMAX) { if (i & 1) x[i] = __viaddmax_s32(x[i], c, d + i); else x[i] = __vimax3_s32(x[i], c + i, d); }
+            if (OP == OP_MIX_MAX_VIADDMAX) { if (i & 1) x[i] = __viaddmax_s32(x[i], c, d + i); else x[i] = max(x[i], c + i) ^ d; }
+            if (OP == OP_MIX_MAX3_FFMA) { if (i & 1) f[i] = fmaf(f[i], 1.0001f, 0.5f); else x[i] = __vimax3_s32(x[i], c + i, d); }
+            if (OP == OP_VIADDMAX_ONLY) x[i] = __viaddmax_s32(x[i], c, d + i);
+            if (OP == OP_MAX_ONLY) x[i] = max(x[i], c + i) ^ d;
         }
     }
     const long long t1 = clock64();
@@ -185,6 +192,7 @@ int main() {
 #define ALU(OPNAME) run("alu " #OPNAME, [&] { alu_rate_kernel<OPNAME><<<sms, 512>>>(iters, d_cycles, d_sink, 3); }, sms, d_cycles, w, "lane-op")
         ALU(OP_IMAD); ALU(OP_IADD3); ALU(OP_VIADDMIN); ALU(OP_VIMIN3); ALU(OP_MIN); ALU(OP_REDUX); ALU(OP_LOP3);
         ALU(OP_ISETP_SEL); ALU(OP_FFMA); ALU(OP_IMAD_MIN); ALU(OP_SHFL); ALU(OP_LDS);
+        ALU(OP_MIX_MAX3_IMAD); ALU(OP_MIX_MAX3_VIADDMAX); ALU(OP_MIX_MAX_VIADDMAX); ALU(OP_MIX_MAX3_FFMA); ALU(OP_VIADDMAX_ONLY); ALU(OP_MAX_ONLY);
     }
     return 0;
 }
