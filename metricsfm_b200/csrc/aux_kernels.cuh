@@ -105,69 +105,131 @@ __device__ __forceinline__ int4 merge_knn_shares(const int4 *__restrict__ knn, i
 }
 
 // ------------------------------------------------------------------------------------------------ finalize
-struct FinalizeParams {
+// Block-wide ordered compaction helper: returns this thread's output slot among the `keep` threads of the block
+// (ascending thread index) and adds the block's total to `running` (identical in every thread).
+__device__ __forceinline__ int block_rank(bool keep, int &running, int *warp_excl, int *chunk_total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
+    const int prefix = __popc(ballot & ((1u << lane) - 1u));
+    if (lane == 0) warp_excl[warp] = __popc(ballot);
+    __syncthreads();
+    if (warp == 0) {
+        const int v = (lane < nwarps) ? warp_excl[lane] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        warp_excl[lane] = incl - v;
+        if (lane == 31) *chunk_total = incl;
+    }
+    __syncthreads();
+    const int slot = running + warp_excl[warp] + prefix;
+    running += *chunk_total;
+    __syncthreads();
+    return slot;
+}
+
+// Stage 1 — ratio test.  One CTA per pair scans its query rows in ascending order (the order of
+// fine_matching_graph.cc:116-133 / feature_matching.cpp:56-64) and writes the one-way candidates
+// (query row, nearest reference row, "good" flag) compacted into the pair's scratch region.  With `gather` set it also
+// copies each candidate's reference descriptor row + column key into the candidate scratch image, which the matching
+// kernel then searches against the query image to find the best query of that reference row (mutual cross-check).
+struct SelectParams {
     const PairDesc *pairs;
-    const int4 *knn;                    // per-batch kNN scratch
-    int2 *matches;                      // per-batch scratch; pair p writes its list from row knn_off
-    uint8_t *good;                      // same indexing
-    int32_t *counts;                    // [n_pairs]
+    const int4 *knn;
+    int32_t nshare;
     float ratio, ratio_good, max_dist_sq;
-    int32_t mutual, orientation;
-    int32_t nshare;                     // column shares per kNN row (MatchKernelCfg CSPLIT)
+    int32_t *cand_q, *cand_j;  // [forward kNN rows], pair p writes from row knn_off
+    uint8_t *cand_good;
+    int32_t *counts;           // [n_pairs]
+    int32_t gather;
+    const uint8_t *desc_arena;
+    const int32_t *ckeys;
+    uint8_t *cand_desc;        // [forward kNN rows][128]
+    int32_t *cand_ckeys;
 };
 
-// One CTA per pair.  Rows are scanned in ascending query order, 1024 at a time, and kept matches are written in
-// that order (the order of fine_matching_graph.cc:116-133 / feature_matching.cpp:56-64).
-__global__ void __launch_bounds__(1024) finalize_kernel(const FinalizeParams fp) {
+__global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectParams sp) {
     __shared__ int warp_excl[32];
     __shared__ int chunk_total;
-    const PairDesc pd = fp.pairs[blockIdx.x];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const PairDesc pd = sp.pairs[blockIdx.x];
     int running = 0;
     for (int base = 0; base < pd.qry_rows; base += blockDim.x) {
         const int q = base + threadIdx.x;
         bool keep = false, is_good = false;
         int nn0 = -1;
         if (q < pd.qry_rows) {
-            const int4 k = merge_knn_shares(fp.knn, pd.knn_off + q, fp.nshare);
+            const int4 k = merge_knn_shares(sp.knn, pd.knn_off + q, sp.nshare);
             if (k.x >= 0 && k.y >= 0) {
                 const float d0 = (float)k.z, d1 = (float)k.w;
                 const float r = __fdiv_rn(d0, d1);  // IEEE divide; 0/0 = NaN fails every comparison
-                keep = r < fp.ratio;
-                if (fp.max_dist_sq > 0.0f) keep = keep && (d0 < fp.max_dist_sq);
-                if (keep && fp.mutual)  // the twin's row nn0 holds the best query of reference row nn0 (lowest index on ties)
-                    keep = merge_knn_shares(fp.knn, pd.rev_off + k.x, fp.nshare).x == q;
-                is_good = keep && fp.ratio_good > 0.0f && r < fp.ratio_good;
+                keep = r < sp.ratio;
+                if (sp.max_dist_sq > 0.0f) keep = keep && (d0 < sp.max_dist_sq);
+                is_good = keep && sp.ratio_good > 0.0f && r < sp.ratio_good;
                 nn0 = k.x;
             }
         }
-        const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
-        const int prefix = __popc(ballot & ((1u << lane) - 1u));
-        if (lane == 0) warp_excl[warp] = __popc(ballot);
-        __syncthreads();
-        if (warp == 0) {
-            const int v = (lane < nwarps) ? warp_excl[lane] : 0;
-            int incl = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += n;
-            }
-            warp_excl[lane] = incl - v;
-            if (lane == 31) chunk_total = incl;
-        }
-        __syncthreads();
+        const int slot = block_rank(keep, running, warp_excl, &chunk_total);
         if (keep) {
-            const int64_t pos = pd.knn_off + running + warp_excl[warp] + prefix;
-            int2 m;
-            if (fp.orientation == 0) { m.x = nn0; m.y = q; } else { m.x = q; m.y = nn0; }
-            fp.matches[pos] = m;
-            if (fp.good) fp.good[pos] = is_good ? 1 : 0;
+            sp.cand_q[pd.knn_off + slot] = q;
+            sp.cand_j[pd.knn_off + slot] = nn0;
+            sp.cand_good[pd.knn_off + slot] = is_good ? 1 : 0;
         }
-        running += chunk_total;
-        __syncthreads();
     }
-    if (threadIdx.x == 0) fp.counts[blockIdx.x] = running;
+    if (threadIdx.x == 0) sp.counts[blockIdx.x] = running;
+    if (!sp.gather) return;
+    __syncthreads();  // the candidate list written above is read back by other warps of this CTA
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int i = warp; i < running; i += nwarps) {
+        const int j = sp.cand_j[pd.knn_off + i];
+        const uint32_t w = reinterpret_cast<const uint32_t *>(sp.desc_arena + (pd.ref_off + j) * kDim)[lane];
+        reinterpret_cast<uint32_t *>(sp.cand_desc + (pd.knn_off + i) * kDim)[lane] = w;
+        if (lane == 0) sp.cand_ckeys[pd.knn_off + i] = sp.ckeys[pd.ref_off + j];
+    }
+}
+
+// Stage 2 — (mutual check and) emission.  Candidate i of pair p survives the mutual check iff the nearest query row of
+// its reference row (row i of the pair's twin kNN region) is the candidate's own query row.
+struct EmitParams {
+    const PairDesc *pairs;
+    const int4 *knn;
+    int32_t nshare;
+    int64_t twin_base;         // twin kNN row of candidate i of pair p = twin_base + knn_off + i
+    const int32_t *cand_q, *cand_j;
+    const uint8_t *cand_good;
+    const int32_t *cand_counts;
+    int2 *matches;             // per-batch scratch; pair p writes its list from row knn_off
+    uint8_t *good;
+    int32_t *counts;           // [n_pairs] surviving matches
+    int32_t mutual, orientation;
+};
+
+__global__ void __launch_bounds__(1024) emit_matches_kernel(const EmitParams ep) {
+    __shared__ int warp_excl[32];
+    __shared__ int chunk_total;
+    const PairDesc pd = ep.pairs[blockIdx.x];
+    const int n = ep.cand_counts[blockIdx.x];
+    int running = 0;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        bool keep = i < n;
+        int q = -1, j = -1;
+        if (keep) {
+            q = ep.cand_q[pd.knn_off + i];
+            j = ep.cand_j[pd.knn_off + i];
+            if (ep.mutual) keep = merge_knn_shares(ep.knn, ep.twin_base + pd.knn_off + i, ep.nshare).x == q;
+        }
+        const int slot = block_rank(keep, running, warp_excl, &chunk_total);
+        if (keep) {
+            int2 m;
+            if (ep.orientation == 0) { m.x = j; m.y = q; } else { m.x = q; m.y = j; }
+            ep.matches[pd.knn_off + slot] = m;
+            if (ep.good) ep.good[pd.knn_off + slot] = ep.cand_good[pd.knn_off + i];
+        }
+    }
+    if (threadIdx.x == 0) ep.counts[blockIdx.x] = running;
 }
 
 // Exclusive scan of the per-pair counts into int64 offsets[n+1]; single CTA (n is a per-batch pair count).

@@ -47,11 +47,13 @@ __host__ __device__ constexpr int32_t make_ckey(uint32_t nb, int j) { return -8 
 __host__ __device__ constexpr int32_t ckey_to_norm(int32_t ckey) { return (7 - ckey) >> 3; }
 
 struct PairDesc {
-    int32_t ref_img, qry_img;  // tensor-map slots
+    int32_t ref_img, qry_img;  // tensor-map slots (the slot after the last image maps the candidate scratch)
     int32_t ref_rows, qry_rows;
-    int64_t ref_off, qry_off;  // first row in the arenas
+    int64_t ref_off, qry_off;  // first row in the column-key arena (query side: candidate scratch when cand_idx >= 0)
     int64_t knn_off;           // first row of this pair in the per-batch kNN scratch
-    int64_t rev_off;           // first row of the role-swapped twin of this pair in the kNN scratch (-1: none)
+    int32_t qry_row_base;      // row coordinate of query row 0 in the query tensor map (0 for whole-image maps)
+    int32_t cand_idx;          // >= 0: the query rows are this pair's gathered mutual-check candidates and their
+                               // number is counts[cand_idx] (known only on the device); -1: ordinary image rows
 };
 
 struct WorkItem {
@@ -62,6 +64,8 @@ struct WorkItem {
 struct MatchKernelParams {
     const CUtensorMap *maps;      // [max_images] one 2-D map per image: {128 B, rows}, box {128 B, kBoxRows rows}, SW128
     const int32_t *ckeys;         // arena of column keys (see make_ckey)
+    const int32_t *cand_ckeys;    // column keys of the gathered candidate rows (query side of cand_idx >= 0 pairs)
+    const int32_t *counts;        // per-pair candidate counts
     const PairDesc *pairs;
     const WorkItem *items;
     int32_t n_items;
@@ -175,18 +179,19 @@ match_pairs_kernel(const MatchKernelParams p) {
         // =========================================================== TMA producer
         if (ptx::elect_one()) {
             uint32_t g = 0, a = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++a) {
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const WorkItem wi = p.items[item];
                 const PairDesc pd = p.pairs[wi.pair];
                 const CUtensorMap *qmap = p.maps + pd.qry_img;
                 const CUtensorMap *rmap = p.maps + pd.ref_img;
+                if (pd.cand_idx >= 0 && wi.row0 >= p.counts[pd.cand_idx]) continue;  // item past the candidate list
                 const uint32_t abuf = a & 1;
                 ptx::mbar_wait_backoff(&a_empty[abuf], ((a >> 1) & 1) ^ 1);
                 ptx::mbar_arrive_expect_tx(&a_full[abuf], Cfg::kABytes);
 #pragma unroll
                 for (int s = 0; s < STRIPS * kStripRows / kBoxRows; ++s)
                     ptx::tma_load_2d(sA + abuf * Cfg::kABytes + s * kBoxRows * kDim, qmap, &a_full[abuf], 0,
-                                     wi.row0 + s * kBoxRows);
+                                     pd.qry_row_base + wi.row0 + s * kBoxRows);
                 const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
                 for (int t = 0; t < ntiles; ++t, ++g) {
                     const uint32_t st = g % STAGES;
@@ -200,6 +205,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                     ptx::mbar_arrive_expect_tx(&k_full[ks], TILE_N * 4);
                     ptx::bulk_load_1d(sKey + ks * TILE_N, p.ckeys + pd.ref_off + (int64_t)t * TILE_N, TILE_N * 4, &k_full[ks]);
                 }
+                ++a;
             }
         }
     } else if (warp == Cfg::kEpiWarps + 1) {
@@ -207,9 +213,10 @@ match_pairs_kernel(const MatchKernelParams p) {
         if (ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::make_idesc_i8(kStripRows, TILE_N, 0, 0);
             uint32_t g = 0, a = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++a) {
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const WorkItem wi = p.items[item];
                 const PairDesc pd = p.pairs[wi.pair];
+                if (pd.cand_idx >= 0 && wi.row0 >= p.counts[pd.cand_idx]) continue;
                 const uint32_t abuf = a & 1;
                 ptx::mbar_wait_backoff(&a_full[abuf], (a >> 1) & 1);
                 const uint32_t a_addr = ptx::smem_u32(sA + abuf * Cfg::kABytes);
@@ -236,6 +243,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                     ptx::mma_commit(&b_empty[st]);    // B stage reusable once every strip's MMAs have read it
                 }
                 ptx::mma_commit(&a_empty[abuf]);      // A buffer reusable
+                ++a;
             }
         }
     } else if (warp < Cfg::kEpiWarps) {
@@ -269,12 +277,14 @@ match_pairs_kernel(const MatchKernelParams p) {
         const uint32_t t_empty_base = ptx::smem_u32(t_empty + strip);
         // ring positions are carried incrementally (no divisions in the tile loop)
         uint32_t ks = 0, k_phase = 0, buf = 0, t_phase = 0, a = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++a) {
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const WorkItem wi = p.items[item];
             const PairDesc pd = p.pairs[wi.pair];
+            const int qry_rows = pd.cand_idx >= 0 ? p.counts[pd.cand_idx] : pd.qry_rows;
+            if (wi.row0 >= qry_rows) continue;
             const int q = wi.row0 + row_local;
-            const bool valid = q < pd.qry_rows;
-            const int na = valid ? ckey_to_norm(p.ckeys[pd.qry_off + q]) : 0;
+            const bool valid = q < qry_rows;
+            const int na = valid ? ckey_to_norm((pd.cand_idx >= 0 ? p.cand_ckeys : p.ckeys)[pd.qry_off + q]) : 0;
             // rows past the image end hold zeros; park their state where nothing can flag a group
             int S0 = valid ? INT_MIN : 0x20000000, S1 = S0, J0 = -1, J1 = -1;
             const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
@@ -349,6 +359,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                 out.w = (S1 > kAbsent) ? na - S1 : INT_MAX;
                 p.knn[(pd.knn_off + q) * CSPLIT + share] = out;
             }
+            ++a;
         }
     }
 

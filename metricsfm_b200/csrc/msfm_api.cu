@@ -39,7 +39,7 @@ constexpr int kItemRows = kStrips * msfm::kStripRows;
 
 // Per-batch scratch bounds (rows).  16 Mi query rows -> 256 MiB kNN scratch + 128 MiB match scratch.
 constexpr int64_t kBatchMaxQueryRows = 16ll << 20;
-constexpr int64_t kBatchMaxRefRows = 16ll << 20;  // twin kNN rows (mutual cross-check)
+constexpr int64_t kBatchMaxQueryRowsMutual = 4ll << 20;  // mutual: + 128 B of gathered candidate row per query row
 constexpr int64_t kBatchMaxPairs = 16384;
 
 struct DeviceBuf {
@@ -79,10 +79,12 @@ struct msfm_ctx {
     std::vector<ImageSlot> images;
     EncodeTiledFn encode = nullptr;
 
+    DeviceBuf cand_q, cand_j, cand_good, cand_counts, cand_desc, cand_ckeys;  // one-way candidates + gathered rows
     DeviceBuf staging, knn, matches, good, counts, offsets, pairdesc, items, tight_matches, tight_good;
     void *h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_f1 = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_k2 = nullptr, ev_k3 = nullptr,
+                ev_f1 = nullptr;
 
     msfm_timing timing{};
     uint32_t debug_flags = 0;  // MSFM_DEBUG_FLAGS environment variable (timing experiments)
@@ -224,23 +226,26 @@ msfm_status reserve_locked(msfm_ctx *ctx, int32_t image_id, int32_t rows, int64_
 
 struct BatchPlan {
     std::vector<PairDesc> pairs;     // forward pair descriptors (only pairs passing the gate)
-    std::vector<PairDesc> twins;     // role-swapped twins (mutual cross-check), appended after `pairs` on the device
+    std::vector<PairDesc> twins;     // mutual cross-check: candidate rows of pair p searched against its query image
     std::vector<int64_t> src_index;  // index into the caller's pair list
-    std::vector<WorkItem> items;     // twin items carry pair = -1 - twin index until finish_plan()
-    int64_t query_rows = 0;          // forward kNN rows (= match scratch rows)
-    int64_t twin_rows = 0;           // kNN rows of the twins
+    std::vector<WorkItem> items;     // forward work items
+    std::vector<WorkItem> twin_items;
+    int64_t query_rows = 0;          // forward kNN rows (= candidate / match scratch rows)
     int64_t ops = 0;
+    bool mutual = false;
     bool has_empty = false;          // some pair has no work items: its kNN rows must read "absent"
-    int64_t knn_rows() const { return query_rows + twin_rows; }
+    int64_t knn_rows() const { return mutual ? 2 * query_rows : query_rows; }
 };
 
-msfm_status launch_match_kernel(msfm_ctx *ctx, const BatchPlan &plan) {
+msfm_status launch_match_kernel(msfm_ctx *ctx, size_t first_item, size_t n_items) {
     msfm::MatchKernelParams kp;
     kp.maps = ctx->d_maps;
     kp.ckeys = ctx->norms;
+    kp.cand_ckeys = static_cast<const int32_t *>(ctx->cand_ckeys.ptr);
+    kp.counts = static_cast<const int32_t *>(ctx->cand_counts.ptr);
     kp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
-    kp.items = static_cast<const WorkItem *>(ctx->items.ptr);
-    kp.n_items = (int32_t)plan.items.size();
+    kp.items = static_cast<const WorkItem *>(ctx->items.ptr) + first_item;
+    kp.n_items = (int32_t)n_items;
     kp.stats = nullptr;
     kp.debug_flags = ctx->debug_flags;
     kp.knn = static_cast<int4 *>(ctx->knn.ptr);
@@ -250,50 +255,89 @@ msfm_status launch_match_kernel(msfm_ctx *ctx, const BatchPlan &plan) {
     else
         msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, false><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
     MSFM_CUDA(ctx, cudaGetLastError());
+    ctx->timing.match_launches += 1;
+    ctx->timing.total_launches += 1;
     return MSFM_OK;
 }
 
-// Resolve the forward <-> twin cross references once the batch is complete.
-void finish_plan(BatchPlan &plan) {
-    const int32_t nb = (int32_t)plan.pairs.size();
-    for (PairDesc &t : plan.twins) t.knn_off += plan.query_rows;
-    for (PairDesc &f : plan.pairs)
-        if (f.rev_off >= 0) f.rev_off += plan.query_rows;
-    for (WorkItem &w : plan.items)
-        if (w.pair < 0) w.pair = nb + (-1 - w.pair);
+// The candidate scratch "image" (gathered reference rows of the one-way matches) and its tensor map, which lives in
+// the slot after the last image.
+msfm_status ensure_cand_scratch(msfm_ctx *ctx, int64_t rows) {
+    msfm_status st;
+    if ((st = ensure(ctx, ctx->cand_ckeys, (size_t)rows * 4)) != MSFM_OK) return st;
+    if (ctx->cand_desc.ptr && ctx->cand_desc.bytes >= (size_t)rows * kDim) return MSFM_OK;
+    if ((st = ensure(ctx, ctx->cand_desc, (size_t)rows * kDim)) != MSFM_OK) return st;
+    CUtensorMap m;
+    memset(&m, 0, sizeof m);
+    cuuint64_t dims[2] = {(cuuint64_t)kDim, (cuuint64_t)(ctx->cand_desc.bytes / kDim)};
+    cuuint64_t strides[1] = {(cuuint64_t)kDim};
+    cuuint32_t box[2] = {(cuuint32_t)kDim, (cuuint32_t)msfm::kBoxRows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = ctx->encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ctx->cand_desc.ptr, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, MSFM_ERR_CUDA, "cuTensorMapEncodeTiled (candidate scratch) failed with CUresult %d", (int)r);
+    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_maps + ctx->max_images, &m, sizeof m, cudaMemcpyHostToDevice, ctx->stream));
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MSFM_OK;
 }
 
-// Upload the plan, run the matching kernel (timed), leave the kNN rows in scratch.
+// Complete the batch: twin descriptors (one per forward pair) and their work items.  Twin p searches the gathered
+// candidate rows of pair p (rows [knn_off, knn_off + count_p) of the candidate scratch, count known only on the device)
+// against pair p's query image; its kNN rows mirror the forward region, shifted by query_rows.
+void finish_plan(msfm_ctx *ctx, BatchPlan &plan) {
+    if (!plan.mutual) return;
+    const int32_t nb = (int32_t)plan.pairs.size();
+    plan.twins.reserve(nb);
+    for (int32_t pi = 0; pi < nb; ++pi) {
+        const PairDesc &f = plan.pairs[pi];
+        PairDesc tw;
+        tw.ref_img = f.qry_img;
+        tw.qry_img = ctx->max_images;  // candidate scratch map
+        tw.ref_rows = f.qry_rows;
+        tw.qry_rows = f.qry_rows;      // upper bound; the device reads counts[cand_idx]
+        tw.ref_off = f.qry_off;
+        tw.qry_off = f.knn_off;        // row in cand_ckeys
+        tw.knn_off = plan.query_rows + f.knn_off;
+        tw.qry_row_base = (int32_t)f.knn_off;
+        tw.cand_idx = pi;
+        plan.twins.push_back(tw);
+        if (f.ref_rows > 0)
+            for (int32_t row0 = 0; row0 < f.qry_rows; row0 += kItemRows) plan.twin_items.push_back({nb + pi, row0});
+    }
+    // items that can actually hold candidates (low row0) first, the mostly empty tail last: balances the persistent CTAs
+    std::stable_sort(plan.twin_items.begin(), plan.twin_items.end(), [](const WorkItem &x, const WorkItem &y) { return x.row0 < y.row0; });
+}
+
+// Upload the plan and run the forward matching launch (timed); leaves the kNN rows in scratch.
 msfm_status run_match_stage(msfm_ctx *ctx, const BatchPlan &plan) {
     msfm_status st;
     const size_t fw_bytes = plan.pairs.size() * sizeof(PairDesc);
     const size_t tw_bytes = plan.twins.size() * sizeof(PairDesc);
     const size_t pd_bytes = fw_bytes + tw_bytes;
-    const size_t it_bytes = plan.items.size() * sizeof(WorkItem);
+    const size_t it_fw = plan.items.size() * sizeof(WorkItem), it_tw = plan.twin_items.size() * sizeof(WorkItem);
     if ((st = ensure(ctx, ctx->pairdesc, pd_bytes)) != MSFM_OK) return st;
-    if ((st = ensure(ctx, ctx->items, it_bytes)) != MSFM_OK) return st;
+    if ((st = ensure(ctx, ctx->items, it_fw + it_tw)) != MSFM_OK) return st;
     if ((st = ensure(ctx, ctx->knn, (size_t)plan.knn_rows() * kCsplit * sizeof(int4))) != MSFM_OK) return st;
-    if ((st = ensure_pinned(ctx, pd_bytes + it_bytes + 64)) != MSFM_OK) return st;
+    if ((st = ensure(ctx, ctx->cand_counts, plan.pairs.size() * 4)) != MSFM_OK) return st;
+    if ((st = ensure_pinned(ctx, pd_bytes + it_fw + it_tw + 64)) != MSFM_OK) return st;
     // the pinned staging area is reused per batch: the previous batch has been synchronised by its D2H
     char *hp = static_cast<char *>(ctx->h_pinned);
     memcpy(hp, plan.pairs.data(), fw_bytes);
     if (tw_bytes) memcpy(hp + fw_bytes, plan.twins.data(), tw_bytes);
-    memcpy(hp + pd_bytes, plan.items.data(), it_bytes);
+    memcpy(hp + pd_bytes, plan.items.data(), it_fw);
+    if (it_tw) memcpy(hp + pd_bytes + it_fw, plan.twin_items.data(), it_tw);
     MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->pairdesc.ptr, hp, pd_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->items.ptr, hp + pd_bytes, it_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    if (plan.has_empty) MSFM_CUDA(ctx, cudaMemsetAsync(ctx->knn.ptr, 0xFF, (size_t)plan.knn_rows() * kCsplit * sizeof(int4), ctx->stream));
+    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->items.ptr, hp + pd_bytes, it_fw + it_tw, cudaMemcpyHostToDevice, ctx->stream));
+    if (plan.has_empty) MSFM_CUDA(ctx, cudaMemsetAsync(ctx->knn.ptr, 0xFF, (size_t)plan.query_rows * kCsplit * sizeof(int4), ctx->stream));
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
-    if ((st = launch_match_kernel(ctx, plan)) != MSFM_OK) return st;
+    if (!plan.items.empty() && (st = launch_match_kernel(ctx, 0, plan.items.size())) != MSFM_OK) return st;
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
-    ctx->timing.match_launches += 1;
-    ctx->timing.total_launches += 1;
     ctx->timing.int8_ops += plan.ops;
     return MSFM_OK;
 }
 
-// Adds pair (ref, qry) and, for the mutual cross-check, its role-swapped twin (best query of every reference row =
-// nearest neighbour of that row among the query rows).
-void plan_add_pair(msfm_ctx *ctx, BatchPlan &plan, int64_t src, int32_t ref, int32_t qry, bool mutual) {
+void plan_add_pair(msfm_ctx *ctx, BatchPlan &plan, int64_t src, int32_t ref, int32_t qry) {
     const ImageSlot &r = ctx->images[ref], &q = ctx->images[qry];
     PairDesc pd;
     pd.ref_img = ref;
@@ -303,7 +347,8 @@ void plan_add_pair(msfm_ctx *ctx, BatchPlan &plan, int64_t src, int32_t ref, int
     pd.ref_off = r.off;
     pd.qry_off = q.off;
     pd.knn_off = plan.query_rows;
-    pd.rev_off = mutual ? plan.twin_rows : -1;
+    pd.qry_row_base = 0;
+    pd.cand_idx = -1;
     const int32_t pidx = (int32_t)plan.pairs.size();
     plan.pairs.push_back(pd);
     plan.src_index.push_back(src);
@@ -312,28 +357,12 @@ void plan_add_pair(msfm_ctx *ctx, BatchPlan &plan, int64_t src, int32_t ref, int
     if (work)
         for (int32_t row0 = 0; row0 < q.rows; row0 += kItemRows) plan.items.push_back({pidx, row0});
     plan.query_rows += q.rows;
-    if (mutual) {
-        PairDesc tw;
-        tw.ref_img = qry;
-        tw.qry_img = ref;
-        tw.ref_rows = q.rows;
-        tw.qry_rows = r.rows;
-        tw.ref_off = q.off;
-        tw.qry_off = r.off;
-        tw.knn_off = plan.twin_rows;
-        tw.rev_off = -1;
-        const int32_t tidx = (int32_t)plan.twins.size();
-        plan.twins.push_back(tw);
-        if (work)
-            for (int32_t row0 = 0; row0 < r.rows; row0 += kItemRows) plan.items.push_back({-1 - tidx, row0});
-        plan.twin_rows += r.rows;
-    }
     plan.ops += 2ll * r.rows * q.rows * kDim;
 }
 
-msfm_status accumulate_kernel_time(msfm_ctx *ctx) {
+msfm_status accumulate_kernel_time(msfm_ctx *ctx, cudaEvent_t e0, cudaEvent_t e1) {
     float ms = 0.f;
-    MSFM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1));
+    MSFM_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
     ctx->timing.match_kernel_ms += ms;
     return MSFM_OK;
 }
@@ -343,20 +372,11 @@ msfm_status knn_single(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, BatchPla
     msfm_status st;
     if ((st = check_image_id(ctx, ref_id, true)) != MSFM_OK) return st;
     if ((st = check_image_id(ctx, query_id, true)) != MSFM_OK) return st;
-    plan_add_pair(ctx, plan, 0, ref_id, query_id, false);
-    finish_plan(plan);
+    plan_add_pair(ctx, plan, 0, ref_id, query_id);
     ctx->timing = msfm_timing{};
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
     if (plan.query_rows == 0) return MSFM_OK;
-    if (plan.items.empty()) {
-        // no reference rows: every neighbour is absent
-        if ((st = ensure(ctx, ctx->knn, (size_t)plan.query_rows * kCsplit * sizeof(int4))) != MSFM_OK) return st;
-        std::vector<int4> none((size_t)plan.query_rows * kCsplit, make_int4(-1, -1, INT_MAX, INT_MAX));
-        MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->knn.ptr, none.data(), none.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
-        MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        return MSFM_OK;
-    }
-    return run_match_stage(ctx, plan);
+    return run_match_stage(ctx, plan);  // a pair without work items leaves "absent" rows (memset)
 }
 
 msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const msfm_params *params, msfm_result *out,
@@ -374,7 +394,9 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
     }
     ctx->timing = msfm_timing{};
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
+    const bool mutual = params->mutual != 0;
     const bool want_good = params->ratio_good > 0.0f && (resident || out->good);
+    const int64_t max_rows = mutual ? kBatchMaxQueryRowsMutual : kBatchMaxQueryRows;
     int64_t written = 0;  // matches written to the caller so far
     int64_t total = 0;
     if (!resident) out->offsets[0] = 0;
@@ -383,55 +405,80 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
     while (next < n_pairs) {
         // ---- carve the next batch
         BatchPlan plan;
+        plan.mutual = mutual;
         const int64_t first = next;
         while (next < n_pairs && (int64_t)plan.pairs.size() < kBatchMaxPairs) {
             const ImageSlot &r = ctx->images[pairs[next].ref], &q = ctx->images[pairs[next].query];
             const bool gated = r.rows < params->min_keypoints || q.rows < params->min_keypoints;
             if (!gated) {
-                if (!plan.pairs.empty() &&
-                    (plan.query_rows + q.rows > kBatchMaxQueryRows || plan.twin_rows + r.rows > kBatchMaxRefRows))
-                    break;
-                plan_add_pair(ctx, plan, next, pairs[next].ref, pairs[next].query, params->mutual != 0);
+                if (!plan.pairs.empty() && plan.query_rows + q.rows > max_rows) break;
+                plan_add_pair(ctx, plan, next, pairs[next].ref, pairs[next].query);
             }
             ++next;
         }
         const int64_t last = next;
-        finish_plan(plan);
+        finish_plan(ctx, plan);
         const int nb = (int)plan.pairs.size();
         std::vector<int64_t> batch_offsets;
         if (nb > 0 && plan.query_rows > 0) {
-            if (!plan.items.empty()) {
-                if ((st = run_match_stage(ctx, plan)) != MSFM_OK) return st;
-            } else {
-                if ((st = ensure(ctx, ctx->pairdesc, nb * sizeof(PairDesc))) != MSFM_OK) return st;
-                if ((st = ensure(ctx, ctx->knn, (size_t)plan.knn_rows() * kCsplit * sizeof(int4))) != MSFM_OK) return st;
-                MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->pairdesc.ptr, plan.pairs.data(), nb * sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream));
-                MSFM_CUDA(ctx, cudaMemsetAsync(ctx->knn.ptr, 0xFF, (size_t)plan.knn_rows() * kCsplit * sizeof(int4), ctx->stream));
-                MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            }
-            // ---- ratio / mutual / compaction
-            if ((st = ensure(ctx, ctx->matches, (size_t)plan.query_rows * sizeof(int2))) != MSFM_OK) return st;
-            if (want_good && (st = ensure(ctx, ctx->good, (size_t)plan.query_rows)) != MSFM_OK) return st;
+            const size_t rows = (size_t)plan.query_rows;
+            if ((st = ensure(ctx, ctx->cand_q, rows * 4)) != MSFM_OK) return st;
+            if ((st = ensure(ctx, ctx->cand_j, rows * 4)) != MSFM_OK) return st;
+            if ((st = ensure(ctx, ctx->cand_good, rows)) != MSFM_OK) return st;
+            if (mutual && (st = ensure_cand_scratch(ctx, plan.query_rows)) != MSFM_OK) return st;
+            if ((st = ensure(ctx, ctx->matches, rows * sizeof(int2))) != MSFM_OK) return st;
+            if (want_good && (st = ensure(ctx, ctx->good, rows)) != MSFM_OK) return st;
             if ((st = ensure(ctx, ctx->counts, (size_t)nb * 4)) != MSFM_OK) return st;
             if ((st = ensure(ctx, ctx->offsets, (size_t)(nb + 1) * 8)) != MSFM_OK) return st;
-            if ((st = ensure(ctx, ctx->tight_matches, (size_t)plan.query_rows * sizeof(int2))) != MSFM_OK) return st;
-            if (want_good && (st = ensure(ctx, ctx->tight_good, (size_t)plan.query_rows)) != MSFM_OK) return st;
-            msfm::FinalizeParams fp;
-            fp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
-            fp.knn = static_cast<const int4 *>(ctx->knn.ptr);
-            fp.matches = static_cast<int2 *>(ctx->matches.ptr);
-            fp.good = want_good ? static_cast<uint8_t *>(ctx->good.ptr) : nullptr;
-            fp.counts = static_cast<int32_t *>(ctx->counts.ptr);
-            fp.ratio = params->ratio;
-            fp.ratio_good = params->ratio_good;
-            fp.max_dist_sq = params->max_dist_sq;
-            fp.mutual = params->mutual != 0;
-            fp.orientation = params->orientation;
-            fp.nshare = kCsplit;
-            msfm::finalize_kernel<<<nb, 1024, 0, ctx->stream>>>(fp);
-            msfm::scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(fp.counts, nb, static_cast<int64_t *>(ctx->offsets.ptr));
+            if ((st = ensure(ctx, ctx->tight_matches, rows * sizeof(int2))) != MSFM_OK) return st;
+            if (want_good && (st = ensure(ctx, ctx->tight_good, rows)) != MSFM_OK) return st;
+            // ---- forward 2-NN
+            if ((st = run_match_stage(ctx, plan)) != MSFM_OK) return st;
+            // ---- ratio test -> one-way candidates (+ gather of their reference rows for the mutual check)
+            msfm::SelectParams sp;
+            sp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
+            sp.knn = static_cast<const int4 *>(ctx->knn.ptr);
+            sp.nshare = kCsplit;
+            sp.ratio = params->ratio;
+            sp.ratio_good = params->ratio_good;
+            sp.max_dist_sq = params->max_dist_sq;
+            sp.cand_q = static_cast<int32_t *>(ctx->cand_q.ptr);
+            sp.cand_j = static_cast<int32_t *>(ctx->cand_j.ptr);
+            sp.cand_good = static_cast<uint8_t *>(ctx->cand_good.ptr);
+            sp.counts = static_cast<int32_t *>(ctx->cand_counts.ptr);
+            sp.gather = mutual ? 1 : 0;
+            sp.desc_arena = ctx->desc;
+            sp.ckeys = ctx->norms;
+            sp.cand_desc = static_cast<uint8_t *>(ctx->cand_desc.ptr);
+            sp.cand_ckeys = static_cast<int32_t *>(ctx->cand_ckeys.ptr);
+            msfm::select_candidates_kernel<<<nb, 1024, 0, ctx->stream>>>(sp);
+            MSFM_CUDA(ctx, cudaGetLastError());
+            ctx->timing.total_launches += 1;
+            // ---- mutual cross-check: nearest query row of every candidate's reference row
+            MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k2, ctx->stream));
+            if (mutual && !plan.twin_items.empty() &&
+                (st = launch_match_kernel(ctx, plan.items.size(), plan.twin_items.size())) != MSFM_OK)
+                return st;
+            MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k3, ctx->stream));
+            // ---- emission, offsets, tight gather
+            msfm::EmitParams ep;
+            ep.pairs = sp.pairs;
+            ep.knn = sp.knn;
+            ep.nshare = kCsplit;
+            ep.twin_base = plan.query_rows;
+            ep.cand_q = sp.cand_q;
+            ep.cand_j = sp.cand_j;
+            ep.cand_good = sp.cand_good;
+            ep.cand_counts = sp.counts;
+            ep.matches = static_cast<int2 *>(ctx->matches.ptr);
+            ep.good = want_good ? static_cast<uint8_t *>(ctx->good.ptr) : nullptr;
+            ep.counts = static_cast<int32_t *>(ctx->counts.ptr);
+            ep.mutual = mutual ? 1 : 0;
+            ep.orientation = params->orientation;
+            msfm::emit_matches_kernel<<<nb, 1024, 0, ctx->stream>>>(ep);
+            msfm::scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(ep.counts, nb, static_cast<int64_t *>(ctx->offsets.ptr));
             msfm::gather_matches_kernel<<<nb, 256, 0, ctx->stream>>>(
-                fp.pairs, fp.counts, static_cast<const int64_t *>(ctx->offsets.ptr), fp.matches, fp.good,
+                ep.pairs, ep.counts, static_cast<const int64_t *>(ctx->offsets.ptr), ep.matches, ep.good,
                 static_cast<int2 *>(ctx->tight_matches.ptr), want_good ? static_cast<uint8_t *>(ctx->tight_good.ptr) : nullptr);
             MSFM_CUDA(ctx, cudaGetLastError());
             MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_f1, ctx->stream));
@@ -441,13 +488,14 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             MSFM_CUDA(ctx, cudaMemcpyAsync(batch_offsets.data(), ctx->offsets.ptr, (size_t)(nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
             MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             ctx->timing.d2h_bytes += (nb + 1) * 8;
-            if (!plan.items.empty() && (st = accumulate_kernel_time(ctx)) != MSFM_OK) return st;
+            if ((st = accumulate_kernel_time(ctx, ctx->ev_k0, ctx->ev_k1)) != MSFM_OK) return st;
+            if ((st = accumulate_kernel_time(ctx, ctx->ev_k2, ctx->ev_k3)) != MSFM_OK) return st;
             {
-                float ms = 0.f;
-                if (!plan.items.empty()) {
-                    MSFM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_k1, ctx->ev_f1));
-                    ctx->timing.finalize_ms += ms;
-                }
+                float ms_all = 0.f, ms_a = 0.f, ms_b = 0.f;
+                MSFM_CUDA(ctx, cudaEventElapsedTime(&ms_all, ctx->ev_k0, ctx->ev_f1));
+                MSFM_CUDA(ctx, cudaEventElapsedTime(&ms_a, ctx->ev_k0, ctx->ev_k1));
+                MSFM_CUDA(ctx, cudaEventElapsedTime(&ms_b, ctx->ev_k2, ctx->ev_k3));
+                ctx->timing.finalize_ms += ms_all - ms_a - ms_b;
             }
             const int64_t bt = batch_offsets[nb];
             total += bt;
@@ -547,7 +595,7 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return bail(MSFM_ERR_CUDA);
     ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MSFM_ERR_CUDA);
-    cudaEvent_t *evs[] = {&ctx->ev_begin, &ctx->ev_end, &ctx->ev_k0, &ctx->ev_k1, &ctx->ev_f1};
+    cudaEvent_t *evs[] = {&ctx->ev_begin, &ctx->ev_end, &ctx->ev_k0, &ctx->ev_k1, &ctx->ev_k2, &ctx->ev_k3, &ctx->ev_f1};
     for (cudaEvent_t *e : evs)
         if (cudaEventCreate(e) != cudaSuccess) return bail(MSFM_ERR_CUDA);
     if (cfg->external_desc_arena) {
@@ -561,7 +609,8 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
         if (cudaMalloc(&ctx->norms, (size_t)ctx->arena_rows * 4) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
         ctx->own_arena = true;
     }
-    if (cudaMalloc(&ctx->d_maps, (size_t)ctx->max_images * sizeof(CUtensorMap)) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
+    // one tensor map per image + one for the candidate scratch
+    if (cudaMalloc(&ctx->d_maps, (size_t)(ctx->max_images + 1) * sizeof(CUtensorMap)) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
     if (cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, false>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::kSmemAlloc) != cudaSuccess ||
         cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, true>,
@@ -575,7 +624,8 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
     if (!ctx) return MSFM_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DeviceBuf *bufs[] = {&ctx->staging, &ctx->knn, &ctx->matches, &ctx->good, &ctx->counts, &ctx->offsets,
+    DeviceBuf *bufs[] = {&ctx->cand_q, &ctx->cand_j, &ctx->cand_good, &ctx->cand_counts, &ctx->cand_desc, &ctx->cand_ckeys,
+                         &ctx->staging, &ctx->knn, &ctx->matches, &ctx->good, &ctx->counts, &ctx->offsets,
                          &ctx->pairdesc, &ctx->items, &ctx->tight_matches, &ctx->tight_good};
     for (DeviceBuf *b : bufs)
         if (b->ptr) cudaFree(b->ptr);
@@ -585,7 +635,7 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
         if (ctx->norms) cudaFree(ctx->norms);
     }
     if (ctx->d_maps) cudaFree(ctx->d_maps);
-    cudaEvent_t evs[] = {ctx->ev_begin, ctx->ev_end, ctx->ev_k0, ctx->ev_k1, ctx->ev_f1};
+    cudaEvent_t evs[] = {ctx->ev_begin, ctx->ev_end, ctx->ev_k0, ctx->ev_k1, ctx->ev_k2, ctx->ev_k3, ctx->ev_f1};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -732,7 +782,7 @@ msfm_status msfm_knn2(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_t *
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
     MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->timing.d2h_bytes = (int64_t)n * 16;
-    if (!plan.items.empty() && (st = accumulate_kernel_time(ctx)) != MSFM_OK) return st;
+    if ((st = accumulate_kernel_time(ctx, ctx->ev_k0, ctx->ev_k1)) != MSFM_OK) return st;
     MSFM_CUDA(ctx, cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev_begin, ctx->ev_end));
     return MSFM_OK;
 }
@@ -757,7 +807,7 @@ msfm_status msfm_colbest(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_
     MSFM_CUDA(ctx, cudaMemcpyAsync(best_query, d_best, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
     MSFM_CUDA(ctx, cudaMemcpyAsync(best_dist, d_dist, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
     MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (!plan.items.empty() && (st = accumulate_kernel_time(ctx)) != MSFM_OK) return st;
+    if ((st = accumulate_kernel_time(ctx, ctx->ev_k0, ctx->ev_k1)) != MSFM_OK) return st;
     return MSFM_OK;
 }
 
