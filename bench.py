@@ -327,7 +327,7 @@ def run_native(args):
                        "pairs_per_step_all_gpus": int(len(pairs)), "parallelism": f"pair-sharded x{world}, table replicated",
                        "l2": "flushed between timed steps (256 MiB write)", "matches_per_step_rank0": int(n_matches)},
             "roofline": {"bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TFLOP/s", "frac": achieved_tops / peak_tops,
-                         "traffic": None, "kernel": "match_pairs_kernel<2,128,4>",
+                         "traffic": None, "kernel": "match_pairs_kernel<2,128,6,2,2>",
                          "note": "int8 tensor ops (2 per MAC), i.e. TOP/s; algorithmic ops = 2*M*N*128 per pair; peak = 2 x "
                                  f"bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks_src}); spec dense int8 = 4500",
                          "frac_of_spec_int8": achieved_tops / INT8_SPEC_PEAK_TOPS, "kernel_ms_per_step": kern_avg_ms,
