@@ -169,7 +169,7 @@ def run_reference(args):
 def run_native(args):
     import torch
     import torch.distributed as dist
-    from metricsfm_b200 import scheduler, synth
+    from metricsfm_b200 import distributed as D, scheduler, synth
     from metricsfm_b200.matcher import Matcher
 
     rank = int(os.environ.get("RANK", "0"))
@@ -208,20 +208,19 @@ def run_native(args):
                 external_norm_arena=norm_arena.data_ptr())
     lib_stream = torch.cuda.ExternalStream(m.cuda_stream(), device=dev)
 
+    owner, ranges = D.block_ranges(n_global, rows_padded, world)
+
     def stage_table():
         """Pack + upload this rank's images (H2D), reserve the others, replicate over NCCL.  Returns H2D bytes."""
         m.release_all()
         for gid in range(n_global):
-            if gid // n_local == rank:
+            if owner[gid] == rank:
                 m.upload(gid, host_desc[gid - rank * n_local])
             else:
                 m.reserve(gid, rows)
         if world > 1:
             lib_stream.synchronize()
-            for src in range(world):
-                lo, hi = src * n_local * rows_padded, (src + 1) * n_local * rows_padded
-                dist.broadcast(desc_arena[lo:hi], src=src)
-                dist.broadcast(norm_arena[lo:hi], src=src)
+            D.replicate_arena(desc_arena, norm_arena, ranges, dist)   # NCCL broadcast per owner block
             torch.cuda.synchronize()
         return n_local * rows * 128
 

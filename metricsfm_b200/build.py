@@ -44,5 +44,21 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+HOST_DIR = os.path.join(PKG_DIR, "host")
+SHIM_BIN = os.path.join(HOST_DIR, "shim_selftest")
+
+
+def build_host_shim(force: bool = False) -> str:
+    """Compile the C++ mirror of the reference's matcher interface + its self-test driver against the C ABI library."""
+    srcs = [os.path.join(HOST_DIR, f) for f in ("shim_selftest.cc", "feature_matching_b200.cc")]
+    deps = srcs + [os.path.join(HOST_DIR, f) for f in ("feature_matching_b200.h", "cv_standin.h")] + [LIB_PATH]
+    if not force and os.path.exists(SHIM_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(SHIM_BIN) for d in deps):
+        return SHIM_BIN
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-o", SHIM_BIN] + srcs + ["-L" + CSRC, "-lmsfm_match", "-Wl,-rpath,$ORIGIN/../csrc"]
+    subprocess.check_call(cmd)
+    return SHIM_BIN
+
+
 if __name__ == "__main__":
     print(build_native(force="--force" in sys.argv, verbose=True))
+    print(build_host_shim(force="--force" in sys.argv))

@@ -235,3 +235,36 @@ def test_full_size_properties_20k(oracle_mod, matcher):
     ids2, dists2 = matcher.knn2(0, 1)
     np.testing.assert_array_equal(ids, ids2)
     np.testing.assert_array_equal(dists, dists2)
+
+
+def test_cpp_host_shim_matches_oracle(oracle_mod, native_lib, tmp_path):
+    """The C++ mirror of the reference interface (cv::Mat CV_32FC1 in, vector<pair<int,int>> out), driven the way
+    MetricSfM would drive FeatureMatching::KNNMatching / the FLANN-layout kNN / BuildMatchGraph's loops."""
+    import subprocess
+    from metricsfm_b200 import build
+    exe = build.build_host_shim()
+    col = synth.Collection(700, seed=51)
+    d1, d2 = col.image_u8(0, 700), col.image_u8(1, 611)
+    raw = tmp_path / "desc.f32"
+    np.concatenate([d1, d2]).astype(np.float32).tofile(raw)
+    out = subprocess.check_output([exe, str(raw), str(len(d1)), str(len(d2))], text=True).split("\n")
+    it = iter(out)
+    head = next(it).split()
+    assert head[0] == "KNNMatching" and head[1] == "1"
+    got = np.array([next(it).split() for _ in range(int(head[2]))], dtype=np.int32).reshape(-1, 2)
+    exp = oracle_mod.match_pair_u8(d2, d1, 0.5, orientation=1)["pairs"]      # index on image 2, queries = image 1
+    np.testing.assert_array_equal(got, exp)
+    head = next(it).split()
+    assert head[0] == "KNN2" and head[1] == "1"
+    rows = np.array([next(it).split() for _ in range(int(head[2]))], dtype=np.float64)
+    oids, odists = oracle_mod.knn2_u8(d1, d2)
+    np.testing.assert_array_equal(rows[:, :2].astype(np.int32), oids)
+    np.testing.assert_array_equal(rows[:, 2:].astype(np.float32), odists)
+    assert next(it).split() == ["MatchPairs", "1"]
+    for ref, qry in ((d1, d2), (d2, d1)):
+        head = next(it).split()
+        n = int(head[5])
+        got = np.array([next(it).split() for _ in range(n)], dtype=np.int32).reshape(-1, 3)
+        exp = oracle_mod.match_pair_u8(ref, qry, 0.85, ratio_good=0.6)
+        np.testing.assert_array_equal(got[:, :2], exp["pairs"])
+        np.testing.assert_array_equal(got[:, 2], exp["good"])

@@ -1,0 +1,82 @@
+"""CPU tests of the host-side logic: synthetic collections, candidate pair lists, the multi-GPU pair scheduler."""
+import numpy as np
+import pytest
+
+from metricsfm_b200 import scheduler, synth
+
+
+def test_synth_is_deterministic_and_sift_like():
+    a = synth.Collection(512, seed=3)
+    b = synth.Collection(512, seed=3)
+    x, y = a.image_u8(7), b.image_u8(7)
+    np.testing.assert_array_equal(x, y)
+    assert x.dtype == np.uint8 and x.shape == (512, 128)
+    norms = (x.astype(np.int64) ** 2).sum(1)
+    assert 2.3e5 < norms.mean() < 2.7e5            # ||q||^2 ~ 512^2, the real-SIFT regime
+    assert not np.array_equal(a.image_u8(8), x)
+    u = a.image_unit(7)
+    np.testing.assert_allclose(np.linalg.norm(u, axis=1), 1.0, atol=1e-5)
+    np.testing.assert_array_equal(synth.quantize_512(u), x)
+
+
+def test_pair_lists():
+    p = synth.exhaustive_pairs(100)
+    assert p.shape == (4950, 2) and (p[:, 0] < p[:, 1]).all()
+    assert (np.diff(p[:, 0]) >= 0).all()            # grouped by the first image like the reference's idx1 loop
+    g = synth.gps_neighbour_pairs(400, k=30)
+    assert (g[:, 0] < g[:, 1]).all() and len(np.unique(g, axis=0)) == len(g)
+    assert 400 * 15 <= len(g) <= 400 * 30
+    r = synth.retrieval_pairs(500, partners=40)
+    assert (r[:, 0] < r[:, 1]).all() and len(np.unique(r, axis=0)) == len(r)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_shard_pairs_partitions_and_balances(world):
+    rng = np.random.default_rng(world)
+    rows = rng.integers(1000, 33000, size=300)
+    pairs = synth.gps_neighbour_pairs(300, k=20)
+    shards = scheduler.shard_pairs(pairs, rows, world)
+    assert len(shards) == world
+    allidx = np.concatenate(shards)
+    np.testing.assert_array_equal(np.sort(allidx), np.arange(len(pairs)))     # a partition: nothing lost, nothing twice
+    cost = scheduler.pair_costs(pairs, rows).astype(np.float64)
+    loads = np.array([cost[s].sum() for s in shards])
+    assert loads.max() <= 1.08 * loads.mean() + cost.max()                    # LPT balance
+    for s in shards:
+        assert (np.diff(s) > 0).all()                                         # original order kept inside a rank
+
+
+def test_shard_pairs_degenerate():
+    rows = np.array([100, 200, 300])
+    assert [len(s) for s in scheduler.shard_pairs(np.zeros((0, 2), np.int32), rows, 4)] == [0, 0, 0, 0]
+    one = scheduler.shard_pairs(np.array([[0, 1]]), rows, 4)
+    assert sorted(len(s) for s in one) == [0, 0, 0, 1]
+
+
+def test_stitch_results_roundtrip():
+    rng = np.random.default_rng(0)
+    n = 37
+    counts = rng.integers(0, 6, size=n)
+    offsets = np.concatenate([[0], np.cumsum(counts)])
+    matches = rng.integers(0, 1000, size=(offsets[-1], 2)).astype(np.int32)
+    good = rng.integers(0, 2, size=offsets[-1]).astype(np.uint8)
+    ok = rng.integers(0, 2, size=n).astype(np.int32)
+    shards = [np.sort(rng.choice(n, size=n // 3, replace=False))]
+    rest = np.setdiff1d(np.arange(n), shards[0])
+    shards += [rest[::2], rest[1::2]]
+    results = []
+    for idx in shards:
+        so = np.concatenate([[0], np.cumsum(counts[idx])])
+        m = np.concatenate([matches[offsets[p]:offsets[p + 1]] for p in idx]) if len(idx) else np.zeros((0, 2), np.int32)
+        g = np.concatenate([good[offsets[p]:offsets[p + 1]] for p in idx]) if len(idx) else np.zeros((0,), np.uint8)
+        results.append(dict(offsets=so, ok=ok[idx], matches=m, good=g))
+    o2, ok2, m2, g2 = scheduler.stitch_results(n, shards, results)
+    np.testing.assert_array_equal(o2, offsets)
+    np.testing.assert_array_equal(ok2, ok)
+    np.testing.assert_array_equal(m2, matches)
+    np.testing.assert_array_equal(g2, good)
+
+
+def test_image_owner_blocks():
+    own = scheduler.image_owner(10, 4)
+    assert own.tolist() == [0, 0, 0, 1, 1, 1, 2, 2, 2, 3]
