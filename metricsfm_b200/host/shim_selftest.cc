@@ -1,6 +1,6 @@
 // shim_selftest.cc — drives the C++ mirror of the reference interface exactly the way the reference would
 // (cv::Mat CV_32FC1 in, vector<pair<int,int>> out) and prints the match lists so that tests/test_gpu_parity.py can
-// compare them with the oracle.  Input: a raw file of two float32 matrices; output: text on stdout.
+// check them.  Input: a raw file of two float32 matrices; output: text on stdout.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
