@@ -94,8 +94,8 @@ struct MatchKernelCfg {
     static constexpr int kSmemA = 0;
     static constexpr int kSmemB = kSmemA + 2 * kABytes;
     static constexpr int kSmemKey = kSmemB + STAGES * kBBytes;
-    static constexpr int kSmemShare = kSmemKey + kKeySlots * TILE_N * 4;       // [STRIPS*128 rows][CSPLIT] u64
-    static constexpr int kSmemBar = kSmemShare + STRIPS * kStripRows * CSPLIT * 8;
+    static constexpr int kSmemShare = kSmemKey + kKeySlots * TILE_N * 4;       // [STRIPS*128 rows][CSPLIT] int4
+    static constexpr int kSmemBar = kSmemShare + STRIPS * kStripRows * CSPLIT * 16;
     static constexpr int kNumBars = 2 + 2 + STAGES + STAGES + kKeySlots + 2 * TBUFS * STRIPS;
     static constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
     static constexpr int kSmemBytes = kSmemTmemPtr + 16;
@@ -145,7 +145,7 @@ match_pairs_kernel(const MatchKernelParams p) {
     uint8_t *sA = smem + Cfg::kSmemA;
     uint8_t *sB = smem + Cfg::kSmemB;
     int32_t *sKey = reinterpret_cast<int32_t *>(smem + Cfg::kSmemKey);
-    unsigned long long *sShare = reinterpret_cast<unsigned long long *>(smem + Cfg::kSmemShare);
+    int4 *sShare = reinterpret_cast<int4 *>(smem + Cfg::kSmemShare);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
     uint64_t *a_full = bars;                         // [2]
     uint64_t *a_empty = a_full + 2;                  // [2]
@@ -169,7 +169,7 @@ match_pairs_kernel(const MatchKernelParams p) {
     }
     if (warp == Cfg::kEpiWarps + 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
     if (warp < Cfg::kEpiWarps)  // threshold-sharing slots {score, item tag} start out "no information"
-        for (int i = threadIdx.x; i < STRIPS * kStripRows * CSPLIT; i += Cfg::kEpiWarps * 32) sShare[i] = ~0ull;
+        for (int i = threadIdx.x; i < STRIPS * kStripRows * CSPLIT; i += Cfg::kEpiWarps * 32) sShare[i] = make_int4(0, 0, -1, 0);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -258,7 +258,8 @@ match_pairs_kernel(const MatchKernelParams p) {
         //   (branch-free top-2-of-8 network + merge), in ascending column order; ties never displace (strict >), hence
         //   lowest-index tie-breaking inside a share.  Then the accumulator is handed back to the MMA warp.
         // Column shares (CSPLIT = 2): the two threads of a row keep independent top-2 states over their own columns
-        //   (merged by the consumer kernels) but publish their second-best score; theta = max(own S1, partner S1 - 1).
+        //   (merged by the consumer kernels) but publish their two best scores;
+        //   theta = max(own S1, partner S1 - 1, min(own S0, partner S0 - 1)).
         //   The "- 1" keeps every element that merely TIES the partner's second best in play, because the partner's
         //   columns may lie to the right of it; elements strictly below two known scores can never reach the top-2.
         const int share = warp / (4 * STRIPS);
@@ -306,8 +307,10 @@ match_pairs_kernel(const MatchKernelParams p) {
                 const int nbmin = ckey_to_norm(__reduce_max_sync(0xFFFFFFFFu, ckmax));
                 int theta = S1;
                 if (CSPLIT > 1) {
-                    const uint2 peer = ptx::lds_v2_volatile(peer_slot);  // {second-best score, item tag}
-                    if (peer.y == a && (int)peer.x > INT_MIN) theta = max(theta, (int)peer.x - 1);
+                    // peer's {S0 - 1, S1 - 1, item tag}: the row's final second best is >= its own S1, >= the peer's S1
+                    // and >= min(S0_own, S0_peer); peer scores count minus one (see above)
+                    const int4 peer = ptx::lds_v4_volatile(peer_slot);
+                    if ((uint32_t)peer.z == a) theta = __vimax3_s32(theta, peer.y, min(S0, peer.x));
                 }
                 const int T = (theta + nbmin) >> 1;
                 ptx::tmem_ld_wait();
@@ -346,7 +349,8 @@ match_pairs_kernel(const MatchKernelParams p) {
                             if (DEBUG && p.stats && lane == 0) atomicAdd(p.stats, 1ull);
                         }
                     }
-                    if (CSPLIT > 1 && touched) ptx::sts_v2_volatile(my_slot, (uint32_t)S1, a);
+                    if (CSPLIT > 1 && touched)
+                        ptx::sts_v4_volatile(my_slot, max(S0, INT_MIN + 1) - 1, max(S1, INT_MIN + 1) - 1, (int)a, 0);
                 }
                 if (++ks == Cfg::kKeySlots) { ks = 0; k_phase ^= 1; }
                 if (++buf == TBUFS) { buf = 0; t_phase ^= 1; }
