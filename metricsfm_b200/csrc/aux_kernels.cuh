@@ -142,6 +142,7 @@ struct SelectParams {
     int32_t nshare;
     float ratio, ratio_good, max_dist_sq;
     int32_t *cand_q, *cand_j;  // [forward kNN rows], pair p writes from row knn_off
+    int32_t *cand_d0;          // squared distance of the candidate (seeds the mutual search)
     uint8_t *cand_good;
     int32_t *counts;           // [n_pairs]
     int32_t gather;
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
     for (int base = 0; base < pd.qry_rows; base += blockDim.x) {
         const int q = base + threadIdx.x;
         bool keep = false, is_good = false;
-        int nn0 = -1;
+        int nn0 = -1, dist0 = 0;
         if (q < pd.qry_rows) {
             const int4 k = merge_knn_shares(sp.knn, pd.knn_off + q, sp.nshare);
             if (k.x >= 0 && k.y >= 0) {
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
                 if (sp.max_dist_sq > 0.0f) keep = keep && (d0 < sp.max_dist_sq);
                 is_good = keep && sp.ratio_good > 0.0f && r < sp.ratio_good;
                 nn0 = k.x;
+                dist0 = k.z;
             }
         }
         const int slot = block_rank(keep, running, warp_excl, &chunk_total);
@@ -176,6 +178,7 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
             sp.cand_q[pd.knn_off + slot] = q;
             sp.cand_j[pd.knn_off + slot] = nn0;
             sp.cand_good[pd.knn_off + slot] = is_good ? 1 : 0;
+            sp.cand_d0[pd.knn_off + slot] = dist0;
         }
     }
     if (threadIdx.x == 0) sp.counts[blockIdx.x] = running;

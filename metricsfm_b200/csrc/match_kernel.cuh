@@ -65,6 +65,7 @@ struct MatchKernelParams {
     const CUtensorMap *maps;      // [max_images] one 2-D map per image: {128 B, rows}, box {128 B, kBoxRows rows}, SW128
     const int32_t *ckeys;         // arena of column keys (see make_ckey)
     const int32_t *cand_ckeys;    // column keys of the gathered candidate rows (query side of cand_idx >= 0 pairs)
+    const int32_t *cand_d0;       // squared distance of each candidate to the query row that proposed it
     const int32_t *counts;        // per-pair candidate counts
     const PairDesc *pairs;
     const WorkItem *items;
@@ -288,6 +289,10 @@ match_pairs_kernel(const MatchKernelParams p) {
             const int na = valid ? ckey_to_norm((pd.cand_idx >= 0 ? p.cand_ckeys : p.ckeys)[pd.qry_off + q]) : 0;
             // rows past the image end hold zeros; park their state where nothing can flag a group
             int S0 = valid ? INT_MIN : 0x20000000, S1 = S0, J0 = -1, J1 = -1;
+            // Mutual-check items only need the nearest row, and one row at distance d0 is known to exist (the query
+            // row that proposed this candidate): start both slots just below its score so that only rows at least as
+            // close are ever scored exactly.  The placeholders carry id -1 and are dropped by the consumers.
+            if (pd.cand_idx >= 0 && valid) S0 = S1 = na - p.cand_d0[pd.qry_off + q] - 1;
             const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
             int jtile = share * kCols;  // first column of this warp's share in the current tile
             for (int t = 0; t < ntiles; ++t, jtile += TILE_N) {

@@ -79,7 +79,7 @@ struct msfm_ctx {
     std::vector<ImageSlot> images;
     EncodeTiledFn encode = nullptr;
 
-    DeviceBuf cand_q, cand_j, cand_good, cand_counts, cand_desc, cand_ckeys;  // one-way candidates + gathered rows
+    DeviceBuf cand_q, cand_j, cand_d0, cand_good, cand_counts, cand_desc, cand_ckeys;  // one-way candidates + gathered rows
     DeviceBuf staging, knn, matches, good, counts, offsets, pairdesc, items, tight_matches, tight_good;
     void *h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
@@ -242,6 +242,7 @@ msfm_status launch_match_kernel(msfm_ctx *ctx, size_t first_item, size_t n_items
     kp.maps = ctx->d_maps;
     kp.ckeys = ctx->norms;
     kp.cand_ckeys = static_cast<const int32_t *>(ctx->cand_ckeys.ptr);
+    kp.cand_d0 = static_cast<const int32_t *>(ctx->cand_d0.ptr);
     kp.counts = static_cast<const int32_t *>(ctx->cand_counts.ptr);
     kp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
     kp.items = static_cast<const WorkItem *>(ctx->items.ptr) + first_item;
@@ -424,6 +425,7 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             const size_t rows = (size_t)plan.query_rows;
             if ((st = ensure(ctx, ctx->cand_q, rows * 4)) != MSFM_OK) return st;
             if ((st = ensure(ctx, ctx->cand_j, rows * 4)) != MSFM_OK) return st;
+            if ((st = ensure(ctx, ctx->cand_d0, rows * 4)) != MSFM_OK) return st;
             if ((st = ensure(ctx, ctx->cand_good, rows)) != MSFM_OK) return st;
             if (mutual && (st = ensure_cand_scratch(ctx, plan.query_rows)) != MSFM_OK) return st;
             if ((st = ensure(ctx, ctx->matches, rows * sizeof(int2))) != MSFM_OK) return st;
@@ -444,6 +446,7 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             sp.max_dist_sq = params->max_dist_sq;
             sp.cand_q = static_cast<int32_t *>(ctx->cand_q.ptr);
             sp.cand_j = static_cast<int32_t *>(ctx->cand_j.ptr);
+            sp.cand_d0 = static_cast<int32_t *>(ctx->cand_d0.ptr);
             sp.cand_good = static_cast<uint8_t *>(ctx->cand_good.ptr);
             sp.counts = static_cast<int32_t *>(ctx->cand_counts.ptr);
             sp.gather = mutual ? 1 : 0;
@@ -624,7 +627,7 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
     if (!ctx) return MSFM_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DeviceBuf *bufs[] = {&ctx->cand_q, &ctx->cand_j, &ctx->cand_good, &ctx->cand_counts, &ctx->cand_desc, &ctx->cand_ckeys,
+    DeviceBuf *bufs[] = {&ctx->cand_q, &ctx->cand_j, &ctx->cand_d0, &ctx->cand_good, &ctx->cand_counts, &ctx->cand_desc, &ctx->cand_ckeys,
                          &ctx->staging, &ctx->knn, &ctx->matches, &ctx->good, &ctx->counts, &ctx->offsets,
                          &ctx->pairdesc, &ctx->items, &ctx->tight_matches, &ctx->tight_good};
     for (DeviceBuf *b : bufs)
