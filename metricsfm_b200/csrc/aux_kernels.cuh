@@ -131,69 +131,6 @@ __device__ __forceinline__ int block_rank(bool keep, int &running, int *warp_exc
     return slot;
 }
 
-// Stage 0 — verification of speculative seeds.  A forward row is verified iff its merged result holds
-// min(2, ref_rows) real neighbours (placeholders carry id -1).  Verified rows refresh their seed (second-best score
-// minus 12.5 % of the second-best distance) for later partner images; unverified rows are listed in ascending order
-// and their descriptor rows gathered into the scratch image for an unseeded re-run.
-struct VerifyParams {
-    const PairDesc *pairs;
-    const int4 *knn;
-    int32_t nshare;
-    int32_t *seeds;            // per arena row
-    const uint8_t *desc_arena;
-    const int32_t *ckeys;
-    int32_t *redo_q;           // [forward kNN rows], pair p writes from row knn_off
-    int32_t *redo_counts;      // [n_pairs]
-    uint8_t *scratch_desc;
-    int32_t *scratch_ckeys;
-};
-
-__device__ __forceinline__ int seed_from(int na, int d1) { return (na - d1) - (d1 >> 3); }
-
-__global__ void __launch_bounds__(1024) verify_seeds_kernel(const VerifyParams vp) {
-    __shared__ int warp_excl[32];
-    __shared__ int chunk_total;
-    const PairDesc pd = vp.pairs[blockIdx.x];
-    const int need = pd.ref_rows < 2 ? pd.ref_rows : 2;
-    int running = 0;
-    for (int base = 0; base < pd.qry_rows; base += blockDim.x) {
-        const int q = base + threadIdx.x;
-        bool redo = false;
-        if (q < pd.qry_rows) {
-            const int4 k = merge_knn_shares(vp.knn, pd.knn_off + q, vp.nshare);
-            const int have = (k.x >= 0) + (k.y >= 0);
-            redo = have < need;
-            if (!redo && need == 2) vp.seeds[pd.qry_off + q] = seed_from(ckey_to_norm(vp.ckeys[pd.qry_off + q]), k.w);
-        }
-        const int slot = block_rank(redo, running, warp_excl, &chunk_total);
-        if (redo) vp.redo_q[pd.knn_off + slot] = q;
-    }
-    if (threadIdx.x == 0) vp.redo_counts[blockIdx.x] = running;
-    if (running == 0) return;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int i = warp; i < running; i += nwarps) {
-        const int q = vp.redo_q[pd.knn_off + i];
-        const uint32_t w = reinterpret_cast<const uint32_t *>(vp.desc_arena + (pd.qry_off + q) * kDim)[lane];
-        reinterpret_cast<uint32_t *>(vp.scratch_desc + (pd.knn_off + i) * kDim)[lane] = w;
-        if (lane == 0) vp.scratch_ckeys[pd.knn_off + i] = vp.ckeys[pd.qry_off + q];
-    }
-}
-
-// Copy the re-done rows (kNN rows redo_base + knn_off + i) over the unverified forward rows and refresh their seeds.
-__global__ void scatter_redo_kernel(const PairDesc *__restrict__ pairs, int4 *__restrict__ knn, int nshare, int64_t redo_base,
-                                    const int32_t *__restrict__ redo_q, const int32_t *__restrict__ redo_counts,
-                                    int32_t *__restrict__ seeds, const int32_t *__restrict__ ckeys) {
-    const PairDesc pd = pairs[blockIdx.x];
-    const int n = redo_counts[blockIdx.x];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int q = redo_q[pd.knn_off + i];
-        for (int s = 0; s < nshare; ++s) knn[(pd.knn_off + q) * nshare + s] = knn[(redo_base + pd.knn_off + i) * nshare + s];
-        const int4 k = merge_knn_shares(knn, pd.knn_off + q, nshare);
-        if (k.y >= 0) seeds[pd.qry_off + q] = seed_from(ckey_to_norm(ckeys[pd.qry_off + q]), k.w);
-    }
-}
-
 // Stage 1 — ratio test.  One CTA per pair scans its query rows in ascending order (the order of
 // fine_matching_graph.cc:116-133 / feature_matching.cpp:56-64) and writes the one-way candidates
 // (query row, nearest reference row, "good" flag) compacted into the pair's scratch region.  With `gather` set it also

@@ -52,14 +52,9 @@ struct PairDesc {
     int64_t ref_off, qry_off;  // first row in the column-key arena (query side: candidate scratch when cand_idx >= 0)
     int64_t knn_off;           // first row of this pair in the per-batch kNN scratch
     int32_t qry_row_base;      // row coordinate of query row 0 in the query tensor map (0 for whole-image maps)
-    int32_t cand_idx;          // >= 0: the query rows were gathered into the scratch image by an earlier kernel and
-                               // their number is counts[cand_idx] (known only on the device); -1: ordinary image rows
-    int32_t mode;              // kModeImage / kModeMutual / kModeRedo
-    int32_t pad_;
+    int32_t cand_idx;          // >= 0: the query rows are this pair's gathered mutual-check candidates and their
+                               // number is counts[cand_idx] (known only on the device); -1: ordinary image rows
 };
-constexpr int32_t kModeImage = 0;   // query rows of an image; may start from speculative per-row seeds (see seeds)
-constexpr int32_t kModeMutual = 1;  // gathered candidate reference rows; nearest row only, seeded by the known distance
-constexpr int32_t kModeRedo = 2;    // gathered query rows whose speculative seed could not be verified; no seed
 
 struct WorkItem {
     int32_t pair;  // index into PairDesc[]
@@ -71,9 +66,6 @@ struct MatchKernelParams {
     const int32_t *ckeys;         // arena of column keys (see make_ckey)
     const int32_t *cand_ckeys;    // column keys of the gathered candidate rows (query side of cand_idx >= 0 pairs)
     const int32_t *cand_d0;       // squared distance of each candidate to the query row that proposed it
-    const int32_t *seeds;         // per arena row: speculative lower bound of the row's second-best SCORE, learned from
-                                  // the row's results against earlier partner images; null = no seeding.  A seeded row
-                                  // whose two slots are not both beaten by real columns is re-done without seed.
     const int32_t *counts;        // per-pair candidate counts
     const PairDesc *pairs;
     const WorkItem *items;
@@ -300,10 +292,7 @@ match_pairs_kernel(const MatchKernelParams p) {
             // Mutual-check items only need the nearest row, and one row at distance d0 is known to exist (the query
             // row that proposed this candidate): start both slots just below its score so that only rows at least as
             // close are ever scored exactly.  The placeholders carry id -1 and are dropped by the consumers.
-            if (pd.mode == kModeMutual && valid) S0 = S1 = na - p.cand_d0[pd.qry_off + q] - 1;
-            // Speculative start (forward items): placeholders at the seed score.  Exact whenever two real columns beat
-            // them; otherwise the row comes out with a missing neighbour and the host re-does it (kModeRedo).
-            if (pd.mode == kModeImage && p.seeds != nullptr && valid) S0 = S1 = p.seeds[pd.qry_off + q];
+            if (pd.cand_idx >= 0 && valid) S0 = S1 = na - p.cand_d0[pd.qry_off + q] - 1;
             const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
             int jtile = share * kCols;  // first column of this warp's share in the current tile
             for (int t = 0; t < ntiles; ++t, jtile += TILE_N) {

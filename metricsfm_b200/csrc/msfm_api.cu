@@ -39,7 +39,7 @@ constexpr int kItemRows = kStrips * msfm::kStripRows;
 
 // Per-batch scratch bounds (rows).  16 Mi query rows -> 256 MiB kNN scratch + 128 MiB match scratch.
 constexpr int64_t kBatchMaxQueryRows = 16ll << 20;
-constexpr int64_t kBatchMaxQueryRowsScratch = 4ll << 20;  // with the scratch image: + 128 B of gathered row per query row
+constexpr int64_t kBatchMaxQueryRowsMutual = 4ll << 20;  // mutual: + 128 B of gathered candidate row per query row
 constexpr int64_t kBatchMaxPairs = 16384;
 
 struct DeviceBuf {
@@ -79,14 +79,12 @@ struct msfm_ctx {
     std::vector<ImageSlot> images;
     EncodeTiledFn encode = nullptr;
 
-    DeviceBuf seeds, redo_q, redo_counts;  // speculative per-row seeds + rows to re-do (see verify_seeds_kernel)
-    bool use_seeds = true;                // MSFM_SEEDS=0 disables the speculation (A/B experiments)
     DeviceBuf cand_q, cand_j, cand_d0, cand_good, cand_counts, cand_desc, cand_ckeys;  // one-way candidates + gathered rows
     DeviceBuf staging, knn, matches, good, counts, offsets, pairdesc, items, tight_matches, tight_good;
     void *h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_k2 = nullptr, ev_k3 = nullptr,
-                ev_k4 = nullptr, ev_k5 = nullptr, ev_f1 = nullptr;
+                ev_f1 = nullptr;
 
     msfm_timing timing{};
     uint32_t debug_flags = 0;  // MSFM_DEBUG_FLAGS environment variable (timing experiments)
@@ -232,25 +230,20 @@ struct BatchPlan {
     std::vector<int64_t> src_index;  // index into the caller's pair list
     std::vector<WorkItem> items;     // forward work items
     std::vector<WorkItem> twin_items;
-    std::vector<PairDesc> redos;     // speculative seeding: unverified rows of pair p re-run without seed
-    std::vector<WorkItem> redo_items;
     int64_t query_rows = 0;          // forward kNN rows (= candidate / match scratch rows)
     int64_t ops = 0;
     bool mutual = false;
-    bool seeded = false;
     bool has_empty = false;          // some pair has no work items: its kNN rows must read "absent"
-    // the second half of the kNN scratch mirrors the forward region: first for the re-done rows, then for the twins
-    int64_t knn_rows() const { return (mutual || seeded) ? 2 * query_rows : query_rows; }
+    int64_t knn_rows() const { return mutual ? 2 * query_rows : query_rows; }
 };
 
-msfm_status launch_match_kernel(msfm_ctx *ctx, size_t first_item, size_t n_items, const DeviceBuf *counts, bool seeded) {
+msfm_status launch_match_kernel(msfm_ctx *ctx, size_t first_item, size_t n_items) {
     msfm::MatchKernelParams kp;
     kp.maps = ctx->d_maps;
     kp.ckeys = ctx->norms;
     kp.cand_ckeys = static_cast<const int32_t *>(ctx->cand_ckeys.ptr);
     kp.cand_d0 = static_cast<const int32_t *>(ctx->cand_d0.ptr);
-    kp.counts = counts ? static_cast<const int32_t *>(counts->ptr) : nullptr;
-    kp.seeds = seeded ? static_cast<const int32_t *>(ctx->seeds.ptr) : nullptr;
+    kp.counts = static_cast<const int32_t *>(ctx->cand_counts.ptr);
     kp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
     kp.items = static_cast<const WorkItem *>(ctx->items.ptr) + first_item;
     kp.n_items = (int32_t)n_items;
@@ -290,55 +283,31 @@ msfm_status ensure_cand_scratch(msfm_ctx *ctx, int64_t rows) {
     return MSFM_OK;
 }
 
-// Complete the batch with the descriptors + work items of the two follow-up launches.  Both search rows that an earlier
-// kernel gathers into the scratch image at rows [knn_off, knn_off + count_p) (count known only on the device), and both
-// write kNN rows into the mirror region [query_rows + knn_off, ...):
-//   redo p  (speculative seeding): unverified query rows of pair p against pair p's reference image, unseeded;
-//   twin p  (mutual cross-check) : candidate reference rows of pair p against pair p's query image, nearest row only.
-// Device pair array = pairs ++ twins ++ redos.
+// Complete the batch: twin descriptors (one per forward pair) and their work items.  Twin p searches the gathered
+// candidate rows of pair p (rows [knn_off, knn_off + count_p) of the candidate scratch, count known only on the device)
+// against pair p's query image; its kNN rows mirror the forward region, shifted by query_rows.
 void finish_plan(msfm_ctx *ctx, BatchPlan &plan) {
+    if (!plan.mutual) return;
     const int32_t nb = (int32_t)plan.pairs.size();
-    auto by_row0 = [](const WorkItem &x, const WorkItem &y) { return x.row0 < y.row0; };
-    if (plan.mutual) {
-        plan.twins.reserve(nb);
-        for (int32_t pi = 0; pi < nb; ++pi) {
-            const PairDesc &f = plan.pairs[pi];
-            PairDesc tw = f;
-            tw.ref_img = f.qry_img;
-            tw.qry_img = ctx->max_images;  // scratch map
-            tw.ref_rows = f.qry_rows;
-            tw.qry_rows = f.qry_rows;      // upper bound; the device reads counts[cand_idx]
-            tw.ref_off = f.qry_off;
-            tw.qry_off = f.knn_off;        // row in the scratch key array
-            tw.knn_off = plan.query_rows + f.knn_off;
-            tw.qry_row_base = (int32_t)f.knn_off;
-            tw.cand_idx = pi;
-            tw.mode = msfm::kModeMutual;
-            plan.twins.push_back(tw);
-            if (f.ref_rows > 0)
-                for (int32_t row0 = 0; row0 < f.qry_rows; row0 += kItemRows) plan.twin_items.push_back({nb + pi, row0});
-        }
-        // items that can actually hold rows (low row0) first, the mostly empty tail last: balances the persistent CTAs
-        std::stable_sort(plan.twin_items.begin(), plan.twin_items.end(), by_row0);
+    plan.twins.reserve(nb);
+    for (int32_t pi = 0; pi < nb; ++pi) {
+        const PairDesc &f = plan.pairs[pi];
+        PairDesc tw;
+        tw.ref_img = f.qry_img;
+        tw.qry_img = ctx->max_images;  // candidate scratch map
+        tw.ref_rows = f.qry_rows;
+        tw.qry_rows = f.qry_rows;      // upper bound; the device reads counts[cand_idx]
+        tw.ref_off = f.qry_off;
+        tw.qry_off = f.knn_off;        // row in cand_ckeys
+        tw.knn_off = plan.query_rows + f.knn_off;
+        tw.qry_row_base = (int32_t)f.knn_off;
+        tw.cand_idx = pi;
+        plan.twins.push_back(tw);
+        if (f.ref_rows > 0)
+            for (int32_t row0 = 0; row0 < f.qry_rows; row0 += kItemRows) plan.twin_items.push_back({nb + pi, row0});
     }
-    if (plan.seeded) {
-        const int32_t base = nb + (int32_t)plan.twins.size();
-        plan.redos.reserve(nb);
-        for (int32_t pi = 0; pi < nb; ++pi) {
-            const PairDesc &f = plan.pairs[pi];
-            PairDesc rd = f;
-            rd.qry_img = ctx->max_images;
-            rd.qry_off = f.knn_off;
-            rd.knn_off = plan.query_rows + f.knn_off;
-            rd.qry_row_base = (int32_t)f.knn_off;
-            rd.cand_idx = pi;
-            rd.mode = msfm::kModeRedo;
-            plan.redos.push_back(rd);
-            if (f.ref_rows > 0)
-                for (int32_t row0 = 0; row0 < f.qry_rows; row0 += kItemRows) plan.redo_items.push_back({base + pi, row0});
-        }
-        std::stable_sort(plan.redo_items.begin(), plan.redo_items.end(), by_row0);
-    }
+    // items that can actually hold candidates (low row0) first, the mostly empty tail last: balances the persistent CTAs
+    std::stable_sort(plan.twin_items.begin(), plan.twin_items.end(), [](const WorkItem &x, const WorkItem &y) { return x.row0 < y.row0; });
 }
 
 // Upload the plan and run the forward matching launch (timed); leaves the kNN rows in scratch.
@@ -346,30 +315,24 @@ msfm_status run_match_stage(msfm_ctx *ctx, const BatchPlan &plan) {
     msfm_status st;
     const size_t fw_bytes = plan.pairs.size() * sizeof(PairDesc);
     const size_t tw_bytes = plan.twins.size() * sizeof(PairDesc);
-    const size_t rd_bytes = plan.redos.size() * sizeof(PairDesc);
-    const size_t pd_bytes = fw_bytes + tw_bytes + rd_bytes;
-    const size_t it_fw = plan.items.size() * sizeof(WorkItem), it_tw = plan.twin_items.size() * sizeof(WorkItem),
-                 it_rd = plan.redo_items.size() * sizeof(WorkItem);
-    const size_t it_bytes = it_fw + it_tw + it_rd;
+    const size_t pd_bytes = fw_bytes + tw_bytes;
+    const size_t it_fw = plan.items.size() * sizeof(WorkItem), it_tw = plan.twin_items.size() * sizeof(WorkItem);
     if ((st = ensure(ctx, ctx->pairdesc, pd_bytes)) != MSFM_OK) return st;
-    if ((st = ensure(ctx, ctx->items, it_bytes)) != MSFM_OK) return st;
+    if ((st = ensure(ctx, ctx->items, it_fw + it_tw)) != MSFM_OK) return st;
     if ((st = ensure(ctx, ctx->knn, (size_t)plan.knn_rows() * kCsplit * sizeof(int4))) != MSFM_OK) return st;
     if ((st = ensure(ctx, ctx->cand_counts, plan.pairs.size() * 4)) != MSFM_OK) return st;
-    if ((st = ensure(ctx, ctx->redo_counts, plan.pairs.size() * 4)) != MSFM_OK) return st;
-    if ((st = ensure_pinned(ctx, pd_bytes + it_bytes + 64)) != MSFM_OK) return st;
+    if ((st = ensure_pinned(ctx, pd_bytes + it_fw + it_tw + 64)) != MSFM_OK) return st;
     // the pinned staging area is reused per batch: the previous batch has been synchronised by its D2H
     char *hp = static_cast<char *>(ctx->h_pinned);
     memcpy(hp, plan.pairs.data(), fw_bytes);
     if (tw_bytes) memcpy(hp + fw_bytes, plan.twins.data(), tw_bytes);
-    if (rd_bytes) memcpy(hp + fw_bytes + tw_bytes, plan.redos.data(), rd_bytes);
     memcpy(hp + pd_bytes, plan.items.data(), it_fw);
     if (it_tw) memcpy(hp + pd_bytes + it_fw, plan.twin_items.data(), it_tw);
-    if (it_rd) memcpy(hp + pd_bytes + it_fw + it_tw, plan.redo_items.data(), it_rd);
     MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->pairdesc.ptr, hp, pd_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->items.ptr, hp + pd_bytes, it_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->items.ptr, hp + pd_bytes, it_fw + it_tw, cudaMemcpyHostToDevice, ctx->stream));
     if (plan.has_empty) MSFM_CUDA(ctx, cudaMemsetAsync(ctx->knn.ptr, 0xFF, (size_t)plan.query_rows * kCsplit * sizeof(int4), ctx->stream));
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
-    if (!plan.items.empty() && (st = launch_match_kernel(ctx, 0, plan.items.size(), nullptr, plan.seeded)) != MSFM_OK) return st;
+    if (!plan.items.empty() && (st = launch_match_kernel(ctx, 0, plan.items.size())) != MSFM_OK) return st;
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
     ctx->timing.int8_ops += plan.ops;
     return MSFM_OK;
@@ -387,8 +350,6 @@ void plan_add_pair(msfm_ctx *ctx, BatchPlan &plan, int64_t src, int32_t ref, int
     pd.knn_off = plan.query_rows;
     pd.qry_row_base = 0;
     pd.cand_idx = -1;
-    pd.mode = msfm::kModeImage;
-    pd.pad_ = 0;
     const int32_t pidx = (int32_t)plan.pairs.size();
     plan.pairs.push_back(pd);
     plan.src_index.push_back(src);
@@ -435,14 +396,8 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
     ctx->timing = msfm_timing{};
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
     const bool mutual = params->mutual != 0;
-    const bool seeded = ctx->use_seeds;
     const bool want_good = params->ratio_good > 0.0f && (resident || out->good);
-    const int64_t max_rows = (mutual || seeded) ? kBatchMaxQueryRowsScratch : kBatchMaxQueryRows;
-    if (seeded) {
-        // seeds are learned within one call only: every row starts unseeded (0x80808080 lies below every real score)
-        if ((st = ensure(ctx, ctx->seeds, (size_t)ctx->arena_rows * 4)) != MSFM_OK) return st;
-        MSFM_CUDA(ctx, cudaMemsetAsync(ctx->seeds.ptr, 0x80, (size_t)ctx->arena_rows * 4, ctx->stream));
-    }
+    const int64_t max_rows = mutual ? kBatchMaxQueryRowsMutual : kBatchMaxQueryRows;
     int64_t written = 0;  // matches written to the caller so far
     int64_t total = 0;
     if (!resident) out->offsets[0] = 0;
@@ -452,7 +407,6 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
         // ---- carve the next batch
         BatchPlan plan;
         plan.mutual = mutual;
-        plan.seeded = seeded;
         const int64_t first = next;
         while (next < n_pairs && (int64_t)plan.pairs.size() < kBatchMaxPairs) {
             const ImageSlot &r = ctx->images[pairs[next].ref], &q = ctx->images[pairs[next].query];
@@ -473,8 +427,7 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             if ((st = ensure(ctx, ctx->cand_j, rows * 4)) != MSFM_OK) return st;
             if ((st = ensure(ctx, ctx->cand_d0, rows * 4)) != MSFM_OK) return st;
             if ((st = ensure(ctx, ctx->cand_good, rows)) != MSFM_OK) return st;
-            if ((mutual || seeded) && (st = ensure_cand_scratch(ctx, plan.query_rows)) != MSFM_OK) return st;
-            if (seeded && (st = ensure(ctx, ctx->redo_q, rows * 4)) != MSFM_OK) return st;
+            if (mutual && (st = ensure_cand_scratch(ctx, plan.query_rows)) != MSFM_OK) return st;
             if ((st = ensure(ctx, ctx->matches, rows * sizeof(int2))) != MSFM_OK) return st;
             if (want_good && (st = ensure(ctx, ctx->good, rows)) != MSFM_OK) return st;
             if ((st = ensure(ctx, ctx->counts, (size_t)nb * 4)) != MSFM_OK) return st;
@@ -483,34 +436,6 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             if (want_good && (st = ensure(ctx, ctx->tight_good, rows)) != MSFM_OK) return st;
             // ---- forward 2-NN
             if ((st = run_match_stage(ctx, plan)) != MSFM_OK) return st;
-            // ---- speculative seeds: verify, re-run the unverified rows without seed, patch them in
-            MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k4, ctx->stream));
-            MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k5, ctx->stream));
-            if (seeded) {
-                msfm::VerifyParams vp;
-                vp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
-                vp.knn = static_cast<const int4 *>(ctx->knn.ptr);
-                vp.nshare = kCsplit;
-                vp.seeds = static_cast<int32_t *>(ctx->seeds.ptr);
-                vp.desc_arena = ctx->desc;
-                vp.ckeys = ctx->norms;
-                vp.redo_q = static_cast<int32_t *>(ctx->redo_q.ptr);
-                vp.redo_counts = static_cast<int32_t *>(ctx->redo_counts.ptr);
-                vp.scratch_desc = static_cast<uint8_t *>(ctx->cand_desc.ptr);
-                vp.scratch_ckeys = static_cast<int32_t *>(ctx->cand_ckeys.ptr);
-                msfm::verify_seeds_kernel<<<nb, 1024, 0, ctx->stream>>>(vp);
-                MSFM_CUDA(ctx, cudaGetLastError());
-                MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k4, ctx->stream));
-                if (!plan.redo_items.empty() &&
-                    (st = launch_match_kernel(ctx, plan.items.size() + plan.twin_items.size(), plan.redo_items.size(), &ctx->redo_counts,
-                                              false)) != MSFM_OK)
-                    return st;
-                MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k5, ctx->stream));
-                msfm::scatter_redo_kernel<<<nb, 256, 0, ctx->stream>>>(vp.pairs, static_cast<int4 *>(ctx->knn.ptr), kCsplit, plan.query_rows,
-                                                                      vp.redo_q, vp.redo_counts, vp.seeds, vp.ckeys);
-                MSFM_CUDA(ctx, cudaGetLastError());
-                ctx->timing.total_launches += 2;
-            }
             // ---- ratio test -> one-way candidates (+ gather of their reference rows for the mutual check)
             msfm::SelectParams sp;
             sp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
@@ -535,7 +460,7 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             // ---- mutual cross-check: nearest query row of every candidate's reference row
             MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k2, ctx->stream));
             if (mutual && !plan.twin_items.empty() &&
-                (st = launch_match_kernel(ctx, plan.items.size(), plan.twin_items.size(), &ctx->cand_counts, false)) != MSFM_OK)
+                (st = launch_match_kernel(ctx, plan.items.size(), plan.twin_items.size())) != MSFM_OK)
                 return st;
             MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k3, ctx->stream));
             // ---- emission, offsets, tight gather
@@ -568,14 +493,12 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             ctx->timing.d2h_bytes += (nb + 1) * 8;
             if ((st = accumulate_kernel_time(ctx, ctx->ev_k0, ctx->ev_k1)) != MSFM_OK) return st;
             if ((st = accumulate_kernel_time(ctx, ctx->ev_k2, ctx->ev_k3)) != MSFM_OK) return st;
-            if ((st = accumulate_kernel_time(ctx, ctx->ev_k4, ctx->ev_k5)) != MSFM_OK) return st;
             {
-                float ms_all = 0.f, ms_a = 0.f, ms_b = 0.f, ms_c = 0.f;
+                float ms_all = 0.f, ms_a = 0.f, ms_b = 0.f;
                 MSFM_CUDA(ctx, cudaEventElapsedTime(&ms_all, ctx->ev_k0, ctx->ev_f1));
                 MSFM_CUDA(ctx, cudaEventElapsedTime(&ms_a, ctx->ev_k0, ctx->ev_k1));
                 MSFM_CUDA(ctx, cudaEventElapsedTime(&ms_b, ctx->ev_k2, ctx->ev_k3));
-                MSFM_CUDA(ctx, cudaEventElapsedTime(&ms_c, ctx->ev_k4, ctx->ev_k5));
-                ctx->timing.finalize_ms += ms_all - ms_a - ms_b - ms_c;
+                ctx->timing.finalize_ms += ms_all - ms_a - ms_b;
             }
             const int64_t bt = batch_offsets[nb];
             total += bt;
@@ -665,7 +588,6 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
     ctx->arena_rows = round_up(cfg->arena_rows, kAlignRows);
     ctx->images.resize(cfg->max_images);
     if (const char *dbg = getenv("MSFM_DEBUG_FLAGS")) ctx->debug_flags = (uint32_t)strtoul(dbg, nullptr, 0);
-    if (const char *sd = getenv("MSFM_SEEDS")) ctx->use_seeds = atoi(sd) != 0;
 
     auto bail = [&](msfm_status st) {
         msfm_destroy(ctx);
@@ -676,7 +598,7 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return bail(MSFM_ERR_CUDA);
     ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MSFM_ERR_CUDA);
-    cudaEvent_t *evs[] = {&ctx->ev_begin, &ctx->ev_end, &ctx->ev_k0, &ctx->ev_k1, &ctx->ev_k2, &ctx->ev_k3, &ctx->ev_k4, &ctx->ev_k5, &ctx->ev_f1};
+    cudaEvent_t *evs[] = {&ctx->ev_begin, &ctx->ev_end, &ctx->ev_k0, &ctx->ev_k1, &ctx->ev_k2, &ctx->ev_k3, &ctx->ev_f1};
     for (cudaEvent_t *e : evs)
         if (cudaEventCreate(e) != cudaSuccess) return bail(MSFM_ERR_CUDA);
     if (cfg->external_desc_arena) {
@@ -705,7 +627,7 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
     if (!ctx) return MSFM_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DeviceBuf *bufs[] = {&ctx->seeds, &ctx->redo_q, &ctx->redo_counts, &ctx->cand_q, &ctx->cand_j, &ctx->cand_d0, &ctx->cand_good, &ctx->cand_counts, &ctx->cand_desc, &ctx->cand_ckeys,
+    DeviceBuf *bufs[] = {&ctx->cand_q, &ctx->cand_j, &ctx->cand_d0, &ctx->cand_good, &ctx->cand_counts, &ctx->cand_desc, &ctx->cand_ckeys,
                          &ctx->staging, &ctx->knn, &ctx->matches, &ctx->good, &ctx->counts, &ctx->offsets,
                          &ctx->pairdesc, &ctx->items, &ctx->tight_matches, &ctx->tight_good};
     for (DeviceBuf *b : bufs)
@@ -716,7 +638,7 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
         if (ctx->norms) cudaFree(ctx->norms);
     }
     if (ctx->d_maps) cudaFree(ctx->d_maps);
-    cudaEvent_t evs[] = {ctx->ev_begin, ctx->ev_end, ctx->ev_k0, ctx->ev_k1, ctx->ev_k2, ctx->ev_k3, ctx->ev_k4, ctx->ev_k5, ctx->ev_f1};
+    cudaEvent_t evs[] = {ctx->ev_begin, ctx->ev_end, ctx->ev_k0, ctx->ev_k1, ctx->ev_k2, ctx->ev_k3, ctx->ev_f1};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
