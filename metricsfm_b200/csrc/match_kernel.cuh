@@ -294,11 +294,16 @@ match_pairs_kernel(const MatchKernelParams p) {
             // close are ever scored exactly.  The placeholders carry id -1 and are dropped by the consumers.
             if (pd.cand_idx >= 0 && valid) S0 = S1 = na - p.cand_d0[pd.qry_off + q] - 1;
             const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
+            long long acc_wait = 0, acc_load = 0, acc_p1 = 0, acc_p2 = 0, acc_hot = 0;
             int jtile = share * kCols;  // first column of this warp's share in the current tile
             for (int t = 0; t < ntiles; ++t, jtile += TILE_N) {
                 // ---- pull this warp's whole share of the accumulator tile into registers and release TMEM at once
+                long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                const bool prof = DEBUG && (p.debug_flags & 8u) && p.stats != nullptr;
+                if (prof) c0 = clock64();
                 ptx::mbar_wait_a(t_full_base + buf * (STRIPS * 8), t_phase);
                 ptx::tc_fence_after();
+                if (prof) c1 = clock64();
                 const uint32_t tile_taddr = warp_taddr + buf * (STRIPS * TILE_N);
                 uint32_t acc[kCols / 16][16];
 #pragma unroll
@@ -322,6 +327,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive_a(t_empty_base + buf * (STRIPS * 8));
+                if (prof) c2 = clock64();
                 if (DEBUG && (p.debug_flags & 6u)) {  // experiments: 2/4 = TMEM loads + hand-back only
                     if (acc[0][0] == 0x7fffffffu) S1 = 0;
                 } else {
@@ -335,6 +341,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                         const int m3 = __vimax3_s32((int)v[6], (int)v[7], m1);
                         hot[gq] = __any_sync(0xFFFFFFFFu, max(m2, m3) > T);
                     }
+                    if (prof) c3 = clock64();
                     // ---- phase 2: exact scoring of the hot groups straight from the registers
                     bool touched = false;
 #pragma unroll
@@ -351,14 +358,29 @@ match_pairs_kernel(const MatchKernelParams p) {
                             const int jb8 = jtile + gq * 8;
                             merge_top2(g0 >> 3, jb8 + ((g0 & 7) ^ 7), g1 >> 3, jb8 + ((g1 & 7) ^ 7), S0, J0, S1, J1);
                             touched = true;
-                            if (DEBUG && p.stats && lane == 0) atomicAdd(p.stats, 1ull);
+                            if (prof) ++acc_hot;
                         }
                     }
                     if (CSPLIT > 1 && touched)
                         ptx::sts_v4_volatile(my_slot, max(S0, INT_MIN + 1) - 1, max(S1, INT_MIN + 1) - 1, (int)a, 0);
                 }
+                if (prof) {  // per-warp cycle accounting of the tile loop (debug flag 8)
+                    const long long c4 = clock64();
+                    acc_wait += c1 - c0;  // waiting for the accumulator
+                    acc_load += c2 - c1;  // TMEM loads + keys + threshold + hand-back
+                    acc_p1 += c3 - c2;    // phase 1
+                    acc_p2 += c4 - c3;    // phase 2 + publish
+                }
                 if (++ks == Cfg::kKeySlots) { ks = 0; k_phase ^= 1; }
                 if (++buf == TBUFS) { buf = 0; t_phase ^= 1; }
+            }
+            if (DEBUG && (p.debug_flags & 8u) && p.stats != nullptr && lane == 0) {
+                atomicAdd(p.stats + 0, (unsigned long long)acc_hot);
+                atomicAdd(p.stats + 1, (unsigned long long)acc_wait);
+                atomicAdd(p.stats + 2, (unsigned long long)acc_load);
+                atomicAdd(p.stats + 3, (unsigned long long)acc_p1);
+                atomicAdd(p.stats + 4, (unsigned long long)acc_p2);
+                atomicAdd(p.stats + 5, (unsigned long long)ntiles);
             }
             if (valid) {
                 int4 out;

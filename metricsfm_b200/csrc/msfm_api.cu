@@ -79,6 +79,7 @@ struct msfm_ctx {
     std::vector<ImageSlot> images;
     EncodeTiledFn encode = nullptr;
 
+    DeviceBuf dbg_stats;  // debug flag 8: per-phase cycle counters of the matching kernel, dumped at destroy
     DeviceBuf cand_q, cand_j, cand_d0, cand_good, cand_counts, cand_desc, cand_ckeys;  // one-way candidates + gathered rows
     DeviceBuf staging, knn, matches, good, counts, offsets, pairdesc, items, tight_matches, tight_good;
     void *h_pinned = nullptr;
@@ -247,7 +248,7 @@ msfm_status launch_match_kernel(msfm_ctx *ctx, size_t first_item, size_t n_items
     kp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
     kp.items = static_cast<const WorkItem *>(ctx->items.ptr) + first_item;
     kp.n_items = (int32_t)n_items;
-    kp.stats = nullptr;
+    kp.stats = static_cast<unsigned long long *>(ctx->dbg_stats.ptr);  // null unless MSFM_DEBUG_FLAGS & 8
     kp.debug_flags = ctx->debug_flags;
     kp.knn = static_cast<int4 *>(ctx->knn.ptr);
     const int grid = std::max(1, std::min<int>(ctx->num_sms, kp.n_items));
@@ -619,6 +620,11 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
         cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, true>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::kSmemAlloc) != cudaSuccess)
         return bail(MSFM_ERR_CUDA);
+    if (ctx->debug_flags & 8u) {
+        if (cudaMalloc(&ctx->dbg_stats.ptr, 64) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
+        ctx->dbg_stats.bytes = 64;
+        cudaMemset(ctx->dbg_stats.ptr, 0, 64);
+    }
     *out = ctx;
     return MSFM_OK;
 }
@@ -627,6 +633,14 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
     if (!ctx) return MSFM_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->dbg_stats.ptr) {
+        unsigned long long h[8] = {0};
+        cudaMemcpy(h, ctx->dbg_stats.ptr, 64, cudaMemcpyDeviceToHost);
+        const double wt = h[5] ? (double)h[5] : 1.0;
+        fprintf(stderr, "[msfm debug] warp-tiles %llu | hot groups/warp-tile %.3f | cycles/warp-tile: wait-acc %.1f load+thresh %.1f "
+                        "phase1 %.1f phase2 %.1f\n", h[5], h[0] / wt, h[1] / wt, h[2] / wt, h[3] / wt, h[4] / wt);
+        cudaFree(ctx->dbg_stats.ptr);
+    }
     DeviceBuf *bufs[] = {&ctx->cand_q, &ctx->cand_j, &ctx->cand_d0, &ctx->cand_good, &ctx->cand_counts, &ctx->cand_desc, &ctx->cand_ckeys,
                          &ctx->staging, &ctx->knn, &ctx->matches, &ctx->good, &ctx->counts, &ctx->offsets,
                          &ctx->pairdesc, &ctx->items, &ctx->tight_matches, &ctx->tight_good};
