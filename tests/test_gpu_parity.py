@@ -268,3 +268,49 @@ def test_cpp_host_shim_matches_oracle(oracle_mod, native_lib, tmp_path):
         exp = oracle_mod.match_pair_u8(ref, qry, 0.85, ratio_good=0.6)
         np.testing.assert_array_equal(got[:, :2], exp["pairs"])
         np.testing.assert_array_equal(got[:, 2], exp["good"])
+
+
+def test_adversarial_norm_spread_and_near_ties(oracle_mod, matcher):
+    """Inputs that defeat the pruning filter (huge spread of reference norms, scores within 1 of each other across
+    column shares and tiles): results must stay bit-exact, only slower."""
+    rng = np.random.default_rng(91)
+    ref = rng.integers(0, 256, size=(1300, 128), dtype=np.uint8)
+    ref[::3] //= 8                      # a third of the rows with tiny norms, interleaved inside every tile
+    ref[1::7] = 255 - ref[1::7] // 16   # and some with huge norms
+    qry = rng.integers(0, 256, size=(700, 128), dtype=np.uint8)
+    # near-ties: copies of a query row differing by +-1 in one coordinate, scattered over tiles and both column shares
+    base = qry[5].copy()
+    for n, j in enumerate((3, 70, 130, 200, 640, 705, 1290)):
+        r = base.copy()
+        r[n] = np.clip(int(r[n]) + (1 if n % 2 else -1), 0, 255)
+        ref[j] = r
+    ref[64] = base                      # exact hit in the second column share of tile 0
+    ref[900] = base                     # and an equal-distance duplicate far to the right (must lose the tie)
+    _upload_pair(matcher, ref, qry)
+    ids, dists = _check_knn(oracle_mod, matcher, ref, qry)
+    assert ids[5, 0] == 64 and ids[5, 1] == 900 and dists[5, 0] == 0 and dists[5, 1] == 0
+    for mutual in (False, True):
+        res = matcher.match_pairs([(0, 1), (1, 0)], 0.9, ratio_good=0.7, mutual=mutual)
+        for p, (r, q) in enumerate(((ref, qry), (qry, ref))):
+            exp = oracle_mod.match_pair_u8(r, q, 0.9, mutual=mutual, ratio_good=0.7)
+            np.testing.assert_array_equal(res.pair(p), exp["pairs"])
+            np.testing.assert_array_equal(res.pair_good(p), exp["good"])
+
+
+def test_many_small_and_uneven_pairs(oracle_mod, matcher):
+    """Guided-pair-list shape: many pairs of uneven, ragged sizes in one call (work items of every fill level)."""
+    rng = np.random.default_rng(93)
+    sizes = [int(x) for x in rng.integers(20, 1400, size=24)] + [255, 256, 257, 511, 512, 513]
+    col = synth.Collection(1400, seed=61)
+    imgs = [col.image_u8(i, r) for i, r in enumerate(sizes)]
+    matcher.release_all()
+    for i, d in enumerate(imgs):
+        matcher.upload(i, d)
+    pairs = synth.gps_neighbour_pairs(len(sizes), k=5, seed=3)
+    pairs = np.concatenate([pairs, pairs[::3, ::-1]])          # some pairs in both orientations
+    res = matcher.match_pairs(pairs, 0.85, ratio_good=0.6, mutual=True)
+    assert res.ok.all()
+    for p, (r, q) in enumerate(pairs):
+        exp = oracle_mod.match_pair_u8(imgs[r], imgs[q], 0.85, mutual=True, ratio_good=0.6)
+        np.testing.assert_array_equal(res.pair(p), exp["pairs"], err_msg=f"pair {p} = ({r},{q})")
+        np.testing.assert_array_equal(res.pair_good(p), exp["good"])
