@@ -29,10 +29,10 @@ using msfm::PairDesc;
 using msfm::WorkItem;
 
 // Kernel configuration of this build.
-constexpr int kStrips = 2;   // query strips (128 rows each) per work item
-constexpr int kTileN = 128;  // reference rows per tile (UMMA N)
-constexpr int kStages = 6;   // B-tile ring depth
-constexpr int kCsplit = 2;   // epilogue warps per (strip, quarter): column shares
+constexpr int kStrips = 4;   // query strips (128 rows each) per work item
+constexpr int kTileN = 64;   // reference rows per tile (UMMA N)
+constexpr int kStages = 8;   // B-tile ring depth
+constexpr int kCsplit = 1;   // epilogue warps per (strip, quarter): column shares
 constexpr int kTbufs = 2;    // TMEM accumulator buffers per strip
 using KCfg = msfm::MatchKernelCfg<kStrips, kTileN, kStages, kCsplit, kTbufs>;
 constexpr int kItemRows = kStrips * msfm::kStripRows;
