@@ -39,7 +39,7 @@ constexpr int kItemRows = kStrips * msfm::kStripRows;
 
 // Per-batch scratch bounds (rows).  16 Mi query rows -> 256 MiB kNN scratch + 128 MiB match scratch.
 constexpr int64_t kBatchMaxQueryRows = 16ll << 20;
-constexpr int64_t kBatchMaxQueryRowsMutual = 4ll << 20;  // mutual: + 128 B of gathered candidate row per query row
+constexpr int64_t kBatchMaxQueryRowsMutual = 16ll << 20;  // mutual: + 128 B of gathered candidate row per query row
 constexpr int64_t kBatchMaxPairs = 16384;
 
 struct DeviceBuf {
