@@ -314,3 +314,26 @@ def test_many_small_and_uneven_pairs(oracle_mod, matcher):
         exp = oracle_mod.match_pair_u8(imgs[r], imgs[q], 0.85, mutual=True, ratio_good=0.6)
         np.testing.assert_array_equal(res.pair(p), exp["pairs"], err_msg=f"pair {p} = ({r},{q})")
         np.testing.assert_array_equal(res.pair_good(p), exp["good"])
+
+
+def test_full_size_properties_32k(oracle_mod, matcher):
+    """Config #5 shape (32 768 rows per image): sampled optimality + self-consistency through the batched entry point."""
+    col = synth.Collection(32768, seed=4)
+    a, b = col.image_u8(0), col.image_u8(1)
+    _upload_pair(matcher, a, b)
+    ids, dists = matcher.knn2(0, 1)
+    rng = np.random.default_rng(5)
+    sample = np.sort(rng.choice(32768, size=192, replace=False))
+    oids, odists = oracle_mod.knn2_u8(a, b[sample])
+    np.testing.assert_array_equal(ids[sample], oids)
+    np.testing.assert_array_equal(dists[sample], odists)
+    res = matcher.match_pairs([(0, 1)], 0.85, ratio_good=0.6, mutual=True)
+    m = res.pair(0)
+    assert len(m) > 500 and (np.diff(m[:, 1]) > 0).all() and len(np.unique(m[:, 0])) == len(m)
+    # every emitted match is the query's nearest neighbour, passes the ratio, and is mutual (checked on the host)
+    np.testing.assert_array_equal(ids[m[:, 1], 0], m[:, 0])
+    r = dists[m[:, 1], 0] / dists[m[:, 1], 1]
+    assert (r < np.float32(0.85)).all()
+    np.testing.assert_array_equal(res.pair_good(0), (r < np.float32(0.6)).astype(np.uint8))
+    back_ids, _ = matcher.knn2(1, 0)                # nearest query row of every reference row
+    np.testing.assert_array_equal(back_ids[m[:, 0], 0], m[:, 1])
