@@ -29,6 +29,9 @@
  *   accept iff (float)d0/(float)d1 < ratio (IEEE fp32 divide, strict; NaN => reject), and, when mutual,
  *   argmin_q' d(q',nn0) == q (lowest q' on ties); a pair with M < min_keypoints or N < min_keypoints is rejected
  *   as a whole (ok = 0, no matches), like feature_matching.cpp:30-33.  Missing neighbours: id = -1, dist = +inf.
+ * Float regime: float rows are quantised to u8 by the packer, so d0/d1 carries a relative error of a few 1e-3; with
+ *   msfm_config.keep_float + msfm_params.rescore_band the rows near a ratio threshold are decided on exact fp32
+ *   distances instead (the match lists then agree with an fp32 brute-force matcher to <= 1e-4 of the matches).
  */
 #ifndef MSFM_MATCH_H_
 #define MSFM_MATCH_H_
@@ -41,7 +44,7 @@ extern "C" {
 #endif
 
 #define MSFM_DIM 128              /* descriptor length (SIFT-128), bytes per packed row */
-#define MSFM_ABI_VERSION 1
+#define MSFM_ABI_VERSION 2
 #define MSFM_MAX_ROWS_PER_IMAGE 1000000 /* idx_max_per_image, src/basic_structs.h:171 */
 
 typedef enum msfm_status {
@@ -66,7 +69,10 @@ typedef struct msfm_config {
      * norms: arena_rows 32-bit words (an opaque per-row side table derived from the squared norms). */
     void *external_desc_arena;
     void *external_norm_arena;
-    int32_t reserved[4];     /* must be zero */
+    /* 1: msfm_upload_f32 also keeps the caller's float rows in HBM (512 B per row, library-owned) so that
+     * msfm_match_pairs can re-score ratio-boundary rows exactly in fp32 (msfm_params.rescore_band). */
+    int32_t keep_float;
+    int32_t reserved[3];     /* must be zero */
 } msfm_config;
 
 typedef struct msfm_params {
@@ -78,6 +84,11 @@ typedef struct msfm_params {
     int32_t min_keypoints; /* pairs with fewer rows on either side are rejected; reference value 20 */
     int32_t orientation;   /* 0: emit (ref_index, query_index)  fine_matching_graph.cc:121,127
                               1: emit (query_index, ref_index)  feature_matching.cpp:60-61 */
+    float rescore_band;    /* float regime (both images uploaded with msfm_upload_f32 on a keep_float context):
+                              > 0: query rows whose quantised d0/d1 lies within ratio*(1 +- band) or
+                              ratio_good*(1 +- band) are re-scored by exact fp32 brute force on the retained float
+                              rows (squared L2 accumulated in index order like nanoflann.hpp:376-383) and the ratio
+                              tests are repeated on the fp32 distances; 0 = decide on the quantised distances */
 } msfm_params;
 
 /* One candidate pair: the kNN index is "built" on image `ref`, rows of image `query` are the queries

@@ -30,12 +30,13 @@ EXPORTED_SYMBOLS = [
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_images", C.c_int32), ("arena_rows", C.c_int64),
-                ("external_desc_arena", C.c_void_p), ("external_norm_arena", C.c_void_p), ("reserved", C.c_int32 * 4)]
+                ("external_desc_arena", C.c_void_p), ("external_norm_arena", C.c_void_p), ("keep_float", C.c_int32),
+                ("reserved", C.c_int32 * 3)]
 
 
 class Params(C.Structure):
     _fields_ = [("ratio", C.c_float), ("ratio_good", C.c_float), ("max_dist_sq", C.c_float), ("mutual", C.c_int32),
-                ("min_keypoints", C.c_int32), ("orientation", C.c_int32)]
+                ("min_keypoints", C.c_int32), ("orientation", C.c_int32), ("rescore_band", C.c_float)]
 
 
 class Pair(C.Structure):

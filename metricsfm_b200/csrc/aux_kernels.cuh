@@ -131,6 +131,163 @@ __device__ __forceinline__ int block_rank(bool keep, int &running, int *warp_exc
     return slot;
 }
 
+// ------------------------------------------------------------------------------------------------ float regime
+// Float descriptors are quantised to u8 by the packer, so the ratio d0/d1 of the integer path carries a relative error
+// of a few 1e-3 and rows close to a ratio threshold can land on the other side of it than an fp32 matcher would put
+// them (north_star: ratio-boundary flip rate <= 1e-4 of the matches).  With the caller's float rows retained in HBM,
+//   mark_band_kernel     lists, per pair, the query rows whose quantised ratio lies within +-band of a threshold
+//   rescore_band_kernel  recomputes their 2-NN by exact fp32 brute force over the whole reference image (squared L2
+//                        accumulated in index order with separate multiply and add, the arithmetic of
+//                        nanoflann.hpp:376-383 compiled without contraction), repeats the ratio tests on those
+//                        distances and overwrites the row's kNN entry with the decision
+// Rows outside the band keep the integer decision: their ratio is off the threshold by many times the quantisation error.
+constexpr int kRescoredFlag = 0x40000000;  // in knn[row].x: {id0 | flag, bit0 keep | bit1 good, int d0, fp32 d0 bits}
+constexpr int kRescoreRows = 16;           // band rows a CTA scores together against the reference image
+
+struct BandParams {
+    const PairDesc *pairs;
+    int4 *knn;
+    int32_t nshare;
+    float ratio, ratio_good, max_dist_sq, band;
+    int32_t *band_q;       // [forward kNN rows], pair p writes from row knn_off
+    int32_t *band_counts;  // [n_pairs]
+    const float *fdesc;    // retained float rows, same row offsets as the packed arena
+    const uint8_t *desc_arena;
+};
+
+__global__ void __launch_bounds__(1024) mark_band_kernel(const BandParams bp) {
+    __shared__ int warp_excl[32];
+    __shared__ int chunk_total;
+    const PairDesc pd = bp.pairs[blockIdx.x];
+    int running = 0;
+    if (pd.fscale2 > 0.0f) {
+        for (int base = 0; base < pd.qry_rows; base += blockDim.x) {
+            const int q = base + threadIdx.x;
+            bool in_band = false;
+            if (q < pd.qry_rows) {
+                const int4 k = merge_knn_shares(bp.knn, pd.knn_off + q, bp.nshare);
+                if (k.x >= 0 && k.y >= 0) {
+                    const float r = __fdiv_rn((float)k.z, (float)k.w);
+                    in_band = fabsf(r - bp.ratio) <= bp.band * bp.ratio;
+                    if (bp.ratio_good > 0.0f) in_band = in_band || fabsf(r - bp.ratio_good) <= bp.band * bp.ratio_good;
+                }
+            }
+            const int slot = block_rank(in_band, running, warp_excl, &chunk_total);
+            if (in_band) bp.band_q[pd.knn_off + slot] = q;
+        }
+    }
+    if (threadIdx.x == 0) bp.band_counts[blockIdx.x] = running;
+}
+
+__device__ __forceinline__ bool fknn_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
+
+__global__ void __launch_bounds__(256) rescore_band_kernel(const BandParams bp, int n_pairs) {
+    __shared__ float sq[kRescoreRows][kDim];
+    __shared__ float red_d[8][kRescoreRows][2];
+    __shared__ int red_i[8][kRescoreRows][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
+        const PairDesc pd = bp.pairs[p];
+        const int n_band = bp.band_counts[p];
+        const float *ref = bp.fdesc + pd.ref_off * kDim;
+        for (int c0 = 0; c0 < n_band; c0 += kRescoreRows) {
+            const int nq = min(kRescoreRows, n_band - c0);
+            __syncthreads();  // previous chunk's shared data is no longer read
+            for (int i = threadIdx.x; i < kRescoreRows * kDim; i += blockDim.x) {
+                const int qi = i / kDim, k = i % kDim;
+                sq[qi][k] = qi < nq ? bp.fdesc[(pd.qry_off + bp.band_q[pd.knn_off + c0 + qi]) * kDim + k] : 0.0f;
+            }
+            __syncthreads();
+            float d0[kRescoreRows], d1[kRescoreRows];
+            int i0[kRescoreRows], i1[kRescoreRows];
+#pragma unroll
+            for (int qi = 0; qi < kRescoreRows; ++qi) { d0[qi] = d1[qi] = INFINITY; i0[qi] = i1[qi] = -1; }
+            for (int j = threadIdx.x; j < pd.ref_rows; j += blockDim.x) {
+                float acc[kRescoreRows];
+#pragma unroll
+                for (int qi = 0; qi < kRescoreRows; ++qi) acc[qi] = 0.0f;
+                const float4 *r4 = reinterpret_cast<const float4 *>(ref + (int64_t)j * kDim);
+#pragma unroll 4
+                for (int k4 = 0; k4 < kDim / 4; ++k4) {
+                    const float4 r = __ldg(r4 + k4);
+#pragma unroll
+                    for (int qi = 0; qi < kRescoreRows; ++qi) {
+                        const float4 a = *reinterpret_cast<const float4 *>(&sq[qi][4 * k4]);
+                        float t;
+                        t = __fsub_rn(a.x, r.x); acc[qi] = __fadd_rn(acc[qi], __fmul_rn(t, t));
+                        t = __fsub_rn(a.y, r.y); acc[qi] = __fadd_rn(acc[qi], __fmul_rn(t, t));
+                        t = __fsub_rn(a.z, r.z); acc[qi] = __fadd_rn(acc[qi], __fmul_rn(t, t));
+                        t = __fsub_rn(a.w, r.w); acc[qi] = __fadd_rn(acc[qi], __fmul_rn(t, t));
+                    }
+                }
+#pragma unroll
+                for (int qi = 0; qi < kRescoreRows; ++qi) {  // j ascends per thread: strict '<' keeps the lowest index
+                    const float d = acc[qi];
+                    if (d < d0[qi]) { d1[qi] = d0[qi]; i1[qi] = i0[qi]; d0[qi] = d; i0[qi] = j; }
+                    else if (d < d1[qi]) { d1[qi] = d; i1[qi] = j; }
+                }
+            }
+            // merge the per-thread top-2 lists: warp shuffles, then across the 8 warps through shared memory
+#pragma unroll
+            for (int qi = 0; qi < kRescoreRows; ++qi) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float e0 = __shfl_xor_sync(0xFFFFFFFFu, d0[qi], o), e1 = __shfl_xor_sync(0xFFFFFFFFu, d1[qi], o);
+                    const int j0 = __shfl_xor_sync(0xFFFFFFFFu, i0[qi], o), j1 = __shfl_xor_sync(0xFFFFFFFFu, i1[qi], o);
+                    const bool mine = i0[qi] >= 0 && (j0 < 0 || fknn_less(d0[qi], i0[qi], e0, j0));
+                    // winner w, loser l of the two heads; second = best of {w's second, l's head}
+                    const float wd0 = mine ? d0[qi] : e0, wd1 = mine ? d1[qi] : e1, ld0 = mine ? e0 : d0[qi];
+                    const int wi0 = mine ? i0[qi] : j0, wi1 = mine ? i1[qi] : j1, li0 = mine ? j0 : i0[qi];
+                    const bool second_from_w = wi1 >= 0 && (li0 < 0 || fknn_less(wd1, wi1, ld0, li0));
+                    d0[qi] = wd0; i0[qi] = wi0;
+                    d1[qi] = second_from_w ? wd1 : ld0;
+                    i1[qi] = second_from_w ? wi1 : li0;
+                }
+                if (lane == 0) { red_d[warp][qi][0] = d0[qi]; red_d[warp][qi][1] = d1[qi]; red_i[warp][qi][0] = i0[qi]; red_i[warp][qi][1] = i1[qi]; }
+            }
+            __syncthreads();
+            if (threadIdx.x < nq) {
+                const int qi = threadIdx.x;
+                float b0 = INFINITY, b1 = INFINITY;
+                int c0i = -1, c1i = -1;
+                for (int w = 0; w < 8; ++w)
+                    for (int s = 0; s < 2; ++s) {
+                        const float d = red_d[w][qi][s];
+                        const int i = red_i[w][qi][s];
+                        if (i < 0) continue;
+                        if (c0i < 0 || fknn_less(d, i, b0, c0i)) { b1 = b0; c1i = c0i; b0 = d; c0i = i; }
+                        else if (c1i < 0 || fknn_less(d, i, b1, c1i)) { b1 = d; c1i = i; }
+                    }
+                const int q = bp.band_q[pd.knn_off + c0 + qi];
+                int flags = 0;
+                if (c0i >= 0 && c1i >= 0) {
+                    const float r = __fdiv_rn(b0, b1);
+                    bool keep = r < bp.ratio;
+                    if (bp.max_dist_sq > 0.0f) keep = keep && (b0 * pd.fscale2 < bp.max_dist_sq);
+                    const bool good = keep && bp.ratio_good > 0.0f && r < bp.ratio_good;
+                    flags = (keep ? 1 : 0) | (good ? 2 : 0);
+                }
+                // integer distance of the fp32 nearest neighbour (seeds the mutual search of this candidate)
+                int di = 0;
+                if (c0i >= 0) {
+                    const uint32_t *qa = reinterpret_cast<const uint32_t *>(bp.desc_arena + (pd.qry_off + q) * kDim);
+                    const uint32_t *rb = reinterpret_cast<const uint32_t *>(bp.desc_arena + (pd.ref_off + c0i) * kDim);
+                    uint32_t na = 0, nb = 0, ab = 0;
+                    for (int k = 0; k < kDim / 4; ++k) { na = __dp4a(qa[k], qa[k], na); nb = __dp4a(rb[k], rb[k], nb); ab = __dp4a(qa[k], rb[k], ab); }
+                    di = (int)(na + nb - 2u * ab);
+                }
+                int4 out;
+                out.x = (c0i >= 0 ? c0i : 0) | kRescoredFlag;
+                out.y = flags;
+                out.z = di;
+                out.w = __float_as_int(b0);
+                bp.knn[(pd.knn_off + q) * bp.nshare] = out;
+                for (int s = 1; s < bp.nshare; ++s) bp.knn[(pd.knn_off + q) * bp.nshare + s] = make_int4(-1, -1, INT_MAX, INT_MAX);
+            }
+        }
+    }
+}
+
 // Stage 1 — ratio test.  One CTA per pair scans its query rows in ascending order (the order of
 // fine_matching_graph.cc:116-133 / feature_matching.cpp:56-64) and writes the one-way candidates
 // (query row, nearest reference row, "good" flag) compacted into the pair's scratch region.  With `gather` set it also
@@ -163,7 +320,12 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
         int nn0 = -1, dist0 = 0;
         if (q < pd.qry_rows) {
             const int4 k = merge_knn_shares(sp.knn, pd.knn_off + q, sp.nshare);
-            if (k.x >= 0 && k.y >= 0) {
+            if (k.x >= 0 && (k.x & kRescoredFlag)) {  // decided on exact fp32 distances by rescore_band_kernel
+                keep = (k.y & 1) != 0;
+                is_good = (k.y & 2) != 0;
+                nn0 = k.x & ~kRescoredFlag;
+                dist0 = k.z;
+            } else if (k.x >= 0 && k.y >= 0) {
                 const float d0 = (float)k.z, d1 = (float)k.w;
                 const float r = __fdiv_rn(d0, d1);  // IEEE divide; 0/0 = NaN fails every comparison
                 keep = r < sp.ratio;

@@ -54,6 +54,8 @@ struct PairDesc {
     int32_t qry_row_base;      // row coordinate of query row 0 in the query tensor map (0 for whole-image maps)
     int32_t cand_idx;          // >= 0: the query rows are this pair's gathered mutual-check candidates and their
                                // number is counts[cand_idx] (known only on the device); -1: ordinary image rows
+    float fscale2;             // float regime: (quantisation scale)^2 when both images keep their float rows, else 0
+    int32_t pad_;
 };
 
 struct WorkItem {

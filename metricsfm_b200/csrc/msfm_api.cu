@@ -49,6 +49,8 @@ struct DeviceBuf {
 
 struct ImageSlot {
     bool present = false;
+    bool has_float = false;  // float rows retained (keep_float context, msfm_upload_f32)
+    float scale = 0.0f;      // quantisation scale of the float upload
     int32_t rows = 0;
     int32_t rows_padded = 0;
     int64_t off = 0;
@@ -74,6 +76,7 @@ struct msfm_ctx {
     std::vector<Extent> free_list;
     uint8_t *desc = nullptr;
     int32_t *norms = nullptr;  // column-key arena: ckey = -8*||row||^2 + (7 - row%8), see match_kernel.cuh
+    float *fdesc = nullptr;    // keep_float: the callers' float rows, same row offsets as `desc` (512 B per row)
     bool own_arena = false;
     CUtensorMap *d_maps = nullptr;
     std::vector<ImageSlot> images;
@@ -81,6 +84,7 @@ struct msfm_ctx {
 
     DeviceBuf dbg_stats;  // debug flag 8: per-phase cycle counters of the matching kernel, dumped at destroy
     DeviceBuf cand_q, cand_j, cand_d0, cand_good, cand_counts, cand_desc, cand_ckeys;  // one-way candidates + gathered rows
+    DeviceBuf band_q, band_counts;  // float regime: query rows near a ratio threshold, per pair
     DeviceBuf staging, knn, matches, good, counts, offsets, pairdesc, items, tight_matches, tight_good;
     void *h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
@@ -235,6 +239,7 @@ struct BatchPlan {
     int64_t ops = 0;
     bool mutual = false;
     bool has_empty = false;          // some pair has no work items: its kNN rows must read "absent"
+    bool any_float = false;          // some pair has retained float rows on both sides (rescoring possible)
     int64_t knn_rows() const { return mutual ? 2 * query_rows : query_rows; }
 };
 
@@ -303,6 +308,8 @@ void finish_plan(msfm_ctx *ctx, BatchPlan &plan) {
         tw.knn_off = plan.query_rows + f.knn_off;
         tw.qry_row_base = (int32_t)f.knn_off;
         tw.cand_idx = pi;
+        tw.fscale2 = 0.0f;
+        tw.pad_ = 0;
         plan.twins.push_back(tw);
         if (f.ref_rows > 0)
             for (int32_t row0 = 0; row0 < f.qry_rows; row0 += kItemRows) plan.twin_items.push_back({nb + pi, row0});
@@ -351,6 +358,9 @@ void plan_add_pair(msfm_ctx *ctx, BatchPlan &plan, int64_t src, int32_t ref, int
     pd.knn_off = plan.query_rows;
     pd.qry_row_base = 0;
     pd.cand_idx = -1;
+    pd.fscale2 = (r.has_float && q.has_float && r.scale == q.scale) ? r.scale * r.scale : 0.0f;
+    pd.pad_ = 0;
+    if (pd.fscale2 > 0.0f) plan.any_float = true;
     const int32_t pidx = (int32_t)plan.pairs.size();
     plan.pairs.push_back(pd);
     plan.src_index.push_back(src);
@@ -437,6 +447,27 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             if (want_good && (st = ensure(ctx, ctx->tight_good, rows)) != MSFM_OK) return st;
             // ---- forward 2-NN
             if ((st = run_match_stage(ctx, plan)) != MSFM_OK) return st;
+            // ---- float regime: rows near a ratio threshold are decided on exact fp32 distances
+            if (params->rescore_band > 0.0f && ctx->fdesc && plan.any_float) {
+                if ((st = ensure(ctx, ctx->band_q, rows * 4)) != MSFM_OK) return st;
+                if ((st = ensure(ctx, ctx->band_counts, (size_t)nb * 4)) != MSFM_OK) return st;
+                msfm::BandParams bp;
+                bp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
+                bp.knn = static_cast<int4 *>(ctx->knn.ptr);
+                bp.nshare = kCsplit;
+                bp.ratio = params->ratio;
+                bp.ratio_good = params->ratio_good;
+                bp.max_dist_sq = params->max_dist_sq;
+                bp.band = params->rescore_band;
+                bp.band_q = static_cast<int32_t *>(ctx->band_q.ptr);
+                bp.band_counts = static_cast<int32_t *>(ctx->band_counts.ptr);
+                bp.fdesc = ctx->fdesc;
+                bp.desc_arena = ctx->desc;
+                msfm::mark_band_kernel<<<nb, 1024, 0, ctx->stream>>>(bp);
+                msfm::rescore_band_kernel<<<std::min(nb, 4 * ctx->num_sms), 256, 0, ctx->stream>>>(bp, nb);
+                MSFM_CUDA(ctx, cudaGetLastError());
+                ctx->timing.total_launches += 2;
+            }
             // ---- ratio test -> one-way candidates (+ gather of their reference rows for the mutual check)
             msfm::SelectParams sp;
             sp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
@@ -573,6 +604,7 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
     if (!cfg || !out) return MSFM_ERR_INVALID_ARG;
     *out = nullptr;
     if (cfg->max_images <= 0 || cfg->arena_rows <= 0) return MSFM_ERR_INVALID_ARG;
+    if (cfg->reserved[0] || cfg->reserved[1] || cfg->reserved[2]) return MSFM_ERR_INVALID_ARG;
     if ((cfg->external_desc_arena == nullptr) != (cfg->external_norm_arena == nullptr)) return MSFM_ERR_INVALID_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return MSFM_ERR_CUDA;
@@ -613,6 +645,9 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
         if (cudaMalloc(&ctx->norms, (size_t)ctx->arena_rows * 4) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
         ctx->own_arena = true;
     }
+    if (cfg->keep_float) {
+        if (cudaMalloc(&ctx->fdesc, (size_t)ctx->arena_rows * kDim * sizeof(float)) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
+    }
     // one tensor map per image + one for the candidate scratch
     if (cudaMalloc(&ctx->d_maps, (size_t)(ctx->max_images + 1) * sizeof(CUtensorMap)) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
     if (cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, false>,
@@ -641,7 +676,8 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
                         "phase1 %.1f phase2 %.1f\n", h[5], h[0] / wt, h[1] / wt, h[2] / wt, h[3] / wt, h[4] / wt);
         cudaFree(ctx->dbg_stats.ptr);
     }
-    DeviceBuf *bufs[] = {&ctx->cand_q, &ctx->cand_j, &ctx->cand_d0, &ctx->cand_good, &ctx->cand_counts, &ctx->cand_desc, &ctx->cand_ckeys,
+    if (ctx->fdesc) cudaFree(ctx->fdesc);
+    DeviceBuf *bufs[] = {&ctx->band_q, &ctx->band_counts, &ctx->cand_q, &ctx->cand_j, &ctx->cand_d0, &ctx->cand_good, &ctx->cand_counts, &ctx->cand_desc, &ctx->cand_ckeys,
                          &ctx->staging, &ctx->knn, &ctx->matches, &ctx->good, &ctx->counts, &ctx->offsets,
                          &ctx->pairdesc, &ctx->items, &ctx->tight_matches, &ctx->tight_good};
     for (DeviceBuf *b : bufs)
@@ -714,6 +750,12 @@ msfm_status msfm_upload_f32(msfm_ctx *ctx, int32_t image_id, const float *desc, 
     msfm::pack_f32_kernel<<<blocks, 256, 0, ctx->stream>>>(static_cast<const float *>(ctx->staging.ptr), row_stride_floats, rows,
                                                           s.rows_padded, scale, ctx->desc + off * kDim, ctx->norms + off);
     MSFM_CUDA(ctx, cudaGetLastError());
+    if (ctx->fdesc && rows > 0) {
+        MSFM_CUDA(ctx, cudaMemcpy2DAsync(ctx->fdesc + off * kDim, kDim * sizeof(float), ctx->staging.ptr, (size_t)row_stride_floats * sizeof(float),
+                                         kDim * sizeof(float), (size_t)rows, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->images[image_id].has_float = true;
+        ctx->images[image_id].scale = scale;
+    }
     MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MSFM_OK;
 }

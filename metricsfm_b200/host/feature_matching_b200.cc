@@ -55,6 +55,7 @@ bool FeatureMatchingB200::Match(cv::Mat &d1, cv::Mat &d2, bool mutual, std::vect
     prm.mutual = mutual ? 1 : 0;
     prm.min_keypoints = opt_.th_reject;
     prm.orientation = 1;  // (i1, i2), ascending i1 (feature_matching.cpp:56-64)
+    prm.rescore_band = 0.f;
     std::vector<int32_t> buf((size_t)(d1.rows > 0 ? d1.rows : 1) * 2);
     int64_t offsets[2] = {0, 0};
     int32_t okflag = 0;
@@ -151,6 +152,7 @@ bool MatchGraphB200::MatchPairs(const std::vector<std::vector<int>> &match_graph
     prm.mutual = mutual ? 1 : 0;
     prm.min_keypoints = th_reject;
     prm.orientation = 0;  // (ptid1, ptid2) ascending ptid2 (fine_matching_graph.cc:121,127)
+    prm.rescore_band = 0.f;
     msfm_result res;
     res.offsets = offsets.data();
     res.ok = okflags.data();

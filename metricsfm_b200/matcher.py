@@ -52,7 +52,7 @@ class Matcher:
     """One context = one GPU: packed descriptor table in HBM + the batched pair matcher."""
 
     def __init__(self, device: int = 0, max_images: int = 1024, arena_rows: int = 1 << 20, external_desc_arena: int = 0,
-                 external_norm_arena: int = 0):
+                 external_norm_arena: int = 0, keep_float: bool = False):
         self._L = _lib.load()
         cfg = Config()
         cfg.device = device
@@ -60,6 +60,7 @@ class Matcher:
         cfg.arena_rows = arena_rows
         cfg.external_desc_arena = external_desc_arena or None
         cfg.external_norm_arena = external_norm_arena or None
+        cfg.keep_float = int(bool(keep_float))  # float uploads are retained for fp32 re-scoring (rescore_band)
         h = C.c_void_p()
         st = self._L.msfm_create(C.byref(cfg), C.byref(h))
         if st != _lib.MSFM_OK:
@@ -167,8 +168,9 @@ class Matcher:
 
     # ------------------------------------------------------------------ batched pair matching
     @staticmethod
-    def _params(ratio, ratio_good, max_dist_sq, mutual, min_keypoints, orientation) -> Params:
+    def _params(ratio, ratio_good, max_dist_sq, mutual, min_keypoints, orientation, rescore_band=0.0) -> Params:
         p = Params()
+        p.rescore_band = rescore_band
         p.ratio, p.ratio_good, p.max_dist_sq = ratio, ratio_good, max_dist_sq
         p.mutual, p.min_keypoints, p.orientation = int(bool(mutual)), int(min_keypoints), int(orientation)
         return p
@@ -179,9 +181,11 @@ class Matcher:
         return a
 
     def match_pairs(self, pairs, ratio: float = 0.6, *, ratio_good: float = 0.0, max_dist_sq: float = 0.0, mutual: bool = False,
-                    min_keypoints: int = 20, orientation: int = 0, capacity: int | None = None, out: MatchResult | None = None
-                    ) -> MatchResult:
-        """pairs: [n, 2] (ref image, query image).  Returns per-pair match lists, ascending query index."""
+                    min_keypoints: int = 20, orientation: int = 0, capacity: int | None = None, out: MatchResult | None = None,
+                    rescore_band: float = 0.0) -> MatchResult:
+        """pairs: [n, 2] (ref image, query image).  Returns per-pair match lists, ascending query index.
+        rescore_band > 0 (float uploads on a keep_float context): rows whose quantised ratio lies within that relative
+        band of a threshold are decided on exact fp32 distances."""
         pa = self._pairs(pairs)
         n = pa.shape[0]
         if out is None:
@@ -202,7 +206,7 @@ class Matcher:
         res.matches = _host_ptr(out.matches)[0]
         res.good = out.good.ctypes.data_as(_lib._u8p) if out.good is not None else None
         res.match_capacity = out.matches.shape[0]
-        prm = self._params(ratio, ratio_good, max_dist_sq, mutual, min_keypoints, orientation)
+        prm = self._params(ratio, ratio_good, max_dist_sq, mutual, min_keypoints, orientation, rescore_band)
         self._check(self._L.msfm_match_pairs(self._h, pa.ctypes.data, n, C.byref(prm), C.byref(res)))
         total = int(out.offsets[n])
         return MatchResult(out.offsets, out.ok, out.matches[:total], out.good[:total] if out.good is not None else None)

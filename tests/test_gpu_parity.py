@@ -337,3 +337,54 @@ def test_full_size_properties_32k(oracle_mod, matcher):
     np.testing.assert_array_equal(res.pair_good(0), (r < np.float32(0.6)).astype(np.uint8))
     back_ids, _ = matcher.knn2(1, 0)                # nearest query row of every reference row
     np.testing.assert_array_equal(back_ids[m[:, 0], 0], m[:, 1])
+
+
+# ---------------------------------------------------------------------------------------------------- float regime
+def _fp32_lists(oracle_mod, ref_f, qry_f, ratio, ratio_good, mutual):
+    """Match list of an exact fp32 brute-force matcher (squared L2 accumulated in index order, nanoflann.hpp:376-383)."""
+    ids, dists = oracle_mod.knn2_f32(ref_f, qry_f)
+    cb = oracle_mod.colbest_f32(ref_f, qry_f)[0] if mutual else None
+    return oracle_mod.ratio_select(ids, dists, ref_f.shape[0], ratio, col_best=cb, ratio_good=ratio_good)
+
+
+@pytest.mark.parametrize("mutual", [False, True])
+def test_float_regime_rescoring_matches_fp32_matcher(oracle_mod, native_lib, mutual):
+    """Unit-norm float descriptors (the CUDASIFT container, feature_extractor_cuda_sift.cpp:75-80), scale 512: with the
+    float rows retained and a 3 % re-scoring band the match lists equal those of an exact fp32 matcher (north_star
+    tolerance: <= 1e-4 of the matches flip; here none may), while the purely quantised path does flip some."""
+    from metricsfm_b200.matcher import Matcher
+    rows, n_img = 4096, 4
+    col = synth.Collection(rows, seed=11)
+    imgs = [col.image_unit(i) for i in range(n_img)]
+    pairs = [(0, 1), (2, 3), (1, 2), (3, 0)]
+    with Matcher(device=0, max_images=8, arena_rows=1 << 16, keep_float=True) as m:
+        for i, x in enumerate(imgs):
+            m.upload(i, x, scale=512.0)
+        res = m.match_pairs(pairs, 0.85, ratio_good=0.6, mutual=mutual, rescore_band=0.03)
+        raw = m.match_pairs(pairs, 0.85, ratio_good=0.6, mutual=mutual)
+    total = flips = flips_raw = good_diff = 0
+    for p, (r, q) in enumerate(pairs):
+        exp, exp_good = _fp32_lists(oracle_mod, imgs[r], imgs[q], 0.85, 0.6, mutual)
+        got, got_good = res.pair(p), res.pair_good(p)
+        se, sg = {tuple(x) for x in exp}, {tuple(x) for x in got}
+        flips += len(se ^ sg)
+        flips_raw += len(se ^ {tuple(x) for x in raw.pair(p)})
+        total += len(se)
+        ge = {tuple(x): int(f) for x, f in zip(exp, exp_good)}
+        good_diff += sum(1 for x, f in zip(got, got_good) if tuple(x) in ge and ge[tuple(x)] != int(f))
+        assert (np.diff(got[:, 1]) > 0).all()
+    assert total > 1000
+    assert flips == 0, f"{flips} of {total} matches differ from the fp32 matcher"
+    assert good_diff == 0
+    assert flips_raw > 0  # the reason the re-scoring band exists
+
+
+def test_float_regime_needs_retained_rows(oracle_mod, matcher):
+    """rescore_band on a context without retained float rows, or on u8 uploads, is a no-op (integer decision)."""
+    col = synth.Collection(1024, seed=12)
+    a, b = col.image_u8(0), col.image_u8(1)
+    _upload_pair(matcher, a, b)
+    r0 = matcher.match_pairs([(0, 1)], 0.85, ratio_good=0.6, mutual=True)
+    r1 = matcher.match_pairs([(0, 1)], 0.85, ratio_good=0.6, mutual=True, rescore_band=0.05)
+    np.testing.assert_array_equal(r0.pair(0), r1.pair(0))
+    np.testing.assert_array_equal(r0.pair_good(0), r1.pair_good(0))

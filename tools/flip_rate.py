@@ -1,7 +1,15 @@
 """Float-regime report (north_star: "where the reference uses float-normalized descriptors, the ratio-boundary flip rate
-is reported"): match lists of the u8 path (q = min(255, rint(512 x)), what the packer stores — the CUDA path is
-bit-identical to the u8 oracle by the GPU parity tests) versus exact fp32 brute force on the unit-norm float rows
-(the reference's CUDASIFT container, feature_extractor_cuda_sift.cpp:75-80).  CPU only; prints one JSON line."""
+is reported and must stay within a stated tolerance (<= 1e-4 of matches)").
+
+Inputs: unit-norm float rows (the reference's CUDASIFT container, feature_extractor_cuda_sift.cpp:75-80), uploaded with
+scale 512.  Reference answer: exact fp32 brute force (oracle.knn2_f32: squared L2 accumulated in index order,
+nanoflann.hpp:376-383) + ratio test (+ mutual).  Compared:
+  quantised  the u8 path alone (q = min(255, rint(512 x)), what the packer stores)
+  rescored   the CUDA path with msfm_config.keep_float and msfm_params.rescore_band (rows near a ratio threshold are
+             decided on exact fp32 distances)
+Run on a GPU box (`python tools/flip_rate.py [--rows 8192] [--pairs 6] [--band 0.03]`); prints one JSON line.  With
+--cpu-only the rescored column is skipped (no GPU needed)."""
+import argparse
 import json
 import os
 import sys
@@ -14,30 +22,54 @@ from metricsfm_b200 import synth  # noqa: E402
 from oracle import oracle  # noqa: E402
 
 
-def main(rows=8192, n_pairs=3):
-    col = synth.Collection(rows, seed=0)
-    out = {}
-    for ratio in (0.5, 0.6, 0.85):
-        flips = total = nn0_diff = nn1_diff = nrows = 0
-        for p in range(n_pairs):
-            a, b = col.image_unit(2 * p), col.image_unit(2 * p + 1)
-            fi, fd = oracle.knn2_f32(a, b)
-            qa, qb = oracle.quantize_f32(a, 512.0), oracle.quantize_f32(b, 512.0)
-            qi, qd = oracle.knn2_u8(qa, qb)
-            fm, _ = oracle.ratio_select(fi, fd, rows, ratio)
-            qm, _ = oracle.ratio_select(qi, qd, rows, ratio)
-            sf, sq = {tuple(x) for x in fm}, {tuple(x) for x in qm}
-            flips += len(sf ^ sq)
-            total += len(sf)
-            nn0_diff += int((fi[:, 0] != qi[:, 0]).sum())
-            nn1_diff += int((fi[:, 1] != qi[:, 1]).sum())
-            nrows += rows
-        out[f"ratio_{ratio}"] = {"matches_fp32": total, "symmetric_difference": flips, "flip_rate": flips / max(total, 1)}
-    out["nn0_identity_diff_rate"] = nn0_diff / nrows
-    out["nn1_identity_diff_rate"] = nn1_diff / nrows
-    out["rows"] = rows
-    out["pairs"] = n_pairs
-    out["tolerance_target"] = 1e-4
+_cache = {}
+
+
+def lists_fp32(key, a, b, ratio, good, mutual):
+    if key not in _cache:  # the fp32 brute force is the slow part: once per pair
+        _cache[key] = (oracle.knn2_f32(a, b), oracle.colbest_f32(a, b)[0])
+    (ids, dists), cb = _cache[key]
+    return oracle.ratio_select(ids, dists, a.shape[0], ratio, col_best=cb if mutual else None, ratio_good=good)[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=8192)
+    ap.add_argument("--pairs", type=int, default=6)
+    ap.add_argument("--band", type=float, default=0.03)
+    ap.add_argument("--cpu-only", action="store_true")
+    args = ap.parse_args()
+    col = synth.Collection(args.rows, seed=0)
+    n_img = 2 * args.pairs
+    imgs = [col.image_unit(i) for i in range(n_img)]
+    pairs = [(2 * p, 2 * p + 1) for p in range(args.pairs)]
+    out = {"rows": args.rows, "pairs": args.pairs, "band": args.band, "tolerance_target": 1e-4, "scale": 512.0}
+    m = None
+    if not args.cpu_only:
+        from metricsfm_b200.matcher import Matcher
+        m = Matcher(device=0, max_images=n_img, arena_rows=n_img * (args.rows + 256), keep_float=True)
+        for i, x in enumerate(imgs):
+            m.upload(i, x, scale=512.0)
+    for mutual in (False, True):
+        for ratio in (0.5, 0.6, 0.85):
+            total = fl_q = fl_r = 0
+            res_q = m.match_pairs(pairs, ratio, mutual=mutual) if m else None
+            res_r = m.match_pairs(pairs, ratio, mutual=mutual, rescore_band=args.band) if m else None
+            for p, (r, q) in enumerate(pairs):
+                ref = {tuple(x) for x in lists_fp32((r, q), imgs[r], imgs[q], ratio, 0.0, mutual)}
+                total += len(ref)
+                if m:
+                    fl_q += len(ref ^ {tuple(x) for x in res_q.pair(p)})
+                    fl_r += len(ref ^ {tuple(x) for x in res_r.pair(p)})
+                else:
+                    qa, qb = oracle.quantize_f32(imgs[r], 512.0), oracle.quantize_f32(imgs[q], 512.0)
+                    fl_q += len(ref ^ {tuple(x) for x in oracle.match_pair_u8(qa, qb, ratio, mutual=mutual)["pairs"]})
+            key = f"ratio_{ratio}{'_mutual' if mutual else ''}"
+            out[key] = {"matches_fp32": total, "flips_quantised": fl_q, "flip_rate_quantised": fl_q / max(total, 1)}
+            if m:
+                out[key].update({"flips_rescored": fl_r, "flip_rate_rescored": fl_r / max(total, 1)})
+    if m:
+        m.close()
     print(json.dumps(out))
 
 
