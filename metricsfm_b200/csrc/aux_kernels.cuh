@@ -153,6 +153,7 @@ struct BandParams {
     int32_t *band_counts;  // [n_pairs]
     const float *fdesc;    // retained float rows, same row offsets as the packed arena
     const uint8_t *desc_arena;
+    const int32_t *ckeys;
 };
 
 __global__ void __launch_bounds__(1024) mark_band_kernel(const BandParams bp) {
@@ -182,7 +183,9 @@ __global__ void __launch_bounds__(1024) mark_band_kernel(const BandParams bp) {
 __device__ __forceinline__ bool fknn_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
 
 __global__ void __launch_bounds__(256) rescore_band_kernel(const BandParams bp, int n_pairs) {
-    __shared__ float sq[kRescoreRows][kDim];
+    __shared__ float sq[kRescoreRows][kDim];                  // band rows, float
+    __shared__ __align__(16) uint32_t sq8[kRescoreRows][kDim / 4];  // the same rows, packed u8
+    __shared__ int s_na[kRescoreRows], s_thr[kRescoreRows];
     __shared__ float red_d[8][kRescoreRows][2];
     __shared__ int red_i[8][kRescoreRows][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -190,6 +193,8 @@ __global__ void __launch_bounds__(256) rescore_band_kernel(const BandParams bp, 
         const PairDesc pd = bp.pairs[p];
         const int n_band = bp.band_counts[p];
         const float *ref = bp.fdesc + pd.ref_off * kDim;
+        const uint8_t *ref8 = bp.desc_arena + pd.ref_off * kDim;
+        const int32_t *refk = bp.ckeys + pd.ref_off;
         for (int c0 = 0; c0 < n_band; c0 += kRescoreRows) {
             const int nq = min(kRescoreRows, n_band - c0);
             __syncthreads();  // previous chunk's shared data is no longer read
@@ -197,34 +202,61 @@ __global__ void __launch_bounds__(256) rescore_band_kernel(const BandParams bp, 
                 const int qi = i / kDim, k = i % kDim;
                 sq[qi][k] = qi < nq ? bp.fdesc[(pd.qry_off + bp.band_q[pd.knn_off + c0 + qi]) * kDim + k] : 0.0f;
             }
+            for (int i = threadIdx.x; i < kRescoreRows * (kDim / 4); i += blockDim.x) {
+                const int qi = i / (kDim / 4), k = i % (kDim / 4);
+                sq8[qi][k] = qi < nq ? reinterpret_cast<const uint32_t *>(bp.desc_arena + (pd.qry_off + bp.band_q[pd.knn_off + c0 + qi]) * kDim)[k] : 0u;
+            }
+            if (threadIdx.x < kRescoreRows) {
+                const int qi = threadIdx.x;
+                int na = 0, thr = -1;  // rows past the chunk end never pass the prefilter
+                if (qi < nq) {
+                    const int q = bp.band_q[pd.knn_off + c0 + qi];
+                    na = ckey_to_norm(bp.ckeys[pd.qry_off + q]);
+                    // Prefilter on the quantised distance: a row whose integer distance exceeds the integer second
+                    // best by more than ~3 % (ten times the quantisation error) cannot be an fp32 top-2 neighbour.
+                    const int d1 = merge_knn_shares(bp.knn, pd.knn_off + q, bp.nshare).w;
+                    thr = d1 + (d1 >> 5) + 256;
+                }
+                s_na[qi] = na;
+                s_thr[qi] = thr;
+            }
             __syncthreads();
             float d0[kRescoreRows], d1[kRescoreRows];
             int i0[kRescoreRows], i1[kRescoreRows];
 #pragma unroll
             for (int qi = 0; qi < kRescoreRows; ++qi) { d0[qi] = d1[qi] = INFINITY; i0[qi] = i1[qi] = -1; }
             for (int j = threadIdx.x; j < pd.ref_rows; j += blockDim.x) {
-                float acc[kRescoreRows];
+                uint32_t ab[kRescoreRows];
 #pragma unroll
-                for (int qi = 0; qi < kRescoreRows; ++qi) acc[qi] = 0.0f;
-                const float4 *r4 = reinterpret_cast<const float4 *>(ref + (int64_t)j * kDim);
-#pragma unroll 4
-                for (int k4 = 0; k4 < kDim / 4; ++k4) {
-                    const float4 r = __ldg(r4 + k4);
+                for (int qi = 0; qi < kRescoreRows; ++qi) ab[qi] = 0u;
+                const uint4 *r16 = reinterpret_cast<const uint4 *>(ref8 + (int64_t)j * kDim);
+#pragma unroll 2
+                for (int k4 = 0; k4 < kDim / 16; ++k4) {
+                    const uint4 r = __ldg(r16 + k4);
 #pragma unroll
                     for (int qi = 0; qi < kRescoreRows; ++qi) {
-                        const float4 a = *reinterpret_cast<const float4 *>(&sq[qi][4 * k4]);
-                        float t;
-                        t = __fsub_rn(a.x, r.x); acc[qi] = __fadd_rn(acc[qi], __fmul_rn(t, t));
-                        t = __fsub_rn(a.y, r.y); acc[qi] = __fadd_rn(acc[qi], __fmul_rn(t, t));
-                        t = __fsub_rn(a.z, r.z); acc[qi] = __fadd_rn(acc[qi], __fmul_rn(t, t));
-                        t = __fsub_rn(a.w, r.w); acc[qi] = __fadd_rn(acc[qi], __fmul_rn(t, t));
+                        const uint4 a = *reinterpret_cast<const uint4 *>(&sq8[qi][4 * k4]);
+                        ab[qi] = __dp4a(a.x, r.x, ab[qi]);
+                        ab[qi] = __dp4a(a.y, r.y, ab[qi]);
+                        ab[qi] = __dp4a(a.z, r.z, ab[qi]);
+                        ab[qi] = __dp4a(a.w, r.w, ab[qi]);
                     }
                 }
+                const int nb = ckey_to_norm(refk[j]);
 #pragma unroll
-                for (int qi = 0; qi < kRescoreRows; ++qi) {  // j ascends per thread: strict '<' keeps the lowest index
-                    const float d = acc[qi];
-                    if (d < d0[qi]) { d1[qi] = d0[qi]; i1[qi] = i0[qi]; d0[qi] = d; i0[qi] = j; }
-                    else if (d < d1[qi]) { d1[qi] = d; i1[qi] = j; }
+                for (int qi = 0; qi < kRescoreRows; ++qi) {
+                    const int dint = s_na[qi] + nb - 2 * (int)ab[qi];
+                    if (dint <= s_thr[qi]) {  // rare: exact fp32 distance, accumulated in index order without contraction
+                        float acc = 0.0f;
+                        const float *rf = ref + (int64_t)j * kDim;
+                        for (int k = 0; k < kDim; ++k) {
+                            const float t = __fsub_rn(sq[qi][k], __ldg(rf + k));
+                            acc = __fadd_rn(acc, __fmul_rn(t, t));
+                        }
+                        // j ascends per thread: strict '<' keeps the lowest index
+                        if (acc < d0[qi]) { d1[qi] = d0[qi]; i1[qi] = i0[qi]; d0[qi] = acc; i0[qi] = j; }
+                        else if (acc < d1[qi]) { d1[qi] = acc; i1[qi] = j; }
+                    }
                 }
             }
             // merge the per-thread top-2 lists: warp shuffles, then across the 8 warps through shared memory
@@ -307,6 +339,7 @@ struct SelectParams {
     const int32_t *ckeys;
     uint8_t *cand_desc;        // [forward kNN rows][128]
     int32_t *cand_ckeys;
+    int32_t float_mutual;      // float regime with re-scoring: widen the mutual search by the quantisation slack
 };
 
 __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectParams sp) {
@@ -340,7 +373,9 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
             sp.cand_q[pd.knn_off + slot] = q;
             sp.cand_j[pd.knn_off + slot] = nn0;
             sp.cand_good[pd.knn_off + slot] = is_good ? 1 : 0;
-            sp.cand_d0[pd.knn_off + slot] = dist0;
+            // float regime: a query row that is a few 1e-3 farther in quantised units may be the nearer one in fp32,
+            // so the mutual search keeps every row within ~3 % of the candidate's distance (see emit_matches_kernel)
+            sp.cand_d0[pd.knn_off + slot] = (sp.float_mutual && pd.fscale2 > 0.0f) ? dist0 + (dist0 >> 5) + 256 : dist0;
         }
     }
     if (threadIdx.x == 0) sp.counts[blockIdx.x] = running;
@@ -369,7 +404,18 @@ struct EmitParams {
     uint8_t *good;
     int32_t *counts;           // [n_pairs] surviving matches
     int32_t mutual, orientation;
+    const float *fdesc;        // float regime with re-scoring: retained float rows (else null)
 };
+
+// Exact fp32 squared distance, accumulated in index order without contraction (nanoflann.hpp:376-383).
+__device__ __forceinline__ float sqdist_f32_rows(const float *__restrict__ a, const float *__restrict__ b) {
+    float acc = 0.0f;
+    for (int k = 0; k < kDim; ++k) {
+        const float t = __fsub_rn(__ldg(a + k), __ldg(b + k));
+        acc = __fadd_rn(acc, __fmul_rn(t, t));
+    }
+    return acc;
+}
 
 __global__ void __launch_bounds__(1024) emit_matches_kernel(const EmitParams ep) {
     __shared__ int warp_excl[32];
@@ -384,7 +430,18 @@ __global__ void __launch_bounds__(1024) emit_matches_kernel(const EmitParams ep)
         if (keep) {
             q = ep.cand_q[pd.knn_off + i];
             j = ep.cand_j[pd.knn_off + i];
-            if (ep.mutual) keep = merge_knn_shares(ep.knn, ep.twin_base + pd.knn_off + i, ep.nshare).x == q;
+            if (ep.mutual) {
+                const int4 tw = merge_knn_shares(ep.knn, ep.twin_base + pd.knn_off + i, ep.nshare);
+                keep = tw.x == q;
+                if (ep.fdesc && pd.fscale2 > 0.0f && tw.x >= 0 && tw.y >= 0 && (tw.x == q || tw.y == q)) {
+                    // two query rows within the quantisation slack of reference row j: decide on fp32 distances
+                    const float *rj = ep.fdesc + (pd.ref_off + j) * kDim;
+                    const float da = sqdist_f32_rows(ep.fdesc + (pd.qry_off + tw.x) * kDim, rj);
+                    const float db = sqdist_f32_rows(ep.fdesc + (pd.qry_off + tw.y) * kDim, rj);
+                    const int best = (db < da || (db == da && tw.y < tw.x)) ? tw.y : tw.x;
+                    keep = best == q;
+                }
+            }
         }
         const int slot = block_rank(keep, running, warp_excl, &chunk_total);
         if (keep) {

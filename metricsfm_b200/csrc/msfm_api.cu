@@ -463,6 +463,7 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
                 bp.band_counts = static_cast<int32_t *>(ctx->band_counts.ptr);
                 bp.fdesc = ctx->fdesc;
                 bp.desc_arena = ctx->desc;
+                bp.ckeys = ctx->norms;
                 msfm::mark_band_kernel<<<nb, 1024, 0, ctx->stream>>>(bp);
                 msfm::rescore_band_kernel<<<std::min(nb, 4 * ctx->num_sms), 256, 0, ctx->stream>>>(bp, nb);
                 MSFM_CUDA(ctx, cudaGetLastError());
@@ -481,6 +482,8 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             sp.cand_d0 = static_cast<int32_t *>(ctx->cand_d0.ptr);
             sp.cand_good = static_cast<uint8_t *>(ctx->cand_good.ptr);
             sp.counts = static_cast<int32_t *>(ctx->cand_counts.ptr);
+            const bool float_rescoring = params->rescore_band > 0.0f && ctx->fdesc && plan.any_float;
+            sp.float_mutual = (mutual && float_rescoring) ? 1 : 0;
             sp.gather = mutual ? 1 : 0;
             sp.desc_arena = ctx->desc;
             sp.ckeys = ctx->norms;
@@ -510,6 +513,7 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             ep.counts = static_cast<int32_t *>(ctx->counts.ptr);
             ep.mutual = mutual ? 1 : 0;
             ep.orientation = params->orientation;
+            ep.fdesc = float_rescoring ? ctx->fdesc : nullptr;
             msfm::emit_matches_kernel<<<nb, 1024, 0, ctx->stream>>>(ep);
             msfm::scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(ep.counts, nb, static_cast<int64_t *>(ctx->offsets.ptr));
             msfm::gather_matches_kernel<<<nb, 256, 0, ctx->stream>>>(

@@ -54,7 +54,9 @@ def main():
         for ratio in (0.5, 0.6, 0.85):
             total = fl_q = fl_r = 0
             res_q = m.match_pairs(pairs, ratio, mutual=mutual) if m else None
+            ms_q = m.timing()["total_ms"] if m else None
             res_r = m.match_pairs(pairs, ratio, mutual=mutual, rescore_band=args.band) if m else None
+            ms_r = m.timing()["total_ms"] if m else None
             for p, (r, q) in enumerate(pairs):
                 ref = {tuple(x) for x in lists_fp32((r, q), imgs[r], imgs[q], ratio, 0.0, mutual)}
                 total += len(ref)
@@ -67,7 +69,8 @@ def main():
             key = f"ratio_{ratio}{'_mutual' if mutual else ''}"
             out[key] = {"matches_fp32": total, "flips_quantised": fl_q, "flip_rate_quantised": fl_q / max(total, 1)}
             if m:
-                out[key].update({"flips_rescored": fl_r, "flip_rate_rescored": fl_r / max(total, 1)})
+                out[key].update({"flips_rescored": fl_r, "flip_rate_rescored": fl_r / max(total, 1),
+                                 "device_ms_quantised": ms_q, "device_ms_rescored": ms_r})
     if m:
         m.close()
     print(json.dumps(out))
