@@ -59,6 +59,29 @@ def build_host_shim(force: bool = False) -> str:
     return SHIM_BIN
 
 
+STORE_LIB = os.path.join(HOST_DIR, "libmsfm_store.so")
+GRAPH_LIB = os.path.join(HOST_DIR, "libmsfm_graph.so")
+
+
+def _newer(target: str, deps) -> bool:
+    return os.path.exists(target) and all(os.path.getmtime(d) <= os.path.getmtime(target) for d in deps if os.path.exists(d))
+
+
+def build_host_libs(force: bool = False):
+    """libmsfm_store.so (the reference's on-disk formats, host only) and libmsfm_graph.so (the fine-matching-graph
+    driver = store + GPU matcher)."""
+    inc = os.path.join(PKG_DIR, "..", "include")
+    store_src = os.path.join(HOST_DIR, "msfm_store.cc")
+    graph_src = os.path.join(HOST_DIR, "msfm_graph.cc")
+    common = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared"]
+    if force or not _newer(STORE_LIB, [store_src, os.path.join(inc, "msfm_store.h"), os.path.abspath(__file__)]):
+        subprocess.check_call(common + ["-o", STORE_LIB, store_src])
+    if force or not _newer(GRAPH_LIB, [graph_src, store_src, LIB_PATH, os.path.join(inc, "msfm_graph.h"), os.path.abspath(__file__)]):
+        subprocess.check_call(common + ["-o", GRAPH_LIB, graph_src, store_src, "-L" + CSRC, "-lmsfm_match", "-Wl,-rpath,$ORIGIN/../csrc"])
+    return STORE_LIB, GRAPH_LIB
+
+
 if __name__ == "__main__":
     print(build_native(force="--force" in sys.argv, verbose=True))
     print(build_host_shim(force="--force" in sys.argv))
+    print(*build_host_libs(force="--force" in sys.argv))

@@ -1,0 +1,168 @@
+// msfm_graph.cc — FineMatchingGraph::BuildMatchGraph rebuilt around the GPU matcher (include/msfm_graph.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/msfm_graph.h"
+#include "../../include/msfm_match.h"
+#include "../../include/msfm_store.h"
+
+namespace {
+
+int fail(char *err, size_t cap, int code, const char *fmt, ...) {
+    if (err && cap) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(err, cap, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+struct Image {
+    msfm_feature_info info{};
+    std::vector<float> xy;  // centred keypoints
+    bool needed = false, loaded = false;
+};
+
+}  // namespace
+
+extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const int64_t *offsets, const int32_t *list,
+                                      const msfm_graph_options *opt, msfm_verify_fn verify, void *user, char *err, size_t err_cap) {
+    if (!fold || num_imgs < 0 || !offsets || !opt) return fail(err, err_cap, -1, "null argument");
+    if (err && err_cap) err[0] = '\0';
+
+    // ---- resume: which images still have to be matched (fine_matching_graph.cc:49-54)
+    std::vector<int32_t> missing((size_t)num_imgs);
+    int32_t n_missing = 0;
+    if (msfm_match_index_missing(fold, num_imgs, missing.data(), &n_missing) != 0) return fail(err, err_cap, -2, "match_index.txt unreadable");
+    if (n_missing == 0) return 0;
+    missing.resize(n_missing);
+    std::vector<char> is_missing((size_t)num_imgs, 0);
+    for (int32_t i : missing) is_missing[i] = 1;
+    std::vector<int32_t> existing;
+    for (int32_t i = 0; i < num_imgs; ++i)
+        if (!is_missing[i]) existing.push_back(i);
+    std::vector<int32_t> graph((size_t)num_imgs * num_imgs, 0);
+    if (msfm_graph_recover(fold, num_imgs, existing.data(), (int32_t)existing.size(), graph.data()) != 0)
+        return fail(err, err_cap, -2, "existing match files unreadable");
+
+    // ---- the images this run touches, their feature headers
+    std::vector<Image> imgs((size_t)num_imgs);
+    std::vector<msfm_pair> pairs;
+    for (int32_t idx1 : missing)
+        for (int64_t j = offsets[idx1]; j < offsets[idx1 + 1]; ++j) {
+            const int32_t idx2 = list[j];
+            if (idx2 < 0 || idx2 >= num_imgs) return fail(err, err_cap, -1, "partner index %d of image %d out of range", idx2, idx1);
+            imgs[idx1].needed = imgs[idx2].needed = true;
+            pairs.push_back({idx1, idx2});  // index on idx1, queries = rows of idx2 (fine_matching_graph.cc:81,99)
+        }
+    int64_t arena_rows = 0;
+    char path[4096];
+    for (int32_t i = 0; i < num_imgs; ++i) {
+        if (!imgs[i].needed) continue;
+        if (msfm_feature_path(fold, i, path, sizeof path) != 0 || msfm_feature_stat(path, &imgs[i].info) != 0)
+            return fail(err, err_cap, -2, "feature file of image %d missing or malformed", i);
+        const msfm_feature_info &fi = imgs[i].info;
+        if (fi.desc_rows > 0 && (fi.desc_cols != 128 || (fi.desc_type != 5 && fi.desc_type != 0)))
+            return fail(err, err_cap, -3, "image %d: descriptors must be N x 128 CV_32FC1 or CV_8UC1 (got cols %d type %d)", i, fi.desc_cols, fi.desc_type);
+        if (fi.desc_rows != fi.num_pts) return fail(err, err_cap, -3, "image %d: %d keypoints but %d descriptor rows", i, fi.num_pts, fi.desc_rows);
+        arena_rows += (fi.desc_rows + 255) / 256 * 256 + 256;
+    }
+
+    // ---- stage every needed image in HBM once (replaces the per-idx1 flann_build_index and the per-pair re-reads)
+    msfm_ctx *ctx = nullptr;
+    if (!pairs.empty()) {
+        msfm_config cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.device = opt->device;
+        cfg.max_images = num_imgs;
+        cfg.arena_rows = arena_rows > 0 ? arena_rows : 256;
+        cfg.keep_float = opt->rescore_band > 0.0f ? 1 : 0;
+        msfm_status st = msfm_create(&cfg, &ctx);
+        if (st != MSFM_OK) return fail(err, err_cap, -4, "msfm_create: %s", msfm_status_string(st));
+    }
+    auto bail = [&](int code, const std::string &msg) {
+        if (ctx) msfm_destroy(ctx);
+        return fail(err, err_cap, code, "%s", msg.c_str());
+    };
+    std::vector<char> staging;
+    for (int32_t i = 0; ctx && i < num_imgs; ++i) {
+        if (!imgs[i].needed) continue;
+        const msfm_feature_info &fi = imgs[i].info;
+        imgs[i].xy.resize((size_t)fi.num_pts * 2);
+        staging.resize((size_t)fi.desc_rows * 128 * fi.desc_elem_size + 16);
+        msfm_feature_path(fold, i, path, sizeof path);
+        if (msfm_feature_read(path, &fi, nullptr, nullptr, imgs[i].xy.data(), staging.data(), (int64_t)128 * fi.desc_elem_size) != 0)
+            return bail(-2, "feature file of image " + std::to_string(i) + " truncated");
+        msfm_status st = fi.desc_type == 0
+                             ? msfm_upload_u8(ctx, i, reinterpret_cast<const uint8_t *>(staging.data()), fi.desc_rows, 128)
+                             : msfm_upload_f32(ctx, i, reinterpret_cast<const float *>(staging.data()), fi.desc_rows, 128, opt->descriptor_scale);
+        if (st != MSFM_OK) return bail(-4, std::string("upload: ") + msfm_last_error(ctx));
+    }
+
+    // ---- the whole candidate pair list in one batch: "all" list + good flags per pair
+    std::vector<int64_t> moff(pairs.size() + 1, 0);
+    std::vector<int32_t> okflags(pairs.size(), 0);
+    int64_t capacity = 0;
+    for (const msfm_pair &pr : pairs) capacity += imgs[pr.query].info.desc_rows;
+    std::vector<int32_t> mbuf((size_t)(capacity > 0 ? capacity : 1) * 2);
+    std::vector<uint8_t> gbuf((size_t)(capacity > 0 ? capacity : 1));
+    if (!pairs.empty()) {
+        msfm_params prm;
+        memset(&prm, 0, sizeof prm);
+        prm.ratio = opt->th_all;
+        prm.ratio_good = opt->th_good;
+        prm.mutual = opt->mutual;
+        prm.min_keypoints = opt->min_keypoints;
+        prm.orientation = 0;  // (ptid1, ptid2) ascending ptid2 (fine_matching_graph.cc:121,127)
+        prm.rescore_band = opt->rescore_band;
+        msfm_result res;
+        res.offsets = moff.data();
+        res.ok = okflags.data();
+        res.matches = reinterpret_cast<int32_t(*)[2]>(mbuf.data());
+        res.good = gbuf.data();
+        res.match_capacity = capacity;
+        msfm_status st = msfm_match_pairs(ctx, pairs.data(), (int64_t)pairs.size(), &prm, &res);
+        if (st != MSFM_OK) return bail(-4, std::string("msfm_match_pairs: ") + msfm_last_error(ctx));
+    }
+    if (ctx) msfm_destroy(ctx);
+
+    // ---- verification seam + output, in the reference's order (idx1 ascending over the missing list, partners in
+    //      list order); match_index.txt gets its line when idx1 is complete (fine_matching_graph.cc:137-191)
+    size_t p = 0;
+    std::vector<int32_t> keep, kept;
+    for (int32_t idx1 : missing) {
+        for (int64_t j = offsets[idx1]; j < offsets[idx1 + 1]; ++j, ++p) {
+            const int32_t idx2 = list[j];
+            const int32_t n = (int32_t)(moff[p + 1] - moff[p]);
+            const int32_t(*m)[2] = reinterpret_cast<const int32_t(*)[2]>(mbuf.data()) + moff[p];
+            const uint8_t *g = gbuf.data() + moff[p];
+            if (!okflags[p]) continue;
+            keep.resize((size_t)n);
+            int32_t n_keep = 0;
+            int accept = 1;
+            if (verify) {
+                accept = verify(user, idx1, idx2, imgs[idx1].xy.data(), imgs[idx1].info.num_pts, imgs[idx2].xy.data(),
+                                imgs[idx2].info.num_pts, m, g, n, keep.data(), &n_keep);
+            } else {
+                int32_t n_good = 0;
+                for (int32_t k = 0; k < n; ++k) n_good += g[k];
+                accept = n_good >= opt->min_good;
+                for (int32_t k = 0; k < n; ++k) keep[k] = k;
+                n_keep = n;
+            }
+            if (!accept) continue;
+            kept.resize((size_t)n_keep * 2);
+            for (int32_t k = 0; k < n_keep; ++k) { kept[2 * k] = m[keep[k]][0]; kept[2 * k + 1] = m[keep[k]][1]; }
+            if (msfm_match_append(fold, idx1, idx2, reinterpret_cast<const int32_t(*)[2]>(kept.data()), n_keep) != 0)
+                return fail(err, err_cap, -2, "cannot append to the match file of image %d", idx1);
+            graph[(size_t)idx1 * num_imgs + idx2] = n_keep;
+        }
+        if (msfm_match_index_append(fold, idx1) != 0) return fail(err, err_cap, -2, "cannot append to match_index.txt");
+    }
+    if (msfm_graph_write(fold, num_imgs, graph.data()) != 0) return fail(err, err_cap, -2, "cannot write graph_matching.txt");
+    return 0;
+}

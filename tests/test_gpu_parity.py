@@ -1,6 +1,8 @@
 """GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the CPU oracle on
 the same seeded inputs, against the committed golden vectors of the reference engine, and through size-independent
 properties at full size.  Bar: bit-exact ids, distances and match lists (integer regime)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -388,3 +390,62 @@ def test_float_regime_needs_retained_rows(oracle_mod, matcher):
     r1 = matcher.match_pairs([(0, 1)], 0.85, ratio_good=0.6, mutual=True, rescore_band=0.05)
     np.testing.assert_array_equal(r0.pair(0), r1.pair(0))
     np.testing.assert_array_equal(r0.pair_good(0), r1.pair_good(0))
+
+
+# ---------------------------------------------------------------------------------------------------- graph driver
+def test_build_match_graph_driver_writes_reference_files(oracle_mod, native_lib, tmp_path):
+    """FineMatchingGraph::BuildMatchGraph rebuilt on the GPU matcher: feature files in, <idx>_match / match_index.txt /
+    graph_matching.txt out — byte-identical to the reference's control flow driven by the CPU oracle's match lists,
+    including resume after an interrupted run."""
+    import shutil
+    from metricsfm_b200 import build, store
+    from oracle import store_oracle as so
+    build.build_host_libs()
+    n_img = 6
+    col = synth.Collection(1500, seed=21)
+    rows = [1500, 1200, 900, 1500, 19, 640]                       # image 4 is below the 20-keypoint gate
+    imgs = [col.image_u8(i, r) for i, r in enumerate(rows)]
+    rng = np.random.default_rng(5)
+    fold_gpu, fold_ref = str(tmp_path / "gpu"), str(tmp_path / "ref")
+    os.makedirs(fold_gpu), os.makedirs(fold_ref)
+    for i, d in enumerate(imgs):
+        xy = rng.uniform(0, 3000, size=(d.shape[0], 2)).astype(np.float32)
+        # VLSIFT container: integer-valued floats in a CV_32FC1 matrix (odd images) / CV_8UC1 rows (even images)
+        store.feature_write(store.feature_path(fold_gpu, i), rows=3000, cols=4000, xy_pixel=xy,
+                            desc=d.astype(np.float32) if i % 2 else d)
+    adj = [[1, 2, 4], [0, 3], [5], [], [0], [2, 3]]
+    offs = np.cumsum([0] + [len(a) for a in adj]).astype(np.int64)
+    lst = np.array([j for a in adj for j in a], np.int32)
+
+    def match_fn(i1, i2):
+        r = oracle_mod.match_pair_u8(imgs[i1], imgs[i2], 0.85, ratio_good=0.6, mutual=True, min_keypoints=20)
+        return r["ok"], r["pairs"], r["good"]
+
+    # interrupted run: images 0 and 1 already finished (their files come from the reference flow)
+    so.build_match_graph_files(fold_ref, [adj[0], adj[1]] + [[] for _ in range(4)], match_fn, min_good=5)
+    os.remove(fold_ref + "//graph_matching.txt")
+    open(fold_ref + "//match_index.txt", "w").write("0\n1\n")
+    for name in ("0_match", "1_match", "match_index.txt"):
+        shutil.copy(fold_ref + "//" + name, fold_gpu + "//" + name)
+    so.build_match_graph_files(fold_ref, adj, match_fn, min_good=5)
+    store.build_match_graph(fold_gpu, offs, lst, mutual=True, min_keypoints=20, min_good=5)
+    names = sorted(f for f in os.listdir(fold_ref))
+    assert names == sorted(f for f in os.listdir(fold_gpu) if not f.endswith("_feature"))
+    assert {"0_match", "2_match", "graph_matching.txt", "match_index.txt"} <= set(names)
+    for name in names:
+        assert open(fold_ref + "//" + name, "rb").read() == open(fold_gpu + "//" + name, "rb").read(), name
+    # a second call finds nothing missing and leaves the files alone
+    before = {n: os.path.getmtime(fold_gpu + "//" + n) for n in names}
+    store.build_match_graph(fold_gpu, offs, lst, mutual=True, min_keypoints=20, min_good=5)
+    assert before == {n: os.path.getmtime(fold_gpu + "//" + n) for n in names}
+    # the verification seam: keep only the good matches of accepted pairs
+    fold_v = str(tmp_path / "verify")
+    os.makedirs(fold_v)
+    for i in range(n_img):
+        shutil.copy(store.feature_path(fold_gpu, i), store.feature_path(fold_v, i))
+    store.build_match_graph(fold_v, offs, lst, mutual=True, min_keypoints=20,
+                            verify=lambda i1, i2, xy1, xy2, m, g: (int(g.sum()) >= 5, np.nonzero(g)[0]))
+    ids, lists = store.match_read(fold_v, 0)
+    exp = oracle_mod.match_pair_u8(imgs[0], imgs[1], 0.85, ratio_good=0.6, mutual=True)
+    assert ids[0] == 1
+    np.testing.assert_array_equal(lists[0], exp["pairs"][exp["good"] == 1])
