@@ -8,8 +8,8 @@
  *                -> every image's descriptors are read from its <idx>_feature file and staged in HBM once, the whole
  *                   candidate pair list of the missing images goes through msfm_match_pairs in one batch
  *   verify     GeoVerification::GeoVerificationFundamental on the good set, F-filter on the all set (:137-153)
- *                -> the msfm_verify_fn seam; NULL keeps every "all" match of a pair that has at
- *                   least `min_good` good matches
+ *                -> msfm_graph_options.geo_verify: msfm_geo_verify on the GPU for the whole batch; or the msfm_verify_fn
+ *                   callback seam; with neither, every "all" match of a pair with >= `min_good` good matches is kept
  *   output     WriteOutMatches per accepted pair, match_index.txt line per finished idx1, graph_matching.txt (:181-193)
  * The files written are byte-identical to what the reference writes for the same match lists.
  */
@@ -33,6 +33,10 @@ typedef struct msfm_graph_options {
                                 needs >= 30 points, utils/geo_verification.cc:30-58); 0 = keep all */
     float descriptor_scale;  /* float descriptors: quantisation scale (1 for 512-scaled VLSIFT rows, 512 for unit-norm) */
     float rescore_band;      /* float descriptors: fp32 re-scoring band (msfm_params.rescore_band); 0 = off */
+    int32_t geo_verify;      /* 1 (and no callback): the reference's GeoVerificationFundamental stages on the GPU for the
+                                whole batch (msfm_geo_verify: >= 30 good matches, RANSAC-F 3 px, >= 30 inliers, then the
+                                F-filter of the "all" set); rejected pairs leave no record, like the reference */
+    uint32_t geo_seed;       /* RANSAC stream of msfm_geo_verify */
 } msfm_graph_options;
 
 /* Geo-verification seam.  xy1/xy2: centred keypoints of both images as stored in the feature files; matches: the

@@ -168,6 +168,33 @@ msfm_status msfm_last_timing(const msfm_ctx *ctx, msfm_timing *out);
  * its own events around calls (bench.py) or order foreign work (a collective filling the table) against it. */
 msfm_status msfm_get_stream(const msfm_ctx *ctx, void **cuda_stream);
 
+/* ---- geometric verification of the matched pairs (the stage after the hot path) ---------- */
+/* FineMatchingGraph::BuildMatchGraph verifies every pair (fine_matching_graph.cc:137-153) with
+ *   A  GeoVerificationFundamental(pt_good): >= min_points good matches, F by RANSAC (7-point, error = max of the two
+ *      squared point-to-epipolar-line distances <= th^2 like cv::findFundamentalMat FM_RANSAC), >= min_inliers inliers
+ *      (utils/geo_verification.cc:30-58)
+ *   B  GeoVerificationFundamental(pt_all, F): keep the "all" matches with |distance(p2, F p1)| < th, double arithmetic
+ *      (utils/geo_verification.cc:60-79)
+ * Here the whole batch runs on the GPU, one CTA per pair.  RANSAC draws are counter-based (seed, pair, hypothesis):
+ * reproducible, but not OpenCV's RNG stream, so stage A agrees with the reference statistically, stage B exactly
+ * given F. */
+typedef struct msfm_geo_params {
+    float th_epipolar;     /* 3.0  utils/geo_verification.cc:45,66 */
+    int32_t min_points;    /* 30   utils/geo_verification.cc:33 */
+    int32_t min_inliers;   /* 30   utils/geo_verification.cc:53 */
+    int32_t iters;         /* RANSAC hypotheses per pair (each yields up to 3 models); 0 = 1024 */
+    uint64_t seed;
+} msfm_geo_params;
+/* pairs/offsets/matches/good: the result of msfm_match_pairs with orientation 0 and ratio_good set.
+ * image_xy[i]: host pointer to the centred keypoints (x, y) of image i as stored in its feature file, or NULL for
+ * images no pair touches; image_npts[i] their number.  Outputs (host): pair_ok[n_pairs], pair_inliers[n_pairs]
+ * (stage-A inliers among the good matches), keep[offsets[n_pairs]] (stage-B mask over the "all" matches; all zero for
+ * rejected pairs), F[n_pairs][9] row-major or NULL. */
+msfm_status msfm_geo_verify(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const int64_t *offsets,
+                            const int32_t (*matches)[2], const uint8_t *good, const float *const *image_xy,
+                            const int32_t *image_npts, int32_t n_images, const msfm_geo_params *gp, int32_t *pair_ok,
+                            int32_t *pair_inliers, uint8_t *keep, double *F);
+
 /* ---- GPU-side cross-check kernel (CUDA cores, dp4a); used by the tests to localise faults, never by the fast path */
 msfm_status msfm_knn2_crosscheck(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_t *ids, float *dists);
 

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "msfm_abi_version", "msfm_status_string", "msfm_create", "msfm_destroy", "msfm_last_error", "msfm_upload_u8",
     "msfm_upload_f32", "msfm_reserve", "msfm_release", "msfm_release_all", "msfm_image_info", "msfm_table_ptrs",
     "msfm_download_packed", "msfm_knn2", "msfm_colbest", "msfm_match_pairs", "msfm_match_pairs_resident",
-    "msfm_last_timing", "msfm_get_stream", "msfm_knn2_crosscheck",
+    "msfm_last_timing", "msfm_get_stream", "msfm_knn2_crosscheck", "msfm_geo_verify",
 ]
 
 
@@ -37,6 +37,11 @@ class Config(C.Structure):
 class Params(C.Structure):
     _fields_ = [("ratio", C.c_float), ("ratio_good", C.c_float), ("max_dist_sq", C.c_float), ("mutual", C.c_int32),
                 ("min_keypoints", C.c_int32), ("orientation", C.c_int32), ("rescore_band", C.c_float)]
+
+
+class GeoParams(C.Structure):
+    _fields_ = [("th_epipolar", C.c_float), ("min_points", C.c_int32), ("min_inliers", C.c_int32), ("iters", C.c_int32),
+                ("seed", C.c_uint64)]
 
 
 class Pair(C.Structure):
@@ -88,6 +93,7 @@ def load() -> C.CDLL:
     L.msfm_last_timing.argtypes = [vp, C.POINTER(Timing)]
     L.msfm_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.msfm_knn2_crosscheck.argtypes = [vp, C.c_int32, C.c_int32, vp, vp]
+    L.msfm_geo_verify.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp, C.c_int32, C.POINTER(GeoParams), vp, vp, vp, vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
         if name not in ("msfm_abi_version", "msfm_status_string", "msfm_last_error"):

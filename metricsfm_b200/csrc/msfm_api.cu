@@ -19,6 +19,7 @@
 
 #include "../../include/msfm_match.h"
 #include "aux_kernels.cuh"
+#include "geo_kernels.cuh"
 #include "match_kernel.cuh"
 
 namespace {
@@ -897,6 +898,97 @@ msfm_status msfm_get_stream(const msfm_ctx *ctx, void **cuda_stream) {
     if (!ctx || !cuda_stream) return MSFM_ERR_INVALID_ARG;
     *cuda_stream = static_cast<void *>(ctx->stream);
     return MSFM_OK;
+}
+
+msfm_status msfm_geo_verify(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const int64_t *offsets,
+                            const int32_t (*matches)[2], const uint8_t *good, const float *const *image_xy,
+                            const int32_t *image_npts, int32_t n_images, const msfm_geo_params *gp, int32_t *pair_ok,
+                            int32_t *pair_inliers, uint8_t *keep, double *F) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (n_pairs < 0 || !gp || (n_pairs > 0 && (!pairs || !offsets || !pair_ok || !pair_inliers || !image_xy || !image_npts)))
+        return fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_geo_verify: null argument");
+    if (n_pairs == 0) return MSFM_OK;
+    const int64_t total = offsets[n_pairs];
+    if (total < 0 || (total > 0 && (!matches || !good || !keep))) return fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_geo_verify: null match buffers");
+    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    // keypoints of the images the pairs touch, concatenated
+    std::vector<int64_t> xy_off((size_t)n_images + 1, 0);
+    std::vector<char> used((size_t)n_images, 0);
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        if (pairs[p].ref < 0 || pairs[p].ref >= n_images || pairs[p].query < 0 || pairs[p].query >= n_images)
+            return fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_geo_verify: pair %lld names an image outside [0, %d)", (long long)p, n_images);
+        used[pairs[p].ref] = used[pairs[p].query] = 1;
+    }
+    for (int32_t i = 0; i < n_images; ++i) {
+        if (used[i] && (image_npts[i] < 0 || (image_npts[i] > 0 && !image_xy[i])))
+            return fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_geo_verify: image %d has no keypoints", i);
+        xy_off[i + 1] = xy_off[i] + (used[i] ? image_npts[i] : 0);
+    }
+    for (int64_t p = 0; p < n_pairs; ++p)
+        for (int64_t k = offsets[p]; k < offsets[p + 1]; ++k)
+            if (matches[k][0] < 0 || matches[k][0] >= image_npts[pairs[p].ref] || matches[k][1] < 0 || matches[k][1] >= image_npts[pairs[p].query])
+                return fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_geo_verify: match %lld of pair %lld indexes past the keypoints", (long long)k, (long long)p);
+    const int64_t n_xy = xy_off[n_images];
+    std::vector<float> xy((size_t)std::max<int64_t>(n_xy, 1) * 2);
+    for (int32_t i = 0; i < n_images; ++i)
+        if (used[i] && image_npts[i] > 0) memcpy(xy.data() + 2 * xy_off[i], image_xy[i], (size_t)image_npts[i] * 8);
+    std::vector<int32_t> pimg((size_t)n_pairs * 2);
+    for (int64_t p = 0; p < n_pairs; ++p) { pimg[2 * p] = pairs[p].ref; pimg[2 * p + 1] = pairs[p].query; }
+
+    DeviceBuf d_xy, d_xyoff, d_off, d_m, d_g, d_pimg, d_ok, d_inl, d_keep, d_F;
+    DeviceBuf *bufs[] = {&d_xy, &d_xyoff, &d_off, &d_m, &d_g, &d_pimg, &d_ok, &d_inl, &d_keep, &d_F};
+    auto cleanup = [&](msfm_status st) {
+        cudaStreamSynchronize(ctx->stream);
+        for (DeviceBuf *b : bufs)
+            if (b->ptr) cudaFree(b->ptr);
+        return st;
+    };
+    msfm_status st;
+    const size_t tot = (size_t)std::max<int64_t>(total, 1);
+    if ((st = ensure(ctx, d_xy, xy.size() * 4)) != MSFM_OK || (st = ensure(ctx, d_xyoff, xy_off.size() * 8)) != MSFM_OK ||
+        (st = ensure(ctx, d_off, (size_t)(n_pairs + 1) * 8)) != MSFM_OK || (st = ensure(ctx, d_m, tot * 8)) != MSFM_OK ||
+        (st = ensure(ctx, d_g, tot)) != MSFM_OK || (st = ensure(ctx, d_pimg, pimg.size() * 4)) != MSFM_OK ||
+        (st = ensure(ctx, d_ok, (size_t)n_pairs * 4)) != MSFM_OK || (st = ensure(ctx, d_inl, (size_t)n_pairs * 4)) != MSFM_OK ||
+        (st = ensure(ctx, d_keep, tot)) != MSFM_OK || (st = ensure(ctx, d_F, (size_t)n_pairs * 72)) != MSFM_OK)
+        return cleanup(st);
+    cudaMemcpyAsync(d_xy.ptr, xy.data(), xy.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_xyoff.ptr, xy_off.data(), xy_off.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_off.ptr, offsets, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (total > 0) {
+        cudaMemcpyAsync(d_m.ptr, matches, (size_t)total * 8, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_g.ptr, good, (size_t)total, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    cudaMemcpyAsync(d_pimg.ptr, pimg.data(), pimg.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    msfm::GeoParams kp;
+    kp.offsets = static_cast<const int64_t *>(d_off.ptr);
+    kp.matches = static_cast<const int2 *>(d_m.ptr);
+    kp.good = static_cast<const uint8_t *>(d_g.ptr);
+    kp.pair_img = static_cast<const int32_t *>(d_pimg.ptr);
+    kp.xy = static_cast<const float *>(d_xy.ptr);
+    kp.xy_off = static_cast<const int64_t *>(d_xyoff.ptr);
+    kp.th = gp->th_epipolar;
+    kp.min_points = gp->min_points;
+    kp.min_inliers = gp->min_inliers;
+    kp.iters = gp->iters > 0 ? gp->iters : 1024;
+    kp.seed = gp->seed;
+    kp.pair_ok = static_cast<int32_t *>(d_ok.ptr);
+    kp.pair_inliers = static_cast<int32_t *>(d_inl.ptr);
+    kp.keep = static_cast<uint8_t *>(d_keep.ptr);
+    kp.F = static_cast<double *>(d_F.ptr);
+    cudaEventRecord(ctx->ev_k0, ctx->stream);
+    msfm::geo_verify_kernel<<<(int)std::min<int64_t>(n_pairs, 8 * ctx->num_sms), msfm::kGeoThreads, 0, ctx->stream>>>(kp, (int)n_pairs);
+    cudaEventRecord(ctx->ev_k1, ctx->stream);
+    if (cudaGetLastError() != cudaSuccess) return cleanup(fail(ctx, MSFM_ERR_CUDA, "geo_verify_kernel launch failed"));
+    cudaMemcpyAsync(pair_ok, d_ok.ptr, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(pair_inliers, d_inl.ptr, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (total > 0) cudaMemcpyAsync(keep, d_keep.ptr, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream);
+    if (F) cudaMemcpyAsync(F, d_F.ptr, (size_t)n_pairs * 72, cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return cleanup(fail(ctx, MSFM_ERR_CUDA, "msfm_geo_verify: %s", cudaGetErrorString(cudaGetLastError())));
+    ctx->timing = msfm_timing{};
+    cudaEventElapsedTime(&ctx->timing.finalize_ms, ctx->ev_k0, ctx->ev_k1);
+    ctx->timing.total_launches = 1;
+    return cleanup(MSFM_OK);
 }
 
 msfm_status msfm_knn2_crosscheck(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_t *ids, float *dists) {

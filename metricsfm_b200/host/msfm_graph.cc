@@ -128,6 +128,28 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
         msfm_status st = msfm_match_pairs(ctx, pairs.data(), (int64_t)pairs.size(), &prm, &res);
         if (st != MSFM_OK) return bail(-4, std::string("msfm_match_pairs: ") + msfm_last_error(ctx));
     }
+    // ---- GeoVerificationFundamental for the whole batch on the GPU (fine_matching_graph.cc:137-153)
+    std::vector<int32_t> geo_ok;
+    std::vector<uint8_t> geo_keep;
+    if (ctx && opt->geo_verify && !verify && !pairs.empty()) {
+        std::vector<const float *> xy_ptr((size_t)num_imgs, nullptr);
+        std::vector<int32_t> npts((size_t)num_imgs, 0);
+        for (int32_t i = 0; i < num_imgs; ++i)
+            if (imgs[i].needed) { xy_ptr[i] = imgs[i].xy.data(); npts[i] = imgs[i].info.num_pts; }
+        msfm_geo_params gp;
+        memset(&gp, 0, sizeof gp);
+        gp.th_epipolar = 3.0f;   // utils/geo_verification.cc:45,66
+        gp.min_points = 30;      // :33
+        gp.min_inliers = 30;     // :53
+        gp.iters = 1024;
+        gp.seed = opt->geo_seed;
+        geo_ok.assign(pairs.size(), 0);
+        std::vector<int32_t> inl(pairs.size(), 0);
+        geo_keep.assign((size_t)(moff[pairs.size()] > 0 ? moff[pairs.size()] : 1), 0);
+        msfm_status st = msfm_geo_verify(ctx, pairs.data(), (int64_t)pairs.size(), moff.data(), reinterpret_cast<const int32_t(*)[2]>(mbuf.data()),
+                                         gbuf.data(), xy_ptr.data(), npts.data(), num_imgs, &gp, geo_ok.data(), inl.data(), geo_keep.data(), nullptr);
+        if (st != MSFM_OK) return bail(-4, std::string("msfm_geo_verify: ") + msfm_last_error(ctx));
+    }
     if (ctx) msfm_destroy(ctx);
 
     // ---- verification seam + output, in the reference's order (idx1 ascending over the missing list, partners in
@@ -147,6 +169,10 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
             if (verify) {
                 accept = verify(user, idx1, idx2, imgs[idx1].xy.data(), imgs[idx1].info.num_pts, imgs[idx2].xy.data(),
                                 imgs[idx2].info.num_pts, m, g, n, keep.data(), &n_keep);
+            } else if (!geo_ok.empty()) {
+                accept = geo_ok[p];
+                for (int32_t k = 0; k < n; ++k)
+                    if (geo_keep[moff[p] + k]) keep[n_keep++] = k;
             } else {
                 int32_t n_good = 0;
                 for (int32_t k = 0; k < n; ++k) n_good += g[k];

@@ -220,6 +220,35 @@ class Matcher:
         self._check(self._L.msfm_match_pairs_resident(self._h, pa.ctypes.data, pa.shape[0], C.byref(prm), C.byref(total)))
         return total.value
 
+    def geo_verify(self, pairs, result: "MatchResult", image_xy: dict, *, th_epipolar: float = 3.0, min_points: int = 30,
+                   min_inliers: int = 30, iters: int = 1024, seed: int = 0):
+        """Batched GeoVerificationFundamental (utils/geo_verification.cc:30-79) of the pairs of a match_pairs result
+        (orientation 0, ratio_good set).  image_xy: {image id: [n, 2] float32 centred keypoints}.  Returns
+        (pair_ok [n] int32, pair_inliers [n] int32, keep [total] uint8, F [n, 3, 3] float64)."""
+        pa = self._pairs(pairs)
+        n = pa.shape[0]
+        n_images = int(pa.max()) + 1 if n else 0
+        xy_keep, ptrs, npts = [], (C.c_void_p * max(n_images, 1))(), np.zeros((max(n_images, 1),), np.int32)
+        for i, xy in image_xy.items():
+            if i < n_images:
+                a = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+                xy_keep.append(a)
+                ptrs[i] = a.ctypes.data
+                npts[i] = a.shape[0]
+        gp = _lib.GeoParams(th_epipolar, min_points, min_inliers, iters, seed)
+        total = int(result.offsets[n])
+        ok = np.zeros((max(n, 1),), np.int32)
+        inl = np.zeros((max(n, 1),), np.int32)
+        keep = np.zeros((max(total, 1),), np.uint8)
+        F = np.zeros((max(n, 1), 3, 3), np.float64)
+        offs = np.ascontiguousarray(result.offsets, np.int64)
+        m = np.ascontiguousarray(result.matches, np.int32)
+        g = np.ascontiguousarray(result.good if result.good is not None else np.ones((total,), np.uint8), np.uint8)
+        self._check(self._L.msfm_geo_verify(self._h, pa.ctypes.data, n, offs.ctypes.data, m.ctypes.data if total else None,
+                                            g.ctypes.data if total else None, C.cast(ptrs, C.c_void_p), npts.ctypes.data, n_images,
+                                            C.byref(gp), ok.ctypes.data, inl.ctypes.data, keep.ctypes.data, F.ctypes.data))
+        return ok[:n], inl[:n], keep[:total], F[:n]
+
     def cuda_stream(self) -> int:
         """Raw cudaStream_t of this context (wrap with torch.cuda.ExternalStream to record events on it)."""
         s = C.c_void_p()

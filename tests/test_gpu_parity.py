@@ -449,3 +449,117 @@ def test_build_match_graph_driver_writes_reference_files(oracle_mod, native_lib,
     exp = oracle_mod.match_pair_u8(imgs[0], imgs[1], 0.85, ratio_good=0.6, mutual=True)
     assert ids[0] == 1
     np.testing.assert_array_equal(lists[0], exp["pairs"][exp["good"] == 1])
+
+
+# ---------------------------------------------------------------------------------------------------- geo-verification
+def _two_view_scene(rng, n_true, n_out, noise=0.5, f=3000.0):
+    """Centred pixel coordinates of n_true correspondences of a rigid scene in two views + n_out random outliers."""
+    X = np.concatenate([rng.uniform(-40, 40, (n_true, 2)), rng.uniform(60, 140, (n_true, 1))], 1)
+    ang = np.deg2rad(rng.uniform(4, 10))
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    t = np.array([rng.uniform(8, 15), rng.uniform(-2, 2), rng.uniform(-1, 1)])
+    p1 = f * X[:, :2] / X[:, 2:3]
+    Xc = X @ R.T + t
+    p2 = f * Xc[:, :2] / Xc[:, 2:3]
+    p1 = p1 + rng.normal(0, noise, p1.shape)
+    p2 = p2 + rng.normal(0, noise, p2.shape)
+    o1, o2 = rng.uniform(-1800, 1800, (n_out, 2)), rng.uniform(-1800, 1800, (n_out, 2))
+    return np.concatenate([p1, o1]).astype(np.float32), np.concatenate([p2, o2]).astype(np.float32)
+
+
+def test_geo_verification_against_opencv_and_restatement(matcher):
+    """Batched GPU GeoVerificationFundamental (utils/geo_verification.cc:30-79): stage B is exact given F (numpy
+    restatement); stage A agrees with cv2.findFundamentalMat(FM_RANSAC, 3 px) on decisions and inlier sets."""
+    import cv2
+    from metricsfm_b200.matcher import MatchResult
+    from oracle import geo_oracle as go
+    rng = np.random.default_rng(31)
+    scenes = [(_two_view_scene(rng, 400, 130), 380),      # rigid scene, 25 % outliers, 380 "good" of 530 "all"
+              (_two_view_scene(rng, 90, 60), 120),
+              (_two_view_scene(rng, 25, 0), 25),          # fewer than 30 good matches: rejected before RANSAC
+              (_two_view_scene(rng, 0, 300), 200),        # no geometry at all: rejected (inliers < 30)
+              (_two_view_scene(rng, 3000, 900), 2600)]    # more good matches than the shared-memory point cap
+    image_xy, pairs, offsets, matches, good = {}, [], [0], [], []
+    for s, ((p1, p2), n_good) in enumerate(scenes):
+        n = len(p1)
+        perm1, perm2 = rng.permutation(n), rng.permutation(n)      # keypoint ids are not in match order
+        xy1, xy2 = np.empty_like(p1), np.empty_like(p2)
+        xy1[perm1], xy2[perm2] = p1, p2
+        image_xy[2 * s], image_xy[2 * s + 1] = xy1, xy2
+        pairs.append((2 * s, 2 * s + 1))
+        m = np.stack([perm1, perm2], 1).astype(np.int32)
+        gflag = np.zeros((n,), np.uint8)
+        gflag[rng.choice(n, n_good, replace=False)] = 1
+        matches.append(m), good.append(gflag), offsets.append(offsets[-1] + n)
+    res = MatchResult(offsets=np.array(offsets, np.int64), ok=np.ones((len(pairs),), np.int32), matches=np.concatenate(matches),
+                      good=np.concatenate(good))
+    ok, inl, keep, F = matcher.geo_verify(pairs, res, image_xy, seed=7)
+    ok2, inl2, keep2, F2 = matcher.geo_verify(pairs, res, image_xy, seed=7)
+    np.testing.assert_array_equal(ok, ok2), np.testing.assert_array_equal(keep, keep2), np.testing.assert_array_equal(F, F2)
+    assert ok.tolist() == [1, 1, 0, 0, 1]
+    for s, ((p1, p2), n_good) in enumerate(scenes):
+        a, b = offsets[s], offsets[s + 1]
+        g = good[s].astype(bool)
+        k = keep[a:b].astype(bool)
+        if not ok[s]:
+            assert not k.any()
+            continue
+        # exact restatement around the returned F: stage-A inlier count and stage-B mask
+        eok, einl, ekeep = go.verify_pair(p1[g], p2[g], p1, p2, F[s])
+        assert eok and einl == inl[s]
+        np.testing.assert_array_equal(k, ekeep)
+        # statistical parity with OpenCV's RANSAC
+        Fcv, mask = cv2.findFundamentalMat(p1[g], p2[g], cv2.FM_RANSAC, 3.0, 0.99)
+        n_cv = int(mask.sum())
+        n_true = [400, 90, 25, 0, 3000][s]
+        true_good = int(g[:n_true].sum())
+        # OpenCV stops at 99 % confidence, so its consensus set is a lower bound; the true correspondences among the
+        # good matches (plus the odd outlier that happens to lie on an epipolar line) are the upper bound
+        assert n_cv >= 30 and 0.97 * n_cv - 3 <= inl[s] <= true_good + 0.06 * (g.sum() - true_good) + 3, (inl[s], n_cv, true_good)
+        kcv = go.f_filter(Fcv, p1, p2)
+        # what the filter around OpenCV's F keeps is (nearly) contained in what ours keeps; the excess is bounded by
+        # the ground truth below
+        assert (k & kcv).sum() >= 0.97 * kcv.sum(), ((k & kcv).sum(), kcv.sum())
+        assert k[:n_true].mean() >= 0.97                               # true correspondences survive
+        assert k[n_true:].mean() <= 0.12                               # random outliers rarely lie within 3 px of a line
+    _, _, keep3, _ = matcher.geo_verify(pairs, res, image_xy, seed=8)   # another RANSAC stream: same decisions, ~same sets
+    assert (keep3 != keep).mean() < 0.01
+
+
+def test_build_match_graph_with_gpu_geo_verification(oracle_mod, native_lib, tmp_path):
+    """The driver with the reference's verification stages on the GPU: descriptors decide the matches, keypoints of a
+    rigid two-view scene decide which survive; a pair without common geometry leaves no record."""
+    from metricsfm_b200 import build, store
+    from oracle import geo_oracle as go
+    build.build_host_libs()
+    rng = np.random.default_rng(41)
+    n = 1200
+    col = synth.Collection(n, seed=33)
+    base = col.image_u8(0)
+    # image 1 = image 0 re-observed (same descriptors, permuted, slightly perturbed), image 2 = unrelated descriptors
+    perm = rng.permutation(n)
+    d1 = np.clip(base[perm].astype(np.int32) + rng.integers(-2, 3, size=(n, 128)), 0, 255).astype(np.uint8)
+    d2 = col.image_u8(5)
+    p0, p1 = _two_view_scene(rng, n, 0)
+    xy = [p0, p1[perm], rng.uniform(-1800, 1800, (n, 2)).astype(np.float32)]
+    xy[1][: n // 5] = rng.uniform(-1800, 1800, (n // 5, 2))           # 20 % of the re-observations moved: outliers
+    fold = str(tmp_path)
+    for i, (d, p) in enumerate(zip([base, d1, d2], xy)):
+        # the writer centres pixel coordinates: feed "pixel" coordinates that centre back onto the scene coordinates
+        store.feature_write(store.feature_path(fold, i), rows=4000, cols=4000, xy_pixel=p + 2000.0, desc=d)
+    adj = [[1, 2], [], []]
+    offs = np.cumsum([0] + [len(a) for a in adj]).astype(np.int64)
+    store.build_match_graph(fold, offs, np.array([1, 2], np.int32), geo_verify=True, geo_seed=3)
+    ids, lists = store.match_read(fold, 0)
+    assert ids.tolist() == [1]                                         # the unrelated pair was rejected
+    kept = lists[0]
+    exp = oracle_mod.match_pair_u8(base, d1, 0.85, ratio_good=0.6)["pairs"]
+    assert {tuple(m) for m in kept} <= {tuple(m) for m in exp} and len(kept) > 0.7 * len(exp)
+    # every kept match is a descriptor match whose keypoints agree with ONE epipolar geometry: refit F on them
+    import cv2
+    F, _ = cv2.findFundamentalMat(xy[0][kept[:, 0]], xy[1][kept[:, 1]], cv2.FM_LMEDS)
+    assert go.f_filter(F, xy[0][kept[:, 0]], xy[1][kept[:, 1]], 4.0).mean() > 0.97
+    moved = np.isin(kept[:, 1], np.arange(n // 5))
+    assert moved.mean() < 0.03                                         # the moved keypoints were filtered out
+    g = store.graph_read(fold, 3)
+    assert g[0, 1] == len(kept) and g[0, 2] == 0
