@@ -45,7 +45,7 @@ __device__ __forceinline__ double det3(const double *m) {
 }
 
 // Real roots of c3 x^3 + c2 x^2 + c1 x + c0 (degenerate leading coefficients handled); returns their number.
-__device__ int solve_cubic(double c3, double c2, double c1, double c0, double *r) {
+static __device__ int solve_cubic(double c3, double c2, double c1, double c0, double *r) {
     const double eps = 1e-14;
     if (fabs(c3) < eps * (fabs(c2) + fabs(c1) + fabs(c0) + 1e-300)) {
         if (fabs(c2) < eps * (fabs(c1) + fabs(c0) + 1e-300)) {
@@ -79,7 +79,7 @@ __device__ int solve_cubic(double c3, double c2, double c1, double c0, double *r
 
 // 7-point algorithm: up to three fundamental matrices (row-major, normalised coordinates) through seven correspondences.
 // Null space of the 7 x 9 epipolar system by Gauss-Jordan elimination with full pivoting, then det(F2 + x (F1 - F2)) = 0.
-__device__ int seven_point(const float (&x1)[7], const float (&y1)[7], const float (&x2)[7], const float (&y2)[7], double (*Fout)[9]) {
+static __device__ int seven_point(const float (&x1)[7], const float (&y1)[7], const float (&x2)[7], const float (&y2)[7], double (*Fout)[9]) {
     double A[7][9];
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
