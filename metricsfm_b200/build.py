@@ -9,7 +9,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(CSRC, "libmsfm_match.so")
 SOURCES = ["msfm_api.cu"]
-HEADERS = ["match_kernel.cuh", "aux_kernels.cuh", "sm100_ptx.cuh", os.path.join("..", "..", "include", "msfm_match.h")]
+HEADERS = ["match_kernel.cuh", "aux_kernels.cuh", "geo_kernels.cuh", "sm100_ptx.cuh", os.path.join("..", "..", "include", "msfm_match.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
