@@ -59,6 +59,18 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def ncu_traffic_bytes(pairs_per_step: int, launches_per_step: float):
+    """DRAM bytes per launch of the matching kernel, scaled from the committed `ncu --set full` capture
+    (profiles/r1_match_kernel_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one forward launch and the
+    number of pairs it covered).  None when no capture is committed."""
+    path = os.path.join(ROOT, "profiles", "r1_match_kernel_traffic.json")
+    if not os.path.exists(path) or launches_per_step <= 0:
+        return None
+    with open(path) as f:
+        t = json.load(f)
+    return t["dram_bytes_per_pair"] * pairs_per_step / launches_per_step
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -326,7 +338,8 @@ def run_native(args):
                        "pairs_per_step_all_gpus": int(len(pairs)), "parallelism": f"pair-sharded x{world}, table replicated",
                        "l2": "flushed between timed steps (256 MiB write)", "matches_per_step_rank0": int(n_matches)},
             "roofline": {"bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TFLOP/s", "frac": achieved_tops / peak_tops,
-                         "traffic": None, "kernel": "match_pairs_kernel<2,128,6,2,2>",
+                         "traffic": ncu_traffic_bytes(len(my_pairs), match_launches / max(args.steps, 1)),
+                         "kernel": "match_pairs_kernel<4,64,8,1,2> (4 strips x N=64 tiles, 8 B stages, 2 TMEM buffers per strip)",
                          "note": "int8 tensor ops (2 per MAC), i.e. TOP/s; algorithmic ops = 2*M*N*128 per pair; peak = 2 x "
                                  f"bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks_src}); spec dense int8 = 4500",
                          "frac_of_spec_int8": achieved_tops / INT8_SPEC_PEAK_TOPS, "kernel_ms_per_step": kern_avg_ms,
