@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--mutual", type=int, default=1, help="1 = ratio + mutual cross-check (headline), 0 = ratio only")
+    ap.add_argument("--no-int8-peak", action="store_true", help="skip the cuBLAS int8 GEMM peak measurement (rank 0, N = 1)")
     return ap.parse_args()
 
 
@@ -69,6 +70,35 @@ def ncu_traffic_bytes(pairs_per_step: int, launches_per_step: float):
     with open(path) as f:
         t = json.load(f)
     return t["dram_bytes_per_pair"] * pairs_per_step / launches_per_step
+
+
+def measure_int8_peak(dev):
+    """Dense int8 tensor-core rate of this GPU as cuBLAS delivers it (torch._int_mm, 8192^3, int32 accumulate), with the
+    protocol of MEASURED_PEAKS.json: best of 10 (burst) and back to back for ~2 s (sustained).  TOP/s or None."""
+    import torch
+    try:
+        n = 8192
+        a = torch.randint(-8, 8, (n, n), dtype=torch.int8, device=dev)
+        b = torch.randint(-8, 8, (n, n), dtype=torch.int8, device=dev)
+        for _ in range(3):
+            torch._int_mm(a, b)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch._int_mm(a, b); e1.record(); e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = max(10, int(2000.0 / best))
+        e0.record()
+        for _ in range(iters):
+            torch._int_mm(a, b)
+        e1.record(); e1.synchronize()
+        ops = 2.0 * n ** 3
+        return {"burst_tops": ops / (best * 1e-3) / 1e12, "sustained_tops": ops * iters / (e0.elapsed_time(e1) * 1e-3) / 1e12,
+                "how": "torch._int_mm 8192^3 (cuBLASLt int8, s32 accumulate): best of 10 and back to back for ~2 s"}
+    except Exception as exc:  # noqa: BLE001
+        return {"error": str(exc)[:200]}
 
 
 class ClockSampler:
@@ -322,6 +352,10 @@ def run_native(args):
                "sample": f"first {len(sel)} pairs of the workload ({rows}x{rows}), {secs:.1f} s: nanoflann exact KD-tree on idx1 + 2-NN of "
                          f"idx2 rows + ratio {RATIO_ALL}, OpenMP over queries (reference engine compiled from its own headers)"}
 
+    int8_peak = None
+    if rank == 0 and world == 1 and not args.no_int8_peak:
+        m.close()                      # the library's scratch is not needed any more
+        int8_peak = measure_int8_peak(dev)
     if rank == 0:
         peaks, peaks_src = measured_peaks()
         kern_avg_ms = float(np.mean(kern_ms))
@@ -349,6 +383,10 @@ def run_native(args):
             "match_kernel_launches": int(match_launches),
             "wall_s_timed_region": wall_s,
         }
+        if int8_peak is not None:
+            line["roofline"]["int8_gemm_measured"] = int8_peak
+            if "sustained_tops" in int8_peak:
+                line["roofline"]["frac_of_measured_int8_sustained"] = achieved_tops / int8_peak["sustained_tops"]
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:

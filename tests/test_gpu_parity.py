@@ -318,14 +318,16 @@ def test_many_small_and_uneven_pairs(oracle_mod, matcher):
         np.testing.assert_array_equal(res.pair_good(p), exp["good"])
 
 
-def test_full_size_properties_32k(oracle_mod, matcher):
-    """Config #5 shape (32 768 rows per image): sampled optimality + self-consistency through the batched entry point."""
-    col = synth.Collection(32768, seed=4)
+@pytest.mark.parametrize("rows", [16384, 32768])
+def test_full_size_properties_16k_32k(oracle_mod, matcher, rows):
+    """Config #4 / #5 shapes (16 384 / 32 768 rows per image): sampled optimality + self-consistency through the batched
+    entry point."""
+    col = synth.Collection(rows, seed=4)
     a, b = col.image_u8(0), col.image_u8(1)
     _upload_pair(matcher, a, b)
     ids, dists = matcher.knn2(0, 1)
     rng = np.random.default_rng(5)
-    sample = np.sort(rng.choice(32768, size=192, replace=False))
+    sample = np.sort(rng.choice(rows, size=192, replace=False))
     oids, odists = oracle_mod.knn2_u8(a, b[sample])
     np.testing.assert_array_equal(ids[sample], oids)
     np.testing.assert_array_equal(dists[sample], odists)
