@@ -1,4 +1,6 @@
 """CPU tests of the host-side logic: synthetic collections, candidate pair lists, the multi-GPU pair scheduler."""
+import os
+
 import numpy as np
 import pytest
 
@@ -80,3 +82,19 @@ def test_stitch_results_roundtrip():
 def test_image_owner_blocks():
     own = scheduler.image_owner(10, 4)
     assert own.tolist() == [0, 0, 0, 1, 1, 1, 2, 2, 2, 3]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the native one) prints one JSON line with the
+    contract's keys; tiny shape so that it runs in seconds without a GPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.check_output([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--rows", "512", "--images", "4",
+                                   "--steps", "1", "--warmup", "0"], text=True, timeout=300)
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0
