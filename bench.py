@@ -170,6 +170,32 @@ def cpu_reference_sample(images, pairs, n_pairs: int):
     return n_pairs / dt, ("reference" if use_ref else "port"), cores, dt
 
 
+def flann_forest_sample(images, pairs, n_pairs: int):
+    """Behavioural twin of the reference's PRODUCTION kNN (fine_matching_graph.cc:72-99: FLANN randomized KD forest, 8 trees,
+    64 checks, k = 2) through the cv2.flann_Index build of this image: seconds per pair for index build (once per idx1 in
+    the reference) and for the batch query of one partner.  The reference runs one such query per OpenMP thread
+    (fine_matching_graph.cc:87).  None when cv2 is unavailable."""
+    try:
+        import cv2
+    except Exception:  # noqa: BLE001
+        return None
+    build_s = query_s = 0.0
+    for r, q in pairs[:n_pairs]:
+        ref = np.ascontiguousarray(images[r], dtype=np.float32)
+        qry = np.ascontiguousarray(images[q], dtype=np.float32)
+        t0 = time.perf_counter()
+        index = cv2.flann_Index(ref, dict(algorithm=1, trees=8))
+        t1 = time.perf_counter()
+        index.knnSearch(qry, 2, params=dict(checks=64))
+        t2 = time.perf_counter()
+        build_s += t1 - t0
+        query_s += t2 - t1
+    n = max(1, min(n_pairs, len(pairs)))
+    return {"kd_forest_build_s_per_image": build_s / n, "kd_forest_query_s_per_pair": query_s / n,
+            "what": "one cv2.flann_Index(KDTREE, trees=8) build + one knnSearch(k=2, checks=64) call per pair (approximate search; the "
+                    "production path of fine_matching_graph.cc:72-99 runs one such query per OpenMP thread)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -351,6 +377,10 @@ def run_native(args):
         cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind,
                "sample": f"first {len(sel)} pairs of the workload ({rows}x{rows}), {secs:.1f} s: nanoflann exact KD-tree on idx1 + 2-NN of "
                          f"idx2 rows + ratio {RATIO_ALL}, OpenMP over queries (reference engine compiled from its own headers)"}
+        forest = flann_forest_sample(images, sel, 2)
+        if forest is not None:
+            forest["extrapolated_pairs_per_s_one_query_per_core"] = cores / forest["kd_forest_query_s_per_pair"]
+            cpu["production_kd_forest"] = forest
 
     int8_peak = None
     if rank == 0 and world == 1 and not args.no_int8_peak:
