@@ -248,6 +248,9 @@ def run_native(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # rank 0 prints exactly one JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = os.path.join("/tmp", "nccl_debug_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     n_local, rows = args.images, args.rows
