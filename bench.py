@@ -230,7 +230,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 # ====================================================================================================== native arm
@@ -248,9 +248,6 @@ def run_native(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # rank 0 prints exactly one JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("NCCL_DEBUG_FILE"):
-            os.environ["NCCL_DEBUG_FILE"] = os.path.join("/tmp", "nccl_debug_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     n_local, rows = args.images, args.rows
@@ -284,10 +281,11 @@ def run_native(args):
     def stage_table():
         """Pack + upload this rank's images (H2D), reserve the others, replicate over NCCL.  Returns H2D bytes."""
         m.release_all()
-        for gid in range(n_global):
-            if owner[gid] == rank:
-                m.upload(gid, host_desc[gid - rank * n_local])
-            else:
+        mine = [gid for gid in range(n_global) if owner[gid] == rank]
+        for gid in range(n_global):          # identical allocation order on every rank => identical arena offsets
+            if gid == mine[0]:
+                m.upload_batch(mine, [host_desc[g - rank * n_local] for g in mine])   # one host wait for the block
+            elif owner[gid] != rank:
                 m.reserve(gid, rows)
         if world > 1:
             lib_stream.synchronize()
@@ -424,15 +422,28 @@ def run_native(args):
             line["e2e"] = e2e
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     m.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+JSON_OUT = sys.stdout
+
+
+def claim_stdout():
+    """Rank 0 prints exactly ONE JSON line on stdout.  Native libraries (NCCL's version banner, ...) write to file
+    descriptor 1 directly, so keep a private copy of the real stdout for the JSON line and point fd 1 at stderr."""
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

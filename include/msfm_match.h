@@ -132,13 +132,19 @@ const char *msfm_last_error(const msfm_ctx *ctx);
 /* ---- descriptor packer: once per image (replaces the per-idx1 flann_build_index) ------------------------------- */
 /* u8 rows, row_stride_bytes >= 128.  The library copies; the caller may free `desc` on return. */
 msfm_status msfm_upload_u8(msfm_ctx *ctx, int32_t image_id, const uint8_t *desc, int32_t rows, int64_t row_stride_bytes);
+/* Several images in one call: the copies and packer launches are queued back to back and the host waits once (a
+ * per-image msfm_upload_u8 waits once per image).  row_stride_bytes may be NULL (contiguous 128-byte rows).  On error
+ * the images before the failing one stay uploaded. */
+msfm_status msfm_upload_u8_batch(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const uint8_t *const *descs,
+                                 const int32_t *rows, const int64_t *row_stride_bytes);
 /* float rows (cv::Mat CV_32FC1 rows x 128, database.cc:368-370): q = min(255, max(0, rint(x*scale))).
  * scale = 1 for 512-scaled VLSIFT rows (feature_extractor_vl_sift.cpp:201-203), 512 for unit-norm rows
  * (feature_extractor_cuda_sift.cpp:75-80). */
 msfm_status msfm_upload_f32(msfm_ctx *ctx, int32_t image_id, const float *desc, int32_t rows, int64_t row_stride_floats,
                             float scale);
 /* Reserve table space for an image whose packed rows + norms are written by someone else (a collective during
- * multi-GPU replication) at the returned row offset of the arenas.  Pad rows/norms are initialised here. */
+ * multi-GPU replication) at the returned row offset of the arenas.  Pad rows/norms are initialised here, in stream
+ * order: synchronise the context's stream (msfm_get_stream) before a writer on another stream fills the rows. */
 msfm_status msfm_reserve(msfm_ctx *ctx, int32_t image_id, int32_t rows, int64_t *row_offset);
 msfm_status msfm_release(msfm_ctx *ctx, int32_t image_id);
 msfm_status msfm_release_all(msfm_ctx *ctx);

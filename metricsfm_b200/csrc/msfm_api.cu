@@ -80,6 +80,7 @@ struct msfm_ctx {
     float *fdesc = nullptr;    // keep_float: the callers' float rows, same row offsets as `desc` (512 B per row)
     bool own_arena = false;
     CUtensorMap *d_maps = nullptr;
+    CUtensorMap *h_maps = nullptr;  // pinned mirror of d_maps: tensor maps are uploaded without a host sync
     std::vector<ImageSlot> images;
     EncodeTiledFn encode = nullptr;
 
@@ -194,8 +195,10 @@ msfm_status write_tensor_map(msfm_ctx *ctx, int32_t image_id, int64_t off, int32
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, MSFM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_maps + image_id, &m, sizeof m, cudaMemcpyHostToDevice, ctx->stream));
-    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `m` lives on this stack frame
+    // The pinned slot of this image may still be in flight from an earlier upload of the same id (release + re-upload):
+    // copies on one stream execute in order, and the slot is only rewritten after msfm_release* synchronised the stream.
+    ctx->h_maps[image_id] = m;
+    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_maps + image_id, ctx->h_maps + image_id, sizeof m, cudaMemcpyHostToDevice, ctx->stream));
     return MSFM_OK;
 }
 
@@ -655,6 +658,7 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
     }
     // one tensor map per image + one for the candidate scratch
     if (cudaMalloc(&ctx->d_maps, (size_t)(ctx->max_images + 1) * sizeof(CUtensorMap)) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
+    if (cudaMallocHost(&ctx->h_maps, (size_t)(ctx->max_images + 1) * sizeof(CUtensorMap)) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
     if (cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, false>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::kSmemAlloc) != cudaSuccess ||
         cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, true>,
@@ -693,6 +697,7 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
         if (ctx->norms) cudaFree(ctx->norms);
     }
     if (ctx->d_maps) cudaFree(ctx->d_maps);
+    if (ctx->h_maps) cudaFreeHost(ctx->h_maps);
     cudaEvent_t evs[] = {ctx->ev_begin, ctx->ev_end, ctx->ev_k0, ctx->ev_k1, ctx->ev_k2, ctx->ev_k3, ctx->ev_f1};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
@@ -711,31 +716,64 @@ msfm_status msfm_reserve(msfm_ctx *ctx, int32_t image_id, int32_t rows, int64_t 
     const ImageSlot &s = ctx->images[image_id];
     if (s.rows_padded > s.rows) {
         msfm::init_pad_kernel<<<8, 256, 0, ctx->stream>>>(s.rows, s.rows_padded, ctx->desc + off * kDim, ctx->norms + off);
-        MSFM_CUDA(ctx, cudaGetLastError());
-        MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        MSFM_CUDA(ctx, cudaGetLastError());  // stream-ordered: synchronise msfm_get_stream before a foreign writer fills the rows
     }
     if (row_offset) *row_offset = off;
+    return MSFM_OK;
+}
+
+// One image, enqueued on the context's stream without a host sync.  Contiguous rows go straight into the arena and are
+// keyed in place; strided rows pass through the staging buffer (which the caller must not reuse before a sync).
+static msfm_status upload_u8_enqueue(msfm_ctx *ctx, int32_t image_id, const uint8_t *desc, int32_t rows, int64_t row_stride_bytes,
+                                     bool *used_staging) {
+    if ((rows > 0 && !desc) || row_stride_bytes < kDim) return fail(ctx, MSFM_ERR_INVALID_ARG, "null descriptors or stride < 128 bytes");
+    int64_t off = 0;
+    msfm_status st = reserve_locked(ctx, image_id, rows, &off);
+    if (st != MSFM_OK) return st;
+    const ImageSlot &s = ctx->images[image_id];
+    const int blocks = std::max(1, std::min(4 * ctx->num_sms, (s.rows_padded + 7) / 8));
+    const uint8_t *src = ctx->desc + off * kDim;
+    int64_t src_stride = kDim;
+    if (row_stride_bytes == kDim) {
+        if (rows > 0) MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->desc + off * kDim, desc, (size_t)rows * kDim, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        const size_t bytes = rows > 0 ? (size_t)(rows - 1) * row_stride_bytes + kDim : 0;
+        if ((st = ensure(ctx, ctx->staging, bytes)) != MSFM_OK) return st;
+        if (bytes) MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->staging.ptr, desc, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        src = static_cast<const uint8_t *>(ctx->staging.ptr);
+        src_stride = row_stride_bytes;
+        *used_staging = true;
+    }
+    msfm::pack_u8_kernel<<<blocks, 256, 0, ctx->stream>>>(src, src_stride, rows, s.rows_padded, ctx->desc + off * kDim, ctx->norms + off);
+    MSFM_CUDA(ctx, cudaGetLastError());
     return MSFM_OK;
 }
 
 msfm_status msfm_upload_u8(msfm_ctx *ctx, int32_t image_id, const uint8_t *desc, int32_t rows, int64_t row_stride_bytes) {
     if (!ctx) return MSFM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    if ((rows > 0 && !desc) || row_stride_bytes < kDim) return fail(ctx, MSFM_ERR_INVALID_ARG, "null descriptors or stride < 128 bytes");
     MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
-    int64_t off = 0;
-    msfm_status st = reserve_locked(ctx, image_id, rows, &off);
+    bool staged = false;
+    msfm_status st = upload_u8_enqueue(ctx, image_id, desc, rows, row_stride_bytes, &staged);
     if (st != MSFM_OK) return st;
-    const ImageSlot &s = ctx->images[image_id];
-    const size_t bytes = rows > 0 ? (size_t)(rows - 1) * row_stride_bytes + kDim : 0;
-    if ((st = ensure(ctx, ctx->staging, bytes)) != MSFM_OK) return st;
-    if (bytes) MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->staging.ptr, desc, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    const int blocks = std::max(1, std::min(4 * ctx->num_sms, (s.rows_padded + 7) / 8));
-    msfm::pack_u8_kernel<<<blocks, 256, 0, ctx->stream>>>(static_cast<const uint8_t *>(ctx->staging.ptr), row_stride_bytes, rows,
-                                                         s.rows_padded, ctx->desc + off * kDim, ctx->norms + off);
-    MSFM_CUDA(ctx, cudaGetLastError());
     MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller may free `desc` on return
     return MSFM_OK;
+}
+
+msfm_status msfm_upload_u8_batch(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const uint8_t *const *descs, const int32_t *rows,
+                                 const int64_t *row_stride_bytes) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (n < 0 || (n > 0 && (!image_ids || !descs || !rows))) return fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_upload_u8_batch: null argument");
+    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    msfm_status st = MSFM_OK;
+    for (int32_t i = 0; i < n && st == MSFM_OK; ++i) {
+        bool staged = false;
+        st = upload_u8_enqueue(ctx, image_ids[i], descs[i], rows[i], row_stride_bytes ? row_stride_bytes[i] : kDim, &staged);
+        if (st == MSFM_OK && staged) MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging buffer is reused by the next image
+    }
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // one sync for the batch: the caller may free every `descs[i]` on return
+    return st;
 }
 
 msfm_status msfm_upload_f32(msfm_ctx *ctx, int32_t image_id, const float *desc, int32_t rows, int64_t row_stride_floats, float scale) {

@@ -116,6 +116,30 @@ class Matcher:
             raise TypeError(f"descriptors must be uint8 or float32, got {dtype}")
         del keep
 
+    def upload_batch(self, image_ids, descs) -> None:
+        """Pack several uint8 images in one call (one host wait for the whole batch instead of one per image)."""
+        n = len(image_ids)
+        ids = np.ascontiguousarray(image_ids, np.int32)
+        ptrs = (C.c_void_p * max(n, 1))()
+        rows = np.zeros((max(n, 1),), np.int32)
+        strides = np.full((max(n, 1),), 128, np.int64)
+        keep = []
+        for k, d in enumerate(descs):
+            if hasattr(d, "numpy") and not isinstance(d, np.ndarray):
+                if str(d.dtype) != "torch.uint8" or d.dim() != 2 or (d.shape[0] and d.shape[1] != 128) or (d.shape[0] and d.stride(1) != 1):
+                    raise ValueError("upload_batch takes [rows, 128] uint8 descriptors with contiguous rows")
+                rows[k], strides[k] = d.shape[0], d.stride(0) if d.shape[0] else 128
+            else:
+                d = np.asarray(d)
+                if d.dtype != np.uint8 or d.ndim != 2 or (d.shape[0] and d.shape[1] != 128) or (d.shape[0] and d.strides[1] != 1):
+                    raise ValueError("upload_batch takes [rows, 128] uint8 descriptors with contiguous rows")
+                rows[k], strides[k] = d.shape[0], d.strides[0] if d.shape[0] else 128
+            ptr, ka = _host_ptr(d)
+            ptrs[k] = ptr
+            keep.append(ka)
+        self._check(self._L.msfm_upload_u8_batch(self._h, n, ids.ctypes.data, C.cast(ptrs, C.c_void_p), rows.ctypes.data, strides.ctypes.data))
+        del keep
+
     def reserve(self, image_id: int, rows: int) -> int:
         off = C.c_int64()
         self._check(self._L.msfm_reserve(self._h, image_id, rows, C.byref(off)))

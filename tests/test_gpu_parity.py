@@ -565,3 +565,26 @@ def test_build_match_graph_with_gpu_geo_verification(oracle_mod, native_lib, tmp
     assert moved.mean() < 0.03                                         # the moved keypoints were filtered out
     g = store.graph_read(fold, 3)
     assert g[0, 1] == len(kept) and g[0, 2] == 0
+
+
+def test_upload_batch_equals_single_uploads(oracle_mod, matcher):
+    """msfm_upload_u8_batch (one host wait per batch; contiguous rows go straight into the arena and are keyed in place)
+    leaves the same table as per-image uploads, including a strided member and an empty image."""
+    col = synth.Collection(700, seed=13)
+    imgs = [col.image_u8(0, 700), col.image_u8(1, 513), np.empty((0, 128), np.uint8), col.image_u8(3, 64)]
+    big = np.zeros((2 * 513, 128), np.uint8)
+    big[::2] = imgs[1]
+    matcher.release_all()
+    matcher.upload_batch([0, 1, 2, 3], [imgs[0], big[::2], imgs[2], imgs[3]])
+    for i, d in enumerate(imgs):
+        got, norms = matcher.download_packed(i)
+        np.testing.assert_array_equal(got, d)
+        np.testing.assert_array_equal(norms, (d.astype(np.int64) ** 2).sum(1).astype(np.uint32))
+    ids, dists = matcher.knn2(0, 1)
+    oids, odists = oracle_mod.knn2_u8(imgs[0], imgs[1])
+    np.testing.assert_array_equal(ids, oids)
+    np.testing.assert_array_equal(dists, odists)
+    res = matcher.match_pairs([(0, 1), (1, 3), (0, 2)], 0.85, ratio_good=0.6, mutual=True)
+    exp = oracle_mod.match_pair_u8(imgs[1], imgs[3], 0.85, mutual=True, ratio_good=0.6)
+    np.testing.assert_array_equal(res.pair(1), exp["pairs"])
+    assert res.ok.tolist() == [1, 1, 0]
