@@ -153,6 +153,7 @@ def cpu_reference_sample(images, pairs, n_pairs: int):
     """Time the reference's vendored exact engine (nanoflann; oracle/_ref) — or the oracle port when it is absent —
     on the first n_pairs pairs of the workload, all host threads.  Returns (pairs_per_s, kind, cores, seconds)."""
     from oracle import oracle
+    oracle.use_all_host_threads()   # torchrun exports OMP_NUM_THREADS=1; the reference uses every core (OpenMP default)
     use_ref = oracle.ref_available()
     cores = oracle.ref_lib().ref_nanoflann_max_threads() if use_ref else oracle.max_threads()
     f32 = {}

@@ -59,6 +59,14 @@ int oracle_max_threads(void) {
 #endif
 }
 
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* q = min(255, max(0, rint(x * scale))): the packer's quantisation rule. */
 void oracle_quantize_f32(const float *src, int64_t rows, int64_t src_stride_floats, float scale, uint8_t *dst) {
     for (int64_t r = 0; r < rows; ++r) {

@@ -59,6 +59,17 @@ def max_threads() -> int:
     return int(lib().oracle_max_threads())
 
 
+def use_all_host_threads() -> int:
+    """Size the OpenMP teams of the oracle and of the reference engine from the CPUs this process may run on (launchers
+    like torchrun export OMP_NUM_THREADS=1).  Returns the thread count."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().oracle_set_threads(n)
+    if ref_available():
+        ref_lib().ref_nanoflann_set_threads(n)
+    return n
+
+
 def quantize_f32(desc: np.ndarray, scale: float) -> np.ndarray:
     desc = np.ascontiguousarray(desc, dtype=np.float32)
     assert desc.ndim == 2 and desc.shape[1] == 128

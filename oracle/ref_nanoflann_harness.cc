@@ -46,6 +46,16 @@ int ref_nanoflann_max_threads() {
 #endif
 }
 
+// The reference sizes its OpenMP team from the machine (no omp_set_num_threads anywhere under SfM/src); launchers such as
+// torchrun export OMP_NUM_THREADS=1, so the benchmark arm sets the team size explicitly.
+void ref_nanoflann_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 // Build the KD-tree on image 1's descriptors (rows x 128 float, contiguous).
 void *ref_nanoflann_build(const float *desc1, int32_t rows) {
     RefIndex *ix = new RefIndex();
