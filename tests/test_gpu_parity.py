@@ -588,3 +588,58 @@ def test_upload_batch_equals_single_uploads(oracle_mod, matcher):
     exp = oracle_mod.match_pair_u8(imgs[1], imgs[3], 0.85, mutual=True, ratio_good=0.6)
     np.testing.assert_array_equal(res.pair(1), exp["pairs"])
     assert res.ok.tolist() == [1, 1, 0]
+
+
+def test_maximum_rows_per_image(oracle_mod, native_lib):
+    """MSFM_MAX_ROWS_PER_IMAGE = idx_max_per_image = 1 000 000 (basic_structs.h:171): a million-row image as the
+    reference set (15 625 tiles per work item) and as the query set (1 954 work items), against the oracle."""
+    from metricsfm_b200.matcher import Matcher, MsfmError
+    rng = np.random.default_rng(77)
+    big = rng.integers(0, 40, size=(1_000_000, 128), dtype=np.uint8)
+    big[rng.choice(1_000_000, 5000, replace=False)] += 100               # some structure in the norms
+    small = big[rng.choice(1_000_000, 300, replace=False)].copy()
+    small = np.clip(small.astype(np.int32) + rng.integers(-3, 4, size=small.shape), 0, 255).astype(np.uint8)
+    with Matcher(device=0, max_images=4, arena_rows=1_000_000 + 4096) as m:
+        m.upload(0, big)
+        m.upload(1, small)
+        with pytest.raises(MsfmError):
+            m.reserve(2, 1_000_001)                                          # one row past the limit
+        ids, dists = m.knn2(0, 1)                                            # 300 queries against a million rows
+        oids, odists = oracle_mod.knn2_u8(big, small)
+        np.testing.assert_array_equal(ids, oids)
+        np.testing.assert_array_equal(dists, odists)
+        ids2, dists2 = m.knn2(1, 0)                                          # a million queries against 300 rows
+        sample = np.sort(rng.choice(1_000_000, 4000, replace=False))
+        oids2, odists2 = oracle_mod.knn2_u8(small, big[sample])
+        np.testing.assert_array_equal(ids2[sample], oids2)
+        np.testing.assert_array_equal(dists2[sample], odists2)
+        res = m.match_pairs([(0, 1)], 0.85, ratio_good=0.6, mutual=True)
+        exp = oracle_mod.match_pair_u8(big, small, 0.85, mutual=True, ratio_good=0.6)
+        np.testing.assert_array_equal(res.pair(0), exp["pairs"])
+
+
+def test_many_images_many_pairs_batches(oracle_mod, native_lib):
+    """Collection-scale bookkeeping (configs #3-#5 have 10^3-10^4 images and 10^4-10^5 pairs): 3 000 small images, 40 000
+    retrieval-style pairs => several internal batches (16 384 pairs each); sampled pairs against the oracle, totals
+    against a second call."""
+    from metricsfm_b200.matcher import Matcher
+    n_img = 3000
+    rng = np.random.default_rng(88)
+    sizes = rng.integers(18, 90, size=n_img)                                  # some images below the 20-keypoint gate
+    col = synth.Collection(90, seed=71)
+    imgs = [col.image_u8(i % 50, int(r)) for i, r in enumerate(sizes)]       # 50 distinct scenes re-used
+    pairs = synth.retrieval_pairs(n_img, partners=14, seed=5)
+    assert len(pairs) > 32768
+    with Matcher(device=0, max_images=n_img, arena_rows=n_img * 256) as m:
+        m.upload_batch(list(range(n_img)), imgs)
+        res = m.match_pairs(pairs, 0.85, ratio_good=0.6, mutual=True)
+        total = m.match_pairs_resident(pairs, 0.85, ratio_good=0.6, mutual=True)
+    assert total == len(res.matches) == int(res.offsets[-1])
+    gated = (sizes[pairs[:, 0]] < 20) | (sizes[pairs[:, 1]] < 20)
+    np.testing.assert_array_equal(res.ok, (~gated).astype(np.int32))
+    assert gated.any() and (np.diff(res.offsets) >= 0).all()
+    for p in rng.choice(len(pairs), 150, replace=False).tolist() + [0, 16383, 16384, 32767, 32768, len(pairs) - 1]:
+        r, q = pairs[p]
+        exp = oracle_mod.match_pair_u8(imgs[r], imgs[q], 0.85, mutual=True, ratio_good=0.6)
+        np.testing.assert_array_equal(res.pair(p), exp["pairs"], err_msg=f"pair {p} = ({r},{q})")
+        np.testing.assert_array_equal(res.pair_good(p), exp["good"])
