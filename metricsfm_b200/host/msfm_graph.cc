@@ -1,6 +1,8 @@
 // msfm_graph.cc — FineMatchingGraph::BuildMatchGraph rebuilt around the GPU matcher (include/msfm_graph.h).
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -20,6 +22,17 @@ int fail(char *err, size_t cap, int code, const char *fmt, ...) {
     }
     return code;
 }
+
+// MSFM_GRAPH_VERBOSE=1: wall-clock of every stage on stderr.
+struct StageClock {
+    bool on = getenv("MSFM_GRAPH_VERBOSE") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char *what) {
+        const auto n = std::chrono::steady_clock::now();
+        if (on) fprintf(stderr, "[msfm graph] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
 
 struct Image {
     msfm_feature_info info{};
@@ -49,6 +62,8 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
     if (msfm_graph_recover(fold, num_imgs, existing.data(), (int32_t)existing.size(), graph.data()) != 0)
         return fail(err, err_cap, -2, "existing match files unreadable");
 
+    StageClock clk;
+    clk.lap("resume state");
     // ---- the images this run touches, their feature headers
     std::vector<Image> imgs((size_t)num_imgs);
     std::vector<msfm_pair> pairs;
@@ -72,6 +87,7 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
         arena_rows += (fi.desc_rows + 255) / 256 * 256 + 256;
     }
 
+    clk.lap("feature headers");
     // ---- stage every needed image in HBM once (replaces the per-idx1 flann_build_index and the per-pair re-reads)
     msfm_ctx *ctx = nullptr;
     if (!pairs.empty()) {
@@ -103,6 +119,7 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
         if (st != MSFM_OK) return bail(-4, std::string("upload: ") + msfm_last_error(ctx));
     }
 
+    clk.lap("create + read + upload");
     // ---- the whole candidate pair list in one batch: "all" list + good flags per pair
     std::vector<int64_t> moff(pairs.size() + 1, 0);
     std::vector<int32_t> okflags(pairs.size(), 0);
@@ -128,6 +145,7 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
         msfm_status st = msfm_match_pairs(ctx, pairs.data(), (int64_t)pairs.size(), &prm, &res);
         if (st != MSFM_OK) return bail(-4, std::string("msfm_match_pairs: ") + msfm_last_error(ctx));
     }
+    clk.lap("msfm_match_pairs");
     // ---- GeoVerificationFundamental for the whole batch on the GPU (fine_matching_graph.cc:137-153)
     std::vector<int32_t> geo_ok;
     std::vector<uint8_t> geo_keep;
@@ -150,7 +168,9 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
                                          gbuf.data(), xy_ptr.data(), npts.data(), num_imgs, &gp, geo_ok.data(), inl.data(), geo_keep.data(), nullptr);
         if (st != MSFM_OK) return bail(-4, std::string("msfm_geo_verify: ") + msfm_last_error(ctx));
     }
+    clk.lap("msfm_geo_verify");
     if (ctx) msfm_destroy(ctx);
+    clk.lap("msfm_destroy");
 
     // ---- verification seam + output, in the reference's order (idx1 ascending over the missing list, partners in
     //      list order); match_index.txt gets its line when idx1 is complete (fine_matching_graph.cc:137-191)
@@ -189,6 +209,7 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
         }
         if (msfm_match_index_append(fold, idx1) != 0) return fail(err, err_cap, -2, "cannot append to match_index.txt");
     }
+    clk.lap("verify seam + match files");
     if (msfm_graph_write(fold, num_imgs, graph.data()) != 0) return fail(err, err_cap, -2, "cannot write graph_matching.txt");
     return 0;
 }
