@@ -974,59 +974,61 @@ msfm_status msfm_geo_verify(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pai
     std::vector<int32_t> pimg((size_t)n_pairs * 2);
     for (int64_t p = 0; p < n_pairs; ++p) { pimg[2 * p] = pairs[p].ref; pimg[2 * p + 1] = pairs[p].query; }
 
-    DeviceBuf d_xy, d_xyoff, d_off, d_m, d_g, d_pimg, d_ok, d_inl, d_keep, d_F;
-    DeviceBuf *bufs[] = {&d_xy, &d_xyoff, &d_off, &d_m, &d_g, &d_pimg, &d_ok, &d_inl, &d_keep, &d_F};
-    auto cleanup = [&](msfm_status st) {
-        cudaStreamSynchronize(ctx->stream);
-        for (DeviceBuf *b : bufs)
-            if (b->ptr) cudaFree(b->ptr);
-        return st;
-    };
+    // per-call device buffers, released on every exit path
+    struct Scratch {
+        msfm_ctx *ctx;
+        DeviceBuf xy, xyoff, off, m, g, pimg, ok, inl, keep, F;
+        ~Scratch() {
+            cudaStreamSynchronize(ctx->stream);
+            for (DeviceBuf *b : {&xy, &xyoff, &off, &m, &g, &pimg, &ok, &inl, &keep, &F})
+                if (b->ptr) cudaFree(b->ptr);
+        }
+    } d{ctx};
     msfm_status st;
     const size_t tot = (size_t)std::max<int64_t>(total, 1);
-    if ((st = ensure(ctx, d_xy, xy.size() * 4)) != MSFM_OK || (st = ensure(ctx, d_xyoff, xy_off.size() * 8)) != MSFM_OK ||
-        (st = ensure(ctx, d_off, (size_t)(n_pairs + 1) * 8)) != MSFM_OK || (st = ensure(ctx, d_m, tot * 8)) != MSFM_OK ||
-        (st = ensure(ctx, d_g, tot)) != MSFM_OK || (st = ensure(ctx, d_pimg, pimg.size() * 4)) != MSFM_OK ||
-        (st = ensure(ctx, d_ok, (size_t)n_pairs * 4)) != MSFM_OK || (st = ensure(ctx, d_inl, (size_t)n_pairs * 4)) != MSFM_OK ||
-        (st = ensure(ctx, d_keep, tot)) != MSFM_OK || (st = ensure(ctx, d_F, (size_t)n_pairs * 72)) != MSFM_OK)
-        return cleanup(st);
-    cudaMemcpyAsync(d_xy.ptr, xy.data(), xy.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(d_xyoff.ptr, xy_off.data(), xy_off.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(d_off.ptr, offsets, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if ((st = ensure(ctx, d.xy, xy.size() * 4)) != MSFM_OK || (st = ensure(ctx, d.xyoff, xy_off.size() * 8)) != MSFM_OK ||
+        (st = ensure(ctx, d.off, (size_t)(n_pairs + 1) * 8)) != MSFM_OK || (st = ensure(ctx, d.m, tot * 8)) != MSFM_OK ||
+        (st = ensure(ctx, d.g, tot)) != MSFM_OK || (st = ensure(ctx, d.pimg, pimg.size() * 4)) != MSFM_OK ||
+        (st = ensure(ctx, d.ok, (size_t)n_pairs * 4)) != MSFM_OK || (st = ensure(ctx, d.inl, (size_t)n_pairs * 4)) != MSFM_OK ||
+        (st = ensure(ctx, d.keep, tot)) != MSFM_OK || (st = ensure(ctx, d.F, (size_t)n_pairs * 72)) != MSFM_OK)
+        return st;
+    MSFM_CUDA(ctx, cudaMemcpyAsync(d.xy.ptr, xy.data(), xy.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MSFM_CUDA(ctx, cudaMemcpyAsync(d.xyoff.ptr, xy_off.data(), xy_off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    MSFM_CUDA(ctx, cudaMemcpyAsync(d.off.ptr, offsets, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (total > 0) {
-        cudaMemcpyAsync(d_m.ptr, matches, (size_t)total * 8, cudaMemcpyHostToDevice, ctx->stream);
-        cudaMemcpyAsync(d_g.ptr, good, (size_t)total, cudaMemcpyHostToDevice, ctx->stream);
+        MSFM_CUDA(ctx, cudaMemcpyAsync(d.m.ptr, matches, (size_t)total * 8, cudaMemcpyHostToDevice, ctx->stream));
+        MSFM_CUDA(ctx, cudaMemcpyAsync(d.g.ptr, good, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
     }
-    cudaMemcpyAsync(d_pimg.ptr, pimg.data(), pimg.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    MSFM_CUDA(ctx, cudaMemcpyAsync(d.pimg.ptr, pimg.data(), pimg.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     msfm::GeoParams kp;
-    kp.offsets = static_cast<const int64_t *>(d_off.ptr);
-    kp.matches = static_cast<const int2 *>(d_m.ptr);
-    kp.good = static_cast<const uint8_t *>(d_g.ptr);
-    kp.pair_img = static_cast<const int32_t *>(d_pimg.ptr);
-    kp.xy = static_cast<const float *>(d_xy.ptr);
-    kp.xy_off = static_cast<const int64_t *>(d_xyoff.ptr);
+    kp.offsets = static_cast<const int64_t *>(d.off.ptr);
+    kp.matches = static_cast<const int2 *>(d.m.ptr);
+    kp.good = static_cast<const uint8_t *>(d.g.ptr);
+    kp.pair_img = static_cast<const int32_t *>(d.pimg.ptr);
+    kp.xy = static_cast<const float *>(d.xy.ptr);
+    kp.xy_off = static_cast<const int64_t *>(d.xyoff.ptr);
     kp.th = gp->th_epipolar;
     kp.min_points = gp->min_points;
     kp.min_inliers = gp->min_inliers;
     kp.iters = gp->iters > 0 ? gp->iters : 1024;
     kp.seed = gp->seed;
-    kp.pair_ok = static_cast<int32_t *>(d_ok.ptr);
-    kp.pair_inliers = static_cast<int32_t *>(d_inl.ptr);
-    kp.keep = static_cast<uint8_t *>(d_keep.ptr);
-    kp.F = static_cast<double *>(d_F.ptr);
-    cudaEventRecord(ctx->ev_k0, ctx->stream);
+    kp.pair_ok = static_cast<int32_t *>(d.ok.ptr);
+    kp.pair_inliers = static_cast<int32_t *>(d.inl.ptr);
+    kp.keep = static_cast<uint8_t *>(d.keep.ptr);
+    kp.F = static_cast<double *>(d.F.ptr);
+    MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
     msfm::geo_verify_kernel<<<(int)std::min<int64_t>(n_pairs, 8 * ctx->num_sms), msfm::kGeoThreads, 0, ctx->stream>>>(kp, (int)n_pairs);
-    cudaEventRecord(ctx->ev_k1, ctx->stream);
-    if (cudaGetLastError() != cudaSuccess) return cleanup(fail(ctx, MSFM_ERR_CUDA, "geo_verify_kernel launch failed"));
-    cudaMemcpyAsync(pair_ok, d_ok.ptr, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaMemcpyAsync(pair_inliers, d_inl.ptr, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream);
-    if (total > 0) cudaMemcpyAsync(keep, d_keep.ptr, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream);
-    if (F) cudaMemcpyAsync(F, d_F.ptr, (size_t)n_pairs * 72, cudaMemcpyDeviceToHost, ctx->stream);
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return cleanup(fail(ctx, MSFM_ERR_CUDA, "msfm_geo_verify: %s", cudaGetErrorString(cudaGetLastError())));
+    MSFM_CUDA(ctx, cudaGetLastError());
+    MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
+    MSFM_CUDA(ctx, cudaMemcpyAsync(pair_ok, d.ok.ptr, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MSFM_CUDA(ctx, cudaMemcpyAsync(pair_inliers, d.inl.ptr, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (total > 0) MSFM_CUDA(ctx, cudaMemcpyAsync(keep, d.keep.ptr, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (F) MSFM_CUDA(ctx, cudaMemcpyAsync(F, d.F.ptr, (size_t)n_pairs * 72, cudaMemcpyDeviceToHost, ctx->stream));
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->timing = msfm_timing{};
-    cudaEventElapsedTime(&ctx->timing.finalize_ms, ctx->ev_k0, ctx->ev_k1);
+    MSFM_CUDA(ctx, cudaEventElapsedTime(&ctx->timing.finalize_ms, ctx->ev_k0, ctx->ev_k1));
     ctx->timing.total_launches = 1;
-    return cleanup(MSFM_OK);
+    return MSFM_OK;
 }
 
 msfm_status msfm_knn2_crosscheck(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_t *ids, float *dists) {
