@@ -37,6 +37,9 @@ typedef struct msfm_graph_options {
                                 whole batch (msfm_geo_verify: >= 30 good matches, RANSAC-F 3 px, >= 30 inliers, then the
                                 F-filter of the "all" set); rejected pairs leave no record, like the reference */
     uint32_t geo_seed;       /* RANSAC stream of msfm_geo_verify */
+    int64_t max_batch_rows;  /* the missing images are processed in chunks of consecutive idx1 whose pair lists need at most
+                                this many match slots (sum of query rows) on the host; match_index.txt advances per chunk.
+                                0 = 32 Mi.  Results do not depend on the chunking. */
 } msfm_graph_options;
 
 /* Geo-verification seam.  xy1/xy2: centred keypoints of both images as stored in the feature files; matches: the

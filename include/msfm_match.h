@@ -190,6 +190,8 @@ typedef struct msfm_geo_params {
     int32_t min_inliers;   /* 30   utils/geo_verification.cc:53 */
     int32_t iters;         /* RANSAC hypotheses per pair (each yields up to 3 models); 0 = 1024 */
     uint64_t seed;
+    int64_t pair_index_base; /* added to the pair index in the RANSAC counter, so that a pair list verified in several
+                                calls draws the same hypotheses as in one call */
 } msfm_geo_params;
 /* pairs/offsets/matches/good: the result of msfm_match_pairs with orientation 0 and ratio_good set.
  * image_xy[i]: host pointer to the centred keypoints (x, y) of image i as stored in its feature file, or NULL for

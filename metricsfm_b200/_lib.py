@@ -41,7 +41,7 @@ class Params(C.Structure):
 
 class GeoParams(C.Structure):
     _fields_ = [("th_epipolar", C.c_float), ("min_points", C.c_int32), ("min_inliers", C.c_int32), ("iters", C.c_int32),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("pair_index_base", C.c_int64)]
 
 
 class Pair(C.Structure):

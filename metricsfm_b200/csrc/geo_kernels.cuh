@@ -27,6 +27,7 @@ struct GeoParams {
     float th;                  // epipolar threshold in pixels (3.0)
     int32_t min_points, min_inliers, iters;
     unsigned long long seed;
+    long long pair_base;       // global index of pair 0 of this call (RANSAC counter)
     int32_t *pair_ok;          // [n_pairs]
     int32_t *pair_inliers;     // [n_pairs] stage-A inliers among the good matches
     uint8_t *keep;             // [total matches] stage-B mask
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(kGeoThreads) geo_verify_kernel(const GeoParams
         if (ok && n_pts >= 7) {
             const float th2 = gp.th * scale * gp.th * scale;
             for (int h = threadIdx.x; h < gp.iters; h += kGeoThreads) {
-                unsigned long long st = geo_mix(gp.seed ^ geo_mix(((unsigned long long)p << 32) | (unsigned)h));
+                unsigned long long st = geo_mix(gp.seed ^ geo_mix(((unsigned long long)(gp.pair_base + p) << 32) | (unsigned)h));
                 int idx[7];
                 for (int k = 0; k < 7; ++k) {
                     bool dup;

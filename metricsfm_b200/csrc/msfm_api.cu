@@ -1012,6 +1012,7 @@ msfm_status msfm_geo_verify(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pai
     kp.min_inliers = gp->min_inliers;
     kp.iters = gp->iters > 0 ? gp->iters : 1024;
     kp.seed = gp->seed;
+    kp.pair_base = gp->pair_index_base;
     kp.pair_ok = static_cast<int32_t *>(d.ok.ptr);
     kp.pair_inliers = static_cast<int32_t *>(d.inl.ptr);
     kp.keep = static_cast<uint8_t *>(d.keep.ptr);

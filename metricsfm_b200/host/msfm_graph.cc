@@ -66,13 +66,13 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
     clk.lap("resume state");
     // ---- the images this run touches, their feature headers
     std::vector<Image> imgs((size_t)num_imgs);
-    std::vector<msfm_pair> pairs;
+    bool any_pair = false;
     for (int32_t idx1 : missing)
         for (int64_t j = offsets[idx1]; j < offsets[idx1 + 1]; ++j) {
             const int32_t idx2 = list[j];
             if (idx2 < 0 || idx2 >= num_imgs) return fail(err, err_cap, -1, "partner index %d of image %d out of range", idx2, idx1);
             imgs[idx1].needed = imgs[idx2].needed = true;
-            pairs.push_back({idx1, idx2});  // index on idx1, queries = rows of idx2 (fine_matching_graph.cc:81,99)
+            any_pair = true;
         }
     int64_t arena_rows = 0;
     char path[4096];
@@ -86,11 +86,11 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
         if (fi.desc_rows != fi.num_pts) return fail(err, err_cap, -3, "image %d: %d keypoints but %d descriptor rows", i, fi.num_pts, fi.desc_rows);
         arena_rows += (fi.desc_rows + 255) / 256 * 256 + 256;
     }
-
     clk.lap("feature headers");
+
     // ---- stage every needed image in HBM once (replaces the per-idx1 flann_build_index and the per-pair re-reads)
     msfm_ctx *ctx = nullptr;
-    if (!pairs.empty()) {
+    if (any_pair) {
         msfm_config cfg;
         memset(&cfg, 0, sizeof cfg);
         cfg.device = opt->device;
@@ -118,98 +118,118 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
                              : msfm_upload_f32(ctx, i, reinterpret_cast<const float *>(staging.data()), fi.desc_rows, 128, opt->descriptor_scale);
         if (st != MSFM_OK) return bail(-4, std::string("upload: ") + msfm_last_error(ctx));
     }
-
     clk.lap("create + read + upload");
-    // ---- the whole candidate pair list in one batch: "all" list + good flags per pair
-    std::vector<int64_t> moff(pairs.size() + 1, 0);
-    std::vector<int32_t> okflags(pairs.size(), 0);
-    int64_t capacity = 0;
-    for (const msfm_pair &pr : pairs) capacity += imgs[pr.query].info.desc_rows;
-    std::vector<int32_t> mbuf((size_t)(capacity > 0 ? capacity : 1) * 2);
-    std::vector<uint8_t> gbuf((size_t)(capacity > 0 ? capacity : 1));
-    if (!pairs.empty()) {
-        msfm_params prm;
-        memset(&prm, 0, sizeof prm);
-        prm.ratio = opt->th_all;
-        prm.ratio_good = opt->th_good;
-        prm.mutual = opt->mutual;
-        prm.min_keypoints = opt->min_keypoints;
-        prm.orientation = 0;  // (ptid1, ptid2) ascending ptid2 (fine_matching_graph.cc:121,127)
-        prm.rescore_band = opt->rescore_band;
-        msfm_result res;
-        res.offsets = moff.data();
-        res.ok = okflags.data();
-        res.matches = reinterpret_cast<int32_t(*)[2]>(mbuf.data());
-        res.good = gbuf.data();
-        res.match_capacity = capacity;
-        msfm_status st = msfm_match_pairs(ctx, pairs.data(), (int64_t)pairs.size(), &prm, &res);
-        if (st != MSFM_OK) return bail(-4, std::string("msfm_match_pairs: ") + msfm_last_error(ctx));
+
+    // ---- the missing images in chunks of consecutive idx1 (host match buffers stay bounded; match_index.txt advances
+    //      chunk by chunk, so an interrupted run resumes where it stopped)
+    const int64_t chunk_rows = opt->max_batch_rows > 0 ? opt->max_batch_rows : (32ll << 20);
+    std::vector<const float *> xy_ptr((size_t)num_imgs, nullptr);
+    std::vector<int32_t> npts((size_t)num_imgs, 0);
+    for (int32_t i = 0; i < num_imgs; ++i)
+        if (imgs[i].needed) { xy_ptr[i] = imgs[i].xy.data(); npts[i] = imgs[i].info.num_pts; }
+    std::vector<msfm_pair> pairs;
+    std::vector<int64_t> moff;
+    std::vector<int32_t> okflags, mbuf, geo_ok, inl, keep, kept;
+    std::vector<uint8_t> gbuf, geo_keep;
+    int64_t pair_base = 0;  // global index of the chunk's first pair: keeps the RANSAC streams independent of the chunking
+    size_t mi = 0;
+    while (mi < missing.size()) {
+        const size_t chunk_first = mi;
+        pairs.clear();
+        int64_t capacity = 0;
+        while (mi < missing.size()) {
+            const int32_t idx1 = missing[mi];
+            int64_t need = 0;
+            for (int64_t j = offsets[idx1]; j < offsets[idx1 + 1]; ++j) need += imgs[list[j]].info.desc_rows;
+            if (mi > chunk_first && capacity + need > chunk_rows) break;
+            for (int64_t j = offsets[idx1]; j < offsets[idx1 + 1]; ++j) pairs.push_back({idx1, list[j]});  // index on idx1, queries = idx2 rows
+            capacity += need;
+            ++mi;
+        }
+        moff.assign(pairs.size() + 1, 0);
+        okflags.assign(pairs.size(), 0);
+        mbuf.resize((size_t)(capacity > 0 ? capacity : 1) * 2);
+        gbuf.resize((size_t)(capacity > 0 ? capacity : 1));
+        if (!pairs.empty()) {
+            msfm_params prm;
+            memset(&prm, 0, sizeof prm);
+            prm.ratio = opt->th_all;
+            prm.ratio_good = opt->th_good;
+            prm.mutual = opt->mutual;
+            prm.min_keypoints = opt->min_keypoints;
+            prm.orientation = 0;  // (ptid1, ptid2) ascending ptid2 (fine_matching_graph.cc:121,127)
+            prm.rescore_band = opt->rescore_band;
+            msfm_result res;
+            res.offsets = moff.data();
+            res.ok = okflags.data();
+            res.matches = reinterpret_cast<int32_t(*)[2]>(mbuf.data());
+            res.good = gbuf.data();
+            res.match_capacity = capacity;
+            msfm_status st = msfm_match_pairs(ctx, pairs.data(), (int64_t)pairs.size(), &prm, &res);
+            if (st != MSFM_OK) return bail(-4, std::string("msfm_match_pairs: ") + msfm_last_error(ctx));
+        }
+        clk.lap("msfm_match_pairs");
+        // ---- GeoVerificationFundamental for the chunk on the GPU (fine_matching_graph.cc:137-153)
+        const bool gpu_geo = opt->geo_verify && !verify && !pairs.empty();
+        if (gpu_geo) {
+            msfm_geo_params gp;
+            memset(&gp, 0, sizeof gp);
+            gp.th_epipolar = 3.0f;   // utils/geo_verification.cc:45,66
+            gp.min_points = 30;      // :33
+            gp.min_inliers = 30;     // :53
+            gp.iters = 1024;
+            gp.seed = opt->geo_seed;
+            gp.pair_index_base = pair_base;
+            geo_ok.assign(pairs.size(), 0);
+            inl.assign(pairs.size(), 0);
+            geo_keep.assign((size_t)(moff[pairs.size()] > 0 ? moff[pairs.size()] : 1), 0);
+            msfm_status st = msfm_geo_verify(ctx, pairs.data(), (int64_t)pairs.size(), moff.data(), reinterpret_cast<const int32_t(*)[2]>(mbuf.data()),
+                                             gbuf.data(), xy_ptr.data(), npts.data(), num_imgs, &gp, geo_ok.data(), inl.data(), geo_keep.data(), nullptr);
+            if (st != MSFM_OK) return bail(-4, std::string("msfm_geo_verify: ") + msfm_last_error(ctx));
+            clk.lap("msfm_geo_verify");
+        }
+        // ---- verification seam + output, in the reference's order (idx1 ascending over the missing list, partners in
+        //      list order); match_index.txt gets its line when idx1 is complete (fine_matching_graph.cc:137-191)
+        size_t p = 0;
+        for (size_t k1 = chunk_first; k1 < mi; ++k1) {
+            const int32_t idx1 = missing[k1];
+            for (int64_t j = offsets[idx1]; j < offsets[idx1 + 1]; ++j, ++p) {
+                const int32_t idx2 = list[j];
+                const int32_t n = (int32_t)(moff[p + 1] - moff[p]);
+                const int32_t(*m)[2] = reinterpret_cast<const int32_t(*)[2]>(mbuf.data()) + moff[p];
+                const uint8_t *g = gbuf.data() + moff[p];
+                if (!okflags[p]) continue;
+                keep.resize((size_t)n);
+                int32_t n_keep = 0;
+                int accept = 1;
+                if (verify) {
+                    accept = verify(user, idx1, idx2, imgs[idx1].xy.data(), imgs[idx1].info.num_pts, imgs[idx2].xy.data(),
+                                    imgs[idx2].info.num_pts, m, g, n, keep.data(), &n_keep);
+                } else if (gpu_geo) {
+                    accept = geo_ok[p];
+                    for (int32_t k = 0; k < n; ++k)
+                        if (geo_keep[moff[p] + k]) keep[n_keep++] = k;
+                } else {
+                    int32_t n_good = 0;
+                    for (int32_t k = 0; k < n; ++k) n_good += g[k];
+                    accept = n_good >= opt->min_good;
+                    for (int32_t k = 0; k < n; ++k) keep[k] = k;
+                    n_keep = n;
+                }
+                if (!accept) continue;
+                kept.resize((size_t)n_keep * 2);
+                for (int32_t k = 0; k < n_keep; ++k) { kept[2 * k] = m[keep[k]][0]; kept[2 * k + 1] = m[keep[k]][1]; }
+                if (msfm_match_append(fold, idx1, idx2, reinterpret_cast<const int32_t(*)[2]>(kept.data()), n_keep) != 0)
+                    return bail(-2, "cannot append to the match file of image " + std::to_string(idx1));
+                graph[(size_t)idx1 * num_imgs + idx2] = n_keep;
+            }
+            if (msfm_match_index_append(fold, idx1) != 0) return bail(-2, "cannot append to match_index.txt");
+        }
+        pair_base += (int64_t)pairs.size();
+        clk.lap("verify seam + match files");
     }
-    clk.lap("msfm_match_pairs");
-    // ---- GeoVerificationFundamental for the whole batch on the GPU (fine_matching_graph.cc:137-153)
-    std::vector<int32_t> geo_ok;
-    std::vector<uint8_t> geo_keep;
-    if (ctx && opt->geo_verify && !verify && !pairs.empty()) {
-        std::vector<const float *> xy_ptr((size_t)num_imgs, nullptr);
-        std::vector<int32_t> npts((size_t)num_imgs, 0);
-        for (int32_t i = 0; i < num_imgs; ++i)
-            if (imgs[i].needed) { xy_ptr[i] = imgs[i].xy.data(); npts[i] = imgs[i].info.num_pts; }
-        msfm_geo_params gp;
-        memset(&gp, 0, sizeof gp);
-        gp.th_epipolar = 3.0f;   // utils/geo_verification.cc:45,66
-        gp.min_points = 30;      // :33
-        gp.min_inliers = 30;     // :53
-        gp.iters = 1024;
-        gp.seed = opt->geo_seed;
-        geo_ok.assign(pairs.size(), 0);
-        std::vector<int32_t> inl(pairs.size(), 0);
-        geo_keep.assign((size_t)(moff[pairs.size()] > 0 ? moff[pairs.size()] : 1), 0);
-        msfm_status st = msfm_geo_verify(ctx, pairs.data(), (int64_t)pairs.size(), moff.data(), reinterpret_cast<const int32_t(*)[2]>(mbuf.data()),
-                                         gbuf.data(), xy_ptr.data(), npts.data(), num_imgs, &gp, geo_ok.data(), inl.data(), geo_keep.data(), nullptr);
-        if (st != MSFM_OK) return bail(-4, std::string("msfm_geo_verify: ") + msfm_last_error(ctx));
-    }
-    clk.lap("msfm_geo_verify");
     if (ctx) msfm_destroy(ctx);
     clk.lap("msfm_destroy");
-
-    // ---- verification seam + output, in the reference's order (idx1 ascending over the missing list, partners in
-    //      list order); match_index.txt gets its line when idx1 is complete (fine_matching_graph.cc:137-191)
-    size_t p = 0;
-    std::vector<int32_t> keep, kept;
-    for (int32_t idx1 : missing) {
-        for (int64_t j = offsets[idx1]; j < offsets[idx1 + 1]; ++j, ++p) {
-            const int32_t idx2 = list[j];
-            const int32_t n = (int32_t)(moff[p + 1] - moff[p]);
-            const int32_t(*m)[2] = reinterpret_cast<const int32_t(*)[2]>(mbuf.data()) + moff[p];
-            const uint8_t *g = gbuf.data() + moff[p];
-            if (!okflags[p]) continue;
-            keep.resize((size_t)n);
-            int32_t n_keep = 0;
-            int accept = 1;
-            if (verify) {
-                accept = verify(user, idx1, idx2, imgs[idx1].xy.data(), imgs[idx1].info.num_pts, imgs[idx2].xy.data(),
-                                imgs[idx2].info.num_pts, m, g, n, keep.data(), &n_keep);
-            } else if (!geo_ok.empty()) {
-                accept = geo_ok[p];
-                for (int32_t k = 0; k < n; ++k)
-                    if (geo_keep[moff[p] + k]) keep[n_keep++] = k;
-            } else {
-                int32_t n_good = 0;
-                for (int32_t k = 0; k < n; ++k) n_good += g[k];
-                accept = n_good >= opt->min_good;
-                for (int32_t k = 0; k < n; ++k) keep[k] = k;
-                n_keep = n;
-            }
-            if (!accept) continue;
-            kept.resize((size_t)n_keep * 2);
-            for (int32_t k = 0; k < n_keep; ++k) { kept[2 * k] = m[keep[k]][0]; kept[2 * k + 1] = m[keep[k]][1]; }
-            if (msfm_match_append(fold, idx1, idx2, reinterpret_cast<const int32_t(*)[2]>(kept.data()), n_keep) != 0)
-                return fail(err, err_cap, -2, "cannot append to the match file of image %d", idx1);
-            graph[(size_t)idx1 * num_imgs + idx2] = n_keep;
-        }
-        if (msfm_match_index_append(fold, idx1) != 0) return fail(err, err_cap, -2, "cannot append to match_index.txt");
-    }
-    clk.lap("verify seam + match files");
     if (msfm_graph_write(fold, num_imgs, graph.data()) != 0) return fail(err, err_cap, -2, "cannot write graph_matching.txt");
     return 0;
 }

@@ -259,7 +259,7 @@ class Matcher:
                 xy_keep.append(a)
                 ptrs[i] = a.ctypes.data
                 npts[i] = a.shape[0]
-        gp = _lib.GeoParams(th_epipolar, min_points, min_inliers, iters, seed)
+        gp = _lib.GeoParams(th_epipolar, min_points, min_inliers, iters, seed, 0)
         total = int(result.offsets[n])
         ok = np.zeros((max(n, 1),), np.int32)
         inl = np.zeros((max(n, 1),), np.int32)

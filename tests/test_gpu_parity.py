@@ -643,3 +643,39 @@ def test_many_images_many_pairs_batches(oracle_mod, native_lib):
         exp = oracle_mod.match_pair_u8(imgs[r], imgs[q], 0.85, mutual=True, ratio_good=0.6)
         np.testing.assert_array_equal(res.pair(p), exp["pairs"], err_msg=f"pair {p} = ({r},{q})")
         np.testing.assert_array_equal(res.pair_good(p), exp["good"])
+
+
+def test_build_match_graph_chunking_is_invisible(native_lib, tmp_path):
+    """The driver processes the missing images in bounded chunks (host match buffers, incremental match_index.txt):
+    whatever the chunk size, the files are byte-identical — including the GPU geo-verification's RANSAC draws."""
+    import shutil
+    from metricsfm_b200 import build, store
+    build.build_host_libs()
+    rng = np.random.default_rng(51)
+    n = 900
+    col = synth.Collection(n, seed=44)
+    base = col.image_u8(0)
+    imgs, xys = [], []
+    p0, p1 = _two_view_scene(rng, n, 0)
+    for i in range(6):
+        perm = rng.permutation(n)
+        d = np.clip(base[perm].astype(np.int32) + rng.integers(-2, 3, size=(n, 128)), 0, 255).astype(np.uint8)
+        imgs.append(d)
+        xys.append((p0 if i % 2 == 0 else p1)[perm])                       # even / odd images: the two views of one scene
+    folds = [str(tmp_path / name) for name in ("one", "small", "tiny")]
+    adj = [[1, 3, 5], [2, 4], [3], [0, 5], [], [0]]
+    offs = np.cumsum([0] + [len(a) for a in adj]).astype(np.int64)
+    lst = np.array([j for a in adj for j in a], np.int32)
+    for fold, chunk in zip(folds, (0, 2 * n, 1)):
+        os.makedirs(fold)
+        for i, (d, p) in enumerate(zip(imgs, xys)):
+            store.feature_write(store.feature_path(fold, i), rows=4000, cols=4000, xy_pixel=p + 2000.0, desc=d)
+        store.build_match_graph(fold, offs, lst, geo_verify=True, geo_seed=9, max_batch_rows=chunk)
+    names = sorted(f for f in os.listdir(folds[0]) if not f.endswith("_feature"))
+    assert "0_match" in names and "graph_matching.txt" in names
+    for fold in folds[1:]:
+        assert names == sorted(f for f in os.listdir(fold) if not f.endswith("_feature"))
+        for name in names:
+            assert open(folds[0] + "//" + name, "rb").read() == open(fold + "//" + name, "rb").read(), (fold, name)
+    g = store.graph_read(folds[0], 6)
+    assert g[0, 1] > 300 and g[0, 3] > 300        # different views of the scene: verified
