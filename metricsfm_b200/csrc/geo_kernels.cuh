@@ -184,25 +184,35 @@ __global__ void __launch_bounds__(kGeoThreads) geo_verify_kernel(const GeoParams
         int n_pts = 0;
         float scale = 1.0f;
         if (ok) {
-            // ---- good matches (a strided subsample beyond the cap) into shared memory, isotropically scaled
-            //      (single thread: ordered compaction of a few thousand flags; negligible next to the RANSAC loop)
+            // ---- good matches (a strided subsample beyond the cap) into shared memory, isotropically scaled:
+            //      warp 0 walks the match list 32 entries at a time (ballot + prefix count keeps the list order)
             const int stride = (n_good + kGeoPointCap - 1) / kGeoPointCap;
-            if (threadIdx.x == 0) {
-                int g = 0, k = 0;
+            if (threadIdx.x < 32) {
+                const int lane = threadIdx.x;
+                int g = 0, k = 0;  // good matches seen / points stored so far (warp-uniform)
                 float mx = 1.0f;
-                for (int i = 0; i < n_all; ++i) {
-                    if (!gd[i]) continue;
-                    if (g % stride == 0 && k < kGeoPointCap) {
+                for (int base = 0; base < n_all; base += 32) {
+                    const int i = base + lane;
+                    const bool isg = i < n_all && gd[i] != 0;
+                    const unsigned bg = __ballot_sync(0xFFFFFFFFu, isg);
+                    const int gi = g + __popc(bg & ((1u << lane) - 1u));          // index of this match among the good ones
+                    const bool take = isg && (gi % stride == 0);
+                    const unsigned bt = __ballot_sync(0xFFFFFFFFu, take);
+                    const int ki = k + __popc(bt & ((1u << lane) - 1u));
+                    if (take && ki < kGeoPointCap) {
                         const int2 m = mt[i];
-                        sx1[k] = xy1[2 * m.x]; sy1[k] = xy1[2 * m.x + 1];
-                        sx2[k] = xy2[2 * m.y]; sy2[k] = xy2[2 * m.y + 1];
-                        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(sx1[k]), fabsf(sy1[k])), fmaxf(fabsf(sx2[k]), fabsf(sy2[k]))));
-                        ++k;
+                        const float a = xy1[2 * m.x], b = xy1[2 * m.x + 1], c2 = xy2[2 * m.y], d = xy2[2 * m.y + 1];
+                        sx1[ki] = a; sy1[ki] = b; sx2[ki] = c2; sy2[ki] = d;
+                        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(a), fabsf(b)), fmaxf(fabsf(c2), fabsf(d))));
                     }
-                    ++g;
+                    g += __popc(bg);
+                    k += __popc(bt);
                 }
-                s_cnt[0] = k;
-                s_red_cnt[0] = __float_as_int(1.0f / mx);
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+                if (lane == 0) {
+                    s_cnt[0] = min(k, kGeoPointCap);
+                    s_red_cnt[0] = __float_as_int(1.0f / mx);
+                }
             }
             __syncthreads();
             n_pts = s_cnt[0];
