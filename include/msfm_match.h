@@ -203,6 +203,15 @@ msfm_status msfm_geo_verify(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pai
                             const int32_t *image_npts, int32_t n_images, const msfm_geo_params *gp, int32_t *pair_ok,
                             int32_t *pair_inliers, uint8_t *keep, double *F);
 
+/* The RANSAC part alone, with the consensus set as a per-match mask: what the matcher family's own verification loops
+ * (KNNMatchingWithGeoVerify, feature_matching.cpp:97-138: findFundamentalMat(FM_RANSAC, 3.0) then (…, 1.0), dropping
+ * the outliers after each pass) consume.  `use[k]` selects the matches that take part; inlier_mask[k] = 1 iff match k
+ * took part and its error is within th_epipolar of the best model.  pair_ok as in msfm_geo_verify. */
+msfm_status msfm_geo_ransac(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const int64_t *offsets,
+                            const int32_t (*matches)[2], const uint8_t *use, const float *const *image_xy,
+                            const int32_t *image_npts, int32_t n_images, const msfm_geo_params *gp, int32_t *pair_ok,
+                            int32_t *pair_inliers, uint8_t *inlier_mask, double *F);
+
 /* ---- GPU-side cross-check kernel (CUDA cores, dp4a); used by the tests to localise faults, never by the fast path */
 msfm_status msfm_knn2_crosscheck(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_t *ids, float *dists);
 

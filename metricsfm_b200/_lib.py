@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "msfm_abi_version", "msfm_status_string", "msfm_create", "msfm_destroy", "msfm_last_error", "msfm_upload_u8",
     "msfm_upload_u8_batch", "msfm_upload_f32", "msfm_reserve", "msfm_release", "msfm_release_all", "msfm_image_info", "msfm_table_ptrs",
     "msfm_download_packed", "msfm_knn2", "msfm_colbest", "msfm_match_pairs", "msfm_match_pairs_resident",
-    "msfm_last_timing", "msfm_get_stream", "msfm_knn2_crosscheck", "msfm_geo_verify",
+    "msfm_last_timing", "msfm_get_stream", "msfm_knn2_crosscheck", "msfm_geo_verify", "msfm_geo_ransac",
 ]
 
 
@@ -95,6 +95,7 @@ def load() -> C.CDLL:
     L.msfm_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.msfm_knn2_crosscheck.argtypes = [vp, C.c_int32, C.c_int32, vp, vp]
     L.msfm_geo_verify.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp, C.c_int32, C.POINTER(GeoParams), vp, vp, vp, vp]
+    L.msfm_geo_ransac.argtypes = L.msfm_geo_verify.argtypes
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
         if name not in ("msfm_abi_version", "msfm_status_string", "msfm_last_error"):

@@ -28,6 +28,7 @@ struct GeoParams {
     int32_t min_points, min_inliers, iters;
     unsigned long long seed;
     long long pair_base;       // global index of pair 0 of this call (RANSAC counter)
+    int32_t stage_b;           // 1: keep = F-filter of all matches (stage B); 0: keep = RANSAC inlier mask of the good ones
     int32_t *pair_ok;          // [n_pairs]
     int32_t *pair_inliers;     // [n_pairs] stage-A inliers among the good matches
     uint8_t *keep;             // [total matches] stage-B mask
@@ -300,7 +301,12 @@ __global__ void __launch_bounds__(kGeoThreads) geo_verify_kernel(const GeoParams
         // ---- stage B: one-sided distance of p2 to the epipolar line F p1 on every "all" match (geo_verification.cc:60-79)
         for (int i = threadIdx.x; i < n_all; i += kGeoThreads) {
             uint8_t k = 0;
-            if (ok) {
+            if (ok && !gp.stage_b) {
+                const int2 m = mt[i];
+                k = gd[i] && sym_epi_err<double>(s_F, xy1[2 * m.x], xy1[2 * m.x + 1], xy2[2 * m.y], xy2[2 * m.y + 1]) <=
+                                 (double)gp.th * (double)gp.th
+                        ? 1 : 0;
+            } else if (ok) {
                 const int2 m = mt[i];
                 const double ax = xy1[2 * m.x], ay = xy1[2 * m.x + 1], bx = xy2[2 * m.y], by = xy2[2 * m.y + 1];
                 const double l0 = s_F[0] * ax + s_F[1] * ay + s_F[2], l1 = s_F[3] * ax + s_F[4] * ay + s_F[5],

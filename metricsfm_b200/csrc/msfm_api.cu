@@ -938,10 +938,27 @@ msfm_status msfm_get_stream(const msfm_ctx *ctx, void **cuda_stream) {
     return MSFM_OK;
 }
 
+static msfm_status geo_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const int64_t *offsets, const int32_t (*matches)[2],
+                            const uint8_t *good, const float *const *image_xy, const int32_t *image_npts, int32_t n_images,
+                            const msfm_geo_params *gp, int32_t *pair_ok, int32_t *pair_inliers, uint8_t *keep, double *F, bool stage_b);
+
 msfm_status msfm_geo_verify(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const int64_t *offsets,
                             const int32_t (*matches)[2], const uint8_t *good, const float *const *image_xy,
                             const int32_t *image_npts, int32_t n_images, const msfm_geo_params *gp, int32_t *pair_ok,
                             int32_t *pair_inliers, uint8_t *keep, double *F) {
+    return geo_impl(ctx, pairs, n_pairs, offsets, matches, good, image_xy, image_npts, n_images, gp, pair_ok, pair_inliers, keep, F, true);
+}
+
+msfm_status msfm_geo_ransac(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const int64_t *offsets,
+                            const int32_t (*matches)[2], const uint8_t *use, const float *const *image_xy,
+                            const int32_t *image_npts, int32_t n_images, const msfm_geo_params *gp, int32_t *pair_ok,
+                            int32_t *pair_inliers, uint8_t *inlier_mask, double *F) {
+    return geo_impl(ctx, pairs, n_pairs, offsets, matches, use, image_xy, image_npts, n_images, gp, pair_ok, pair_inliers, inlier_mask, F, false);
+}
+
+static msfm_status geo_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const int64_t *offsets, const int32_t (*matches)[2],
+                            const uint8_t *good, const float *const *image_xy, const int32_t *image_npts, int32_t n_images,
+                            const msfm_geo_params *gp, int32_t *pair_ok, int32_t *pair_inliers, uint8_t *keep, double *F, bool stage_b) {
     if (!ctx) return MSFM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (n_pairs < 0 || !gp || (n_pairs > 0 && (!pairs || !offsets || !pair_ok || !pair_inliers || !image_xy || !image_npts)))
@@ -1013,6 +1030,7 @@ msfm_status msfm_geo_verify(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pai
     kp.iters = gp->iters > 0 ? gp->iters : 1024;
     kp.seed = gp->seed;
     kp.pair_base = gp->pair_index_base;
+    kp.stage_b = stage_b ? 1 : 0;
     kp.pair_ok = static_cast<int32_t *>(d.ok.ptr);
     kp.pair_inliers = static_cast<int32_t *>(d.inl.ptr);
     kp.keep = static_cast<uint8_t *>(d.keep.ptr);

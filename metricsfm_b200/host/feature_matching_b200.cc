@@ -1,6 +1,8 @@
 // feature_matching_b200.cc — see feature_matching_b200.h.  Pure marshalling over the C ABI.
 #include "feature_matching_b200.h"
 
+#include <cmath>
+
 #include <cstring>
 
 namespace objectsfm {
@@ -86,6 +88,112 @@ bool FeatureMatchingB200::Run(std::vector<cv::KeyPoint> &kp1, cv::Mat &descripto
                               cv::Mat &descriptors2, std::vector<std::pair<int, int>> &matches) {
     if ((int)kp1.size() < opt_.th_reject || (int)kp2.size() < opt_.th_reject) return false;
     return Match(descriptors1, descriptors2, true, matches);
+}
+
+bool FindHomographyDLT(const std::vector<cv::Point2f> &pt1, const std::vector<cv::Point2f> &pt2, double H[9]) {
+    const size_t n = pt1.size();
+    if (n < 4 || pt2.size() != n) return false;
+    // Hartley normalisation of both point sets
+    double c1[2] = {0, 0}, c2[2] = {0, 0};
+    for (size_t i = 0; i < n; ++i) { c1[0] += pt1[i].x; c1[1] += pt1[i].y; c2[0] += pt2[i].x; c2[1] += pt2[i].y; }
+    for (double *c : {c1, c2}) { c[0] /= n; c[1] /= n; }
+    double d1 = 0, d2 = 0;
+    for (size_t i = 0; i < n; ++i) {
+        d1 += std::hypot(pt1[i].x - c1[0], pt1[i].y - c1[1]);
+        d2 += std::hypot(pt2[i].x - c2[0], pt2[i].y - c2[1]);
+    }
+    if (!(d1 > 0) || !(d2 > 0)) return false;
+    const double s1 = std::sqrt(2.0) * n / d1, s2 = std::sqrt(2.0) * n / d2;
+    double M[9][9] = {};
+    for (size_t i = 0; i < n; ++i) {
+        const double x = (pt1[i].x - c1[0]) * s1, y = (pt1[i].y - c1[1]) * s1, u = (pt2[i].x - c2[0]) * s2, v = (pt2[i].y - c2[1]) * s2;
+        const double r1[9] = {x, y, 1, 0, 0, 0, -u * x, -u * y, -u}, r2[9] = {0, 0, 0, x, y, 1, -v * x, -v * y, -v};
+        for (int a = 0; a < 9; ++a)
+            for (int b = 0; b < 9; ++b) M[a][b] += r1[a] * r1[b] + r2[a] * r2[b];
+    }
+    // cyclic Jacobi: eigenvector of the smallest eigenvalue of the symmetric 9 x 9 matrix
+    double V[9][9] = {};
+    for (int i = 0; i < 9; ++i) V[i][i] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0;
+        for (int p = 0; p < 9; ++p)
+            for (int q = p + 1; q < 9; ++q) off += M[p][q] * M[p][q];
+        if (off < 1e-26) break;
+        for (int p = 0; p < 9; ++p)
+            for (int q = p + 1; q < 9; ++q) {
+                if (std::fabs(M[p][q]) < 1e-300) continue;
+                const double theta = (M[q][q] - M[p][p]) / (2.0 * M[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 9; ++k) { const double a = M[k][p], b = M[k][q]; M[k][p] = c * a - sn * b; M[k][q] = sn * a + c * b; }
+                for (int k = 0; k < 9; ++k) { const double a = M[p][k], b = M[q][k]; M[p][k] = c * a - sn * b; M[q][k] = sn * a + c * b; }
+                for (int k = 0; k < 9; ++k) { const double a = V[k][p], b = V[k][q]; V[k][p] = c * a - sn * b; V[k][q] = sn * a + c * b; }
+            }
+    }
+    int best = 0;
+    for (int i = 1; i < 9; ++i)
+        if (M[i][i] < M[best][best]) best = i;
+    double h[9];
+    for (int i = 0; i < 9; ++i) h[i] = V[i][best];
+    // denormalise: H = T2^-1 * Hn * T1 with T = [s 0 -s*cx; 0 s -s*cy; 0 0 1]
+    const double T1[9] = {s1, 0, -s1 * c1[0], 0, s1, -s1 * c1[1], 0, 0, 1};
+    const double T2i[9] = {1 / s2, 0, c2[0], 0, 1 / s2, c2[1], 0, 0, 1};
+    double tmp[9], out[9];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) tmp[3 * r + c] = h[3 * r] * T1[c] + h[3 * r + 1] * T1[3 + c] + h[3 * r + 2] * T1[6 + c];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) out[3 * r + c] = T2i[3 * r] * tmp[c] + T2i[3 * r + 1] * tmp[3 + c] + T2i[3 * r + 2] * tmp[6 + c];
+    if (std::fabs(out[8]) < 1e-300) return false;
+    for (int i = 0; i < 9; ++i) H[i] = out[i] / out[8];
+    return true;
+}
+
+bool FeatureMatchingB200::KNNMatchingWithGeoVerify(std::vector<cv::KeyPoint> &kp1, cv::Mat &descriptors1, std::vector<cv::KeyPoint> &kp2,
+                                                   cv::Mat &descriptors2, std::vector<std::pair<int, int>> &matches) {
+    if ((int)kp1.size() < opt_.th_reject || (int)kp2.size() < opt_.th_reject) return false;  // feature_matching.cpp:74-77
+    std::vector<std::pair<int, int>> cur;
+    if (!Match(descriptors1, descriptors2, opt_.mutual, cur)) return false;                   // ratio matches (i1, i2)
+    std::vector<float> xy1(kp1.size() * 2), xy2(kp2.size() * 2);
+    for (size_t i = 0; i < kp1.size(); ++i) { xy1[2 * i] = kp1[i].pt.x; xy1[2 * i + 1] = kp1[i].pt.y; }
+    for (size_t i = 0; i < kp2.size(); ++i) { xy2[2 * i] = kp2[i].pt.x; xy2[2 * i + 1] = kp2[i].pt.y; }
+    const float th_epipolar[2] = {3.0f, 1.0f};                                                  // feature_matching.cpp:97-99
+    for (int iter = 0; iter < 2; ++iter) {
+        if ((int)cur.size() < opt_.th_reject) return false;                                     // :114-117
+        std::vector<cv::Point2f> p1(cur.size()), p2(cur.size());
+        for (size_t k = 0; k < cur.size(); ++k) { p1[k] = kp1[cur[k].first].pt; p2[k] = kp2[cur[k].second].pt; }
+        double H[9];
+        if (FindHomographyDLT(p1, p2, H) && std::fabs(H[0] - 0.995) < 0.01 && std::fabs(H[4] - 0.995) < 0.01 &&
+            std::fabs(H[8] - 0.995) < 0.01)
+            return false;                                                                        // :120-127 (no parallax)
+        // cv::findFundamentalMat(pt1, pt2, status, FM_RANSAC, th) :129-137 -> msfm_geo_ransac; image 1 plays "ref"
+        msfm_pair pair = {0, 1};
+        int64_t offsets[2] = {0, (int64_t)cur.size()};
+        std::vector<int32_t> m(cur.size() * 2);
+        for (size_t k = 0; k < cur.size(); ++k) { m[2 * k] = cur[k].first; m[2 * k + 1] = cur[k].second; }
+        std::vector<uint8_t> use(cur.size(), 1), mask(cur.size(), 0);
+        const float *xy[2] = {xy1.data(), xy2.data()};
+        const int32_t npts[2] = {(int32_t)kp1.size(), (int32_t)kp2.size()};
+        msfm_geo_params gp;
+        memset(&gp, 0, sizeof gp);
+        gp.th_epipolar = th_epipolar[iter];
+        gp.min_points = 8;
+        gp.min_inliers = 0;
+        gp.iters = 1024;
+        gp.seed = (uint64_t)iter;
+        int32_t ok = 0, inl = 0;
+        msfm_status st = msfm_geo_ransac(ctx_, &pair, 1, offsets, reinterpret_cast<const int32_t(*)[2]>(m.data()), use.data(), xy, npts, 2,
+                                         &gp, &ok, &inl, mask.data(), nullptr);
+        if (st != MSFM_OK) {
+            err_ = msfm_last_error(ctx_);
+            return false;
+        }
+        std::vector<std::pair<int, int>> next;
+        for (size_t k = 0; k < cur.size(); ++k)
+            if (mask[k]) next.push_back(cur[k]);
+        cur.swap(next);
+    }
+    matches.insert(matches.end(), cur.begin(), cur.end());                                       // :141-147 (push_back)
+    return true;  // the reference falls off the end here; its callers treat the call as successful
 }
 
 bool FeatureMatchingB200::KNN2(cv::Mat &descriptors1, cv::Mat &descriptors2, int *id, float *dis) {

@@ -52,6 +52,14 @@ public:
     // FeatureMatchingCudaSift::Run kNN part: same as above with the mutual-best-match rule of the declared GPU matchers.
     bool Run(std::vector<cv::KeyPoint> &kp1, cv::Mat &descriptors1, std::vector<cv::KeyPoint> &kp2, cv::Mat &descriptors2,
              std::vector<std::pair<int, int>> &matches);
+    // FeatureMatching::KNNMatchingWithGeoVerify(kp1, d1, kp2, d2, matches) (feature_matching.cpp:67-150): ratio matches as in
+    // KNNMatching, then two verification passes (epipolar threshold 3 px, then 1 px): fewer than th_reject matches =>
+    // false; a least-squares homography close to the identity (diagonal within 0.01 of 0.995) => false (no parallax);
+    // RANSAC-F, outliers dropped.  The matches are APPENDED (the reference push_backs).  RANSAC runs on the GPU
+    // (msfm_geo_ransac); the homography is a normalised DLT without OpenCV's final Levenberg-Marquardt polish, which the
+    // 0.01 test does not resolve.
+    bool KNNMatchingWithGeoVerify(std::vector<cv::KeyPoint> &kp1, cv::Mat &descriptors1, std::vector<cv::KeyPoint> &kp2,
+                                  cv::Mat &descriptors2, std::vector<std::pair<int, int>> &matches);
     // Index on image 1, 2-NN of every row of image 2 in FLANN layout: id[2*N2], dis[2*N2] (squared L2) — exactly the
     // arrays KNNMatchingWithGeoVerify(kp1, kp2, id, dis, matches) and fine_matching_graph.cc:96-99 consume.
     bool KNN2(cv::Mat &descriptors1, cv::Mat &descriptors2, int *id, float *dis);
@@ -63,6 +71,11 @@ private:
     MatcherB200Options opt_;
     std::string err_;
 };
+
+// Least-squares homography pt2 ~ H pt1 (normalised DLT, smallest eigenvector of A^T A by Jacobi sweeps), scaled so that
+// H[8] = 1; false when the system is degenerate.  Stand-in for cv::findHomography(pt1, pt2) with method 0
+// (feature_matching.cpp:115).
+bool FindHomographyDLT(const std::vector<cv::Point2f> &pt1, const std::vector<cv::Point2f> &pt2, double H[9]);
 
 // Batched form of FineMatchingGraph::BuildMatchGraph's matching loops: stage every image once (replaces the per-idx1
 // flann_build_index and the per-pair disk re-reads, fine_matching_graph.cc:69-91), then match the whole candidate pair

@@ -9,7 +9,7 @@
 
 int main(int argc, char **argv) {
     if (argc < 4) {
-        fprintf(stderr, "usage: %s <desc.f32> <rows1> <rows2>\n", argv[0]);
+        fprintf(stderr, "usage: %s <desc.f32> <rows1> <rows2> [<keypoints.f32: xy of image 1 then image 2>]\n", argv[0]);
         return 2;
     }
     const int n1 = atoi(argv[2]), n2 = atoi(argv[3]);
@@ -38,6 +38,38 @@ int main(int argc, char **argv) {
     const bool ok2 = matcher.KNN2(d1, d2, id.data(), dis.data());
     printf("KNN2 %d %d\n", ok2 ? 1 : 0, n2);
     for (int i = 0; i < n2; ++i) printf("%d %d %.1f %.1f\n", id[2 * i], id[2 * i + 1], dis[2 * i], dis[2 * i + 1]);
+
+    if (argc > 4) {  // keypoints given: the verified matcher of feature_matching.cpp:67-150
+        std::vector<float> xy((size_t)(n1 + n2) * 2);
+        FILE *fk = fopen(argv[4], "rb");
+        if (!fk || fread(xy.data(), sizeof(float), xy.size(), fk) != xy.size()) {
+            fprintf(stderr, "cannot read %s\n", argv[4]);
+            return 2;
+        }
+        fclose(fk);
+        for (int i = 0; i < n1; ++i) { kp1[i].pt.x = xy[2 * i]; kp1[i].pt.y = xy[2 * i + 1]; }
+        for (int i = 0; i < n2; ++i) { kp2[i].pt.x = xy[2 * (n1 + i)]; kp2[i].pt.y = xy[2 * (n1 + i) + 1]; }
+        {   // least-squares homography of the unverified ratio matches (the quantity the degeneracy gate looks at)
+            std::vector<cv::Point2f> a, b;
+            for (auto &m : matches) { a.push_back(kp1[m.first].pt); b.push_back(kp2[m.second].pt); }
+            double Ha[9] = {0};
+            const bool oka = objectsfm::FindHomographyDLT(a, b, Ha);
+            printf("HomographyAll %d", oka ? 1 : 0);
+            for (int i = 0; i < 9; ++i) printf(" %.9g", Ha[i]);
+            printf("\n");
+        }
+        std::vector<std::pair<int, int>> verified;
+        const bool okv = matcher.KNNMatchingWithGeoVerify(kp1, d1, kp2, d2, verified);
+        printf("GeoVerify %d %zu\n", okv ? 1 : 0, verified.size());
+        for (auto &m : verified) printf("%d %d\n", m.first, m.second);
+        std::vector<cv::Point2f> p1, p2;
+        for (auto &m : verified) { p1.push_back(kp1[m.first].pt); p2.push_back(kp2[m.second].pt); }
+        double H[9] = {0};
+        const bool okh = objectsfm::FindHomographyDLT(p1, p2, H);
+        printf("Homography %d", okh ? 1 : 0);
+        for (int i = 0; i < 9; ++i) printf(" %.9g", H[i]);
+        printf("\n");
+    }
 
     objectsfm::MatchGraphB200 graph(0, 2, n1 + n2);
     std::vector<std::vector<int>> init = {{1}, {0}};

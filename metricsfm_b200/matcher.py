@@ -245,10 +245,11 @@ class Matcher:
         return total.value
 
     def geo_verify(self, pairs, result: "MatchResult", image_xy: dict, *, th_epipolar: float = 3.0, min_points: int = 30,
-                   min_inliers: int = 30, iters: int = 1024, seed: int = 0):
+                   min_inliers: int = 30, iters: int = 1024, seed: int = 0, ransac_only: bool = False):
         """Batched GeoVerificationFundamental (utils/geo_verification.cc:30-79) of the pairs of a match_pairs result
         (orientation 0, ratio_good set).  image_xy: {image id: [n, 2] float32 centred keypoints}.  Returns
-        (pair_ok [n] int32, pair_inliers [n] int32, keep [total] uint8, F [n, 3, 3] float64)."""
+        (pair_ok [n] int32, pair_inliers [n] int32, keep [total] uint8, F [n, 3, 3] float64).  ransac_only: msfm_geo_ransac —
+        `result.good` selects the participating matches and `keep` is the RANSAC consensus mask instead of the F-filter."""
         pa = self._pairs(pairs)
         n = pa.shape[0]
         n_images = int(pa.max()) + 1 if n else 0
@@ -268,9 +269,11 @@ class Matcher:
         offs = np.ascontiguousarray(result.offsets, np.int64)
         m = np.ascontiguousarray(result.matches, np.int32)
         g = np.ascontiguousarray(result.good if result.good is not None else np.ones((total,), np.uint8), np.uint8)
-        self._check(self._L.msfm_geo_verify(self._h, pa.ctypes.data, n, offs.ctypes.data, m.ctypes.data if total else None,
+        fn = self._L.msfm_geo_ransac if ransac_only else self._L.msfm_geo_verify
+        self._check(fn(self._h, pa.ctypes.data, n, offs.ctypes.data, m.ctypes.data if total else None,
                                             g.ctypes.data if total else None, C.cast(ptrs, C.c_void_p), npts.ctypes.data, n_images,
-                                            C.byref(gp), ok.ctypes.data, inl.ctypes.data, keep.ctypes.data, F.ctypes.data))
+                                            C.byref(gp), ok.ctypes.data, inl.ctypes.data, keep.ctypes.data, F.ctypes.data)
+                    )
         return ok[:n], inl[:n], keep[:total], F[:n]
 
     def cuda_stream(self) -> int:

@@ -679,3 +679,68 @@ def test_build_match_graph_chunking_is_invisible(native_lib, tmp_path):
             assert open(folds[0] + "//" + name, "rb").read() == open(fold + "//" + name, "rb").read(), (fold, name)
     g = store.graph_read(folds[0], 6)
     assert g[0, 1] > 300 and g[0, 3] > 300        # different views of the scene: verified
+
+
+def test_cpp_shim_verified_matcher_vs_opencv_flow(oracle_mod, native_lib, tmp_path):
+    """FeatureMatchingB200::KNNMatchingWithGeoVerify against the reference's flow (feature_matching.cpp:67-150) run with
+    the CPU oracle's ratio matches and cv2: homography-degeneracy gate, RANSAC-F at 3 px then 1 px.  RANSAC parity is
+    statistical (OpenCV's RNG stream cannot be reproduced); the DLT homography is compared with cv2.findHomography."""
+    import subprocess
+    import cv2
+    from metricsfm_b200 import build
+    exe = build.build_host_shim()
+    rng = np.random.default_rng(61)
+    n = 1500
+    col = synth.Collection(n, seed=62)
+    d1 = col.image_u8(0)
+    perm = rng.permutation(n)
+    d2 = np.clip(d1[perm].astype(np.int32) + rng.integers(-2, 3, size=(n, 128)), 0, 255).astype(np.uint8)
+    p1, p2 = _two_view_scene(rng, n, 0, noise=0.3)
+    xy1, xy2 = p1 + 2000.0, p2[perm] + 2000.0
+    xy2[: n // 5] = rng.uniform(0, 4000, (n // 5, 2))                      # 20 % of the re-observations moved: outliers
+
+    def run(xy_b):
+        raw, kpf = tmp_path / "desc.f32", tmp_path / "kp.f32"
+        np.concatenate([d1, d2]).astype(np.float32).tofile(raw)
+        np.concatenate([xy1, xy_b]).astype(np.float32).tofile(kpf)
+        out = subprocess.check_output([exe, str(raw), str(n), str(n), str(kpf)], text=True).split("\n")
+        i = next(k for k, l in enumerate(out) if l.startswith("GeoVerify"))
+        ok, cnt = int(out[i].split()[1]), int(out[i].split()[2])
+        got = np.array([l.split() for l in out[i + 1:i + 1 + cnt]], dtype=np.int32).reshape(-1, 2)
+        h = out[i + 1 + cnt].split()
+        ha = next(l for l in out if l.startswith("HomographyAll")).split()
+        return ok, got, int(h[1]), np.array(h[2:], np.float64).reshape(3, 3), np.array(ha[2:], np.float64).reshape(3, 3)
+
+    ok, got, okh, H, _ = run(xy2)
+    # the reference flow on the CPU
+    cur = oracle_mod.match_pair_u8(d2, d1, 0.5, orientation=1)["pairs"]      # index on image 2, (i1, i2) ascending i1
+    assert {tuple(m) for m in got} <= {tuple(m) for m in cur}
+    for th in (3.0, 1.0):
+        a, b = xy1[cur[:, 0]].astype(np.float32), xy2[cur[:, 1]].astype(np.float32)
+        Hcv, _ = cv2.findHomography(a, b, 0)
+        assert not all(abs(Hcv[i, i] - 0.995) < 0.01 for i in range(3))
+        _, mask = cv2.findFundamentalMat(a, b, cv2.FM_RANSAC, th, 0.99)
+        cur = cur[mask.ravel() > 0]
+    assert ok == 1
+    sg, sc = {tuple(m) for m in got}, {tuple(m) for m in cur}
+    assert len(sg & sc) >= 0.93 * len(sc), (len(sg), len(sc), len(sg & sc))   # OpenCV's consensus is (nearly) contained
+    moved = np.isin(got[:, 1], np.arange(n // 5))
+    assert moved.mean() < 0.02 and len(got) > 0.6 * (n - n // 5) * 0.5
+    # DLT homography of the surviving matches vs OpenCV's least-squares estimate
+    a, b = xy1[got[:, 0]].astype(np.float32), xy2[got[:, 1]].astype(np.float32)
+    Hcv, _ = cv2.findHomography(a, b, 0)
+    assert okh == 1
+    pa = np.concatenate([a, np.ones((len(a), 1), np.float32)], 1).astype(np.float64)
+    qa, qb = pa @ H.T, pa @ Hcv.T
+    err = np.abs(qa[:, :2] / qa[:, 2:] - qb[:, :2] / qb[:, 2:]).max(axis=1)
+    # the scene has depth, so no homography fits it: the algebraic (DLT) and the LM-polished least-squares estimates agree
+    # to a few pixels on a 4000-pixel image, far inside what the 0.01 identity test resolves
+    assert np.median(err) < 8.0 and err.max() < 80.0, (np.median(err), err.max())
+    # no parallax: image 2 observed from the same place => homography ~ identity => the matcher refuses the pair
+    xy_same = (xy1[perm] * 0.995 + rng.normal(0, 0.2, (n, 2))).astype(np.float32)
+    ok2, got2, _, _, Hall = run(xy_same)
+    assert ok2 == 0 and len(got2) == 0
+    allm = oracle_mod.match_pair_u8(d2, d1, 0.5, orientation=1)["pairs"]
+    Hcv, _ = cv2.findHomography(xy1[allm[:, 0]].astype(np.float32), xy_same[allm[:, 1]], 0)
+    np.testing.assert_allclose(Hall, Hcv / Hcv[2, 2], atol=2e-3)              # where the gate matters, DLT == OpenCV's estimate
+    assert all(abs(Hall[i, i] - 0.995) < 0.01 for i in range(3))
