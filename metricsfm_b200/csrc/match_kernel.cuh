@@ -84,7 +84,13 @@ struct MatchKernelCfg {
     // CSPLIT warps share one (strip, 32-row quarter) and split the tile's columns between them; TBUFS accumulator
     // buffers per strip let the MMA of tile t+1 run under the epilogue of tile t.
     static constexpr int kEpiWarps = 4 * STRIPS * CSPLIT;
-    static constexpr int kThreads = (kEpiWarps + 2) * 32;
+    static constexpr int kAuxWarps = (1 + STRIPS + 3) / 4 * 4;       // TMA producer + one MMA issuer per strip, padded to warpgroups
+    static constexpr int kThreads = (kEpiWarps + kAuxWarps) * 32;
+    // Registers: the launch gives every thread 65536 / kThreads (a multiple of 8); the auxiliary warpgroups hand most of
+    // their share to the epilogue warps (setmaxnreg), which hold a 64-column accumulator tile each.
+    static constexpr int kAuxRegs = 24;
+    static constexpr int kLaunchRegs = 65536 / kThreads / 8 * 8;
+    static constexpr int kEpiRegs = (kLaunchRegs * kThreads - kAuxWarps * 32 * kAuxRegs) / (kEpiWarps * 32) / 8 * 8;
     static constexpr int kColsPerWarp = TILE_N / CSPLIT;
     // The producer may refill a key slot once the MMAs that share its B stage have completed; those were issued after
     // every epilogue warp released the accumulator buffer TBUFS tiles earlier; a warp releases a buffer before it has
@@ -164,8 +170,9 @@ match_pairs_kernel(const MatchKernelParams p) {
     if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
 
     if (warp == Cfg::kEpiWarps && lane == 0) {
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
+        // A buffers and B stages are released by the commits of all STRIPS MMA issuers
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], STRIPS); }
+        for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], STRIPS); }
         for (int i = 0; i < Cfg::kKeySlots; ++i) ptx::mbar_init(&k_full[i], 1);
         for (int i = 0; i < TBUFS * STRIPS; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 4 * CSPLIT); }
         ptx::fence_mbar_init();
@@ -178,7 +185,9 @@ match_pairs_kernel(const MatchKernelParams p) {
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp == Cfg::kEpiWarps) {
+    if (warp >= Cfg::kEpiWarps) {
+      ptx::setmaxnreg_dec<Cfg::kAuxRegs>();
+      if (warp == Cfg::kEpiWarps) {
         // =========================================================== TMA producer
         if (ptx::elect_one()) {
             uint32_t g = 0, a = 0;
@@ -211,8 +220,12 @@ match_pairs_kernel(const MatchKernelParams p) {
                 ++a;
             }
         }
-    } else if (warp == Cfg::kEpiWarps + 1) {
-        // =========================================================== MMA issuer
+      } else if (warp <= Cfg::kEpiWarps + STRIPS) {
+        // =========================================================== MMA issuers: warp kEpiWarps + 1 + s feeds strip s
+        // One issuer per strip (one elected lane each): the strips' MMAs are no longer issued in a fixed round-robin order
+        // (a strip whose accumulator buffer is free never queues behind one that is still being drained), and the issuing
+        // instructions are spread over the four SM sub-partitions instead of loading one of them.
+        const int s = warp - (Cfg::kEpiWarps + 1);
         if (ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::make_idesc_i8(kStripRows, TILE_N, 0, 0);
             uint32_t g = 0, a = 0;
@@ -222,7 +235,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                 if (pd.cand_idx >= 0 && wi.row0 >= p.counts[pd.cand_idx]) continue;
                 const uint32_t abuf = a & 1;
                 ptx::mbar_wait_backoff(&a_full[abuf], (a >> 1) & 1);
-                const uint32_t a_addr = ptx::smem_u32(sA + abuf * Cfg::kABytes);
+                const uint32_t a_addr = ptx::smem_u32(sA + abuf * Cfg::kABytes) + s * kStripRows * kDim;
                 const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
                 for (int t = 0; t < ntiles; ++t, ++g) {
                     const uint32_t st = g % STAGES;
@@ -230,27 +243,26 @@ match_pairs_kernel(const MatchKernelParams p) {
                     const uint32_t tph = (g / TBUFS) & 1;
                     ptx::mbar_wait_backoff(&b_full[st], (g / STAGES) & 1);
                     const uint32_t b_addr = ptx::smem_u32(sB + st * Cfg::kBBytes);
+                    ptx::mbar_wait_backoff(&t_empty[buf * STRIPS + s], tph ^ 1);  // accumulator drained by the epilogue
+                    ptx::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (buf * STRIPS + s) * TILE_N;
 #pragma unroll
-                    for (int s = 0; s < STRIPS; ++s) {
-                        ptx::mbar_wait_backoff(&t_empty[buf * STRIPS + s], tph ^ 1);  // accumulator drained by the epilogue
-                        ptx::tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + (buf * STRIPS + s) * TILE_N;
-#pragma unroll
-                        for (int k = 0; k < kDim / 32; ++k) {
-                            const uint64_t da = ptx::make_smem_desc_sw128(a_addr + s * kStripRows * kDim + k * 32);
-                            const uint64_t db = ptx::make_smem_desc_sw128(b_addr + k * 32);
-                            ptx::mma_i8_ss(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
-                        }
-                        ptx::mma_commit(&t_full[buf * STRIPS + s]);  // this strip's accumulators are ready
+                    for (int k = 0; k < kDim / 32; ++k) {
+                        const uint64_t da = ptx::make_smem_desc_sw128(a_addr + k * 32);
+                        const uint64_t db = ptx::make_smem_desc_sw128(b_addr + k * 32);
+                        ptx::mma_i8_ss(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
                     }
-                    ptx::mma_commit(&b_empty[st]);    // B stage reusable once every strip's MMAs have read it
+                    ptx::mma_commit(&t_full[buf * STRIPS + s]);  // this strip's accumulators are ready
+                    ptx::mma_commit(&b_empty[st]);               // one of STRIPS arrivals that free the B stage
                 }
-                ptx::mma_commit(&a_empty[abuf]);      // A buffer reusable
+                ptx::mma_commit(&a_empty[abuf]);                 // one of STRIPS arrivals that free the A buffer
                 ++a;
             }
         }
-    } else if (warp < Cfg::kEpiWarps) {
+      }
+    } else {
         // =========================================================== epilogue (thread = query row x column share)
+        ptx::setmaxnreg_inc<(Cfg::kEpiRegs > 232 ? 232 : Cfg::kEpiRegs)>();
         // Scores s = 2*acc - ||r||^2 (maximise; d = ||q||^2 - s).
         // Phase 1 (filter): stream this warp's share of the strip's accumulator tile through registers once and keep
         //   only the maximum RAW accumulator of every group of 8 columns; a group is flagged when that maximum exceeds
