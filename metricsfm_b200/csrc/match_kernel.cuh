@@ -10,11 +10,15 @@
 // /root/reference/SfM/src/graph/fine_matching_graph.cc:99 (and slam_gps.cc:463, feature_matching.cpp:44,336,409)
 // with the brute-force/mutual-best semantics of the declared GPU matchers (SiftGPU.h:303-308, cudaSift sift.h:97).
 //
-// Roles per CTA ((4*STRIPS*CSPLIT + 2) warps, one CTA per SM, persistent over work items):
+// Roles per CTA (4*STRIPS*CSPLIT epilogue warps + 1 + STRIPS auxiliary warps padded to whole warpgroups; one CTA per SM,
+// persistent over work items):
 //   epilogue warps  warp w owns TMEM lanes 32*(w%4).. of query strip (w/4)%STRIPS and the column share w/(4*STRIPS)
 //                   of every tile (thread = query row x column share)
 //   next warp       TMA producer (one elected lane)
-//   last warp       TMEM allocator + MMA issuer (one elected lane)
+//   next STRIPS     MMA issuers, one per query strip (one elected lane each; the first also owns the TMEM allocation):
+//                   spreads the issue instructions over the four SM sub-partitions and lets every strip advance as soon
+//                   as ITS accumulator buffer is free
+//   (padding warps) idle; the auxiliary warpgroups hand their registers to the epilogue warps (setmaxnreg)
 // Pipelines (all mbarrier based):
 //   A ring (2 deep)     : query strips of a work item, STRIPS x [128 rows x 128 B]
 //   B ring (STAGES)     : reference tiles [TILE_N rows x 128 B]
