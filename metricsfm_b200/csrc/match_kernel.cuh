@@ -245,9 +245,18 @@ match_pairs_kernel(const MatchKernelParams p) {
                     const uint32_t st = g % STAGES;
                     const uint32_t buf = g % TBUFS;
                     const uint32_t tph = (g / TBUFS) & 1;
+                    long long i0 = 0, i1 = 0, i2 = 0;
+                    const bool iprof = DEBUG && (p.debug_flags & 8u) && p.stats != nullptr;
+                    if (iprof) i0 = clock64();
                     ptx::mbar_wait_backoff(&b_full[st], (g / STAGES) & 1);
+                    if (iprof) i1 = clock64();
                     const uint32_t b_addr = ptx::smem_u32(sB + st * Cfg::kBBytes);
                     ptx::mbar_wait_backoff(&t_empty[buf * STRIPS + s], tph ^ 1);  // accumulator drained by the epilogue
+                    if (iprof) {
+                        i2 = clock64();
+                        atomicAdd(p.stats + 40 + 2 * s, (unsigned long long)(i1 - i0));      // issuer: waiting for the B tile
+                        atomicAdd(p.stats + 41 + 2 * s, (unsigned long long)(i2 - i1));      // issuer: waiting for the accumulator buffer
+                    }
                     ptx::tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (buf * STRIPS + s) * TILE_N;
 #pragma unroll

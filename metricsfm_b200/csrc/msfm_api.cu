@@ -665,9 +665,9 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
                              cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::kSmemAlloc) != cudaSuccess)
         return bail(MSFM_ERR_CUDA);
     if (ctx->debug_flags & 8u) {
-        if (cudaMalloc(&ctx->dbg_stats.ptr, 64) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
-        ctx->dbg_stats.bytes = 64;
-        cudaMemset(ctx->dbg_stats.ptr, 0, 64);
+        if (cudaMalloc(&ctx->dbg_stats.ptr, 512) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
+        ctx->dbg_stats.bytes = 512;
+        cudaMemset(ctx->dbg_stats.ptr, 0, 512);
     }
     *out = ctx;
     return MSFM_OK;
@@ -678,11 +678,14 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->dbg_stats.ptr) {
-        unsigned long long h[8] = {0};
-        cudaMemcpy(h, ctx->dbg_stats.ptr, 64, cudaMemcpyDeviceToHost);
+        unsigned long long h[64] = {0};
+        cudaMemcpy(h, ctx->dbg_stats.ptr, 512, cudaMemcpyDeviceToHost);
         const double wt = h[5] ? (double)h[5] : 1.0;
         fprintf(stderr, "[msfm debug] warp-tiles %llu | hot groups/warp-tile %.3f | cycles/warp-tile: wait-acc %.1f load+thresh %.1f "
                         "phase1 %.1f phase2 %.1f\n", h[5], h[0] / wt, h[1] / wt, h[2] / wt, h[3] / wt, h[4] / wt);
+        fprintf(stderr, "[msfm debug] MMA issuers, cycles per tile waiting for (B tile | accumulator buffer):");
+        for (int st = 0; st < 4; ++st) fprintf(stderr, " strip%d %.0f|%.0f", st, h[40 + 2 * st] / (wt / 16.0), h[41 + 2 * st] / (wt / 16.0));
+        fprintf(stderr, "\n");
         cudaFree(ctx->dbg_stats.ptr);
     }
     if (ctx->fdesc) cudaFree(ctx->fdesc);
