@@ -141,6 +141,15 @@ __device__ __forceinline__ int block_rank(bool keep, int &running, int *warp_exc
 //                        nanoflann.hpp:376-383 compiled without contraction), repeats the ratio tests on those
 //                        distances and overwrites the row's kNN entry with the decision
 // Rows outside the band keep the integer decision: their ratio is off the threshold by many times the quantisation error.
+// The fp32 work is confined to the reference rows whose QUANTISED distance is within ~3 % of the row's quantised second
+// best (ten times the quantisation error) -- only those can be fp32 top-2 neighbours.  They are found by the matching
+// kernel itself in "collect" mode (mark_band_kernel gathers the band rows into the candidate scratch image; the tensor
+// pass lists every reference row under the per-row threshold as an event), then
+//   score_events_kernel / second_events_kernel   fp32 distance per event, best and second best per band row (atomicMin
+//                                                on (distance bits, reference row): lowest index wins ties)
+//   finish_band_kernel                           the ratio tests on those distances, kNN entry overwritten
+// rescore_band_kernel does the same search with a dp4a brute force on CUDA cores; it runs only when the event list
+// overflowed (pathological inputs with many near-duplicates) and is the cross-check of the tests.
 constexpr int kRescoredFlag = 0x40000000;  // in knn[row].x: {id0 | flag, bit0 keep | bit1 good, int d0, fp32 d0 bits}
 constexpr int kRescoreRows = 16;           // band rows a CTA scores together against the reference image
 
@@ -154,7 +163,20 @@ struct BandParams {
     const float *fdesc;    // retained float rows, same row offsets as the packed arena
     const uint8_t *desc_arena;
     const int32_t *ckeys;
+    // collect path
+    int32_t *band_thr;               // [forward kNN rows] quantised-distance threshold of each band row
+    unsigned long long *band_state;  // [forward kNN rows][2] best / second best (fp32 distance bits << 32 | reference row)
+    uint8_t *cand_desc;              // candidate scratch image: the band rows' packed descriptors ...
+    int32_t *cand_ckeys;             // ... and their column keys
+    const int4 *events;              // {band row (scratch row), reference row, pair, -} from the collect pass
+    unsigned long long *event_keys;  // [event_cap]
+    const unsigned int *event_count;
+    uint32_t event_cap;
 };
+
+// Quantised-distance threshold under which a reference row may still be an fp32 top-2 neighbour of a band row whose
+// quantised second-best distance is d1.
+__device__ __forceinline__ int band_threshold(int d1) { return d1 + (d1 >> 5) + 256; }
 
 __global__ void __launch_bounds__(1024) mark_band_kernel(const BandParams bp) {
     __shared__ int warp_excl[32];
@@ -165,8 +187,10 @@ __global__ void __launch_bounds__(1024) mark_band_kernel(const BandParams bp) {
         for (int base = 0; base < pd.qry_rows; base += blockDim.x) {
             const int q = base + threadIdx.x;
             bool in_band = false;
+            int d1q = 0;
             if (q < pd.qry_rows) {
                 const int4 k = merge_knn_shares(bp.knn, pd.knn_off + q, bp.nshare);
+                d1q = k.w;
                 if (k.x >= 0 && k.y >= 0) {
                     const float r = __fdiv_rn((float)k.z, (float)k.w);
                     in_band = fabsf(r - bp.ratio) <= bp.band * bp.ratio;
@@ -174,13 +198,105 @@ __global__ void __launch_bounds__(1024) mark_band_kernel(const BandParams bp) {
                 }
             }
             const int slot = block_rank(in_band, running, warp_excl, &chunk_total);
-            if (in_band) bp.band_q[pd.knn_off + slot] = q;
+            if (in_band) {
+                bp.band_q[pd.knn_off + slot] = q;
+                if (bp.band_thr) {
+                    bp.band_thr[pd.knn_off + slot] = band_threshold(d1q);
+                    bp.band_state[2 * (pd.knn_off + slot)] = ~0ull;
+                    bp.band_state[2 * (pd.knn_off + slot) + 1] = ~0ull;
+                }
+            }
         }
     }
     if (threadIdx.x == 0) bp.band_counts[blockIdx.x] = running;
+    if (bp.cand_desc && running > 0) {
+        // gather the band rows (packed descriptor + column key) into the scratch image the collect pass queries
+        __syncthreads();
+        const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+        for (int s = threadIdx.x >> 5; s < running; s += nwarps) {
+            const int64_t src = pd.qry_off + bp.band_q[pd.knn_off + s], dst = pd.knn_off + s;
+            reinterpret_cast<uint32_t *>(bp.cand_desc + dst * kDim)[lane] = reinterpret_cast<const uint32_t *>(bp.desc_arena + src * kDim)[lane];
+            if (lane == 0) bp.cand_ckeys[dst] = bp.ckeys[src];
+        }
+    }
 }
 
 __device__ __forceinline__ bool fknn_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
+
+// Decision of one band row from its fp32 nearest (b0, c0i) and second nearest (b1, c1i) reference rows (-1: none).
+__device__ __forceinline__ void write_rescored(const BandParams &bp, const PairDesc &pd, int q, float b0, int c0i, float b1, int c1i) {
+    int flags = 0;
+    if (c0i >= 0 && c1i >= 0) {
+        const float r = __fdiv_rn(b0, b1);
+        bool keep = r < bp.ratio;
+        if (bp.max_dist_sq > 0.0f) keep = keep && (b0 * pd.fscale2 < bp.max_dist_sq);
+        const bool good = keep && bp.ratio_good > 0.0f && r < bp.ratio_good;
+        flags = (keep ? 1 : 0) | (good ? 2 : 0);
+    }
+    // integer distance of the fp32 nearest neighbour (seeds the mutual search of this candidate)
+    int di = 0;
+    if (c0i >= 0) {
+        const uint32_t *qa = reinterpret_cast<const uint32_t *>(bp.desc_arena + (pd.qry_off + q) * kDim);
+        const uint32_t *rb = reinterpret_cast<const uint32_t *>(bp.desc_arena + (pd.ref_off + c0i) * kDim);
+        uint32_t na = 0, nb = 0, ab = 0;
+        for (int k = 0; k < kDim / 4; ++k) { na = __dp4a(qa[k], qa[k], na); nb = __dp4a(rb[k], rb[k], nb); ab = __dp4a(qa[k], rb[k], ab); }
+        di = (int)(na + nb - 2u * ab);
+    }
+    int4 out;
+    out.x = (c0i >= 0 ? c0i : 0) | kRescoredFlag;
+    out.y = flags;
+    out.z = di;
+    out.w = __float_as_int(b0);
+    bp.knn[(pd.knn_off + q) * bp.nshare] = out;
+    for (int s = 1; s < bp.nshare; ++s) bp.knn[(pd.knn_off + q) * bp.nshare + s] = make_int4(-1, -1, INT_MAX, INT_MAX);
+}
+
+// fp32 squared distance of every collected event; best (distance, reference row) per band row.
+__global__ void __launch_bounds__(256) score_events_kernel(const BandParams bp) {
+    const unsigned n = *bp.event_count;
+    if (n > bp.event_cap) return;  // overflow: rescore_band_kernel takes over
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int4 ev = bp.events[e];
+        const PairDesc pd = bp.pairs[ev.z];
+        const float4 *qf = reinterpret_cast<const float4 *>(bp.fdesc + (pd.qry_off + bp.band_q[ev.x]) * kDim);
+        const float4 *rf = reinterpret_cast<const float4 *>(bp.fdesc + (pd.ref_off + ev.y) * kDim);
+        float acc = 0.0f;  // index order, separate multiply and add (nanoflann.hpp:376-383 without contraction)
+#pragma unroll 4
+        for (int k = 0; k < kDim / 4; ++k) {
+            const float4 a = __ldg(qf + k), b = __ldg(rf + k);
+            float t = __fsub_rn(a.x, b.x); acc = __fadd_rn(acc, __fmul_rn(t, t));
+            t = __fsub_rn(a.y, b.y); acc = __fadd_rn(acc, __fmul_rn(t, t));
+            t = __fsub_rn(a.z, b.z); acc = __fadd_rn(acc, __fmul_rn(t, t));
+            t = __fsub_rn(a.w, b.w); acc = __fadd_rn(acc, __fmul_rn(t, t));
+        }
+        // distances are >= +0, so their bit patterns order like the values; the low word breaks ties by lowest row
+        const unsigned long long key = ((unsigned long long)__float_as_uint(acc) << 32) | (unsigned)ev.y;
+        bp.event_keys[e] = key;
+        atomicMin(bp.band_state + 2 * (int64_t)ev.x, key);
+    }
+}
+
+__global__ void __launch_bounds__(256) second_events_kernel(const BandParams bp) {
+    const unsigned n = *bp.event_count;
+    if (n > bp.event_cap) return;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int64_t row = bp.events[e].x;
+        const unsigned long long key = bp.event_keys[e];
+        if (key != bp.band_state[2 * row]) atomicMin(bp.band_state + 2 * row + 1, key);
+    }
+}
+
+__global__ void __launch_bounds__(256) finish_band_kernel(const BandParams bp) {
+    if (*bp.event_count > bp.event_cap) return;
+    const PairDesc pd = bp.pairs[blockIdx.x];
+    const int n_band = bp.band_counts[blockIdx.x];
+    for (int s = threadIdx.x; s < n_band; s += blockDim.x) {
+        const unsigned long long k0 = bp.band_state[2 * (pd.knn_off + s)], k1 = bp.band_state[2 * (pd.knn_off + s) + 1];
+        const int c0i = k0 == ~0ull ? -1 : (int)(unsigned)k0, c1i = k1 == ~0ull ? -1 : (int)(unsigned)k1;
+        write_rescored(bp, pd, bp.band_q[pd.knn_off + s], c0i < 0 ? INFINITY : __uint_as_float((unsigned)(k0 >> 32)), c0i,
+                       c1i < 0 ? INFINITY : __uint_as_float((unsigned)(k1 >> 32)), c1i);
+    }
+}
 
 __global__ void __launch_bounds__(256) rescore_band_kernel(const BandParams bp, int n_pairs) {
     __shared__ float sq[kRescoreRows][kDim];                  // band rows, float
@@ -189,13 +305,15 @@ __global__ void __launch_bounds__(256) rescore_band_kernel(const BandParams bp, 
     __shared__ float red_d[8][kRescoreRows][2];
     __shared__ int red_i[8][kRescoreRows][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (bp.event_count && *bp.event_count <= bp.event_cap) return;  // the collect path has every event: nothing to do
     for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
         const PairDesc pd = bp.pairs[p];
         const int n_band = bp.band_counts[p];
         const float *ref = bp.fdesc + pd.ref_off * kDim;
         const uint8_t *ref8 = bp.desc_arena + pd.ref_off * kDim;
         const int32_t *refk = bp.ckeys + pd.ref_off;
-        for (int c0 = 0; c0 < n_band; c0 += kRescoreRows) {
+        // chunks of a pair are spread over gridDim.y so that a small batch of pairs still fills the SMs
+        for (int c0 = blockIdx.y * kRescoreRows; c0 < n_band; c0 += gridDim.y * kRescoreRows) {
             const int nq = min(kRescoreRows, n_band - c0);
             __syncthreads();  // previous chunk's shared data is no longer read
             for (int i = threadIdx.x; i < kRescoreRows * kDim; i += blockDim.x) {
@@ -214,8 +332,7 @@ __global__ void __launch_bounds__(256) rescore_band_kernel(const BandParams bp, 
                     na = ckey_to_norm(bp.ckeys[pd.qry_off + q]);
                     // Prefilter on the quantised distance: a row whose integer distance exceeds the integer second
                     // best by more than ~3 % (ten times the quantisation error) cannot be an fp32 top-2 neighbour.
-                    const int d1 = merge_knn_shares(bp.knn, pd.knn_off + q, bp.nshare).w;
-                    thr = d1 + (d1 >> 5) + 256;
+                    thr = band_threshold(merge_knn_shares(bp.knn, pd.knn_off + q, bp.nshare).w);
                 }
                 s_na[qi] = na;
                 s_thr[qi] = thr;
@@ -290,31 +407,7 @@ __global__ void __launch_bounds__(256) rescore_band_kernel(const BandParams bp, 
                         if (c0i < 0 || fknn_less(d, i, b0, c0i)) { b1 = b0; c1i = c0i; b0 = d; c0i = i; }
                         else if (c1i < 0 || fknn_less(d, i, b1, c1i)) { b1 = d; c1i = i; }
                     }
-                const int q = bp.band_q[pd.knn_off + c0 + qi];
-                int flags = 0;
-                if (c0i >= 0 && c1i >= 0) {
-                    const float r = __fdiv_rn(b0, b1);
-                    bool keep = r < bp.ratio;
-                    if (bp.max_dist_sq > 0.0f) keep = keep && (b0 * pd.fscale2 < bp.max_dist_sq);
-                    const bool good = keep && bp.ratio_good > 0.0f && r < bp.ratio_good;
-                    flags = (keep ? 1 : 0) | (good ? 2 : 0);
-                }
-                // integer distance of the fp32 nearest neighbour (seeds the mutual search of this candidate)
-                int di = 0;
-                if (c0i >= 0) {
-                    const uint32_t *qa = reinterpret_cast<const uint32_t *>(bp.desc_arena + (pd.qry_off + q) * kDim);
-                    const uint32_t *rb = reinterpret_cast<const uint32_t *>(bp.desc_arena + (pd.ref_off + c0i) * kDim);
-                    uint32_t na = 0, nb = 0, ab = 0;
-                    for (int k = 0; k < kDim / 4; ++k) { na = __dp4a(qa[k], qa[k], na); nb = __dp4a(rb[k], rb[k], nb); ab = __dp4a(qa[k], rb[k], ab); }
-                    di = (int)(na + nb - 2u * ab);
-                }
-                int4 out;
-                out.x = (c0i >= 0 ? c0i : 0) | kRescoredFlag;
-                out.y = flags;
-                out.z = di;
-                out.w = __float_as_int(b0);
-                bp.knn[(pd.knn_off + q) * bp.nshare] = out;
-                for (int s = 1; s < bp.nshare; ++s) bp.knn[(pd.knn_off + q) * bp.nshare + s] = make_int4(-1, -1, INT_MAX, INT_MAX);
+                write_rescored(bp, pd, bp.band_q[pd.knn_off + c0 + qi], b0, c0i, b1, c1i);
             }
         }
     }

@@ -81,6 +81,11 @@ struct MatchKernelParams {
     unsigned long long *stats;    // optional debug counter (slow-path group visits); null in production
     int4 *knn;                    // [sum qry_rows][CSPLIT] partial {id0, id1, d0, d1} per column share; id = -1 /
                                   // d = INT_MAX when absent; consumers merge the shares with merge_knn_shares()
+    // MODE 1 ("collect", float regime): instead of a top-2 the kernel lists every (query row, reference row) whose
+    // squared distance is <= cand_d0[row], as {scratch row, reference row, cand_idx, 0}
+    int4 *events;
+    unsigned int *event_count;    // total events seen (may exceed event_cap: the consumer then falls back)
+    uint32_t event_cap;
 };
 
 template <int STRIPS, int TILE_N, int STAGES, int CSPLIT, int TBUFS>
@@ -147,7 +152,7 @@ __device__ __forceinline__ void merge_top2(int sa, int ja, int sb, int jb, int &
     J0 = t0 ? ja : J0;
 }
 
-template <int STRIPS, int TILE_N, int STAGES, int CSPLIT, int TBUFS, bool DEBUG>
+template <int STRIPS, int TILE_N, int STAGES, int CSPLIT, int TBUFS, bool DEBUG, int MODE = 0>
 __global__ void __launch_bounds__(MatchKernelCfg<STRIPS, TILE_N, STAGES, CSPLIT, TBUFS>::kThreads, 1)
 match_pairs_kernel(const MatchKernelParams p) {
     using Cfg = MatchKernelCfg<STRIPS, TILE_N, STAGES, CSPLIT, TBUFS>;
@@ -319,6 +324,7 @@ match_pairs_kernel(const MatchKernelParams p) {
             // Mutual-check items only need the nearest row, and one row at distance d0 is known to exist (the query
             // row that proposed this candidate): start both slots just below its score so that only rows at least as
             // close are ever scored exactly.  The placeholders carry id -1 and are dropped by the consumers.
+            // Collect mode keeps that threshold for the whole row: every reference row at distance <= cand_d0 is listed.
             if (pd.cand_idx >= 0 && valid) S0 = S1 = na - p.cand_d0[pd.qry_off + q] - 1;
             const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
             long long acc_wait = 0, acc_load = 0, acc_p1 = 0, acc_p2 = 0, acc_hot = 0;
@@ -380,10 +386,19 @@ match_pairs_kernel(const MatchKernelParams p) {
                             const int key[8] = {16 * (int)v[0] + c0.x, 16 * (int)v[1] + c0.y, 16 * (int)v[2] + c0.z,
                                                 16 * (int)v[3] + c0.w, 16 * (int)v[4] + c1.x, 16 * (int)v[5] + c1.y,
                                                 16 * (int)v[6] + c1.z, 16 * (int)v[7] + c1.w};
-                            int g0, g1;
-                            top2_of8(key, g0, g1);
                             const int jb8 = jtile + gq * 8;
-                            merge_top2(g0 >> 3, jb8 + ((g0 & 7) ^ 7), g1 >> 3, jb8 + ((g1 & 7) ^ 7), S0, J0, S1, J1);
+                            if (MODE == 1) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    if ((key[i] >> 3) > S1) {
+                                        const unsigned slot = atomicAdd(p.event_count, 1u);
+                                        if (slot < p.event_cap) p.events[slot] = make_int4((int)(pd.qry_off + q), jb8 + i, pd.cand_idx, 0);
+                                    }
+                            } else {
+                                int g0, g1;
+                                top2_of8(key, g0, g1);
+                                merge_top2(g0 >> 3, jb8 + ((g0 & 7) ^ 7), g1 >> 3, jb8 + ((g1 & 7) ^ 7), S0, J0, S1, J1);
+                            }
                             touched = true;
                             if (prof) ++acc_hot;
                         }
@@ -409,7 +424,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                 atomicAdd(p.stats + 4, (unsigned long long)acc_p2);
                 atomicAdd(p.stats + 5, (unsigned long long)ntiles);
             }
-            if (valid) {
+            if (valid && MODE == 0) {
                 int4 out;
                 out.x = (S0 > kAbsent) ? J0 : -1;
                 out.y = (S1 > kAbsent) ? J1 : -1;

@@ -87,6 +87,8 @@ struct msfm_ctx {
     DeviceBuf dbg_stats;  // debug flag 8: per-phase cycle counters of the matching kernel, dumped at destroy
     DeviceBuf cand_q, cand_j, cand_d0, cand_good, cand_counts, cand_desc, cand_ckeys;  // one-way candidates + gathered rows
     DeviceBuf band_q, band_counts;  // float regime: query rows near a ratio threshold, per pair
+    DeviceBuf band_thr, band_state, band_events, band_event_keys, band_event_count;  // ... and the collect pass over them
+    int64_t band_event_cap_override = -1;  // MSFM_BAND_EVENT_CAP (tests: 0 forces the brute-force fallback)
     DeviceBuf staging, knn, matches, good, counts, offsets, pairdesc, items, tight_matches, tight_good;
     void *h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
@@ -239,6 +241,9 @@ struct BatchPlan {
     std::vector<int64_t> src_index;  // index into the caller's pair list
     std::vector<WorkItem> items;     // forward work items
     std::vector<WorkItem> twin_items;
+    std::vector<PairDesc> band_twins;  // float regime: band rows of pair p searched against its reference image (collect mode)
+    std::vector<WorkItem> band_items;
+    bool rescoring = false;          // the caller asked for fp32 re-scoring and the context keeps float rows
     int64_t query_rows = 0;          // forward kNN rows (= candidate / match scratch rows)
     int64_t ops = 0;
     bool mutual = false;
@@ -247,13 +252,18 @@ struct BatchPlan {
     int64_t knn_rows() const { return mutual ? 2 * query_rows : query_rows; }
 };
 
-msfm_status launch_match_kernel(msfm_ctx *ctx, size_t first_item, size_t n_items) {
+// collect = false: 2-NN of the items' query rows (forward pairs and mutual twins).  collect = true: the items are band
+// twins; every reference row within band_thr of a band row is appended to the event list instead.
+msfm_status launch_match_kernel(msfm_ctx *ctx, size_t first_item, size_t n_items, bool collect = false, uint32_t event_cap = 0) {
     msfm::MatchKernelParams kp;
     kp.maps = ctx->d_maps;
     kp.ckeys = ctx->norms;
     kp.cand_ckeys = static_cast<const int32_t *>(ctx->cand_ckeys.ptr);
-    kp.cand_d0 = static_cast<const int32_t *>(ctx->cand_d0.ptr);
-    kp.counts = static_cast<const int32_t *>(ctx->cand_counts.ptr);
+    kp.cand_d0 = static_cast<const int32_t *>(collect ? ctx->band_thr.ptr : ctx->cand_d0.ptr);
+    kp.counts = static_cast<const int32_t *>(collect ? ctx->band_counts.ptr : ctx->cand_counts.ptr);
+    kp.events = static_cast<int4 *>(ctx->band_events.ptr);
+    kp.event_count = static_cast<unsigned int *>(ctx->band_event_count.ptr);
+    kp.event_cap = event_cap;
     kp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
     kp.items = static_cast<const WorkItem *>(ctx->items.ptr) + first_item;
     kp.n_items = (int32_t)n_items;
@@ -261,7 +271,9 @@ msfm_status launch_match_kernel(msfm_ctx *ctx, size_t first_item, size_t n_items
     kp.debug_flags = ctx->debug_flags;
     kp.knn = static_cast<int4 *>(ctx->knn.ptr);
     const int grid = std::max(1, std::min<int>(ctx->num_sms, kp.n_items));
-    if (ctx->debug_flags)
+    if (collect)
+        msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, false, 1><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
+    else if (ctx->debug_flags)
         msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, true><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
     else
         msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, false><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
@@ -297,8 +309,27 @@ msfm_status ensure_cand_scratch(msfm_ctx *ctx, int64_t rows) {
 // candidate rows of pair p (rows [knn_off, knn_off + count_p) of the candidate scratch, count known only on the device)
 // against pair p's query image; its kNN rows mirror the forward region, shifted by query_rows.
 void finish_plan(msfm_ctx *ctx, BatchPlan &plan) {
-    if (!plan.mutual) return;
     const int32_t nb = (int32_t)plan.pairs.size();
+    if (plan.rescoring && plan.any_float) {
+        // Band twins: the query rows of pair p that sit near a ratio threshold (gathered into rows [knn_off, knn_off +
+        // band_count_p) of the candidate scratch by mark_band_kernel) against pair p's reference image, collect mode.
+        const int32_t base = nb + (plan.mutual ? nb : 0);
+        for (int32_t pi = 0; pi < nb; ++pi) {
+            const PairDesc &f = plan.pairs[pi];
+            PairDesc tw = f;
+            tw.qry_img = ctx->max_images;  // candidate scratch map
+            tw.qry_off = f.knn_off;        // row in cand_ckeys / band_thr
+            tw.knn_off = 0;                // collect mode writes events, not kNN rows
+            tw.qry_row_base = (int32_t)f.knn_off;
+            tw.cand_idx = pi;
+            tw.fscale2 = 0.0f;
+            plan.band_twins.push_back(tw);
+            if (f.ref_rows > 0 && f.fscale2 > 0.0f)
+                for (int32_t row0 = 0; row0 < f.qry_rows; row0 += kItemRows) plan.band_items.push_back({base + pi, row0});
+        }
+        std::stable_sort(plan.band_items.begin(), plan.band_items.end(), [](const WorkItem &x, const WorkItem &y) { return x.row0 < y.row0; });
+    }
+    if (!plan.mutual) return;
     plan.twins.reserve(nb);
     for (int32_t pi = 0; pi < nb; ++pi) {
         const PairDesc &f = plan.pairs[pi];
@@ -326,9 +357,10 @@ void finish_plan(msfm_ctx *ctx, BatchPlan &plan) {
 msfm_status run_match_stage(msfm_ctx *ctx, const BatchPlan &plan) {
     msfm_status st;
     const size_t fw_bytes = plan.pairs.size() * sizeof(PairDesc);
-    const size_t tw_bytes = plan.twins.size() * sizeof(PairDesc);
-    const size_t pd_bytes = fw_bytes + tw_bytes;
-    const size_t it_fw = plan.items.size() * sizeof(WorkItem), it_tw = plan.twin_items.size() * sizeof(WorkItem);
+    const size_t tw_bytes = plan.twins.size() * sizeof(PairDesc), bt_bytes = plan.band_twins.size() * sizeof(PairDesc);
+    const size_t pd_bytes = fw_bytes + tw_bytes + bt_bytes;
+    const size_t it_fw = plan.items.size() * sizeof(WorkItem);
+    const size_t it_tw = (plan.twin_items.size() + plan.band_items.size()) * sizeof(WorkItem);
     if ((st = ensure(ctx, ctx->pairdesc, pd_bytes)) != MSFM_OK) return st;
     if ((st = ensure(ctx, ctx->items, it_fw + it_tw)) != MSFM_OK) return st;
     if ((st = ensure(ctx, ctx->knn, (size_t)plan.knn_rows() * kCsplit * sizeof(int4))) != MSFM_OK) return st;
@@ -338,8 +370,11 @@ msfm_status run_match_stage(msfm_ctx *ctx, const BatchPlan &plan) {
     char *hp = static_cast<char *>(ctx->h_pinned);
     memcpy(hp, plan.pairs.data(), fw_bytes);
     if (tw_bytes) memcpy(hp + fw_bytes, plan.twins.data(), tw_bytes);
+    if (bt_bytes) memcpy(hp + fw_bytes + tw_bytes, plan.band_twins.data(), bt_bytes);
     memcpy(hp + pd_bytes, plan.items.data(), it_fw);
-    if (it_tw) memcpy(hp + pd_bytes + it_fw, plan.twin_items.data(), it_tw);
+    if (!plan.twin_items.empty()) memcpy(hp + pd_bytes + it_fw, plan.twin_items.data(), plan.twin_items.size() * sizeof(WorkItem));
+    if (!plan.band_items.empty())
+        memcpy(hp + pd_bytes + it_fw + plan.twin_items.size() * sizeof(WorkItem), plan.band_items.data(), plan.band_items.size() * sizeof(WorkItem));
     MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->pairdesc.ptr, hp, pd_bytes, cudaMemcpyHostToDevice, ctx->stream));
     MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->items.ptr, hp + pd_bytes, it_fw + it_tw, cudaMemcpyHostToDevice, ctx->stream));
     if (plan.has_empty) MSFM_CUDA(ctx, cudaMemsetAsync(ctx->knn.ptr, 0xFF, (size_t)plan.query_rows * kCsplit * sizeof(int4), ctx->stream));
@@ -422,6 +457,7 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
         // ---- carve the next batch
         BatchPlan plan;
         plan.mutual = mutual;
+        plan.rescoring = params->rescore_band > 0.0f && ctx->fdesc != nullptr;
         const int64_t first = next;
         while (next < n_pairs && (int64_t)plan.pairs.size() < kBatchMaxPairs) {
             const ImageSlot &r = ctx->images[pairs[next].ref], &q = ctx->images[pairs[next].query];
@@ -442,7 +478,8 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             if ((st = ensure(ctx, ctx->cand_j, rows * 4)) != MSFM_OK) return st;
             if ((st = ensure(ctx, ctx->cand_d0, rows * 4)) != MSFM_OK) return st;
             if ((st = ensure(ctx, ctx->cand_good, rows)) != MSFM_OK) return st;
-            if (mutual && (st = ensure_cand_scratch(ctx, plan.query_rows)) != MSFM_OK) return st;
+            const bool float_rescoring = plan.rescoring && plan.any_float;
+            if ((mutual || float_rescoring) && (st = ensure_cand_scratch(ctx, plan.query_rows)) != MSFM_OK) return st;
             if ((st = ensure(ctx, ctx->matches, rows * sizeof(int2))) != MSFM_OK) return st;
             if (want_good && (st = ensure(ctx, ctx->good, rows)) != MSFM_OK) return st;
             if ((st = ensure(ctx, ctx->counts, (size_t)nb * 4)) != MSFM_OK) return st;
@@ -452,9 +489,16 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             // ---- forward 2-NN
             if ((st = run_match_stage(ctx, plan)) != MSFM_OK) return st;
             // ---- float regime: rows near a ratio threshold are decided on exact fp32 distances
-            if (params->rescore_band > 0.0f && ctx->fdesc && plan.any_float) {
+            if (float_rescoring) {
+                const size_t event_cap = ctx->band_event_cap_override >= 0 ? (size_t)ctx->band_event_cap_override : rows / 2 + 65536;
                 if ((st = ensure(ctx, ctx->band_q, rows * 4)) != MSFM_OK) return st;
                 if ((st = ensure(ctx, ctx->band_counts, (size_t)nb * 4)) != MSFM_OK) return st;
+                if ((st = ensure(ctx, ctx->band_thr, rows * 4)) != MSFM_OK) return st;
+                if ((st = ensure(ctx, ctx->band_state, rows * 16)) != MSFM_OK) return st;
+                if ((st = ensure(ctx, ctx->band_events, std::max<size_t>(event_cap, 1) * 16)) != MSFM_OK) return st;
+                if ((st = ensure(ctx, ctx->band_event_keys, std::max<size_t>(event_cap, 1) * 8)) != MSFM_OK) return st;
+                if ((st = ensure(ctx, ctx->band_event_count, 4)) != MSFM_OK) return st;
+                MSFM_CUDA(ctx, cudaMemsetAsync(ctx->band_event_count.ptr, 0, 4, ctx->stream));
                 msfm::BandParams bp;
                 bp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
                 bp.knn = static_cast<int4 *>(ctx->knn.ptr);
@@ -468,10 +512,29 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
                 bp.fdesc = ctx->fdesc;
                 bp.desc_arena = ctx->desc;
                 bp.ckeys = ctx->norms;
+                bp.band_thr = static_cast<int32_t *>(ctx->band_thr.ptr);
+                bp.band_state = static_cast<unsigned long long *>(ctx->band_state.ptr);
+                bp.cand_desc = static_cast<uint8_t *>(ctx->cand_desc.ptr);
+                bp.cand_ckeys = static_cast<int32_t *>(ctx->cand_ckeys.ptr);
+                bp.events = static_cast<const int4 *>(ctx->band_events.ptr);
+                bp.event_keys = static_cast<unsigned long long *>(ctx->band_event_keys.ptr);
+                bp.event_count = static_cast<const unsigned int *>(ctx->band_event_count.ptr);
+                bp.event_cap = (uint32_t)event_cap;
                 msfm::mark_band_kernel<<<nb, 1024, 0, ctx->stream>>>(bp);
-                msfm::rescore_band_kernel<<<std::min(nb, 4 * ctx->num_sms), 256, 0, ctx->stream>>>(bp, nb);
                 MSFM_CUDA(ctx, cudaGetLastError());
-                ctx->timing.total_launches += 2;
+                // tensor pass in collect mode over the gathered band rows, then fp32 scoring of what it listed
+                if (!plan.band_items.empty() &&
+                    (st = launch_match_kernel(ctx, plan.items.size() + plan.twin_items.size(), plan.band_items.size(), true, bp.event_cap)) != MSFM_OK)
+                    return st;
+                msfm::score_events_kernel<<<4 * ctx->num_sms, 256, 0, ctx->stream>>>(bp);
+                msfm::second_events_kernel<<<4 * ctx->num_sms, 256, 0, ctx->stream>>>(bp);
+                msfm::finish_band_kernel<<<nb, 256, 0, ctx->stream>>>(bp);
+                // brute-force search on CUDA cores: returns at once unless the event list overflowed
+                const int gx = std::min(nb, 4 * ctx->num_sms);
+                const int gy = std::max(1, std::min(32, (4 * ctx->num_sms + gx - 1) / gx));
+                msfm::rescore_band_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(bp, nb);
+                MSFM_CUDA(ctx, cudaGetLastError());
+                ctx->timing.total_launches += 5;
             }
             // ---- ratio test -> one-way candidates (+ gather of their reference rows for the mutual check)
             msfm::SelectParams sp;
@@ -486,7 +549,6 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             sp.cand_d0 = static_cast<int32_t *>(ctx->cand_d0.ptr);
             sp.cand_good = static_cast<uint8_t *>(ctx->cand_good.ptr);
             sp.counts = static_cast<int32_t *>(ctx->cand_counts.ptr);
-            const bool float_rescoring = params->rescore_band > 0.0f && ctx->fdesc && plan.any_float;
             sp.float_mutual = (mutual && float_rescoring) ? 1 : 0;
             sp.gather = mutual ? 1 : 0;
             sp.desc_arena = ctx->desc;
@@ -629,6 +691,7 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
     ctx->arena_rows = round_up(cfg->arena_rows, kAlignRows);
     ctx->images.resize(cfg->max_images);
     if (const char *dbg = getenv("MSFM_DEBUG_FLAGS")) ctx->debug_flags = (uint32_t)strtoul(dbg, nullptr, 0);
+    if (const char *cap = getenv("MSFM_BAND_EVENT_CAP")) ctx->band_event_cap_override = strtoll(cap, nullptr, 0);
 
     auto bail = [&](msfm_status st) {
         msfm_destroy(ctx);
@@ -662,6 +725,8 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
     if (cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, false>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::kSmemAlloc) != cudaSuccess ||
         cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::kSmemAlloc) != cudaSuccess ||
+        cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, false, 1>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::kSmemAlloc) != cudaSuccess)
         return bail(MSFM_ERR_CUDA);
     if (ctx->debug_flags & 8u) {
@@ -689,7 +754,7 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
         cudaFree(ctx->dbg_stats.ptr);
     }
     if (ctx->fdesc) cudaFree(ctx->fdesc);
-    DeviceBuf *bufs[] = {&ctx->band_q, &ctx->band_counts, &ctx->cand_q, &ctx->cand_j, &ctx->cand_d0, &ctx->cand_good, &ctx->cand_counts, &ctx->cand_desc, &ctx->cand_ckeys,
+    DeviceBuf *bufs[] = {&ctx->band_q, &ctx->band_counts, &ctx->band_thr, &ctx->band_state, &ctx->band_events, &ctx->band_event_keys, &ctx->band_event_count, &ctx->cand_q, &ctx->cand_j, &ctx->cand_d0, &ctx->cand_good, &ctx->cand_counts, &ctx->cand_desc, &ctx->cand_ckeys,
                          &ctx->staging, &ctx->knn, &ctx->matches, &ctx->good, &ctx->counts, &ctx->offsets,
                          &ctx->pairdesc, &ctx->items, &ctx->tight_matches, &ctx->tight_good};
     for (DeviceBuf *b : bufs)

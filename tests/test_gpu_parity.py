@@ -383,6 +383,40 @@ def test_float_regime_rescoring_matches_fp32_matcher(oracle_mod, native_lib, mut
     assert flips_raw > 0  # the reason the re-scoring band exists
 
 
+@pytest.mark.parametrize("cap", ["0", "37"])
+def test_float_regime_collect_pass_equals_brute_force(native_lib, monkeypatch, cap):
+    """The band rows' fp32 neighbours come from the tensor kernel's collect pass + per-event scoring; when its event list
+    overflows (forced here with MSFM_BAND_EVENT_CAP) a dp4a brute force over the reference image takes over.  Both must
+    produce identical match lists and good flags, with and without the mutual check, on ragged images."""
+    from metricsfm_b200.matcher import Matcher
+    col = synth.Collection(3000, seed=13)
+    rows = [3000, 2500, 1111, 600, 3000]
+    imgs = [col.image_unit(i)[:r] for i, r in enumerate(rows)]
+    pairs = [(0, 1), (1, 0), (2, 4), (4, 3), (3, 2), (0, 4)]
+
+    def run():
+        out = []
+        with Matcher(device=0, max_images=8, arena_rows=1 << 15, keep_float=True) as m:
+            for i, x in enumerate(imgs):
+                m.upload(i, np.ascontiguousarray(x), scale=512.0)
+            for mutual in (False, True):
+                res = m.match_pairs(pairs, 0.85, ratio_good=0.6, mutual=mutual, rescore_band=0.03)
+                out.append([(res.pair(p).copy(), res.pair_good(p).copy()) for p in range(len(pairs))])
+        return out
+
+    monkeypatch.delenv("MSFM_BAND_EVENT_CAP", raising=False)
+    collected = run()
+    monkeypatch.setenv("MSFM_BAND_EVENT_CAP", cap)
+    brute = run()
+    n = 0
+    for a, b in zip(collected, brute):
+        for (ma, ga), (mb, gb) in zip(a, b):
+            np.testing.assert_array_equal(ma, mb)
+            np.testing.assert_array_equal(ga, gb)
+            n += len(ma)
+    assert n > 1000
+
+
 def test_float_regime_needs_retained_rows(oracle_mod, matcher):
     """rescore_band on a context without retained float rows, or on u8 uploads, is a no-op (integer decision)."""
     col = synth.Collection(1024, seed=12)
