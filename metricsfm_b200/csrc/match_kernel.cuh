@@ -19,6 +19,10 @@
 //                   spreads the issue instructions over the four SM sub-partitions and lets every strip advance as soon
 //                   as ITS accumulator buffer is free
 //   (padding warps) idle; the auxiliary warpgroups hand their registers to the epilogue warps (setmaxnreg)
+//   The service warps share issue slots with the epilogue warps of their sub-partition: their tile loops are unrolled
+//   over the B ring (immediate addresses) and they sleep between polls (see the comment at the role dispatch).
+// MODE 1 ("collect", float regime) replaces the top-2 merge by "append every element under the row's fixed threshold
+// to an event list"; everything else is shared.
 // Pipelines (all mbarrier based):
 //   A ring (2 deep)     : query strips of a work item, STRIPS x [128 rows x 128 B]
 //   B ring (STAGES)     : reference tiles [TILE_N rows x 128 B]
@@ -97,7 +101,7 @@ struct MatchKernelCfg {
     static constexpr int kThreads = (kEpiWarps + kAuxWarps) * 32;
     // Registers: the launch gives every thread 65536 / kThreads (a multiple of 8); the auxiliary warpgroups hand most of
     // their share to the epilogue warps (setmaxnreg), which hold a 64-column accumulator tile each.
-    static constexpr int kAuxRegs = 24;
+    static constexpr int kAuxRegs = 32;
     static constexpr int kLaunchRegs = 65536 / kThreads / 8 * 8;
     static constexpr int kEpiRegs = (kLaunchRegs * kThreads - kAuxWarps * 32 * kAuxRegs) / (kEpiWarps * 32) / 8 * 8;
     static constexpr int kColsPerWarp = TILE_N / CSPLIT;
@@ -105,7 +109,8 @@ struct MatchKernelCfg {
     // every epilogue warp released the accumulator buffer TBUFS tiles earlier; a warp releases a buffer before it has
     // finished reading that tile's keys, but it must finish before it can release the next one:
     // tiles <= t-STAGES-TBUFS-1 are done when tile t is loaded.  +1 for margin.
-    static constexpr int kKeySlots = STAGES + TBUFS + 2;
+    static constexpr int kKeySlots = 2 * STAGES;  // >= STAGES + TBUFS + 1; two rounds of the B ring, so slot = stage + STAGES * (round & 1)
+    static_assert(2 * STAGES >= STAGES + TBUFS + 1 && STAGES % (2 * TBUFS) == 0, "ring position must fix key slot, accumulator buffer and its phase");
     static constexpr int kTmemCols = TBUFS * STRIPS * TILE_N;
     static constexpr int kABytes = STRIPS * kStripRows * kDim;  // one A buffer
     static constexpr int kBBytes = TILE_N * kDim;               // one B stage
@@ -196,85 +201,133 @@ match_pairs_kernel(const MatchKernelParams p) {
 
     if (warp >= Cfg::kEpiWarps) {
       ptx::setmaxnreg_dec<Cfg::kAuxRegs>();
-      if (warp == Cfg::kEpiWarps) {
-        // =========================================================== TMA producer
+      // Aux warp x = warp - kEpiWarps: x = 0 is the TMA loader, x = 1 .. STRIPS are the MMA issuers (one per SM
+      // sub-partition), the rest is padding up to whole warpgroups (setmaxnreg) and goes straight to the final barrier.
+      // Measured with idle dummy warps: a warp that polls an mbarrier (or merely loops on nanosleep(20)) slows the four
+      // epilogue warps of its sub-partition by 7 %, a warp that sleeps 1 us between polls costs nothing, and every
+      // instruction a service warp executes per tile costs its sub-partition ~1.4 cycles.  Hence: long sleeps where the
+      // latency is hidden anyway (the loader runs STAGES tiles ahead, the issuers have a spare accumulator buffer), and
+      // tile loops that walk the B ring unrolled, so that stage / barrier / key-slot addresses are immediates.
+      // Spreading the loads over four loader warps was measured too: more total service work, slower.
+      constexpr unsigned kLoaderSleepNs = 1000, kIssuerSleepNs = 200;
+#define LOADER_WAIT(bar, par) ptx::mbar_wait_backoff<kLoaderSleepNs>(bar, par)
+#define ISSUER_WAIT(bar, par) ptx::mbar_wait_backoff<kIssuerSleepNs>(bar, par)
+      const int x = warp - Cfg::kEpiWarps;
+      if (x == 0) {
+        // =========================================================== TMA loader
+        // The tile loop walks the B ring (unrolled over its STAGES positions, so stage, barrier and key-slot addresses are
+        // immediates); items are switched inside it.  Every instruction here is taken from the issue slots of the
+        // epilogue warps on the same sub-partition (~1.4 cycles each per tile), hence the lean loop and the long sleeps.
         if (ptx::elect_one()) {
-            uint32_t g = 0, a = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const WorkItem wi = p.items[item];
-                const PairDesc pd = p.pairs[wi.pair];
-                const CUtensorMap *qmap = p.maps + pd.qry_img;
-                const CUtensorMap *rmap = p.maps + pd.ref_img;
-                if (pd.cand_idx >= 0 && wi.row0 >= p.counts[pd.cand_idx]) continue;  // item past the candidate list
-                const uint32_t abuf = a & 1;
-                ptx::mbar_wait_backoff(&a_empty[abuf], ((a >> 1) & 1) ^ 1);
-                ptx::mbar_arrive_expect_tx(&a_full[abuf], Cfg::kABytes);
+            int item = (int)blockIdx.x - (int)gridDim.x, left = 0, t = 0;
+            uint32_t a = 0, round = 0;  // items started, trips round the B ring
+            const CUtensorMap *rmap = nullptr;
+            const int32_t *keyp = nullptr;
+            auto next_item = [&]() -> bool {  // next item with work; fetches its query strips
+                for (;;) {
+                    item += gridDim.x;
+                    if (item >= p.n_items) return false;
+                    const WorkItem wi = p.items[item];
+                    const PairDesc pd = p.pairs[wi.pair];
+                    if (pd.cand_idx >= 0 && wi.row0 >= p.counts[pd.cand_idx]) continue;  // item past the candidate list
+                    const CUtensorMap *qmap = p.maps + pd.qry_img;
+                    const uint32_t abuf = a & 1;
+                    LOADER_WAIT(&a_empty[abuf], ((a >> 1) & 1) ^ 1);
+                    ptx::mbar_arrive_expect_tx(&a_full[abuf], Cfg::kABytes);
 #pragma unroll
-                for (int s = 0; s < STRIPS * kStripRows / kBoxRows; ++s)
-                    ptx::tma_load_2d(sA + abuf * Cfg::kABytes + s * kBoxRows * kDim, qmap, &a_full[abuf], 0,
-                                     pd.qry_row_base + wi.row0 + s * kBoxRows);
-                const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
-                for (int t = 0; t < ntiles; ++t, ++g) {
-                    const uint32_t st = g % STAGES;
-                    ptx::mbar_wait_backoff(&b_empty[st], ((g / STAGES) & 1) ^ 1);
+                    for (int s = 0; s < STRIPS * kStripRows / kBoxRows; ++s)
+                        ptx::tma_load_2d(sA + abuf * Cfg::kABytes + s * kBoxRows * kDim, qmap, &a_full[abuf], 0,
+                                         pd.qry_row_base + wi.row0 + s * kBoxRows);
+                    rmap = p.maps + pd.ref_img;
+                    keyp = p.ckeys + pd.ref_off;
+                    left = (pd.ref_rows + TILE_N - 1) / TILE_N;
+                    t = 0;
+                    ++a;
+                    return true;
+                }
+            };
+            bool more = next_item();
+            while (more) {
+#pragma unroll
+                for (int st = 0; st < STAGES; ++st) {
+                    if (!more) break;
+                    LOADER_WAIT(&b_empty[st], (round & 1) ^ 1);
                     ptx::mbar_arrive_expect_tx(&b_full[st], Cfg::kBBytes);
 #pragma unroll
                     for (int h = 0; h < TILE_N / kBoxRows; ++h)
-                        ptx::tma_load_2d(sB + st * Cfg::kBBytes + h * kBoxRows * kDim, rmap, &b_full[st], 0,
-                                         t * TILE_N + h * kBoxRows);
-                    const uint32_t ks = g % Cfg::kKeySlots;
+                        ptx::tma_load_2d(sB + st * Cfg::kBBytes + h * kBoxRows * kDim, rmap, &b_full[st], 0, t + h * kBoxRows);
+                    const uint32_t ks = st + STAGES * (round & 1);
                     ptx::mbar_arrive_expect_tx(&k_full[ks], TILE_N * 4);
-                    ptx::bulk_load_1d(sKey + ks * TILE_N, p.ckeys + pd.ref_off + (int64_t)t * TILE_N, TILE_N * 4, &k_full[ks]);
+                    ptx::bulk_load_1d(sKey + ks * TILE_N, keyp + t, TILE_N * 4, &k_full[ks]);
+                    t += TILE_N;  // first reference row of the next tile
+                    if (--left == 0) more = next_item();
                 }
-                ++a;
+                ++round;
             }
         }
-      } else if (warp <= Cfg::kEpiWarps + STRIPS) {
+      } else if (x >= 1 && x <= STRIPS) {
         // =========================================================== MMA issuers: warp kEpiWarps + 1 + s feeds strip s
         // One issuer per strip (one elected lane each): the strips' MMAs are no longer issued in a fixed round-robin order
         // (a strip whose accumulator buffer is free never queues behind one that is still being drained), and the issuing
         // instructions are spread over the four SM sub-partitions instead of loading one of them.
-        const int s = warp - (Cfg::kEpiWarps + 1);
+        const int s = x - 1;
         if (ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::make_idesc_i8(kStripRows, TILE_N, 0, 0);
-            uint32_t g = 0, a = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const WorkItem wi = p.items[item];
-                const PairDesc pd = p.pairs[wi.pair];
-                if (pd.cand_idx >= 0 && wi.row0 >= p.counts[pd.cand_idx]) continue;
-                const uint32_t abuf = a & 1;
-                ptx::mbar_wait_backoff(&a_full[abuf], (a >> 1) & 1);
-                const uint32_t a_addr = ptx::smem_u32(sA + abuf * Cfg::kABytes) + s * kStripRows * kDim;
-                const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
-                for (int t = 0; t < ntiles; ++t, ++g) {
-                    const uint32_t st = g % STAGES;
-                    const uint32_t buf = g % TBUFS;
-                    const uint32_t tph = (g / TBUFS) & 1;
+            // Same loop shape as the loaders: ring position = stage, accumulator buffer (st % TBUFS) and its phase
+            // ((st / TBUFS) & 1) are compile-time, descriptors are 32-bit low words (68 -> ~35 instructions per tile).
+            const uint32_t b_lo0 = ptx::smem_u32(sB) >> 4;
+            const uint32_t a_lo0 = (ptx::smem_u32(sA) + s * kStripRows * kDim) >> 4;
+            const uint32_t d_tmem0 = tmem_base + s * TILE_N;
+            uint64_t *t_full_s = t_full + s, *t_empty_s = t_empty + s;
+            int item = (int)blockIdx.x - (int)gridDim.x, left = 0;
+            uint32_t a = 0, abuf = 0, a_lo = 0, round = 0;
+            auto next_item = [&]() -> bool {  // next item with work; waits for its query strips
+                for (;;) {
+                    item += gridDim.x;
+                    if (item >= p.n_items) return false;
+                    const WorkItem wi = p.items[item];
+                    const PairDesc pd = p.pairs[wi.pair];
+                    if (pd.cand_idx >= 0 && wi.row0 >= p.counts[pd.cand_idx]) continue;
+                    abuf = a & 1;
+                    ISSUER_WAIT(&a_full[abuf], (a >> 1) & 1);
+                    a_lo = a_lo0 + abuf * (Cfg::kABytes >> 4);
+                    left = (pd.ref_rows + TILE_N - 1) / TILE_N;
+                    ++a;
+                    return true;
+                }
+            };
+            bool more = next_item();
+            while (more) {
+#pragma unroll
+                for (int st = 0; st < STAGES; ++st) {
+                    if (!more) break;
+                    constexpr int kBufStride = STRIPS;  // barriers / accumulators are laid out [TBUFS][STRIPS]
+                    const int buf = st % TBUFS;
                     long long i0 = 0, i1 = 0, i2 = 0;
                     const bool iprof = DEBUG && (p.debug_flags & 8u) && p.stats != nullptr;
                     if (iprof) i0 = clock64();
-                    ptx::mbar_wait_backoff(&b_full[st], (g / STAGES) & 1);
+                    ISSUER_WAIT(&b_full[st], round & 1);
                     if (iprof) i1 = clock64();
-                    const uint32_t b_addr = ptx::smem_u32(sB + st * Cfg::kBBytes);
-                    ptx::mbar_wait_backoff(&t_empty[buf * STRIPS + s], tph ^ 1);  // accumulator drained by the epilogue
+                    ISSUER_WAIT(t_empty_s + buf * kBufStride, ((st / TBUFS) & 1) ^ 1);  // accumulator drained by the epilogue
                     if (iprof) {
                         i2 = clock64();
-                        atomicAdd(p.stats + 40 + 2 * s, (unsigned long long)(i1 - i0));      // issuer: waiting for the B tile
-                        atomicAdd(p.stats + 41 + 2 * s, (unsigned long long)(i2 - i1));      // issuer: waiting for the accumulator buffer
+                        atomicAdd(p.stats + 40 + 2 * s, (unsigned long long)(i1 - i0));  // issuer: waiting for the B tile
+                        atomicAdd(p.stats + 41 + 2 * s, (unsigned long long)(i2 - i1));  // issuer: waiting for the accumulator buffer
                     }
                     ptx::tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (buf * STRIPS + s) * TILE_N;
+                    const uint32_t d_tmem = d_tmem0 + buf * kBufStride * TILE_N;
+                    const uint32_t b_lo = b_lo0 + st * (Cfg::kBBytes >> 4);
+                    ptx::mma_i8_ss_lo<false>(d_tmem, a_lo, b_lo, idesc);
 #pragma unroll
-                    for (int k = 0; k < kDim / 32; ++k) {
-                        const uint64_t da = ptx::make_smem_desc_sw128(a_addr + k * 32);
-                        const uint64_t db = ptx::make_smem_desc_sw128(b_addr + k * 32);
-                        ptx::mma_i8_ss(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
+                    for (int k = 1; k < kDim / 32; ++k) ptx::mma_i8_ss_lo<true>(d_tmem, a_lo + k * 2, b_lo + k * 2, idesc);
+                    ptx::mma_commit(t_full_s + buf * kBufStride);  // this strip's accumulators are ready
+                    ptx::mma_commit(&b_empty[st]);                 // one of STRIPS arrivals that free the B stage
+                    if (--left == 0) {
+                        ptx::mma_commit(&a_empty[abuf]);           // one of STRIPS arrivals that free the A buffer
+                        more = next_item();
                     }
-                    ptx::mma_commit(&t_full[buf * STRIPS + s]);  // this strip's accumulators are ready
-                    ptx::mma_commit(&b_empty[st]);               // one of STRIPS arrivals that free the B stage
                 }
-                ptx::mma_commit(&a_empty[abuf]);                 // one of STRIPS arrivals that free the A buffer
-                ++a;
+                ++round;
             }
         }
       }
@@ -423,6 +476,8 @@ match_pairs_kernel(const MatchKernelParams p) {
                 atomicAdd(p.stats + 3, (unsigned long long)acc_p1);
                 atomicAdd(p.stats + 4, (unsigned long long)acc_p2);
                 atomicAdd(p.stats + 5, (unsigned long long)ntiles);
+                atomicAdd(p.stats + 8 + 2 * quarter, (unsigned long long)acc_wait);  // per SM sub-partition
+                atomicAdd(p.stats + 9 + 2 * quarter, (unsigned long long)(acc_load + acc_p1 + acc_p2));
             }
             if (valid && MODE == 0) {
                 int4 out;

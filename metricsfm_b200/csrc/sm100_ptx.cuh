@@ -104,8 +104,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 // Polling wait with back-off for the single-lane producer / MMA-issuer roles, so that their spinning does not steal
 // issue slots from the epilogue warps that share the SM sub-partition.
+template <unsigned kSleepNs = 20>
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(20);
+    while (!mbar_try_wait(bar, parity)) __nanosleep(kSleepNs);
 }
 
 // Register re-balancing between warpgroups (4 consecutive, 4-aligned warps execute it together).
@@ -155,6 +156,20 @@ __device__ __forceinline__ void mma_i8_ss(uint32_t tmem_d, uint64_t desc_a, uint
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Same, taking the low words of the two shared-memory descriptors (address >> 4; the high words are the constant
+// SW128 / 1024-byte-stride fields): keeps the issuing loop free of 64-bit descriptor arithmetic.
+template <bool kAccumulate>
+__device__ __forceinline__ void mma_i8_ss_lo(uint32_t tmem_d, uint32_t desc_a_lo, uint32_t desc_b_lo, uint32_t idesc) {
+    constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // bits 32.. of make_smem_desc_sw128()
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %4};\n\t"
+        "mov.b64 db, {%2, %4};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(desc_a_lo), "r"(desc_b_lo), "r"(idesc), "r"(kHi), "n"(kAccumulate ? 1 : 0)
         : "memory");
 }
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
