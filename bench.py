@@ -285,7 +285,8 @@ def run_native(args):
         mine = [gid for gid in range(n_global) if owner[gid] == rank]
         for gid in range(n_global):          # identical allocation order on every rank => identical arena offsets
             if gid == mine[0]:
-                m.upload_batch(mine, [host_desc[g - rank * n_local] for g in mine])   # one host wait for the block
+                # page-locked host rows, no host wait: the transfer overlaps the pair planning of match_pairs
+                m.upload_batch(mine, [host_desc[g - rank * n_local] for g in mine], wait=False)
             elif owner[gid] != rank:
                 m.reserve(gid, rows)
         if world > 1:

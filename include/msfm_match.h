@@ -137,6 +137,14 @@ msfm_status msfm_upload_u8(msfm_ctx *ctx, int32_t image_id, const uint8_t *desc,
  * the images before the failing one stay uploaded. */
 msfm_status msfm_upload_u8_batch(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const uint8_t *const *descs,
                                  const int32_t *rows, const int64_t *row_stride_bytes);
+/* Same without the host wait, for callers that stage descriptors in page-locked memory: the copies run on the context's
+ * stream while the host goes on (e.g. into msfm_match_pairs, whose planning then overlaps the transfer).  Every
+ * `descs[i]` must stay valid and unchanged until msfm_sync() or any later call that returns results to the host.
+ * Only contiguous 128-byte rows (row_stride_bytes NULL or 128 everywhere). */
+msfm_status msfm_upload_u8_batch_async(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const uint8_t *const *descs,
+                                       const int32_t *rows, const int64_t *row_stride_bytes);
+/* Wait for everything queued on the context's stream. */
+msfm_status msfm_sync(msfm_ctx *ctx);
 /* float rows (cv::Mat CV_32FC1 rows x 128, database.cc:368-370): q = min(255, max(0, rint(x*scale))).
  * scale = 1 for 512-scaled VLSIFT rows (feature_extractor_vl_sift.cpp:201-203), 512 for unit-norm rows
  * (feature_extractor_cuda_sift.cpp:75-80). */

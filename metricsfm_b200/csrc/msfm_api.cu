@@ -324,10 +324,15 @@ void finish_plan(msfm_ctx *ctx, BatchPlan &plan) {
             tw.cand_idx = pi;
             tw.fscale2 = 0.0f;
             plan.band_twins.push_back(tw);
-            if (f.ref_rows > 0 && f.fscale2 > 0.0f)
-                for (int32_t row0 = 0; row0 < f.qry_rows; row0 += kItemRows) plan.band_items.push_back({base + pi, row0});
         }
-        std::stable_sort(plan.band_items.begin(), plan.band_items.end(), [](const WorkItem &x, const WorkItem &y) { return x.row0 < y.row0; });
+        // items that can actually hold band rows (low row0) first, the mostly empty tail last
+        for (int32_t row0 = 0, any = 1; any; row0 += kItemRows) {
+            any = 0;
+            for (int32_t pi = 0; pi < nb; ++pi) {
+                const PairDesc &f = plan.pairs[pi];
+                if (f.ref_rows > 0 && f.fscale2 > 0.0f && row0 < f.qry_rows) { plan.band_items.push_back({base + pi, row0}); any = 1; }
+            }
+        }
     }
     if (!plan.mutual) return;
     plan.twins.reserve(nb);
@@ -346,11 +351,16 @@ void finish_plan(msfm_ctx *ctx, BatchPlan &plan) {
         tw.fscale2 = 0.0f;
         tw.pad_ = 0;
         plan.twins.push_back(tw);
-        if (f.ref_rows > 0)
-            for (int32_t row0 = 0; row0 < f.qry_rows; row0 += kItemRows) plan.twin_items.push_back({nb + pi, row0});
     }
     // items that can actually hold candidates (low row0) first, the mostly empty tail last: balances the persistent CTAs
-    std::stable_sort(plan.twin_items.begin(), plan.twin_items.end(), [](const WorkItem &x, const WorkItem &y) { return x.row0 < y.row0; });
+    plan.twin_items.reserve(plan.items.size());
+    for (int32_t row0 = 0, any = 1; any; row0 += kItemRows) {
+        any = 0;
+        for (int32_t pi = 0; pi < nb; ++pi) {
+            const PairDesc &f = plan.pairs[pi];
+            if (f.ref_rows > 0 && row0 < f.qry_rows) { plan.twin_items.push_back({nb + pi, row0}); any = 1; }
+        }
+    }
 }
 
 // Upload the plan and run the forward matching launch (timed); leaves the kNN rows in scratch.
@@ -831,20 +841,74 @@ msfm_status msfm_upload_u8(msfm_ctx *ctx, int32_t image_id, const uint8_t *desc,
     return MSFM_OK;
 }
 
+// Batch upload.  Contiguous-row images are reserved first, their host->device copies are queued back to back (runs
+// that are adjacent both in host memory and in the arena become one copy) and the packer launches follow, so the copy
+// engine is not held up by the keying kernels in between; strided images take the per-image staging path.
+static msfm_status upload_u8_batch_locked(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const uint8_t *const *descs, const int32_t *rows,
+                                          const int64_t *row_stride_bytes, bool allow_strided) {
+    if (n < 0 || (n > 0 && (!image_ids || !descs || !rows))) return fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_upload_u8_batch: null argument");
+    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    msfm_status st = MSFM_OK;
+    // A run = images adjacent both in host memory and in the arena: one copy, one packer launch (images start on
+    // multiples of kAlignRows, so row % 8 and with it the column keys do not depend on where the run starts; only the
+    // last image of a run can have pad rows).
+    struct Run { const uint8_t *src; int64_t off; int64_t rows, rows_padded; };
+    std::vector<Run> runs;
+    for (int32_t i = 0; i < n && st == MSFM_OK; ++i) {
+        const int64_t stride = row_stride_bytes ? row_stride_bytes[i] : kDim;
+        if (stride != kDim) {
+            if (!allow_strided) { st = fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_upload_u8_batch_async takes contiguous 128-byte rows only"); break; }
+            bool staged = false;
+            st = upload_u8_enqueue(ctx, image_ids[i], descs[i], rows[i], stride, &staged);
+            if (st == MSFM_OK && staged) MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging buffer is reused by the next image
+            continue;
+        }
+        if (rows[i] > 0 && !descs[i]) { st = fail(ctx, MSFM_ERR_INVALID_ARG, "null descriptors"); break; }
+        int64_t off = 0;
+        if ((st = reserve_locked(ctx, image_ids[i], rows[i], &off)) != MSFM_OK) break;
+        const ImageSlot &sl = ctx->images[image_ids[i]];
+        if (!runs.empty() && runs.back().rows == runs.back().rows_padded && off == runs.back().off + runs.back().rows &&
+            descs[i] == runs.back().src + runs.back().rows * kDim && runs.back().rows + sl.rows_padded < (int64_t)INT32_MAX) {
+            runs.back().rows += sl.rows;
+            runs.back().rows_padded += sl.rows_padded;
+        } else {
+            runs.push_back({descs[i], off, sl.rows, sl.rows_padded});
+        }
+    }
+    for (const Run &r : runs)  // copies back to back, so the copy engine is not held up by the keying kernels
+        if (r.rows > 0) MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->desc + r.off * kDim, r.src, (size_t)r.rows * kDim, cudaMemcpyHostToDevice, ctx->stream));
+    for (const Run &r : runs) {    // keys + pad rows, in place
+        if (r.rows_padded == 0) continue;
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(8 * ctx->num_sms, (r.rows_padded + 7) / 8));
+        uint8_t *d = ctx->desc + r.off * kDim;
+        msfm::pack_u8_kernel<<<blocks, 256, 0, ctx->stream>>>(d, kDim, (int)r.rows, (int)r.rows_padded, d, ctx->norms + r.off);
+    }
+    if (!runs.empty()) MSFM_CUDA(ctx, cudaGetLastError());
+    return st;
+}
+
 msfm_status msfm_upload_u8_batch(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const uint8_t *const *descs, const int32_t *rows,
                                  const int64_t *row_stride_bytes) {
     if (!ctx) return MSFM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    if (n < 0 || (n > 0 && (!image_ids || !descs || !rows))) return fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_upload_u8_batch: null argument");
-    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
-    msfm_status st = MSFM_OK;
-    for (int32_t i = 0; i < n && st == MSFM_OK; ++i) {
-        bool staged = false;
-        st = upload_u8_enqueue(ctx, image_ids[i], descs[i], rows[i], row_stride_bytes ? row_stride_bytes[i] : kDim, &staged);
-        if (st == MSFM_OK && staged) MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging buffer is reused by the next image
-    }
+    const msfm_status st = upload_u8_batch_locked(ctx, n, image_ids, descs, rows, row_stride_bytes, true);
     MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // one sync for the batch: the caller may free every `descs[i]` on return
     return st;
+}
+
+msfm_status msfm_upload_u8_batch_async(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const uint8_t *const *descs, const int32_t *rows,
+                                       const int64_t *row_stride_bytes) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    return upload_u8_batch_locked(ctx, n, image_ids, descs, rows, row_stride_bytes, false);
+}
+
+msfm_status msfm_sync(msfm_ctx *ctx) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MSFM_OK;
 }
 
 msfm_status msfm_upload_f32(msfm_ctx *ctx, int32_t image_id, const float *desc, int32_t rows, int64_t row_stride_floats, float scale) {

@@ -116,8 +116,11 @@ class Matcher:
             raise TypeError(f"descriptors must be uint8 or float32, got {dtype}")
         del keep
 
-    def upload_batch(self, image_ids, descs) -> None:
-        """Pack several uint8 images in one call (one host wait for the whole batch instead of one per image)."""
+    def upload_batch(self, image_ids, descs, wait: bool = True) -> None:
+        """Pack several uint8 images in one call (one host wait for the whole batch instead of one per image).
+        wait=False (msfm_upload_u8_batch_async): no host wait at all -- the copies run while the host goes on; the
+        buffers (page-locked, contiguous rows) must stay valid and unchanged until sync() or the next call that returns
+        results."""
         n = len(image_ids)
         ids = np.ascontiguousarray(image_ids, np.int32)
         ptrs = (C.c_void_p * max(n, 1))()
@@ -137,8 +140,15 @@ class Matcher:
             ptr, ka = _host_ptr(d)
             ptrs[k] = ptr
             keep.append(ka)
-        self._check(self._L.msfm_upload_u8_batch(self._h, n, ids.ctypes.data, C.cast(ptrs, C.c_void_p), rows.ctypes.data, strides.ctypes.data))
+        fn = self._L.msfm_upload_u8_batch if wait else self._L.msfm_upload_u8_batch_async
+        self._check(fn(self._h, n, ids.ctypes.data, C.cast(ptrs, C.c_void_p), rows.ctypes.data, strides.ctypes.data))
+        if not wait:
+            self._inflight = keep  # keep the host buffers alive until the next synchronising call
         del keep
+
+    def sync(self) -> None:
+        self._check(self._L.msfm_sync(self._h))
+        self._inflight = None
 
     def reserve(self, image_id: int, rows: int) -> int:
         off = C.c_int64()

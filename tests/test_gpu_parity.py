@@ -624,6 +624,36 @@ def test_upload_batch_equals_single_uploads(oracle_mod, matcher):
     assert res.ok.tolist() == [1, 1, 0]
 
 
+def test_upload_batch_async_overlaps_and_matches(oracle_mod, matcher):
+    """msfm_upload_u8_batch_async: no host wait, adjacent images coalesced into one copy; the table and the match lists
+    equal the synchronous upload's, strided rows are refused, msfm_sync drains the stream."""
+    import torch
+    from metricsfm_b200.matcher import MsfmError
+    col = synth.Collection(768, seed=14)
+    rows = [768, 512, 300, 0, 256]                       # 768/512/256 are multiples of the arena alignment: one coalesced copy
+    host = torch.empty((sum(rows), 128), dtype=torch.uint8).pin_memory()
+    views, lo = [], 0
+    for i, r in enumerate(rows):
+        host[lo:lo + r].numpy()[:] = col.image_u8(i, r) if r else np.empty((0, 128), np.uint8)
+        views.append(host[lo:lo + r])
+        lo += r
+    matcher.release_all()
+    matcher.upload_batch(list(range(5)), views, wait=False)
+    res = matcher.match_pairs([(0, 1), (2, 4), (1, 4)], 0.85, ratio_good=0.6, mutual=True)   # queued behind the copies
+    matcher.sync()
+    for i, v in enumerate(views):
+        got, norms = matcher.download_packed(i)
+        np.testing.assert_array_equal(got, v.numpy())
+        np.testing.assert_array_equal(norms, (v.numpy().astype(np.int64) ** 2).sum(1).astype(np.uint32))
+    for p, (r, q) in enumerate([(0, 1), (2, 4), (1, 4)]):
+        exp = oracle_mod.match_pair_u8(views[r].numpy(), views[q].numpy(), 0.85, mutual=True, ratio_good=0.6)
+        np.testing.assert_array_equal(res.pair(p), exp["pairs"])
+    matcher.release_all()
+    strided = np.zeros((200, 256), np.uint8)[:, :128]
+    with pytest.raises(MsfmError):
+        matcher.upload_batch([0], [strided], wait=False)
+
+
 def test_maximum_rows_per_image(oracle_mod, native_lib):
     """MSFM_MAX_ROWS_PER_IMAGE = idx_max_per_image = 1 000 000 (basic_structs.h:171): a million-row image as the
     reference set (15 625 tiles per work item) and as the query set (1 954 work items), against the oracle."""
