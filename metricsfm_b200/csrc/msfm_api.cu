@@ -462,24 +462,33 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
     int64_t total = 0;
     if (!resident) out->offsets[0] = 0;
 
+    // Batches are carved (host-only work: pair descriptors + work items) one ahead, while the previous batch runs on the GPU.
+    struct Carved { BatchPlan plan; int64_t first = 0, last = 0; };
     int64_t next = 0;
-    while (next < n_pairs) {
-        // ---- carve the next batch
-        BatchPlan plan;
-        plan.mutual = mutual;
-        plan.rescoring = params->rescore_band > 0.0f && ctx->fdesc != nullptr;
-        const int64_t first = next;
-        while (next < n_pairs && (int64_t)plan.pairs.size() < kBatchMaxPairs) {
+    auto carve = [&](Carved &c) {
+        c.plan = BatchPlan();
+        c.plan.mutual = mutual;
+        c.plan.rescoring = params->rescore_band > 0.0f && ctx->fdesc != nullptr;
+        c.first = next;
+        while (next < n_pairs && (int64_t)c.plan.pairs.size() < kBatchMaxPairs) {
             const ImageSlot &r = ctx->images[pairs[next].ref], &q = ctx->images[pairs[next].query];
             const bool gated = r.rows < params->min_keypoints || q.rows < params->min_keypoints;
             if (!gated) {
-                if (!plan.pairs.empty() && plan.query_rows + q.rows > max_rows) break;
-                plan_add_pair(ctx, plan, next, pairs[next].ref, pairs[next].query);
+                if (!c.plan.pairs.empty() && c.plan.query_rows + q.rows > max_rows) break;
+                plan_add_pair(ctx, c.plan, next, pairs[next].ref, pairs[next].query);
             }
             ++next;
         }
-        const int64_t last = next;
-        finish_plan(ctx, plan);
+        c.last = next;
+        finish_plan(ctx, c.plan);
+    };
+    Carved cur, ahead;
+    bool have = next < n_pairs;
+    if (have) carve(cur);
+    while (have) {
+        BatchPlan &plan = cur.plan;
+        const int64_t first = cur.first, last = cur.last;
+        bool have_next = false, carved_next = false;
         const int nb = (int)plan.pairs.size();
         std::vector<int64_t> batch_offsets;
         if (nb > 0 && plan.query_rows > 0) {
@@ -598,6 +607,10 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             MSFM_CUDA(ctx, cudaGetLastError());
             MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_f1, ctx->stream));
             ctx->timing.total_launches += 3;
+            // ---- plan the next batch while this one runs
+            have_next = next < n_pairs;
+            if (have_next) carve(ahead);
+            carved_next = true;
             // ---- results
             batch_offsets.resize(nb + 1);
             MSFM_CUDA(ctx, cudaMemcpyAsync(batch_offsets.data(), ctx->offsets.ptr, (size_t)(nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -649,6 +662,12 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             }
             written = out->offsets[last];
         }
+        if (!carved_next) {
+            have_next = next < n_pairs;
+            if (have_next) carve(ahead);
+        }
+        std::swap(cur, ahead);
+        have = have_next;
     }
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
     MSFM_CUDA(ctx, cudaEventSynchronize(ctx->ev_end));
