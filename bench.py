@@ -106,10 +106,13 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.lines, self.proc = index, [], None
+    def __init__(self, index: int, enabled: bool = True):
+        self.index, self.lines, self.proc, self.enabled = index, [], None, enabled
+        self.t0 = self.t1 = None   # timed window (perf_counter)
 
     def start(self):
+        if not self.enabled:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -120,9 +123,17 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self) -> dict:
+        if not self.enabled:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampled on rank 0 only"]}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -130,8 +141,16 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        # samples inside the timed window; nvidia-smi needs ~1 s to come up, so it is started before the warm-up steps and
+        # a window shorter than its period falls back to the warm-up + timed span (same kernels, same load)
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        inside = [ln for t, ln in self.lines if t0 <= t <= t1 + 0.1]
+        window = "timed region"
+        if not inside:
+            inside, window = [ln for t, ln in self.lines if t <= t1 + 0.1], "warm-up + timed region (timed region shorter than the sampling period)"
         sm, mx, pw, reasons = [], [], [], set()
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -145,7 +164,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "window": window, "reasons": sorted(reasons)}
 
 
 # ====================================================================================================== reference arm
@@ -305,11 +324,12 @@ def run_native(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value")
+    sampler = ClockSampler(local_rank, enabled=(rank == 0))
+    sampler.start()
     for _ in range(args.warmup):
         m.match_pairs_resident(my_pairs, RATIO_ALL, **kw)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark_begin()
     step_ms, kern_ms, launches, match_launches, ops = [], [], 0, 0, 0
     n_matches = 0
     t_wall0 = time.perf_counter()
@@ -329,6 +349,7 @@ def run_native(args):
         match_launches += t["match_launches"]
         ops = t["int8_ops"]
     barrier()
+    sampler.mark_end()
     wall_s = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     total_ms = float(sum(step_ms))
