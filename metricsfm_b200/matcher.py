@@ -67,6 +67,7 @@ class Matcher:
             raise MsfmError(st, self._L.msfm_status_string(st).decode())
         self._h = h
         self.device = device
+        self._inflight = None  # host buffers of an upload_batch(wait=False) still being copied
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
