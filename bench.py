@@ -302,12 +302,15 @@ def run_native(args):
         """Pack + upload this rank's images (H2D), reserve the others, replicate over NCCL.  Returns H2D bytes."""
         m.release_all()
         mine = [gid for gid in range(n_global) if owner[gid] == rank]
-        for gid in range(n_global):          # identical allocation order on every rank => identical arena offsets
-            if gid == mine[0]:
-                # page-locked host rows, no host wait: the transfer overlaps the pair planning of match_pairs
-                m.upload_batch(mine, [host_desc[g - rank * n_local] for g in mine], wait=False)
-            elif owner[gid] != rank:
-                m.reserve(gid, rows)
+        before = [gid for gid in range(n_global) if gid < mine[0]]
+        after = [gid for gid in range(n_global) if gid > mine[-1]]
+        # identical allocation order on every rank => identical arena offsets; one call per block of foreign images
+        if before:
+            m.reserve_batch(before, [rows] * len(before))
+        # page-locked host rows, no host wait: the transfer overlaps the pair planning of match_pairs
+        m.upload_batch(mine, [host_desc[g - rank * n_local] for g in mine], wait=False)
+        if after:
+            m.reserve_batch(after, [rows] * len(after))
         if world > 1:
             lib_stream.synchronize()
             D.replicate_arena(desc_arena, norm_arena, ranges, dist)   # NCCL broadcast per owner block

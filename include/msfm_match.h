@@ -154,6 +154,8 @@ msfm_status msfm_upload_f32(msfm_ctx *ctx, int32_t image_id, const float *desc, 
  * multi-GPU replication) at the returned row offset of the arenas.  Pad rows/norms are initialised here, in stream
  * order: synchronise the context's stream (msfm_get_stream) before a writer on another stream fills the rows. */
 msfm_status msfm_reserve(msfm_ctx *ctx, int32_t image_id, int32_t rows, int64_t *row_offset);
+/* Several images in one call (row_offsets may be NULL); images before a failing one stay reserved. */
+msfm_status msfm_reserve_batch(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const int32_t *rows, int64_t *row_offsets);
 msfm_status msfm_release(msfm_ctx *ctx, int32_t image_id);
 msfm_status msfm_release_all(msfm_ctx *ctx);
 msfm_status msfm_image_info(const msfm_ctx *ctx, int32_t image_id, int32_t *rows, int64_t *row_offset);

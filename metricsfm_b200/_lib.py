@@ -22,7 +22,7 @@ STATUS_NAMES = {
 # Every symbol include/msfm_match.h declares (tests/test_abi.py checks the two lists against each other).
 EXPORTED_SYMBOLS = [
     "msfm_abi_version", "msfm_status_string", "msfm_create", "msfm_destroy", "msfm_last_error", "msfm_upload_u8",
-    "msfm_upload_u8_batch", "msfm_upload_u8_batch_async", "msfm_sync", "msfm_upload_f32", "msfm_reserve", "msfm_release", "msfm_release_all", "msfm_image_info", "msfm_table_ptrs",
+    "msfm_upload_u8_batch", "msfm_upload_u8_batch_async", "msfm_sync", "msfm_upload_f32", "msfm_reserve", "msfm_reserve_batch", "msfm_release", "msfm_release_all", "msfm_image_info", "msfm_table_ptrs",
     "msfm_download_packed", "msfm_knn2", "msfm_colbest", "msfm_match_pairs", "msfm_match_pairs_resident",
     "msfm_last_timing", "msfm_get_stream", "msfm_knn2_crosscheck", "msfm_geo_verify", "msfm_geo_ransac",
 ]
@@ -84,6 +84,7 @@ def load() -> C.CDLL:
     L.msfm_sync.argtypes = [vp]
     L.msfm_upload_f32.argtypes = [vp, C.c_int32, vp, C.c_int32, C.c_int64, C.c_float]
     L.msfm_reserve.argtypes = [vp, C.c_int32, C.c_int32, _i64p]
+    L.msfm_reserve_batch.argtypes = [vp, C.c_int32, vp, vp, vp]
     L.msfm_release.argtypes = [vp, C.c_int32]
     L.msfm_release_all.argtypes = [vp]
     L.msfm_image_info.argtypes = [vp, C.c_int32, _i32p, _i64p]

@@ -822,6 +822,25 @@ msfm_status msfm_reserve(msfm_ctx *ctx, int32_t image_id, int32_t rows, int64_t 
     return MSFM_OK;
 }
 
+msfm_status msfm_reserve_batch(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const int32_t *rows, int64_t *row_offsets) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (n < 0 || (n > 0 && (!image_ids || !rows))) return fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_reserve_batch: null argument");
+    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int32_t i = 0; i < n; ++i) {
+        int64_t off = 0;
+        const msfm_status st = reserve_locked(ctx, image_ids[i], rows[i], &off);
+        if (st != MSFM_OK) return st;
+        const ImageSlot &s = ctx->images[image_ids[i]];
+        if (s.rows_padded > s.rows) {
+            msfm::init_pad_kernel<<<8, 256, 0, ctx->stream>>>(s.rows, s.rows_padded, ctx->desc + off * kDim, ctx->norms + off);
+            MSFM_CUDA(ctx, cudaGetLastError());
+        }
+        if (row_offsets) row_offsets[i] = off;
+    }
+    return MSFM_OK;
+}
+
 // One image, enqueued on the context's stream without a host sync.  Contiguous rows go straight into the arena and are
 // keyed in place; strided rows pass through the staging buffer (which the caller must not reuse before a sync).
 static msfm_status upload_u8_enqueue(msfm_ctx *ctx, int32_t image_id, const uint8_t *desc, int32_t rows, int64_t row_stride_bytes,

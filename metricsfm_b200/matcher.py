@@ -156,6 +156,16 @@ class Matcher:
         self._check(self._L.msfm_reserve(self._h, image_id, rows, C.byref(off)))
         return off.value
 
+    def reserve_batch(self, image_ids, rows) -> np.ndarray:
+        """msfm_reserve for several images in one call; returns their row offsets."""
+        ids = np.ascontiguousarray(image_ids, np.int32)
+        r = np.ascontiguousarray(rows, np.int32)
+        if ids.shape != r.shape:
+            raise ValueError("image_ids and rows must have the same length")
+        offs = np.zeros(ids.shape, np.int64)
+        self._check(self._L.msfm_reserve_batch(self._h, len(ids), ids.ctypes.data, r.ctypes.data, offs.ctypes.data))
+        return offs
+
     def release(self, image_id: int) -> None:
         self._check(self._L.msfm_release(self._h, image_id))
 

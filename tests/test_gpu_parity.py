@@ -654,6 +654,18 @@ def test_upload_batch_async_overlaps_and_matches(oracle_mod, matcher):
         matcher.upload_batch([0], [strided], wait=False)
 
 
+def test_reserve_batch_equals_single_reserves(matcher):
+    """msfm_reserve_batch lays the images out exactly like one msfm_reserve per image (multi-GPU replication relies on
+    every rank reproducing the same offsets)."""
+    rows = [700, 0, 256, 513, 8192]
+    matcher.release_all()
+    single = [matcher.reserve(i, r) for i, r in enumerate(rows)]
+    matcher.release_all()
+    batch = matcher.reserve_batch(list(range(len(rows))), rows)
+    assert batch.tolist() == single
+    assert [matcher.image_info(i)[0] for i in range(len(rows))] == rows
+
+
 def test_maximum_rows_per_image(oracle_mod, native_lib):
     """MSFM_MAX_ROWS_PER_IMAGE = idx_max_per_image = 1 000 000 (basic_structs.h:171): a million-row image as the
     reference set (15 625 tiles per work item) and as the query set (1 954 work items), against the oracle."""
