@@ -267,7 +267,9 @@ def run_native(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = {"pinned": False, "why": "single process: the CPU baseline keeps every host core"}
     if world > 1:
+        numa = D.pin_to_gpu_numa_node(local_rank)   # before the page-locked staging buffers are allocated
         dist.init_process_group("nccl", device_id=dev)
 
     n_local, rows = args.images, args.rows
@@ -427,7 +429,8 @@ def run_native(args):
             "config": {"workload": f"exhaustive matching of {n_local} web images x {rows} SIFT-128 descriptors ({len(base)} pairs) per GPU "
                                    f"(BASELINE config #2); 2-NN + ratio {RATIO_ALL}/{RATIO_GOOD}" + (" + mutual cross-check" if args.mutual else " (no mutual check)"),
                        "pairs_per_step_all_gpus": int(len(pairs)), "parallelism": f"pair-sharded x{world}, table replicated",
-                       "l2": "flushed between timed steps (256 MiB write)", "matches_per_step_rank0": int(n_matches)},
+                       "l2": "flushed between timed steps (256 MiB write)", "matches_per_step_rank0": int(n_matches),
+                       "host_numa_pinning_rank0": numa},
             "roofline": {"bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TFLOP/s", "frac": achieved_tops / peak_tops,
                          "traffic": ncu_traffic_bytes(len(my_pairs), match_launches / max(args.steps, 1)),
                          "kernel": "match_pairs_kernel<4,64,8,1,2> (4 strips x N=64 tiles, 8 B stages, 2 TMEM buffers per strip)",

@@ -12,9 +12,34 @@ CPU (gloo, world_size 2) and by bench.py on GPUs (nccl).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import scheduler
+
+
+def pin_to_gpu_numa_node(device_index: int) -> dict:
+    """Restrict this process to the CPU cores NVML reports as local to GPU `device_index`, so that the page-locked
+    staging buffers allocated afterwards land on that NUMA node and host->device copies do not cross sockets (with one
+    process per GPU, eight ranks otherwise share whatever node the scheduler put them on).  Returns what was done;
+    never raises (a missing NVML or a refused affinity call leaves the process unchanged)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        target = cores & allowed
+        if not target:
+            return {"pinned": False, "why": "no overlap between NVML affinity and the allowed cores"}
+        if target != allowed:
+            os.sched_setaffinity(0, target)
+        return {"pinned": True, "cores": len(target), "of": len(allowed)}
+    except Exception as exc:  # noqa: BLE001
+        return {"pinned": False, "why": str(exc)[:120]}
 
 
 def block_ranges(n_images: int, rows_padded_per_image, world_size: int):
