@@ -98,3 +98,15 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0
+
+
+def test_numa_pinning_helper_never_raises():
+    """pin_to_gpu_numa_node() reports what it did and leaves the process alone when NVML / the device is missing."""
+    import os
+    from metricsfm_b200 import distributed as D
+    before = os.sched_getaffinity(0)
+    info = D.pin_to_gpu_numa_node(0)
+    assert isinstance(info, dict) and "pinned" in info
+    if not info["pinned"]:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
