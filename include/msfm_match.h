@@ -44,7 +44,7 @@ extern "C" {
 #endif
 
 #define MSFM_DIM 128              /* descriptor length (SIFT-128), bytes per packed row */
-#define MSFM_ABI_VERSION 2
+#define MSFM_ABI_VERSION 3
 #define MSFM_MAX_ROWS_PER_IMAGE 1000000 /* idx_max_per_image, src/basic_structs.h:171 */
 
 typedef enum msfm_status {
@@ -89,7 +89,13 @@ typedef struct msfm_params {
                               ratio_good*(1 +- band) are re-scored by exact fp32 brute force on the retained float
                               rows (squared L2 accumulated in index order like nanoflann.hpp:376-383) and the ratio
                               tests are repeated on the fp32 distances; 0 = decide on the quantised distances */
+    uint32_t flags;        /* MSFM_RATIO_* bits; 0 = the strict rule of MATCH-SPEC */
 } msfm_params;
+
+/* msfm_params.flags */
+#define MSFM_RATIO_REJECT_GT 1u /* SLAMGPS::FeatureMatching's rule (slam_gps.cc:470-477): a row is rejected iff
+                                   d0/d1 > ratio, i.e. accepted iff !(d0/d1 > ratio): non-strict, and 0/0 = NaN passes.
+                                   Applies to ratio and ratio_good alike.  A missing second neighbour still rejects. */
 
 /* One candidate pair: the kNN index is "built" on image `ref`, rows of image `query` are the queries
  * (fine_matching_graph.cc: ref = idx1, query = idx2; feature_matching.cpp:35-44: ref = image 2, query = image 1). */
@@ -119,6 +125,9 @@ typedef struct msfm_timing {
     int32_t total_launches;  /* all kernels launched by the call */
     int64_t d2h_bytes;
     int64_t int8_ops;        /* algorithmic work: sum over matched pairs of 2*M*N*128 */
+    int32_t twin_pairs;      /* mutual check: pairs whose candidates had to take the tensor twin pass (the others were
+                                decided from the forward results alone) */
+    int32_t reserved;
 } msfm_timing;
 
 int32_t msfm_abi_version(void);
@@ -137,22 +146,27 @@ msfm_status msfm_upload_u8(msfm_ctx *ctx, int32_t image_id, const uint8_t *desc,
  * the images before the failing one stay uploaded. */
 msfm_status msfm_upload_u8_batch(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const uint8_t *const *descs,
                                  const int32_t *rows, const int64_t *row_stride_bytes);
-/* Same without the host wait, for callers that stage descriptors in page-locked memory: the copies run on the context's
- * stream while the host goes on (e.g. into msfm_match_pairs, whose planning then overlaps the transfer).  Every
- * `descs[i]` must stay valid and unchanged until msfm_sync() or any later call that returns results to the host.
+/* Same without the host wait, for callers that stage descriptors in page-locked memory.  All table changes run on the
+ * context's UPLOAD stream; a later msfm_match_pairs / msfm_knn2 launch waits (on the device, not on the host) only for the
+ * uploads that cover the images it touches, so staging image group k+1 overlaps matching the pairs of groups <= k.  Every
+ * `descs[i]` must stay valid and unchanged until msfm_sync() or a later call that returns results computed from it.
  * Only contiguous 128-byte rows (row_stride_bytes NULL or 128 everywhere). */
 msfm_status msfm_upload_u8_batch_async(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const uint8_t *const *descs,
                                        const int32_t *rows, const int64_t *row_stride_bytes);
-/* Wait for everything queued on the context's stream. */
+/* Wait for everything queued on the context's streams. */
 msfm_status msfm_sync(msfm_ctx *ctx);
 /* float rows (cv::Mat CV_32FC1 rows x 128, database.cc:368-370): q = min(255, max(0, rint(x*scale))).
  * scale = 1 for 512-scaled VLSIFT rows (feature_extractor_vl_sift.cpp:201-203), 512 for unit-norm rows
  * (feature_extractor_cuda_sift.cpp:75-80). */
 msfm_status msfm_upload_f32(msfm_ctx *ctx, int32_t image_id, const float *desc, int32_t rows, int64_t row_stride_floats,
                             float scale);
+/* Several float images (the reference's container: dense CV_32FC1 rows of 128 floats, e.g. read from <idx>_feature files
+ * into page-locked staging) without a host wait; semantics of msfm_upload_u8_batch_async. */
+msfm_status msfm_upload_f32_batch_async(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const float *const *descs,
+                                        const int32_t *rows, float scale);
 /* Reserve table space for an image whose packed rows + norms are written by someone else (a collective during
- * multi-GPU replication) at the returned row offset of the arenas.  Pad rows/norms are initialised here, in stream
- * order: synchronise the context's stream (msfm_get_stream) before a writer on another stream fills the rows. */
+ * multi-GPU replication) at the returned row offset of the arenas.  Pad rows/norms and the image's tensor map are in
+ * place when the call returns.  Order the foreign writer before matching with msfm_wait_event(). */
 msfm_status msfm_reserve(msfm_ctx *ctx, int32_t image_id, int32_t rows, int64_t *row_offset);
 /* Several images in one call (row_offsets may be NULL); images before a failing one stay reserved. */
 msfm_status msfm_reserve_batch(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const int32_t *rows, int64_t *row_offsets);
@@ -183,6 +197,11 @@ msfm_status msfm_last_timing(const msfm_ctx *ctx, msfm_timing *out);
 /* The CUDA stream (cudaStream_t) every kernel and copy of this context is enqueued on, so a host harness can record
  * its own events around calls (bench.py) or order foreign work (a collective filling the table) against it. */
 msfm_status msfm_get_stream(const msfm_ctx *ctx, void **cuda_stream);
+/* The stream the table uploads run on (a collective that forwards freshly uploaded rows orders itself behind it). */
+msfm_status msfm_get_upload_stream(const msfm_ctx *ctx, void **cuda_stream);
+/* Make every later matching launch of this context wait for `cuda_event` (a cudaEvent_t recorded by the caller, e.g.
+ * after a collective wrote reserved rows on its own stream).  Device-side wait; the host does not block. */
+msfm_status msfm_wait_event(msfm_ctx *ctx, void *cuda_event);
 
 /* ---- geometric verification of the matched pairs (the stage after the hot path) ---------- */
 /* FineMatchingGraph::BuildMatchGraph verifies every pair (fine_matching_graph.cc:137-153) with
@@ -224,6 +243,10 @@ msfm_status msfm_geo_ransac(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pai
 
 /* ---- GPU-side cross-check kernel (CUDA cores, dp4a); used by the tests to localise faults, never by the fast path */
 msfm_status msfm_knn2_crosscheck(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_t *ids, float *dists);
+/* Test hook: capacity of the float regime's event list (-1 = default sizing; 0 forces the brute-force fallback). */
+msfm_status msfm_test_set_band_event_cap(msfm_ctx *ctx, int64_t cap);
+/* Test hook: 1 routes every pair's mutual check through the tensor twin pass (the fallback of the bound-based check). */
+msfm_status msfm_test_force_twin_pass(msfm_ctx *ctx, int32_t on);
 
 #ifdef __cplusplus
 }

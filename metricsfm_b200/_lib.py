@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = [
     "msfm_upload_u8_batch", "msfm_upload_u8_batch_async", "msfm_sync", "msfm_upload_f32", "msfm_reserve", "msfm_reserve_batch", "msfm_release", "msfm_release_all", "msfm_image_info", "msfm_table_ptrs",
     "msfm_download_packed", "msfm_knn2", "msfm_colbest", "msfm_match_pairs", "msfm_match_pairs_resident",
     "msfm_last_timing", "msfm_get_stream", "msfm_knn2_crosscheck", "msfm_geo_verify", "msfm_geo_ransac",
+    "msfm_upload_f32_batch_async", "msfm_get_upload_stream", "msfm_wait_event", "msfm_test_set_band_event_cap", "msfm_test_force_twin_pass",
 ]
 
 
@@ -36,7 +37,10 @@ class Config(C.Structure):
 
 class Params(C.Structure):
     _fields_ = [("ratio", C.c_float), ("ratio_good", C.c_float), ("max_dist_sq", C.c_float), ("mutual", C.c_int32),
-                ("min_keypoints", C.c_int32), ("orientation", C.c_int32), ("rescore_band", C.c_float)]
+                ("min_keypoints", C.c_int32), ("orientation", C.c_int32), ("rescore_band", C.c_float), ("flags", C.c_uint32)]
+
+
+RATIO_REJECT_GT = 1  # msfm_params.flags: SLAMGPS::FeatureMatching's rule (slam_gps.cc:470-477)
 
 
 class GeoParams(C.Structure):
@@ -54,7 +58,8 @@ class Result(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("match_kernel_ms", C.c_float), ("finalize_ms", C.c_float), ("d2h_ms", C.c_float),
-                ("match_launches", C.c_int32), ("total_launches", C.c_int32), ("d2h_bytes", C.c_int64), ("int8_ops", C.c_int64)]
+                ("match_launches", C.c_int32), ("total_launches", C.c_int32), ("d2h_bytes", C.c_int64), ("int8_ops", C.c_int64),
+                ("twin_pairs", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None
@@ -96,6 +101,11 @@ def load() -> C.CDLL:
     L.msfm_match_pairs_resident.argtypes = [vp, vp, C.c_int64, C.POINTER(Params), _i64p]
     L.msfm_last_timing.argtypes = [vp, C.POINTER(Timing)]
     L.msfm_get_stream.argtypes = [vp, C.POINTER(vp)]
+    L.msfm_get_upload_stream.argtypes = [vp, C.POINTER(vp)]
+    L.msfm_wait_event.argtypes = [vp, vp]
+    L.msfm_test_set_band_event_cap.argtypes = [vp, C.c_int64]
+    L.msfm_test_force_twin_pass.argtypes = [vp, C.c_int32]
+    L.msfm_upload_f32_batch_async.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_float]
     L.msfm_knn2_crosscheck.argtypes = [vp, C.c_int32, C.c_int32, vp, vp]
     L.msfm_geo_verify.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp, C.c_int32, C.POINTER(GeoParams), vp, vp, vp, vp]
     L.msfm_geo_ransac.argtypes = L.msfm_geo_verify.argtypes

@@ -158,6 +158,7 @@ struct BandParams {
     int4 *knn;
     int32_t nshare;
     float ratio, ratio_good, max_dist_sq, band;
+    int32_t reject_gt;     // ratio rule, see SelectParams
     int32_t *band_q;       // [forward kNN rows], pair p writes from row knn_off
     int32_t *band_counts;  // [n_pairs]
     const float *fdesc;    // retained float rows, same row offsets as the packed arena
@@ -228,9 +229,9 @@ __device__ __forceinline__ void write_rescored(const BandParams &bp, const PairD
     int flags = 0;
     if (c0i >= 0 && c1i >= 0) {
         const float r = __fdiv_rn(b0, b1);
-        bool keep = r < bp.ratio;
+        bool keep = bp.reject_gt ? !(r > bp.ratio) : (r < bp.ratio);
         if (bp.max_dist_sq > 0.0f) keep = keep && (b0 * pd.fscale2 < bp.max_dist_sq);
-        const bool good = keep && bp.ratio_good > 0.0f && r < bp.ratio_good;
+        const bool good = keep && bp.ratio_good > 0.0f && (bp.reject_gt ? !(r > bp.ratio_good) : (r < bp.ratio_good));
         flags = (keep ? 1 : 0) | (good ? 2 : 0);
     }
     // integer distance of the fp32 nearest neighbour (seeds the mutual search of this candidate)
@@ -413,32 +414,80 @@ __global__ void __launch_bounds__(256) rescore_band_kernel(const BandParams bp, 
     }
 }
 
-// Stage 1 — ratio test.  One CTA per pair scans its query rows in ascending order (the order of
-// fine_matching_graph.cc:116-133 / feature_matching.cpp:56-64) and writes the one-way candidates
-// (query row, nearest reference row, "good" flag) compacted into the pair's scratch region.  With `gather` set it also
-// copies each candidate's reference descriptor row + column key into the candidate scratch image, which the matching
-// kernel then searches against the query image to find the best query of that reference row (mutual cross-check).
+// Stage 1 — ratio test (+ the mutual cross-check without a second GEMM pass).  One CTA per pair scans its query rows in
+// ascending order (the order of fine_matching_graph.cc:116-133 / feature_matching.cpp:56-64) and writes the one-way
+// candidates (query row, nearest reference row, "good" flag) compacted into the pair's scratch region.
+//
+// Mutual check, exact, from what the forward pass already knows.  Candidate (q, j = nn0(q), d0) survives
+// iff no other query row q' has d(q', j) < d0, or == d0 with q' < q (lowest index wins ties, SiftGPU s_col_max).  The
+// rivals q' are of two kinds:
+//   (A) rows whose own nearest neighbour is j: their distance to j is their d0 — every row does one atomicMin of
+//       (d0, q') on a per-pair column table keyed by nn0, which leaves the best of them per reference row;
+//   (B) rows for which j is not the nearest: then d(q', j) >= d1(q') (j is at best their second neighbour), so only rows
+//       with d1(q') <= d0 can beat or tie the candidate.  A true match has a small d0 and almost no row has a second
+//       neighbour that close: the few "dangerous" rows are listed per pair and their distance to j is computed exactly.
+// A pair whose dangerous sets are large (repetitive structure, near-duplicate rows: more than kDangerPerCand rivals for
+// some candidate or more than kDangerListCap listed rows), and every pair of the float regime with re-scoring, falls
+// back to the tensor twin pass: the candidates' reference rows are gathered into the candidate scratch image, which the
+// matching kernel then searches against the query image (twin_counts[pair] > 0 routes the pair there).
+constexpr int kDangerPerCand = 64;
+constexpr int kDangerListCap = 4096;
+constexpr int kCandGood = 1, kCandKilled = 2;  // bits of cand_good[]
+
 struct SelectParams {
     const PairDesc *pairs;
     const int4 *knn;
     int32_t nshare;
     float ratio, ratio_good, max_dist_sq;
+    int32_t reject_gt;         // ratio rule: 0 accept iff r < ratio; 1 accept iff !(r > ratio) (slam_gps.cc:470-477)
     int32_t *cand_q, *cand_j;  // [forward kNN rows], pair p writes from row knn_off
     int32_t *cand_d0;          // squared distance of the candidate (seeds the mutual search)
-    uint8_t *cand_good;
-    int32_t *counts;           // [n_pairs]
-    int32_t gather;
+    uint8_t *cand_good;        // kCandGood | kCandKilled
+    int32_t *counts;           // [n_pairs] one-way candidates
+    int32_t mutual;
+    unsigned long long *colbest;  // [sum of ref rows of the batch] (d0 << 32 | q), initialised to ~0
+    int2 *danger;              // [forward kNN rows] per-pair list of (row, d1) of the dangerous rows
+    int32_t *twin_counts;      // [n_pairs] candidates routed to the tensor twin pass (0: decided here)
+    unsigned int *twin_gate;   // number of pairs routed to the twin pass (the twin launch returns at once when 0)
     const uint8_t *desc_arena;
     const int32_t *ckeys;
     uint8_t *cand_desc;        // [forward kNN rows][128]
     int32_t *cand_ckeys;
     int32_t float_mutual;      // float regime with re-scoring: widen the mutual search by the quantisation slack
+    int32_t force_twin;        // test hook: every pair takes the tensor twin pass
 };
+
+__device__ __forceinline__ bool ratio_accepts(float r, float th, int reject_gt) { return reject_gt ? !(r > th) : (r < th); }
+
+__device__ __forceinline__ unsigned long long colbest_key(int d0, int q) {
+    return ((unsigned long long)(unsigned)d0 << 32) | (unsigned)q;
+}
+
+// Exact squared distance of two packed rows (norms from the column keys).
+__device__ __forceinline__ int sqdist_u8_rows(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, int na, int nb) {
+    const uint4 *pa = reinterpret_cast<const uint4 *>(a), *pb = reinterpret_cast<const uint4 *>(b);
+    uint32_t ab = 0;
+#pragma unroll
+    for (int k = 0; k < kDim / 16; ++k) {
+        const uint4 x = __ldg(pa + k), y = __ldg(pb + k);
+        ab = __dp4a(x.x, y.x, ab);
+        ab = __dp4a(x.y, y.y, ab);
+        ab = __dp4a(x.z, y.z, ab);
+        ab = __dp4a(x.w, y.w, ab);
+    }
+    return na + nb - 2 * (int)ab;
+}
 
 __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectParams sp) {
     __shared__ int warp_excl[32];
     __shared__ int chunk_total;
+    __shared__ int s_d0max, s_overflow;
     const PairDesc pd = sp.pairs[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    // the bound-based check needs integer distances that are final: not in the re-scored float regime
+    const bool bounds = sp.mutual && !sp.force_twin && !(sp.float_mutual && pd.fscale2 > 0.0f);
+    if (threadIdx.x == 0) { s_d0max = -1; s_overflow = 0; }
+    __syncthreads();
     int running = 0;
     for (int base = 0; base < pd.qry_rows; base += blockDim.x) {
         const int q = base + threadIdx.x;
@@ -451,30 +500,93 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
                 is_good = (k.y & 2) != 0;
                 nn0 = k.x & ~kRescoredFlag;
                 dist0 = k.z;
-            } else if (k.x >= 0 && k.y >= 0) {
-                const float d0 = (float)k.z, d1 = (float)k.w;
-                const float r = __fdiv_rn(d0, d1);  // IEEE divide; 0/0 = NaN fails every comparison
-                keep = r < sp.ratio;
-                if (sp.max_dist_sq > 0.0f) keep = keep && (d0 < sp.max_dist_sq);
-                is_good = keep && sp.ratio_good > 0.0f && r < sp.ratio_good;
-                nn0 = k.x;
-                dist0 = k.z;
+            } else {
+                if (k.x >= 0 && k.y >= 0) {
+                    const float d0 = (float)k.z, d1 = (float)k.w;
+                    const float r = __fdiv_rn(d0, d1);  // IEEE divide; 0/0 = NaN fails every comparison
+                    keep = ratio_accepts(r, sp.ratio, sp.reject_gt);
+                    if (sp.max_dist_sq > 0.0f) keep = keep && (d0 < sp.max_dist_sq);
+                    is_good = keep && sp.ratio_good > 0.0f && ratio_accepts(r, sp.ratio_good, sp.reject_gt);
+                    nn0 = k.x;
+                    dist0 = k.z;
+                }
+                // rival kind (A): every row, accepted or not, claims its nearest reference row
+                if (bounds && k.x >= 0) atomicMin(sp.colbest + pd.col_off + k.x, colbest_key(k.z, q));
             }
         }
         const int slot = block_rank(keep, running, warp_excl, &chunk_total);
         if (keep) {
             sp.cand_q[pd.knn_off + slot] = q;
             sp.cand_j[pd.knn_off + slot] = nn0;
-            sp.cand_good[pd.knn_off + slot] = is_good ? 1 : 0;
+            sp.cand_good[pd.knn_off + slot] = is_good ? kCandGood : 0;
             // float regime: a query row that is a few 1e-3 farther in quantised units may be the nearer one in fp32,
             // so the mutual search keeps every row within ~3 % of the candidate's distance (see emit_matches_kernel)
             sp.cand_d0[pd.knn_off + slot] = (sp.float_mutual && pd.fscale2 > 0.0f) ? dist0 + (dist0 >> 5) + 256 : dist0;
+            if (bounds) atomicMax(&s_d0max, dist0);
         }
     }
     if (threadIdx.x == 0) sp.counts[blockIdx.x] = running;
-    if (!sp.gather) return;
-    __syncthreads();  // the candidate list written above is read back by other warps of this CTA
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (!sp.mutual) return;
+    __syncthreads();  // candidate list, s_d0max and this pair's column table are complete (only this CTA writes them)
+    bool overflow = !bounds;
+    if (bounds && running > 0) {
+        // ---- rival kind (B): rows whose second neighbour is at least as close as the weakest candidate's match
+        const int d0max = s_d0max;
+        int nd = 0;
+        for (int base = 0; base < pd.qry_rows; base += blockDim.x) {
+            const int q = base + threadIdx.x;
+            bool dang = false;
+            int d1v = 0;
+            if (q < pd.qry_rows) {
+                const int4 k = merge_knn_shares(sp.knn, pd.knn_off + q, sp.nshare);
+                if (k.y >= 0) { d1v = k.w; dang = d1v <= d0max; }
+            }
+            const int slot = block_rank(dang, nd, warp_excl, &chunk_total);
+            if (dang && slot < kDangerListCap) sp.danger[pd.knn_off + slot] = make_int2(q, d1v);
+        }
+        overflow = nd > kDangerListCap;
+        if (!overflow) {
+            __syncthreads();  // the dangerous list is read by other warps
+            const int2 *dl = sp.danger + pd.knn_off;
+            for (int i = warp; i < running; i += nwarps) {
+                const int q = sp.cand_q[pd.knn_off + i], j = sp.cand_j[pd.knn_off + i], d0 = sp.cand_d0[pd.knn_off + i];
+                bool kill = __ldcg(sp.colbest + pd.col_off + j) != colbest_key(d0, q);  // a kind-(A) rival is closer
+                if (!kill && nd > 0) {
+                    int cnt = 0;
+                    for (int e = lane; e < nd; e += 32) {
+                        const int2 r = dl[e];
+                        cnt += (r.y <= d0 && r.x != q) ? 1 : 0;
+                    }
+                    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+                    if (cnt > kDangerPerCand) {
+                        if (lane == 0) s_overflow = 1;  // too ambiguous for CUDA cores: the whole pair takes the tensor pass
+                    } else if (cnt > 0) {
+                        const uint8_t *rj = sp.desc_arena + (pd.ref_off + j) * kDim;
+                        const int nb = ckey_to_norm(sp.ckeys[pd.ref_off + j]);
+                        bool closer = false;
+                        for (int e = lane; e < nd; e += 32) {
+                            const int2 r = dl[e];
+                            if (r.y <= d0 && r.x != q) {
+                                const int d = sqdist_u8_rows(sp.desc_arena + (pd.qry_off + r.x) * kDim, rj,
+                                                             ckey_to_norm(sp.ckeys[pd.qry_off + r.x]), nb);
+                                closer = closer || d < d0 || (d == d0 && r.x < q);
+                            }
+                        }
+                        kill = __any_sync(0xFFFFFFFFu, closer);
+                    }
+                }
+                if (lane == 0 && kill) sp.cand_good[pd.knn_off + i] |= kCandKilled;
+            }
+            __syncthreads();
+            overflow = s_overflow != 0;
+        }
+    }
+    if (threadIdx.x == 0) {
+        sp.twin_counts[blockIdx.x] = overflow ? running : 0;
+        if (overflow && running > 0) atomicAdd(sp.twin_gate, 1u);
+    }
+    if (!overflow) return;
+    // ---- tensor twin pass for this pair: gather the candidates' reference rows (+ column keys) into the scratch image
     for (int i = warp; i < running; i += nwarps) {
         const int j = sp.cand_j[pd.knn_off + i];
         const uint32_t w = reinterpret_cast<const uint32_t *>(sp.desc_arena + (pd.ref_off + j) * kDim)[lane];
@@ -483,8 +595,9 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
     }
 }
 
-// Stage 2 — (mutual check and) emission.  Candidate i of pair p survives the mutual check iff the nearest query row of
-// its reference row (row i of the pair's twin kNN region) is the candidate's own query row.
+// Stage 2 — emission.  Candidate i of pair p survives the mutual check iff select_candidates_kernel did not kill it, or
+// (pairs routed to the twin pass) iff the nearest query row of its reference row (row i of the pair's twin kNN region)
+// is the candidate's own query row.
 struct EmitParams {
     const PairDesc *pairs;
     const int4 *knn;
@@ -493,6 +606,7 @@ struct EmitParams {
     const int32_t *cand_q, *cand_j;
     const uint8_t *cand_good;
     const int32_t *cand_counts;
+    const int32_t *twin_counts;
     int2 *matches;             // per-batch scratch; pair p writes its list from row knn_off
     uint8_t *good;
     int32_t *counts;           // [n_pairs] surviving matches
@@ -515,15 +629,19 @@ __global__ void __launch_bounds__(1024) emit_matches_kernel(const EmitParams ep)
     __shared__ int chunk_total;
     const PairDesc pd = ep.pairs[blockIdx.x];
     const int n = ep.cand_counts[blockIdx.x];
+    const bool twin = ep.mutual && ep.twin_counts[blockIdx.x] > 0;
     int running = 0;
     for (int base = 0; base < n; base += blockDim.x) {
         const int i = base + threadIdx.x;
         bool keep = i < n;
         int q = -1, j = -1;
+        uint8_t flags = 0;
         if (keep) {
             q = ep.cand_q[pd.knn_off + i];
             j = ep.cand_j[pd.knn_off + i];
-            if (ep.mutual) {
+            flags = ep.cand_good[pd.knn_off + i];
+            if (ep.mutual && !twin) keep = (flags & kCandKilled) == 0;
+            if (twin) {
                 const int4 tw = merge_knn_shares(ep.knn, ep.twin_base + pd.knn_off + i, ep.nshare);
                 keep = tw.x == q;
                 if (ep.fdesc && pd.fscale2 > 0.0f && tw.x >= 0 && tw.y >= 0 && (tw.x == q || tw.y == q)) {
@@ -541,7 +659,7 @@ __global__ void __launch_bounds__(1024) emit_matches_kernel(const EmitParams ep)
             int2 m;
             if (ep.orientation == 0) { m.x = j; m.y = q; } else { m.x = q; m.y = j; }
             ep.matches[pd.knn_off + slot] = m;
-            if (ep.good) ep.good[pd.knn_off + slot] = ep.cand_good[pd.knn_off + i];
+            if (ep.good) ep.good[pd.knn_off + slot] = flags & kCandGood;
         }
     }
     if (threadIdx.x == 0) ep.counts[blockIdx.x] = running;

@@ -64,6 +64,7 @@ struct PairDesc {
                                // number is counts[cand_idx] (known only on the device); -1: ordinary image rows
     float fscale2;             // float regime: (quantisation scale)^2 when both images keep their float rows, else 0
     int32_t pad_;
+    int64_t col_off;           // first entry of this pair in the per-batch column-best table (mutual check, one per ref row)
 };
 
 struct WorkItem {
@@ -90,6 +91,8 @@ struct MatchKernelParams {
     int4 *events;
     unsigned int *event_count;    // total events seen (may exceed event_cap: the consumer then falls back)
     uint32_t event_cap;
+    const unsigned int *gate;     // optional: the whole launch returns at once when *gate == 0 (mutual twin pass with no
+                                  // pair left for the tensor path, see select_candidates_kernel)
 };
 
 template <int STRIPS, int TILE_N, int STAGES, int CSPLIT, int TBUFS>
@@ -181,6 +184,7 @@ match_pairs_kernel(const MatchKernelParams p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (p.gate != nullptr && *p.gate == 0u) return;  // uniform over the grid: nothing was routed to this pass
     if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
 
     if (warp == Cfg::kEpiWarps && lane == 0) {

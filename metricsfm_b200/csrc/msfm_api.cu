@@ -42,6 +42,7 @@ constexpr int kItemRows = kStrips * msfm::kStripRows;
 constexpr int64_t kBatchMaxQueryRows = 16ll << 20;
 constexpr int64_t kBatchMaxQueryRowsMutual = 16ll << 20;  // mutual: + 128 B of gathered candidate row per query row
 constexpr int64_t kBatchMaxPairs = 16384;
+constexpr int64_t kBatchMaxRefRows = 16ll << 20;  // mutual: 8 B of column table per reference row of the batch
 
 struct DeviceBuf {
     void *ptr = nullptr;
@@ -55,6 +56,12 @@ struct ImageSlot {
     int32_t rows = 0;
     int32_t rows_padded = 0;
     int64_t off = 0;
+    uint64_t ready_seq = 0;  // upload mark that covers this image (0: its rows were in place when the upload call returned)
+};
+
+struct UploadMark {
+    uint64_t seq;
+    cudaEvent_t ev;
 };
 
 struct Extent {
@@ -70,7 +77,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 struct msfm_ctx {
     int device = 0;
     int num_sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;         // matching: plans, kernels, result copies
+    cudaStream_t upload_stream = nullptr;  // table changes: host->device copies, packer, tensor maps (overlaps matching)
+    std::vector<UploadMark> marks;         // asynchronous uploads still to be ordered before matching launches
+    std::vector<cudaEvent_t> event_pool;
+    uint64_t upload_seq = 0, waited_seq = 0;
     int32_t max_images = 0;
     int64_t arena_rows = 0;
     int64_t rows_high_water = 0;  // bump pointer
@@ -86,15 +97,18 @@ struct msfm_ctx {
 
     DeviceBuf dbg_stats;  // debug flag 8: per-phase cycle counters of the matching kernel, dumped at destroy
     DeviceBuf cand_q, cand_j, cand_d0, cand_good, cand_counts, cand_desc, cand_ckeys;  // one-way candidates + gathered rows
+    DeviceBuf colbest, twin_counts;  // mutual check: per-pair column table (nearest claimant per reference row); [n_pairs] + gate word
     DeviceBuf band_q, band_counts;  // float regime: query rows near a ratio threshold, per pair
     DeviceBuf band_thr, band_state, band_events, band_event_keys, band_event_count;  // ... and the collect pass over them
-    int64_t band_event_cap_override = -1;  // MSFM_BAND_EVENT_CAP (tests: 0 forces the brute-force fallback)
+    int64_t band_event_cap_override = -1;  // msfm_test_set_band_event_cap (tests: 0 forces the brute-force fallback)
+    bool force_twin = false;               // msfm_test_force_twin_pass
     DeviceBuf staging, knn, matches, good, counts, offsets, pairdesc, items, tight_matches, tight_good;
     void *h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_k2 = nullptr, ev_k3 = nullptr,
                 ev_f1 = nullptr;
 
+    int64_t twin_gate_index = 0;  // the gate word sits after the per-pair twin counts
     msfm_timing timing{};
     uint32_t debug_flags = 0;  // MSFM_DEBUG_FLAGS environment variable (timing experiments)
     std::string err;
@@ -121,9 +135,10 @@ msfm_status fail(msfm_ctx *ctx, msfm_status st, const char *fmt, ...) {
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);          \
     } while (0)
 
-msfm_status ensure(msfm_ctx *ctx, DeviceBuf &b, size_t bytes) {
+msfm_status ensure(msfm_ctx *ctx, DeviceBuf &b, size_t bytes, cudaStream_t also = nullptr) {
     if (b.bytes >= bytes && b.ptr) return MSFM_OK;
     if (b.ptr) {
+        if (also) MSFM_CUDA(ctx, cudaStreamSynchronize(also));
         MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         MSFM_CUDA(ctx, cudaFree(b.ptr));
         b.ptr = nullptr;
@@ -198,15 +213,36 @@ msfm_status write_tensor_map(msfm_ctx *ctx, int32_t image_id, int64_t off, int32
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, MSFM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     // The pinned slot of this image may still be in flight from an earlier upload of the same id (release + re-upload):
-    // copies on one stream execute in order, and the slot is only rewritten after msfm_release* synchronised the stream.
+    // copies on one stream execute in order, and the slot is only rewritten after msfm_release* synchronised the streams.
     ctx->h_maps[image_id] = m;
-    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_maps + image_id, ctx->h_maps + image_id, sizeof m, cudaMemcpyHostToDevice, ctx->stream));
+    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_maps + image_id, ctx->h_maps + image_id, sizeof m, cudaMemcpyHostToDevice, ctx->upload_stream));
     return MSFM_OK;
 }
 
 msfm_status check_image_id(msfm_ctx *ctx, int32_t id, bool must_exist) {
     if (id < 0 || id >= ctx->max_images) return fail(ctx, MSFM_ERR_INVALID_ARG, "image id %d outside [0, %d)", id, ctx->max_images);
     if (must_exist && !ctx->images[id].present) return fail(ctx, MSFM_ERR_NOT_FOUND, "image id %d has not been uploaded", id);
+    return MSFM_OK;
+}
+
+// Upload marks whose event the main stream has waited for (or that a synchronisation has overtaken) go back to the pool.
+void recycle_marks(msfm_ctx *ctx) {
+    for (const UploadMark &m : ctx->marks) ctx->event_pool.push_back(m.ev);
+    ctx->marks.clear();
+    ctx->waited_seq = ctx->upload_seq;
+}
+
+// Order the main stream behind the upload mark `need` (and with it behind every older one: marks complete in order).
+msfm_status wait_for_uploads(msfm_ctx *ctx, uint64_t need) {
+    if (need <= ctx->waited_seq) return MSFM_OK;
+    size_t k = 0;
+    for (; k < ctx->marks.size(); ++k) {
+        if (ctx->marks[k].seq > need) break;
+        if (ctx->marks[k].seq == need) MSFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->marks[k].ev, 0));
+        ctx->event_pool.push_back(ctx->marks[k].ev);  // recorded and (where needed) waited for: reusable in stream order
+    }
+    ctx->marks.erase(ctx->marks.begin(), ctx->marks.begin() + k);
+    ctx->waited_seq = need;
     return MSFM_OK;
 }
 
@@ -245,6 +281,8 @@ struct BatchPlan {
     std::vector<WorkItem> band_items;
     bool rescoring = false;          // the caller asked for fp32 re-scoring and the context keeps float rows
     int64_t query_rows = 0;          // forward kNN rows (= candidate / match scratch rows)
+    int64_t ref_rows = 0;            // sum of reference rows (= entries of the mutual check's column table)
+    uint64_t need_seq = 0;           // newest upload mark among the batch's images
     int64_t ops = 0;
     bool mutual = false;
     bool has_empty = false;          // some pair has no work items: its kNN rows must read "absent"
@@ -254,13 +292,15 @@ struct BatchPlan {
 
 // collect = false: 2-NN of the items' query rows (forward pairs and mutual twins).  collect = true: the items are band
 // twins; every reference row within band_thr of a band row is appended to the event list instead.
-msfm_status launch_match_kernel(msfm_ctx *ctx, size_t first_item, size_t n_items, bool collect = false, uint32_t event_cap = 0) {
+msfm_status launch_match_kernel(msfm_ctx *ctx, size_t first_item, size_t n_items, bool collect = false, uint32_t event_cap = 0, bool twin = false) {
     msfm::MatchKernelParams kp;
     kp.maps = ctx->d_maps;
     kp.ckeys = ctx->norms;
     kp.cand_ckeys = static_cast<const int32_t *>(ctx->cand_ckeys.ptr);
     kp.cand_d0 = static_cast<const int32_t *>(collect ? ctx->band_thr.ptr : ctx->cand_d0.ptr);
-    kp.counts = static_cast<const int32_t *>(collect ? ctx->band_counts.ptr : ctx->cand_counts.ptr);
+    kp.counts = static_cast<const int32_t *>(collect ? ctx->band_counts.ptr : ctx->twin_counts.ptr);
+    // mutual twin pass: the launch returns at once unless select_candidates_kernel routed some pair to it
+    kp.gate = twin ? reinterpret_cast<const unsigned int *>(static_cast<const int32_t *>(ctx->twin_counts.ptr) + ctx->twin_gate_index) : nullptr;
     kp.events = static_cast<int4 *>(ctx->band_events.ptr);
     kp.event_count = static_cast<unsigned int *>(ctx->band_event_count.ptr);
     kp.event_cap = event_cap;
@@ -350,6 +390,7 @@ void finish_plan(msfm_ctx *ctx, BatchPlan &plan) {
         tw.cand_idx = pi;
         tw.fscale2 = 0.0f;
         tw.pad_ = 0;
+        tw.col_off = 0;
         plan.twins.push_back(tw);
     }
     // items that can actually hold candidates (low row0) first, the mostly empty tail last: balances the persistent CTAs
@@ -376,6 +417,7 @@ msfm_status run_match_stage(msfm_ctx *ctx, const BatchPlan &plan) {
     if ((st = ensure(ctx, ctx->knn, (size_t)plan.knn_rows() * kCsplit * sizeof(int4))) != MSFM_OK) return st;
     if ((st = ensure(ctx, ctx->cand_counts, plan.pairs.size() * 4)) != MSFM_OK) return st;
     if ((st = ensure_pinned(ctx, pd_bytes + it_fw + it_tw + 64)) != MSFM_OK) return st;
+    if ((st = wait_for_uploads(ctx, plan.need_seq)) != MSFM_OK) return st;  // asynchronous uploads of the batch's images
     // the pinned staging area is reused per batch: the previous batch has been synchronised by its D2H
     char *hp = static_cast<char *>(ctx->h_pinned);
     memcpy(hp, plan.pairs.data(), fw_bytes);
@@ -409,6 +451,8 @@ void plan_add_pair(msfm_ctx *ctx, BatchPlan &plan, int64_t src, int32_t ref, int
     pd.cand_idx = -1;
     pd.fscale2 = (r.has_float && q.has_float && r.scale == q.scale) ? r.scale * r.scale : 0.0f;
     pd.pad_ = 0;
+    pd.col_off = plan.ref_rows;
+    plan.need_seq = std::max(plan.need_seq, std::max(r.ready_seq, q.ready_seq));
     if (pd.fscale2 > 0.0f) plan.any_float = true;
     const int32_t pidx = (int32_t)plan.pairs.size();
     plan.pairs.push_back(pd);
@@ -418,6 +462,7 @@ void plan_add_pair(msfm_ctx *ctx, BatchPlan &plan, int64_t src, int32_t ref, int
     if (work)
         for (int32_t row0 = 0; row0 < q.rows; row0 += kItemRows) plan.items.push_back({pidx, row0});
     plan.query_rows += q.rows;
+    plan.ref_rows += r.rows;
     plan.ops += 2ll * r.rows * q.rows * kDim;
 }
 
@@ -474,7 +519,7 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             const ImageSlot &r = ctx->images[pairs[next].ref], &q = ctx->images[pairs[next].query];
             const bool gated = r.rows < params->min_keypoints || q.rows < params->min_keypoints;
             if (!gated) {
-                if (!c.plan.pairs.empty() && c.plan.query_rows + q.rows > max_rows) break;
+                if (!c.plan.pairs.empty() && (c.plan.query_rows + q.rows > max_rows || (mutual && c.plan.ref_rows + r.rows > kBatchMaxRefRows))) break;
                 plan_add_pair(ctx, c.plan, next, pairs[next].ref, pairs[next].query);
             }
             ++next;
@@ -526,6 +571,7 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
                 bp.ratio_good = params->ratio_good;
                 bp.max_dist_sq = params->max_dist_sq;
                 bp.band = params->rescore_band;
+                bp.reject_gt = (params->flags & MSFM_RATIO_REJECT_GT) ? 1 : 0;
                 bp.band_q = static_cast<int32_t *>(ctx->band_q.ptr);
                 bp.band_counts = static_cast<int32_t *>(ctx->band_counts.ptr);
                 bp.fdesc = ctx->fdesc;
@@ -555,7 +601,15 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
                 MSFM_CUDA(ctx, cudaGetLastError());
                 ctx->timing.total_launches += 5;
             }
-            // ---- ratio test -> one-way candidates (+ gather of their reference rows for the mutual check)
+            // ---- ratio test -> one-way candidates; mutual check from the forward results (column table + dangerous rows),
+            //      pairs too ambiguous for that are routed to the tensor twin pass
+            if (mutual) {
+                if ((st = ensure(ctx, ctx->colbest, (size_t)std::max<int64_t>(plan.ref_rows, 1) * 8)) != MSFM_OK) return st;
+                if ((st = ensure(ctx, ctx->twin_counts, (size_t)(nb + 1) * 4)) != MSFM_OK) return st;
+                ctx->twin_gate_index = nb;
+                MSFM_CUDA(ctx, cudaMemsetAsync(ctx->colbest.ptr, 0xFF, (size_t)plan.ref_rows * 8, ctx->stream));
+                MSFM_CUDA(ctx, cudaMemsetAsync(static_cast<int32_t *>(ctx->twin_counts.ptr) + nb, 0, 4, ctx->stream));
+            }
             msfm::SelectParams sp;
             sp.pairs = static_cast<const PairDesc *>(ctx->pairdesc.ptr);
             sp.knn = static_cast<const int4 *>(ctx->knn.ptr);
@@ -563,13 +617,19 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             sp.ratio = params->ratio;
             sp.ratio_good = params->ratio_good;
             sp.max_dist_sq = params->max_dist_sq;
+            sp.reject_gt = (params->flags & MSFM_RATIO_REJECT_GT) ? 1 : 0;
             sp.cand_q = static_cast<int32_t *>(ctx->cand_q.ptr);
             sp.cand_j = static_cast<int32_t *>(ctx->cand_j.ptr);
             sp.cand_d0 = static_cast<int32_t *>(ctx->cand_d0.ptr);
             sp.cand_good = static_cast<uint8_t *>(ctx->cand_good.ptr);
             sp.counts = static_cast<int32_t *>(ctx->cand_counts.ptr);
             sp.float_mutual = (mutual && float_rescoring) ? 1 : 0;
-            sp.gather = mutual ? 1 : 0;
+            sp.mutual = mutual ? 1 : 0;
+            sp.force_twin = ctx->force_twin ? 1 : 0;
+            sp.colbest = static_cast<unsigned long long *>(ctx->colbest.ptr);
+            sp.danger = static_cast<int2 *>(ctx->matches.ptr);  // the match scratch is written by the emission afterwards
+            sp.twin_counts = static_cast<int32_t *>(ctx->twin_counts.ptr);
+            sp.twin_gate = reinterpret_cast<unsigned int *>(static_cast<int32_t *>(ctx->twin_counts.ptr) + nb);
             sp.desc_arena = ctx->desc;
             sp.ckeys = ctx->norms;
             sp.cand_desc = static_cast<uint8_t *>(ctx->cand_desc.ptr);
@@ -577,10 +637,10 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             msfm::select_candidates_kernel<<<nb, 1024, 0, ctx->stream>>>(sp);
             MSFM_CUDA(ctx, cudaGetLastError());
             ctx->timing.total_launches += 1;
-            // ---- mutual cross-check: nearest query row of every candidate's reference row
+            // ---- tensor twin pass (nearest query row of every candidate's reference row) for the routed pairs only
             MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k2, ctx->stream));
             if (mutual && !plan.twin_items.empty() &&
-                (st = launch_match_kernel(ctx, plan.items.size(), plan.twin_items.size())) != MSFM_OK)
+                (st = launch_match_kernel(ctx, plan.items.size(), plan.twin_items.size(), false, 0, true)) != MSFM_OK)
                 return st;
             MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k3, ctx->stream));
             // ---- emission, offsets, tight gather
@@ -593,6 +653,7 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             ep.cand_j = sp.cand_j;
             ep.cand_good = sp.cand_good;
             ep.cand_counts = sp.counts;
+            ep.twin_counts = sp.twin_counts;
             ep.matches = static_cast<int2 *>(ctx->matches.ptr);
             ep.good = want_good ? static_cast<uint8_t *>(ctx->good.ptr) : nullptr;
             ep.counts = static_cast<int32_t *>(ctx->counts.ptr);
@@ -613,8 +674,11 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             carved_next = true;
             // ---- results
             batch_offsets.resize(nb + 1);
+            unsigned int twin_pairs = 0;
             MSFM_CUDA(ctx, cudaMemcpyAsync(batch_offsets.data(), ctx->offsets.ptr, (size_t)(nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            if (mutual) MSFM_CUDA(ctx, cudaMemcpyAsync(&twin_pairs, static_cast<int32_t *>(ctx->twin_counts.ptr) + nb, 4, cudaMemcpyDeviceToHost, ctx->stream));
             MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->timing.twin_pairs += (int32_t)twin_pairs;
             ctx->timing.d2h_bytes += (nb + 1) * 8;
             if ((st = accumulate_kernel_time(ctx, ctx->ev_k0, ctx->ev_k1)) != MSFM_OK) return st;
             if ((st = accumulate_kernel_time(ctx, ctx->ev_k2, ctx->ev_k3)) != MSFM_OK) return st;
@@ -719,8 +783,17 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
     ctx->max_images = cfg->max_images;
     ctx->arena_rows = round_up(cfg->arena_rows, kAlignRows);
     ctx->images.resize(cfg->max_images);
-    if (const char *dbg = getenv("MSFM_DEBUG_FLAGS")) ctx->debug_flags = (uint32_t)strtoul(dbg, nullptr, 0);
-    if (const char *cap = getenv("MSFM_BAND_EVENT_CAP")) ctx->band_event_cap_override = strtoll(cap, nullptr, 0);
+    if (const char *dbg = getenv("MSFM_DEBUG_FLAGS")) {
+        ctx->debug_flags = (uint32_t)strtoul(dbg, nullptr, 0);
+#ifndef MSFM_EXPERIMENTS
+        // Bits 1, 2 and 4 skip parts of the epilogue (timing experiments, WRONG match lists): compiled in only with
+        // -DMSFM_EXPERIMENTS.  A production build honours the profiling bit (8: per-phase cycle counters) and says so.
+        if (ctx->debug_flags & ~8u) {
+            fprintf(stderr, "[msfm] MSFM_DEBUG_FLAGS=%s ignored: result-altering experiment flags need a -DMSFM_EXPERIMENTS build\n", dbg);
+            ctx->debug_flags &= 8u;
+        }
+#endif
+    }
 
     auto bail = [&](msfm_status st) {
         msfm_destroy(ctx);
@@ -731,6 +804,7 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return bail(MSFM_ERR_CUDA);
     ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MSFM_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MSFM_ERR_CUDA);
     cudaEvent_t *evs[] = {&ctx->ev_begin, &ctx->ev_end, &ctx->ev_k0, &ctx->ev_k1, &ctx->ev_k2, &ctx->ev_k3, &ctx->ev_f1};
     for (cudaEvent_t *e : evs)
         if (cudaEventCreate(e) != cudaSuccess) return bail(MSFM_ERR_CUDA);
@@ -770,6 +844,7 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
 msfm_status msfm_destroy(msfm_ctx *ctx) {
     if (!ctx) return MSFM_OK;
     cudaSetDevice(ctx->device);
+    if (ctx->upload_stream) cudaStreamSynchronize(ctx->upload_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->dbg_stats.ptr) {
         unsigned long long h[64] = {0};
@@ -786,7 +861,7 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
         cudaFree(ctx->dbg_stats.ptr);
     }
     if (ctx->fdesc) cudaFree(ctx->fdesc);
-    DeviceBuf *bufs[] = {&ctx->band_q, &ctx->band_counts, &ctx->band_thr, &ctx->band_state, &ctx->band_events, &ctx->band_event_keys, &ctx->band_event_count, &ctx->cand_q, &ctx->cand_j, &ctx->cand_d0, &ctx->cand_good, &ctx->cand_counts, &ctx->cand_desc, &ctx->cand_ckeys,
+    DeviceBuf *bufs[] = {&ctx->band_q, &ctx->band_counts, &ctx->band_thr, &ctx->band_state, &ctx->band_events, &ctx->band_event_keys, &ctx->band_event_count, &ctx->cand_q, &ctx->cand_j, &ctx->cand_d0, &ctx->cand_good, &ctx->cand_counts, &ctx->cand_desc, &ctx->cand_ckeys, &ctx->colbest, &ctx->twin_counts,
                          &ctx->staging, &ctx->knn, &ctx->matches, &ctx->good, &ctx->counts, &ctx->offsets,
                          &ctx->pairdesc, &ctx->items, &ctx->tight_matches, &ctx->tight_good};
     for (DeviceBuf *b : bufs)
@@ -801,25 +876,65 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
     cudaEvent_t evs[] = {ctx->ev_begin, ctx->ev_end, ctx->ev_k0, ctx->ev_k1, ctx->ev_k2, ctx->ev_k3, ctx->ev_f1};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
+    for (const UploadMark &m : ctx->marks) cudaEventDestroy(m.ev);
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MSFM_OK;
 }
 
-msfm_status msfm_reserve(msfm_ctx *ctx, int32_t image_id, int32_t rows, int64_t *row_offset) {
-    if (!ctx) return MSFM_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> lock(ctx->mu);
-    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
-    int64_t off = 0;
-    msfm_status st = reserve_locked(ctx, image_id, rows, &off);
-    if (st != MSFM_OK) return st;
-    const ImageSlot &s = ctx->images[image_id];
-    if (s.rows_padded > s.rows) {
-        msfm::init_pad_kernel<<<8, 256, 0, ctx->stream>>>(s.rows, s.rows_padded, ctx->desc + off * kDim, ctx->norms + off);
-        MSFM_CUDA(ctx, cudaGetLastError());  // stream-ordered: synchronise msfm_get_stream before a foreign writer fills the rows
-    }
-    if (row_offset) *row_offset = off;
+// ---------------------------------------------------------------------------------------------------- table uploads
+// Everything that changes the packed table (host->device copies, packer launches, tensor-map writes, pad rows) runs on
+// the context's UPLOAD stream, so that staging overlaps matching on the main stream.  The synchronous entry points wait
+// for the upload stream before they return (the images are then simply "ready"); the *_async ones return at once and
+// leave an upload mark — an event on the upload stream plus a sequence number stored in the images it covers.  A matching
+// launch makes the main stream wait for the newest mark among the images it touches (marks complete in order).
+static msfm_status finish_upload_sync(msfm_ctx *ctx) {
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->upload_stream));
     return MSFM_OK;
+}
+
+static msfm_status leave_upload_mark(msfm_ctx *ctx, const std::vector<int32_t> &ids) {
+    if (ids.empty()) return MSFM_OK;
+    cudaEvent_t ev = nullptr;
+    if (!ctx->event_pool.empty()) { ev = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+    else MSFM_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    const cudaError_t e = cudaEventRecord(ev, ctx->upload_stream);
+    if (e != cudaSuccess) {
+        ctx->event_pool.push_back(ev);
+        return fail(ctx, MSFM_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e));
+    }
+    const uint64_t seq = ++ctx->upload_seq;
+    ctx->marks.push_back({seq, ev});
+    for (int32_t id : ids) ctx->images[id].ready_seq = seq;
+    return MSFM_OK;
+}
+
+// Undo reserve_locked for the images of a call that failed half-way: an image must never stay "present" with unwritten rows.
+static void unreserve_locked(msfm_ctx *ctx, const std::vector<int32_t> &ids) {
+    for (int32_t id : ids) {
+        ImageSlot &s = ctx->images[id];
+        if (!s.present) continue;
+        arena_free(ctx, s.off, s.rows_padded);
+        s = ImageSlot{};
+    }
+}
+
+// CUDA call inside an upload: on failure the images reserved so far by this call are rolled back.
+#define MSFM_CUDA_UPLOAD(ctx, reserved, call)                                                                   \
+    do {                                                                                                       \
+        cudaError_t e__ = (call);                                                                              \
+        if (e__ != cudaSuccess) {                                                                              \
+            cudaStreamSynchronize((ctx)->upload_stream);                                                       \
+            unreserve_locked(ctx, reserved);                                                                   \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? MSFM_ERR_OUT_OF_MEMORY : MSFM_ERR_CUDA,         \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);          \
+        }                                                                                                      \
+    } while (0)
+
+msfm_status msfm_reserve(msfm_ctx *ctx, int32_t image_id, int32_t rows, int64_t *row_offset) {
+    return msfm_reserve_batch(ctx, 1, &image_id, &rows, row_offset);
 }
 
 msfm_status msfm_reserve_batch(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const int32_t *rows, int64_t *row_offsets) {
@@ -827,44 +942,48 @@ msfm_status msfm_reserve_batch(msfm_ctx *ctx, int32_t n, const int32_t *image_id
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (n < 0 || (n > 0 && (!image_ids || !rows))) return fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_reserve_batch: null argument");
     MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
-    for (int32_t i = 0; i < n; ++i) {
+    msfm_status st = MSFM_OK;
+    for (int32_t i = 0; i < n && st == MSFM_OK; ++i) {
         int64_t off = 0;
-        const msfm_status st = reserve_locked(ctx, image_ids[i], rows[i], &off);
-        if (st != MSFM_OK) return st;
+        if ((st = reserve_locked(ctx, image_ids[i], rows[i], &off)) != MSFM_OK) break;
         const ImageSlot &s = ctx->images[image_ids[i]];
         if (s.rows_padded > s.rows) {
-            msfm::init_pad_kernel<<<8, 256, 0, ctx->stream>>>(s.rows, s.rows_padded, ctx->desc + off * kDim, ctx->norms + off);
-            MSFM_CUDA(ctx, cudaGetLastError());
+            msfm::init_pad_kernel<<<8, 256, 0, ctx->upload_stream>>>(s.rows, s.rows_padded, ctx->desc + off * kDim, ctx->norms + off);
+            const std::vector<int32_t> one{image_ids[i]};
+            MSFM_CUDA_UPLOAD(ctx, one, cudaGetLastError());
         }
         if (row_offsets) row_offsets[i] = off;
     }
-    return MSFM_OK;
+    // pad rows and tensor maps are in place when the call returns: a foreign writer (a collective) may fill the rows at once
+    const msfm_status fin = finish_upload_sync(ctx);
+    return st != MSFM_OK ? st : fin;
 }
 
-// One image, enqueued on the context's stream without a host sync.  Contiguous rows go straight into the arena and are
-// keyed in place; strided rows pass through the staging buffer (which the caller must not reuse before a sync).
+// One image, enqueued on the upload stream without a host sync.  Contiguous rows go straight into the arena and are
+// keyed in place; strided rows pass through the staging buffer (which must not be reused before the stream got there).
 static msfm_status upload_u8_enqueue(msfm_ctx *ctx, int32_t image_id, const uint8_t *desc, int32_t rows, int64_t row_stride_bytes,
                                      bool *used_staging) {
     if ((rows > 0 && !desc) || row_stride_bytes < kDim) return fail(ctx, MSFM_ERR_INVALID_ARG, "null descriptors or stride < 128 bytes");
     int64_t off = 0;
     msfm_status st = reserve_locked(ctx, image_id, rows, &off);
     if (st != MSFM_OK) return st;
+    const std::vector<int32_t> mine{image_id};
     const ImageSlot &s = ctx->images[image_id];
     const int blocks = std::max(1, std::min(4 * ctx->num_sms, (s.rows_padded + 7) / 8));
     const uint8_t *src = ctx->desc + off * kDim;
     int64_t src_stride = kDim;
     if (row_stride_bytes == kDim) {
-        if (rows > 0) MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->desc + off * kDim, desc, (size_t)rows * kDim, cudaMemcpyHostToDevice, ctx->stream));
+        if (rows > 0) MSFM_CUDA_UPLOAD(ctx, mine, cudaMemcpyAsync(ctx->desc + off * kDim, desc, (size_t)rows * kDim, cudaMemcpyHostToDevice, ctx->upload_stream));
     } else {
         const size_t bytes = rows > 0 ? (size_t)(rows - 1) * row_stride_bytes + kDim : 0;
-        if ((st = ensure(ctx, ctx->staging, bytes)) != MSFM_OK) return st;
-        if (bytes) MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->staging.ptr, desc, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if ((st = ensure(ctx, ctx->staging, bytes, ctx->upload_stream)) != MSFM_OK) { unreserve_locked(ctx, mine); return st; }
+        if (bytes) MSFM_CUDA_UPLOAD(ctx, mine, cudaMemcpyAsync(ctx->staging.ptr, desc, bytes, cudaMemcpyHostToDevice, ctx->upload_stream));
         src = static_cast<const uint8_t *>(ctx->staging.ptr);
         src_stride = row_stride_bytes;
         *used_staging = true;
     }
-    msfm::pack_u8_kernel<<<blocks, 256, 0, ctx->stream>>>(src, src_stride, rows, s.rows_padded, ctx->desc + off * kDim, ctx->norms + off);
-    MSFM_CUDA(ctx, cudaGetLastError());
+    msfm::pack_u8_kernel<<<blocks, 256, 0, ctx->upload_stream>>>(src, src_stride, rows, s.rows_padded, ctx->desc + off * kDim, ctx->norms + off);
+    MSFM_CUDA_UPLOAD(ctx, mine, cudaGetLastError());
     return MSFM_OK;
 }
 
@@ -875,15 +994,15 @@ msfm_status msfm_upload_u8(msfm_ctx *ctx, int32_t image_id, const uint8_t *desc,
     bool staged = false;
     msfm_status st = upload_u8_enqueue(ctx, image_id, desc, rows, row_stride_bytes, &staged);
     if (st != MSFM_OK) return st;
-    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller may free `desc` on return
-    return MSFM_OK;
+    return finish_upload_sync(ctx);  // the caller may free `desc` on return
 }
 
 // Batch upload.  Contiguous-row images are reserved first, their host->device copies are queued back to back (runs
 // that are adjacent both in host memory and in the arena become one copy) and the packer launches follow, so the copy
 // engine is not held up by the keying kernels in between; strided images take the per-image staging path.
+// `uploaded` receives the ids this call staged (for the upload mark of the asynchronous variant).
 static msfm_status upload_u8_batch_locked(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const uint8_t *const *descs, const int32_t *rows,
-                                          const int64_t *row_stride_bytes, bool allow_strided) {
+                                          const int64_t *row_stride_bytes, bool allow_strided, std::vector<int32_t> &uploaded) {
     if (n < 0 || (n > 0 && (!image_ids || !descs || !rows))) return fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_upload_u8_batch: null argument");
     MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
     msfm_status st = MSFM_OK;
@@ -892,18 +1011,23 @@ static msfm_status upload_u8_batch_locked(msfm_ctx *ctx, int32_t n, const int32_
     // last image of a run can have pad rows).
     struct Run { const uint8_t *src; int64_t off; int64_t rows, rows_padded; };
     std::vector<Run> runs;
+    std::vector<int32_t> in_runs;  // reserved here, copies not queued yet
     for (int32_t i = 0; i < n && st == MSFM_OK; ++i) {
         const int64_t stride = row_stride_bytes ? row_stride_bytes[i] : kDim;
         if (stride != kDim) {
             if (!allow_strided) { st = fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_upload_u8_batch_async takes contiguous 128-byte rows only"); break; }
             bool staged = false;
             st = upload_u8_enqueue(ctx, image_ids[i], descs[i], rows[i], stride, &staged);
-            if (st == MSFM_OK && staged) MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging buffer is reused by the next image
+            if (st == MSFM_OK) {
+                uploaded.push_back(image_ids[i]);
+                if (staged) MSFM_CUDA_UPLOAD(ctx, in_runs, cudaStreamSynchronize(ctx->upload_stream));  // the staging buffer is reused by the next image
+            }
             continue;
         }
         if (rows[i] > 0 && !descs[i]) { st = fail(ctx, MSFM_ERR_INVALID_ARG, "null descriptors"); break; }
         int64_t off = 0;
         if ((st = reserve_locked(ctx, image_ids[i], rows[i], &off)) != MSFM_OK) break;
+        in_runs.push_back(image_ids[i]);
         const ImageSlot &sl = ctx->images[image_ids[i]];
         if (!runs.empty() && runs.back().rows == runs.back().rows_padded && off == runs.back().off + runs.back().rows &&
             descs[i] == runs.back().src + runs.back().rows * kDim && runs.back().rows + sl.rows_padded < (int64_t)INT32_MAX) {
@@ -913,15 +1037,18 @@ static msfm_status upload_u8_batch_locked(msfm_ctx *ctx, int32_t n, const int32_
             runs.push_back({descs[i], off, sl.rows, sl.rows_padded});
         }
     }
+    // On an argument error the images before the failing one stay uploaded (documented); a CUDA failure below rolls back
+    // every image whose rows this call has not provably written.
     for (const Run &r : runs)  // copies back to back, so the copy engine is not held up by the keying kernels
-        if (r.rows > 0) MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->desc + r.off * kDim, r.src, (size_t)r.rows * kDim, cudaMemcpyHostToDevice, ctx->stream));
+        if (r.rows > 0) MSFM_CUDA_UPLOAD(ctx, in_runs, cudaMemcpyAsync(ctx->desc + r.off * kDim, r.src, (size_t)r.rows * kDim, cudaMemcpyHostToDevice, ctx->upload_stream));
     for (const Run &r : runs) {    // keys + pad rows, in place
         if (r.rows_padded == 0) continue;
         const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(8 * ctx->num_sms, (r.rows_padded + 7) / 8));
         uint8_t *d = ctx->desc + r.off * kDim;
-        msfm::pack_u8_kernel<<<blocks, 256, 0, ctx->stream>>>(d, kDim, (int)r.rows, (int)r.rows_padded, d, ctx->norms + r.off);
+        msfm::pack_u8_kernel<<<blocks, 256, 0, ctx->upload_stream>>>(d, kDim, (int)r.rows, (int)r.rows_padded, d, ctx->norms + r.off);
+        MSFM_CUDA_UPLOAD(ctx, in_runs, cudaGetLastError());
     }
-    if (!runs.empty()) MSFM_CUDA(ctx, cudaGetLastError());
+    uploaded.insert(uploaded.end(), in_runs.begin(), in_runs.end());
     return st;
 }
 
@@ -929,23 +1056,56 @@ msfm_status msfm_upload_u8_batch(msfm_ctx *ctx, int32_t n, const int32_t *image_
                                  const int64_t *row_stride_bytes) {
     if (!ctx) return MSFM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    const msfm_status st = upload_u8_batch_locked(ctx, n, image_ids, descs, rows, row_stride_bytes, true);
-    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // one sync for the batch: the caller may free every `descs[i]` on return
-    return st;
+    std::vector<int32_t> uploaded;
+    const msfm_status st = upload_u8_batch_locked(ctx, n, image_ids, descs, rows, row_stride_bytes, true, uploaded);
+    const msfm_status fin = finish_upload_sync(ctx);  // one sync for the batch: the caller may free every `descs[i]` on return
+    return st != MSFM_OK ? st : fin;
 }
 
 msfm_status msfm_upload_u8_batch_async(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const uint8_t *const *descs, const int32_t *rows,
                                        const int64_t *row_stride_bytes) {
     if (!ctx) return MSFM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    return upload_u8_batch_locked(ctx, n, image_ids, descs, rows, row_stride_bytes, false);
+    std::vector<int32_t> uploaded;
+    const msfm_status st = upload_u8_batch_locked(ctx, n, image_ids, descs, rows, row_stride_bytes, false, uploaded);
+    const msfm_status mk = leave_upload_mark(ctx, uploaded);
+    return st != MSFM_OK ? st : mk;
 }
 
 msfm_status msfm_sync(msfm_ctx *ctx) {
     if (!ctx) return MSFM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
     MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->upload_stream));
     MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    recycle_marks(ctx);
+    return MSFM_OK;
+}
+
+// float rows of one image: staged at `stage` (device), quantised + keyed into the arena; with keep_float the rows are
+// copied to the float arena first and packed from there (no staging).
+static msfm_status upload_f32_enqueue(msfm_ctx *ctx, int32_t image_id, const float *desc, int32_t rows, int64_t row_stride_floats, float scale,
+                                      float *stage) {
+    const ImageSlot &s = ctx->images[image_id];
+    const std::vector<int32_t> mine{image_id};
+    const int64_t off = s.off;
+    const float *src = stage;
+    int64_t src_stride = row_stride_floats;
+    if (ctx->fdesc && rows > 0) {
+        // straight into the retained float rows (dense 128-float rows), then packed from there
+        MSFM_CUDA_UPLOAD(ctx, mine, cudaMemcpy2DAsync(ctx->fdesc + off * kDim, kDim * sizeof(float), desc, (size_t)row_stride_floats * sizeof(float),
+                                                      kDim * sizeof(float), (size_t)rows, cudaMemcpyHostToDevice, ctx->upload_stream));
+        src = ctx->fdesc + off * kDim;
+        src_stride = kDim;
+        ctx->images[image_id].has_float = true;
+        ctx->images[image_id].scale = scale;
+    } else if (rows > 0) {
+        const size_t bytes = ((size_t)(rows - 1) * row_stride_floats + kDim) * sizeof(float);
+        MSFM_CUDA_UPLOAD(ctx, mine, cudaMemcpyAsync(stage, desc, bytes, cudaMemcpyHostToDevice, ctx->upload_stream));
+    }
+    const int blocks = std::max(1, std::min(4 * ctx->num_sms, (s.rows_padded + 7) / 8));
+    msfm::pack_f32_kernel<<<blocks, 256, 0, ctx->upload_stream>>>(src, src_stride, rows, s.rows_padded, scale, ctx->desc + off * kDim, ctx->norms + off);
+    MSFM_CUDA_UPLOAD(ctx, mine, cudaGetLastError());
     return MSFM_OK;
 }
 
@@ -958,22 +1118,45 @@ msfm_status msfm_upload_f32(msfm_ctx *ctx, int32_t image_id, const float *desc, 
     int64_t off = 0;
     msfm_status st = reserve_locked(ctx, image_id, rows, &off);
     if (st != MSFM_OK) return st;
-    const ImageSlot &s = ctx->images[image_id];
-    const size_t bytes = rows > 0 ? ((size_t)(rows - 1) * row_stride_floats + kDim) * sizeof(float) : 0;
-    if ((st = ensure(ctx, ctx->staging, bytes)) != MSFM_OK) return st;
-    if (bytes) MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->staging.ptr, desc, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    const int blocks = std::max(1, std::min(4 * ctx->num_sms, (s.rows_padded + 7) / 8));
-    msfm::pack_f32_kernel<<<blocks, 256, 0, ctx->stream>>>(static_cast<const float *>(ctx->staging.ptr), row_stride_floats, rows,
-                                                          s.rows_padded, scale, ctx->desc + off * kDim, ctx->norms + off);
-    MSFM_CUDA(ctx, cudaGetLastError());
-    if (ctx->fdesc && rows > 0) {
-        MSFM_CUDA(ctx, cudaMemcpy2DAsync(ctx->fdesc + off * kDim, kDim * sizeof(float), ctx->staging.ptr, (size_t)row_stride_floats * sizeof(float),
-                                         kDim * sizeof(float), (size_t)rows, cudaMemcpyDeviceToDevice, ctx->stream));
-        ctx->images[image_id].has_float = true;
-        ctx->images[image_id].scale = scale;
+    const size_t bytes = (rows > 0 && !ctx->fdesc) ? ((size_t)(rows - 1) * row_stride_floats + kDim) * sizeof(float) : 0;
+    if ((st = ensure(ctx, ctx->staging, bytes, ctx->upload_stream)) != MSFM_OK) {
+        unreserve_locked(ctx, std::vector<int32_t>{image_id});
+        return st;
     }
-    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return MSFM_OK;
+    if ((st = upload_f32_enqueue(ctx, image_id, desc, rows, row_stride_floats, scale, static_cast<float *>(ctx->staging.ptr))) != MSFM_OK) return st;
+    return finish_upload_sync(ctx);
+}
+
+// Several float images (dense 128-float rows) without a host wait: the rows must sit in page-locked memory and stay
+// valid until msfm_sync() or a later call that returns results.  The staging buffer is used as a ring: every copy into
+// it is queued behind the packer launch that consumed the bytes it overwrites (one stream), so no wait is needed.
+msfm_status msfm_upload_f32_batch_async(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const float *const *descs, const int32_t *rows,
+                                        float scale) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (n < 0 || (n > 0 && (!image_ids || !descs || !rows)) || !(scale > 0.0f))
+        return fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_upload_f32_batch_async: null argument or scale <= 0");
+    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t largest = 0;
+    for (int32_t i = 0; i < n; ++i)
+        if (rows[i] > 0) largest = std::max(largest, (size_t)rows[i] * kDim * sizeof(float));
+    msfm_status st = MSFM_OK;
+    const size_t ring = ctx->fdesc ? 0 : std::max<size_t>(largest, std::min<size_t>((size_t)64 << 20, largest * (size_t)std::max(n, 1)));
+    if (ring && (st = ensure(ctx, ctx->staging, ring, ctx->upload_stream)) != MSFM_OK) return st;
+    std::vector<int32_t> uploaded;
+    size_t pos = 0;
+    for (int32_t i = 0; i < n && st == MSFM_OK; ++i) {
+        if (rows[i] > 0 && !descs[i]) { st = fail(ctx, MSFM_ERR_INVALID_ARG, "null descriptors"); break; }
+        int64_t off = 0;
+        if ((st = reserve_locked(ctx, image_ids[i], rows[i], &off)) != MSFM_OK) break;
+        const size_t bytes = ctx->fdesc ? 0 : (size_t)std::max(rows[i], 0) * kDim * sizeof(float);
+        if (pos + bytes > ctx->staging.bytes) pos = 0;
+        st = upload_f32_enqueue(ctx, image_ids[i], descs[i], rows[i], kDim, scale,
+                                reinterpret_cast<float *>(static_cast<char *>(ctx->staging.ptr) + pos));
+        if (st == MSFM_OK) { uploaded.push_back(image_ids[i]); pos += bytes; }
+    }
+    const msfm_status mk = leave_upload_mark(ctx, uploaded);
+    return st != MSFM_OK ? st : mk;
 }
 
 msfm_status msfm_release(msfm_ctx *ctx, int32_t image_id) {
@@ -982,6 +1165,7 @@ msfm_status msfm_release(msfm_ctx *ctx, int32_t image_id) {
     msfm_status st = check_image_id(ctx, image_id, true);
     if (st != MSFM_OK) return st;
     MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->upload_stream));
     MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ImageSlot &s = ctx->images[image_id];
     arena_free(ctx, s.off, s.rows_padded);
@@ -993,10 +1177,12 @@ msfm_status msfm_release_all(msfm_ctx *ctx) {
     if (!ctx) return MSFM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
     MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->upload_stream));
     MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (ImageSlot &s : ctx->images) s = ImageSlot{};
     ctx->free_list.clear();
     ctx->rows_high_water = 0;
+    recycle_marks(ctx);
     return MSFM_OK;
 }
 
@@ -1027,6 +1213,7 @@ msfm_status msfm_download_packed(msfm_ctx *ctx, int32_t image_id, uint8_t *desc_
     if (st != MSFM_OK) return st;
     MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
     const ImageSlot &s = ctx->images[image_id];
+    MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->upload_stream));
     if (desc_out && s.rows) MSFM_CUDA(ctx, cudaMemcpyAsync(desc_out, ctx->desc + s.off * kDim, (size_t)s.rows * kDim, cudaMemcpyDeviceToHost, ctx->stream));
     if (norms_out && s.rows) MSFM_CUDA(ctx, cudaMemcpyAsync(norms_out, ctx->norms + s.off, (size_t)s.rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
     MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1108,6 +1295,34 @@ msfm_status msfm_last_timing(const msfm_ctx *ctx, msfm_timing *out) {
 msfm_status msfm_get_stream(const msfm_ctx *ctx, void **cuda_stream) {
     if (!ctx || !cuda_stream) return MSFM_ERR_INVALID_ARG;
     *cuda_stream = static_cast<void *>(ctx->stream);
+    return MSFM_OK;
+}
+
+msfm_status msfm_get_upload_stream(const msfm_ctx *ctx, void **cuda_stream) {
+    if (!ctx || !cuda_stream) return MSFM_ERR_INVALID_ARG;
+    *cuda_stream = static_cast<void *>(ctx->upload_stream);
+    return MSFM_OK;
+}
+
+msfm_status msfm_wait_event(msfm_ctx *ctx, void *cuda_event) {
+    if (!ctx || !cuda_event) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    MSFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, static_cast<cudaEvent_t>(cuda_event), 0));
+    return MSFM_OK;
+}
+
+msfm_status msfm_test_force_twin_pass(msfm_ctx *ctx, int32_t on) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->force_twin = on != 0;
+    return MSFM_OK;
+}
+
+msfm_status msfm_test_set_band_event_cap(msfm_ctx *ctx, int64_t cap) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->band_event_cap_override = cap;
     return MSFM_OK;
 }
 

@@ -51,6 +51,7 @@ bool FeatureMatchingB200::Match(cv::Mat &d1, cv::Mat &d2, bool mutual, std::vect
     // index on image 2, queries = rows of image 1 (feature_matching.cpp:35-44)
     msfm_pair pair = {1, 0};
     msfm_params prm;
+    memset(&prm, 0, sizeof prm);
     prm.ratio = opt_.th_ratio;
     prm.ratio_good = 0.f;
     prm.max_dist_sq = 0.f;
@@ -254,6 +255,7 @@ bool MatchGraphB200::MatchPairs(const std::vector<std::vector<int>> &match_graph
     std::vector<int32_t> buf((size_t)(capacity > 0 ? capacity : 1) * 2);
     std::vector<uint8_t> good((size_t)(capacity > 0 ? capacity : 1));
     msfm_params prm;
+    memset(&prm, 0, sizeof prm);
     prm.ratio = th_all;
     prm.ratio_good = th_good;
     prm.max_dist_sq = 0.f;

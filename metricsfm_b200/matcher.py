@@ -144,8 +144,31 @@ class Matcher:
         fn = self._L.msfm_upload_u8_batch if wait else self._L.msfm_upload_u8_batch_async
         self._check(fn(self._h, n, ids.ctypes.data, C.cast(ptrs, C.c_void_p), rows.ctypes.data, strides.ctypes.data))
         if not wait:
-            self._inflight = keep  # keep the host buffers alive until the next synchronising call
+            self._inflight = (self._inflight or []) + keep  # host buffers stay alive until sync() / release_all()
         del keep
+
+    def upload_f32_batch_async(self, image_ids, descs, scale: float = 1.0) -> None:
+        """msfm_upload_f32_batch_async: several float32 [rows, 128] images (dense rows, page-locked memory) without a host
+        wait; the buffers must stay valid and unchanged until sync()."""
+        n = len(image_ids)
+        ids = np.ascontiguousarray(image_ids, np.int32)
+        ptrs = (C.c_void_p * max(n, 1))()
+        rows = np.zeros((max(n, 1),), np.int32)
+        keep = []
+        for k, d in enumerate(descs):
+            is_t = hasattr(d, "numpy") and not isinstance(d, np.ndarray)
+            if not is_t:
+                d = np.asarray(d)
+            dt = str(d.dtype).replace("torch.", "")
+            dense = d.is_contiguous() if is_t else d.flags["C_CONTIGUOUS"]
+            if dt != "float32" or len(d.shape) != 2 or (d.shape[0] and d.shape[1] != 128) or not dense:
+                raise ValueError("upload_f32_batch_async takes dense [rows, 128] float32 descriptors")
+            rows[k] = d.shape[0]
+            ptr, ka = _host_ptr(d)
+            ptrs[k] = ptr
+            keep.append(ka)
+        self._check(self._L.msfm_upload_f32_batch_async(self._h, n, ids.ctypes.data, C.cast(ptrs, C.c_void_p), rows.ctypes.data, scale))
+        self._inflight = (self._inflight or []) + keep
 
     def sync(self) -> None:
         self._check(self._L.msfm_sync(self._h))
@@ -170,7 +193,8 @@ class Matcher:
         self._check(self._L.msfm_release(self._h, image_id))
 
     def release_all(self) -> None:
-        self._check(self._L.msfm_release_all(self._h))
+        self._check(self._L.msfm_release_all(self._h))   # synchronises both streams
+        self._inflight = None
 
     def image_info(self, image_id: int):
         rows, off = C.c_int32(), C.c_int64()
@@ -213,9 +237,10 @@ class Matcher:
 
     # ------------------------------------------------------------------ batched pair matching
     @staticmethod
-    def _params(ratio, ratio_good, max_dist_sq, mutual, min_keypoints, orientation, rescore_band=0.0) -> Params:
+    def _params(ratio, ratio_good, max_dist_sq, mutual, min_keypoints, orientation, rescore_band=0.0, flags=0) -> Params:
         p = Params()
         p.rescore_band = rescore_band
+        p.flags = int(flags)
         p.ratio, p.ratio_good, p.max_dist_sq = ratio, ratio_good, max_dist_sq
         p.mutual, p.min_keypoints, p.orientation = int(bool(mutual)), int(min_keypoints), int(orientation)
         return p
@@ -227,7 +252,7 @@ class Matcher:
 
     def match_pairs(self, pairs, ratio: float = 0.6, *, ratio_good: float = 0.0, max_dist_sq: float = 0.0, mutual: bool = False,
                     min_keypoints: int = 20, orientation: int = 0, capacity: int | None = None, out: MatchResult | None = None,
-                    rescore_band: float = 0.0) -> MatchResult:
+                    rescore_band: float = 0.0, flags: int = 0) -> MatchResult:
         """pairs: [n, 2] (ref image, query image).  Returns per-pair match lists, ascending query index.
         rescore_band > 0 (float uploads on a keep_float context): rows whose quantised ratio lies within that relative
         band of a threshold are decided on exact fp32 distances."""
@@ -251,7 +276,7 @@ class Matcher:
         res.matches = _host_ptr(out.matches)[0]
         res.good = out.good.ctypes.data_as(_lib._u8p) if out.good is not None else None
         res.match_capacity = out.matches.shape[0]
-        prm = self._params(ratio, ratio_good, max_dist_sq, mutual, min_keypoints, orientation, rescore_band)
+        prm = self._params(ratio, ratio_good, max_dist_sq, mutual, min_keypoints, orientation, rescore_band, flags)
         self._check(self._L.msfm_match_pairs(self._h, pa.ctypes.data, n, C.byref(prm), C.byref(res)))
         total = int(out.offsets[n])
         return MatchResult(out.offsets, out.ok, out.matches[:total], out.good[:total] if out.good is not None else None)
@@ -303,6 +328,22 @@ class Matcher:
         self._check(self._L.msfm_get_stream(self._h, C.byref(s)))
         return s.value or 0
 
+    def upload_stream(self) -> int:
+        """Raw cudaStream_t the table uploads run on."""
+        s = C.c_void_p()
+        self._check(self._L.msfm_get_upload_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def wait_event(self, cuda_event: int) -> None:
+        """Later matching launches wait (on the device) for this cudaEvent_t, e.g. torch.cuda.Event.cuda_event."""
+        self._check(self._L.msfm_wait_event(self._h, C.c_void_p(cuda_event)))
+
+    def _test_set_band_event_cap(self, cap: int) -> None:
+        self._check(self._L.msfm_test_set_band_event_cap(self._h, cap))
+
+    def _test_force_twin_pass(self, on: bool) -> None:
+        self._check(self._L.msfm_test_force_twin_pass(self._h, int(bool(on))))
+
     def timing(self) -> dict:
         t = Timing()
         self._check(self._L.msfm_last_timing(self._h, C.byref(t)))
@@ -314,6 +355,12 @@ class Matcher:
         ratio < 0.5, emits (i1, i2) ascending i1.  Returns (ok, matches[n,2])."""
         r = self.match_pairs([(id2, id1)], th_ratio, mutual=mutual, min_keypoints=th_reject, orientation=1)
         return bool(r.ok[0]), r.pair(0).copy()
+
+    def SLAMFeatureMatching(self, id1: int, id2: int, *, th_first_second_ratio: float = 0.8):
+        """SLAMGPS::FeatureMatching kNN + ratio part (slam_gps.cc:438-477): index on id1, queries = rows of id2, a row is
+        rejected iff ratio > th (non-strict; 0/0 = NaN passes), no keypoint gate.  Returns matches [(i1, i2)] ascending i2."""
+        r = self.match_pairs([(id1, id2)], th_first_second_ratio, min_keypoints=0, orientation=0, flags=_lib.RATIO_REJECT_GT)
+        return r.pair(0).copy()
 
     def MatchAgainstIndex(self, idx1: int, idx2: int, *, th_ratio: float = 0.5, th_reject: int = 20, mutual: bool = False):
         """KNNMatchingWithGeoVerify(kp1, kd_tree1, kp2, descriptors2, matches) kNN + ratio part

@@ -184,12 +184,17 @@ void oracle_colbest_f32(const float *ref, int32_t M, const float *query, int32_t
  *   max_dist_sq <= 0 disables the distance gate (SiftGPU distmax analogue on squared L2).
  *   ratio_good > 0: good_flags[k] = 1 iff the same match also passes ratio_good
  *                   (the dual 0.6/0.85 lists of fine_matching_graph.cc:118-131).
+ *   reject_gt: 0 = accept iff d0/d1 < ratio (feature_matching.cpp:45-46, fine_matching_graph.cc:118-129);
+ *              1 = SLAMGPS::FeatureMatching's rule, slam_gps.cc:470-477: `if (ratio > th) continue;`, i.e. accept iff
+ *                  !(d0/d1 > ratio) — non-strict, and 0/0 = NaN is accepted.
  * Returns the number of matches, or -1 when the <min_keypoints gate rejects the pair
  * (feature_matching.cpp:30-33 returns false).
  */
-int32_t oracle_ratio_select(const int32_t *ids, const float *dists, int32_t M, int32_t N, float ratio, float max_dist_sq,
-                            const int32_t *col_best, int32_t min_keypoints, int32_t orientation, float ratio_good,
-                            int32_t *out_pairs /* [N][2] */, uint8_t *good_flags /* [N] or NULL */) {
+static int ratio_pass(float r, float th, int32_t reject_gt) { return reject_gt ? !(r > th) : (r < th); }
+
+int32_t oracle_ratio_select_rule(const int32_t *ids, const float *dists, int32_t M, int32_t N, float ratio, float max_dist_sq,
+                                 const int32_t *col_best, int32_t min_keypoints, int32_t orientation, float ratio_good,
+                                 int32_t reject_gt, int32_t *out_pairs /* [N][2] */, uint8_t *good_flags /* [N] or NULL */) {
     if (M < min_keypoints || N < min_keypoints) return -1;
     int32_t n = 0;
     for (int32_t q = 0; q < N; ++q) {
@@ -197,15 +202,22 @@ int32_t oracle_ratio_select(const int32_t *ids, const float *dists, int32_t M, i
         if (i0 < 0 || i1 < 0) continue; /* fewer than two reference points: no ratio exists */
         const float d0 = dists[2 * q], d1 = dists[2 * q + 1];
         const float r = d0 / d1; /* IEEE fp32 divide; 0/0 = NaN compares false */
-        if (!(r < ratio)) continue;
+        if (!ratio_pass(r, ratio, reject_gt)) continue;
         if (max_dist_sq > 0.0f && !(d0 < max_dist_sq)) continue;
         if (col_best && col_best[i0] != q) continue;
         if (orientation == 0) { out_pairs[2 * n] = i0; out_pairs[2 * n + 1] = q; }
         else { out_pairs[2 * n] = q; out_pairs[2 * n + 1] = i0; }
-        if (good_flags) good_flags[n] = (ratio_good > 0.0f && r < ratio_good) ? 1 : 0;
+        if (good_flags) good_flags[n] = (ratio_good > 0.0f && ratio_pass(r, ratio_good, reject_gt)) ? 1 : 0;
         ++n;
     }
     return n;
+}
+
+int32_t oracle_ratio_select(const int32_t *ids, const float *dists, int32_t M, int32_t N, float ratio, float max_dist_sq,
+                            const int32_t *col_best, int32_t min_keypoints, int32_t orientation, float ratio_good,
+                            int32_t *out_pairs /* [N][2] */, uint8_t *good_flags /* [N] or NULL */) {
+    return oracle_ratio_select_rule(ids, dists, M, N, ratio, max_dist_sq, col_best, min_keypoints, orientation, ratio_good, 0,
+                                    out_pairs, good_flags);
 }
 
 /*

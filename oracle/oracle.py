@@ -35,8 +35,7 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(_ORACLE_SO):
-            build(ref=False)
+        build(ref=False)   # make: a no-op when _build/liboracle.so is newer than match_oracle.c
         L = C.CDLL(_ORACLE_SO)
         L.oracle_max_threads.restype = C.c_int
         L.oracle_quantize_f32.argtypes = [_f32p, C.c_int64, C.c_int64, C.c_float, _u8p]
@@ -47,6 +46,9 @@ def lib() -> C.CDLL:
         L.oracle_ratio_select.argtypes = [_i32p, _f32p, C.c_int32, C.c_int32, C.c_float, C.c_float, _i32p, C.c_int32,
                                           C.c_int32, C.c_float, _i32p, _u8p]
         L.oracle_ratio_select.restype = C.c_int32
+        L.oracle_ratio_select_rule.argtypes = [_i32p, _f32p, C.c_int32, C.c_int32, C.c_float, C.c_float, _i32p, C.c_int32,
+                                               C.c_int32, C.c_float, C.c_int32, _i32p, _u8p]
+        L.oracle_ratio_select_rule.restype = C.c_int32
         _lib = L
     return _lib
 
@@ -120,8 +122,9 @@ def colbest_f32(ref: np.ndarray, query: np.ndarray):
 
 
 def ratio_select(ids, dists, m_ref: int, ratio: float, *, max_dist_sq: float = 0.0, col_best=None, min_keypoints: int = 20,
-                 orientation: int = 0, ratio_good: float = 0.0):
-    """Returns (pairs [n,2] int32, good_flags [n] uint8) or (None, None) when the <min_keypoints gate rejects."""
+                 orientation: int = 0, ratio_good: float = 0.0, reject_gt: bool = False):
+    """Returns (pairs [n,2] int32, good_flags [n] uint8) or (None, None) when the <min_keypoints gate rejects.
+    reject_gt: SLAMGPS::FeatureMatching's rule (slam_gps.cc:470-477), accept iff !(d0/d1 > ratio)."""
     ids = np.ascontiguousarray(ids, dtype=np.int32).reshape(-1, 2)
     dists = np.ascontiguousarray(dists, dtype=np.float32).reshape(-1, 2)
     n = ids.shape[0]
@@ -130,16 +133,16 @@ def ratio_select(ids, dists, m_ref: int, ratio: float, *, max_dist_sq: float = 0
     cb = None
     if col_best is not None:
         cb = np.ascontiguousarray(col_best, dtype=np.int32)
-    cnt = lib().oracle_ratio_select(_p(ids, _i32p), _p(dists, _f32p), m_ref, n, ratio, max_dist_sq,
-                                    _p(cb, _i32p) if cb is not None else None, min_keypoints, orientation, ratio_good,
-                                    _p(pairs, _i32p), _p(flags, _u8p))
+    cnt = lib().oracle_ratio_select_rule(_p(ids, _i32p), _p(dists, _f32p), m_ref, n, ratio, max_dist_sq,
+                                         _p(cb, _i32p) if cb is not None else None, min_keypoints, orientation, ratio_good,
+                                         1 if reject_gt else 0, _p(pairs, _i32p), _p(flags, _u8p))
     if cnt < 0:
         return None, None
     return pairs[:cnt].copy(), flags[:cnt].copy()
 
 
 def match_pair_u8(ref, query, ratio: float, *, mutual: bool = False, max_dist_sq: float = 0.0, min_keypoints: int = 20,
-                  orientation: int = 0, ratio_good: float = 0.0):
+                  orientation: int = 0, ratio_good: float = 0.0, reject_gt: bool = False):
     """Whole path for one pair.  Returns dict(ok, ids, dists, pairs, good)."""
     ref = np.ascontiguousarray(ref, dtype=np.uint8).reshape(-1, 128)
     query = np.ascontiguousarray(query, dtype=np.uint8).reshape(-1, 128)
@@ -148,7 +151,7 @@ def match_pair_u8(ref, query, ratio: float, *, mutual: bool = False, max_dist_sq
     ids, dists = knn2_u8(ref, query)
     cb = colbest_u8(ref, query)[0] if mutual else None
     pairs, good = ratio_select(ids, dists, ref.shape[0], ratio, max_dist_sq=max_dist_sq, col_best=cb,
-                               min_keypoints=min_keypoints, orientation=orientation, ratio_good=ratio_good)
+                               min_keypoints=min_keypoints, orientation=orientation, ratio_good=ratio_good, reject_gt=reject_gt)
     return dict(ok=True, ids=ids, dists=dists, pairs=pairs, good=good)
 
 

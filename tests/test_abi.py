@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(native_lib):
 
 
 def test_abi_version_and_status_strings(native_lib):
-    assert native_lib.msfm_abi_version() == 2  # v2: msfm_config.keep_float, msfm_params.rescore_band
+    assert native_lib.msfm_abi_version() == 3  # v2: msfm_config.keep_float, msfm_params.rescore_band
     assert native_lib.msfm_status_string(0) == b"ok"
     assert b"sm_100" in native_lib.msfm_status_string(6)
 

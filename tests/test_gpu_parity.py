@@ -383,10 +383,10 @@ def test_float_regime_rescoring_matches_fp32_matcher(oracle_mod, native_lib, mut
     assert flips_raw > 0  # the reason the re-scoring band exists
 
 
-@pytest.mark.parametrize("cap", ["0", "37"])
-def test_float_regime_collect_pass_equals_brute_force(native_lib, monkeypatch, cap):
+@pytest.mark.parametrize("cap", [0, 37])
+def test_float_regime_collect_pass_equals_brute_force(native_lib, cap):
     """The band rows' fp32 neighbours come from the tensor kernel's collect pass + per-event scoring; when its event list
-    overflows (forced here with MSFM_BAND_EVENT_CAP) a dp4a brute force over the reference image takes over.  Both must
+    overflows (forced here through the msfm_test_set_band_event_cap hook) a dp4a brute force over the reference image takes over.  Both must
     produce identical match lists and good flags, with and without the mutual check, on ragged images."""
     from metricsfm_b200.matcher import Matcher
     col = synth.Collection(3000, seed=13)
@@ -394,9 +394,10 @@ def test_float_regime_collect_pass_equals_brute_force(native_lib, monkeypatch, c
     imgs = [col.image_unit(i)[:r] for i, r in enumerate(rows)]
     pairs = [(0, 1), (1, 0), (2, 4), (4, 3), (3, 2), (0, 4)]
 
-    def run():
+    def run(event_cap=-1):
         out = []
         with Matcher(device=0, max_images=8, arena_rows=1 << 15, keep_float=True) as m:
+            m._test_set_band_event_cap(event_cap)
             for i, x in enumerate(imgs):
                 m.upload(i, np.ascontiguousarray(x), scale=512.0)
             for mutual in (False, True):
@@ -404,10 +405,8 @@ def test_float_regime_collect_pass_equals_brute_force(native_lib, monkeypatch, c
                 out.append([(res.pair(p).copy(), res.pair_good(p).copy()) for p in range(len(pairs))])
         return out
 
-    monkeypatch.delenv("MSFM_BAND_EVENT_CAP", raising=False)
     collected = run()
-    monkeypatch.setenv("MSFM_BAND_EVENT_CAP", cap)
-    brute = run()
+    brute = run(cap)
     n = 0
     for a, b in zip(collected, brute):
         for (ma, ga), (mb, gb) in zip(a, b):
@@ -820,3 +819,158 @@ def test_cpp_shim_verified_matcher_vs_opencv_flow(oracle_mod, native_lib, tmp_pa
     Hcv, _ = cv2.findHomography(xy1[allm[:, 0]].astype(np.float32), xy_same[allm[:, 1]], 0)
     np.testing.assert_allclose(Hall, Hcv / Hcv[2, 2], atol=2e-3)              # where the gate matters, DLT == OpenCV's estimate
     assert all(abs(Hall[i, i] - 0.995) < 0.01 for i in range(3))
+
+
+# ---------------------------------------------------------------------------------------------------- round 2
+def _adversarial_mutual_images(seed=5):
+    """Images built to stress the mutual check: near-duplicate clusters (tiny second-neighbour distances => large
+    'dangerous' sets), exact duplicates (ties in both directions), and ordinary SIFT-like rows in between."""
+    rng = np.random.default_rng(seed)
+    col = synth.Collection(1500, seed=seed)
+    base = col.image_u8(0, 60).astype(np.int16)
+    clus = np.repeat(base, 30, axis=0) + rng.integers(-1, 2, size=(1800, 128))          # 60 clusters x 30 near-copies
+    clus = np.clip(clus, 0, 255).astype(np.uint8)
+    a = np.concatenate([col.image_u8(1, 900), clus[:900], col.image_u8(1, 40)], axis=0)  # + 40 exact duplicates of its head
+    b = np.concatenate([clus[600:1500], col.image_u8(2, 1000), col.image_u8(1, 40)[::-1]], axis=0)
+    c = np.concatenate([clus[::2], clus[1::2][:300]], axis=0)
+    d = col.image_u8(3, 1500)
+    return [np.ascontiguousarray(x) for x in (a, b, c, d)]
+
+
+@pytest.mark.parametrize("ratio,flags", [(0.85, 0), (0.97, 0), (0.999, 1)])
+def test_mutual_check_bound_path_and_twin_path_vs_oracle(oracle_mod, native_lib, ratio, flags):
+    """The mutual cross-check is decided from the forward results (column table + exactly scored 'dangerous' rows) and
+    falls back to the tensor twin pass for ambiguous pairs.  Both routes, and the forced-twin route, must reproduce the
+    oracle's column-best rule bit for bit — also on near-duplicate clusters and exact ties."""
+    from metricsfm_b200.matcher import Matcher
+    imgs = _adversarial_mutual_images()
+    pairs = [(r, q) for r in range(4) for q in range(4)]
+    with Matcher(device=0, max_images=8, arena_rows=1 << 15) as m:
+        for i, x in enumerate(imgs):
+            m.upload(i, x)
+        auto = m.match_pairs(pairs, ratio, ratio_good=0.6, mutual=True, flags=flags)
+        t_auto = m.timing()
+        m._test_force_twin_pass(True)
+        forced = m.match_pairs(pairs, ratio, ratio_good=0.6, mutual=True, flags=flags)
+        t_forced = m.timing()
+        m._test_force_twin_pass(False)
+        oneway = m.match_pairs(pairs, ratio, ratio_good=0.6, mutual=False, flags=flags)
+    assert t_forced["twin_pairs"] > t_auto["twin_pairs"] > 0      # the clusters overflow, the ordinary pairs do not
+    assert t_auto["twin_pairs"] < len(pairs)
+    n = 0
+    for p, (r, q) in enumerate(pairs):
+        exp = oracle_mod.match_pair_u8(imgs[r], imgs[q], ratio, mutual=True, ratio_good=0.6, reject_gt=bool(flags))
+        np.testing.assert_array_equal(auto.pair(p), exp["pairs"], err_msg=f"bound route, pair ({r},{q})")
+        np.testing.assert_array_equal(forced.pair(p), exp["pairs"], err_msg=f"twin route, pair ({r},{q})")
+        np.testing.assert_array_equal(auto.pair_good(p), exp["good"])
+        np.testing.assert_array_equal(forced.pair_good(p), exp["good"])
+        ow = oracle_mod.match_pair_u8(imgs[r], imgs[q], ratio, mutual=False, ratio_good=0.6, reject_gt=bool(flags))
+        np.testing.assert_array_equal(oneway.pair(p), ow["pairs"])
+        n += len(exp["pairs"])
+    assert n > 500
+
+
+def test_mutual_check_ordinary_collection_never_needs_the_twin_pass(oracle_mod, native_lib):
+    col = synth.Collection(4096, seed=77)
+    imgs = [col.image_u8(i) for i in range(4)]
+    pairs = [(0, 1), (1, 2), (2, 3), (3, 0), (0, 2)]
+    from metricsfm_b200.matcher import Matcher
+    with Matcher(device=0, max_images=4, arena_rows=1 << 15) as m:
+        for i, x in enumerate(imgs):
+            m.upload(i, x)
+        res = m.match_pairs(pairs, 0.85, ratio_good=0.6, mutual=True)
+        t = m.timing()
+    assert t["twin_pairs"] == 0 and t["match_launches"] >= 1
+    for p, (r, q) in enumerate(pairs):
+        exp = oracle_mod.match_pair_u8(imgs[r], imgs[q], 0.85, mutual=True, ratio_good=0.6)
+        np.testing.assert_array_equal(res.pair(p), exp["pairs"])
+        np.testing.assert_array_equal(res.pair_good(p), exp["good"])
+
+
+def test_slam_ratio_rule(oracle_mod, matcher):
+    """SLAMGPS::FeatureMatching (slam_gps.cc:470-477) rejects a row iff ratio > 0.80: non-strict, and 0/0 = NaN passes.
+    Rows with d0 = d1 = 0 (duplicated reference rows) and rows sitting exactly on the threshold tell the rules apart."""
+    col = synth.Collection(700, seed=91)
+    ref = col.image_u8(0, 700)
+    qry = col.image_u8(1, 600)
+    ref[10] = ref[11] = qry[5]              # d0 = d1 = 0 for query row 5: NaN ratio
+    # query row 7: d0/d1 == 0.5 exactly (d0 = 8, d1 = 16 against two crafted reference rows)
+    qry[7] = 100
+    ref[20] = 100; ref[20, :2] = 102        # d = 4 + 4 = 8
+    ref[21] = 100; ref[21, :4] = 102        # d = 16
+    _upload_pair(matcher, ref, qry)
+    from metricsfm_b200 import _lib
+    for th in (0.5, 0.8):
+        got = matcher.match_pairs([(0, 1)], th, min_keypoints=0, flags=_lib.RATIO_REJECT_GT)
+        exp = oracle_mod.match_pair_u8(ref, qry, th, min_keypoints=0, reject_gt=True)
+        np.testing.assert_array_equal(got.pair(0), exp["pairs"])
+        strict = matcher.match_pairs([(0, 1)], th, min_keypoints=0)
+        exp_s = oracle_mod.match_pair_u8(ref, qry, th, min_keypoints=0)
+        np.testing.assert_array_equal(strict.pair(0), exp_s["pairs"])
+        assert 5 in got.pair(0)[:, 1] and 5 not in strict.pair(0)[:, 1]
+    at_half = matcher.match_pairs([(0, 1)], 0.5, min_keypoints=0, flags=_lib.RATIO_REJECT_GT).pair(0)
+    assert 7 in at_half[:, 1] and 7 not in matcher.match_pairs([(0, 1)], 0.5, min_keypoints=0).pair(0)[:, 1]
+    np.testing.assert_array_equal(matcher.SLAMFeatureMatching(0, 1, th_first_second_ratio=0.8),
+                                  oracle_mod.match_pair_u8(ref, qry, 0.8, min_keypoints=0, reject_gt=True)["pairs"])
+
+
+def test_async_upload_groups_overlap_matching(oracle_mod, native_lib):
+    """Images staged in groups on the upload stream (u8 and f32, no host wait) while earlier groups are matched: every
+    launch waits on the device for exactly the uploads it needs; lists equal those of synchronous uploads."""
+    import torch
+    from metricsfm_b200.matcher import Matcher
+    col = synth.Collection(2048, seed=17)
+    n = 12
+    rows = [2048 - 37 * i for i in range(n)]
+    u8 = torch.empty((n, 2048, 128), dtype=torch.uint8).pin_memory()
+    f32 = torch.empty((n, 2048, 128), dtype=torch.float32).pin_memory()
+    for i in range(n):
+        u8[i, :rows[i]] = torch.from_numpy(col.image_u8(i, rows[i]))
+        f32[i, :rows[i]] = u8[i, :rows[i]].float()
+    groups = [list(range(g, g + 4)) for g in range(0, n, 4)]
+    all_pairs = synth.exhaustive_pairs(n)
+    with Matcher(device=0, max_images=n, arena_rows=n * 2048 + 4096) as m:
+        for i in range(n):
+            m.upload(i, u8[i, :rows[i]].numpy())
+        ref = m.match_pairs(all_pairs, 0.85, ratio_good=0.6, mutual=True)
+        for use_f32 in (False, True):
+            m.release_all()
+            got = {}
+            for g, ids in enumerate(groups):
+                if use_f32:
+                    m.upload_f32_batch_async(ids, [f32[i, :rows[i]] for i in ids], scale=1.0)
+                else:
+                    m.upload_batch(ids, [u8[i, :rows[i]] for i in ids], wait=False)
+            for g, ids in enumerate(groups):     # pairs whose newest image lies in group g
+                sel = [k for k, (a, b) in enumerate(all_pairs) if max(a, b) // 4 == g]
+                res = m.match_pairs(all_pairs[sel], 0.85, ratio_good=0.6, mutual=True)
+                for j, k in enumerate(sel):
+                    got[k] = (res.pair(j).copy(), res.pair_good(j).copy())
+            m.sync()
+            for k in range(len(all_pairs)):
+                np.testing.assert_array_equal(got[k][0], ref.pair(k))
+                np.testing.assert_array_equal(got[k][1], ref.pair_good(k))
+    exp = oracle_mod.match_pair_u8(u8[0, :rows[0]].numpy(), u8[1, :rows[1]].numpy(), 0.85, mutual=True, ratio_good=0.6)
+    np.testing.assert_array_equal(ref.pair(0), exp["pairs"])
+
+
+def test_failed_batch_upload_leaves_no_half_uploaded_image(matcher):
+    """An upload that fails must not leave an image 'present' with unwritten rows: the failing id of a batch is
+    absent afterwards, the images before it stay uploaded, and a retry succeeds."""
+    from metricsfm_b200.matcher import MsfmError
+    col = synth.Collection(300, seed=3)
+    a, b = col.image_u8(0, 300), col.image_u8(1, 200)
+    matcher.release_all()
+    matcher.upload(2, a)
+    with pytest.raises(MsfmError):
+        matcher.upload_batch([0, 2, 1], [a, b, b])          # id 2 exists already
+    assert matcher.image_info(0)[0] == 300
+    with pytest.raises(MsfmError):
+        matcher.image_info(1)
+    with pytest.raises(MsfmError):
+        matcher.upload(5, a[:, :64])                          # malformed rows never reserve
+    with pytest.raises(MsfmError):
+        matcher.image_info(5)
+    matcher.upload(1, b)
+    got, _ = matcher.download_packed(1)
+    np.testing.assert_array_equal(got, b)
