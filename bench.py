@@ -1,20 +1,30 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the pairwise SIFT-128 matching hot path.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path (one JSON line on rank 0)
-  python bench.py --impl reference [--steps K] [--warmup W]      # the reference's own CPU engine on the host cores
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 2|3|4|5]     # this repo's CUDA path, one JSON line
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # one rank per GPU (NCCL)
+  python bench.py --gpus N --engine single ...                                   # ONE process, C++ multi-GPU engine
+  python bench.py --impl reference [--steps K] [--warmup W]                      # the reference's CPU engine
 
-Metric (BASELINE.json): image-pairs/sec on 8k x 8k SIFT-128.  A *step* is one pass of the hot path over the whole
-candidate pair list of the workload: BASELINE config #2, exhaustive matching of 100 web images x 8192 descriptors
-(4,950 pairs) per GPU — 2-NN + ratio (0.85 "all" / 0.6 "good", fine_matching_graph.cc:42-43) + mutual cross-check.
-  value : pairs/s with the packed descriptor table already resident in HBM (device-timed, CUDA events on the
-          library's stream, L2 flushed between steps, max over ranks)
-  e2e   : pairs/s through the public API from HOST buffers: per step pack+upload every image from pinned memory
-          (H2D), replicate the table over NCCL when N > 1, match, and copy the match lists back (D2H)
-  roofline: the tcgen05 matching kernel against the dense int8 tensor-core peak
-  cpu_baseline: the reference's vendored exact kNN engine (oracle/_ref, nanoflann) on a bounded sample, same inputs
-Multi-GPU (weak scaling): every rank owns 100 images and 4,950 pairs; the table is replicated once
-(torch.distributed/NCCL broadcast into the library's arena), then ranks match independently (no data-path collective).
+Metric (BASELINE.json): image-pairs/sec on SIFT-128 descriptor sets; a *step* is one pass of the hot path — 2-NN + ratio
+(0.85 "all" / 0.6 "good", fine_matching_graph.cc:42-43) + mutual cross-check — over the whole candidate pair list.
+Workloads (BASELINE.json configs; synthetic descriptors generated on the GPU, metricsfm_b200/synth_gpu.py):
+  2 (default)  100 web images x 8192 per GPU, exhaustive pairs (4,950 per GPU).  With N GPUs ONE collection of 100*N images
+               is matched: the images are staged in contiguous blocks (one per GPU) but paired exhaustively within the N
+               interleaved classes id mod N, so every shard reads rows that arrived over NCCL.  Weak scaling.
+  3            aerial block, 1,000 x 20,000, GPS-neighbour guided pair list (~30k pairs).      Strong scaling.
+  4            web collection, 5,000 x 16,384, ~200k retrieval-candidate pairs.                Strong scaling.
+  5            aerial survey, 10,000 x 32,768, ~500k guided pairs (41.9 GB table per replica). Strong scaling.
+Numbers in the line:
+  value   pairs/s with the packed table resident in HBM (CUDA events on the library's stream, L2 flushed between steps,
+          max over ranks)
+  e2e     pairs/s through the public API from page-locked HOST rows: per step every image is packed + uploaded (H2D, in
+          groups on the upload stream), replicated over NCCL when N > 1, matched as soon as its group has landed, and the
+          match lists are copied back (D2H).  The host rows are float32 (the reference's CV_32FC1 container) for
+          workload 2, uint8 otherwise (--e2e-dtype).
+  parity  after the timed regions rank 0 re-generates the images of sampled pairs (also pairs matched on other ranks, also
+          images this rank received over NCCL), runs the CPU oracle on them and compares the match lists bit for bit
+  roofline / cpu_baseline: see DESIGN.md §6
 """
 from __future__ import annotations
 
@@ -35,6 +45,17 @@ if ROOT not in sys.path:
 RATIO_ALL, RATIO_GOOD = 0.85, 0.6
 INT8_SPEC_PEAK_TOPS = 4500.0
 
+WORKLOADS = {
+    2: dict(label="exhaustive matching of {ipg} web images x {rows} SIFT-128 descriptors ({ppg} pairs) per GPU (BASELINE config #2)",
+            images_per_gpu=100, rows=8192, scaling="weak", e2e_dtype="f32", groups=4, parity_pairs=32),
+    3: dict(label="aerial block of {images} images x {rows} descriptors, GPS-neighbour guided pair list (BASELINE config #3)",
+            images=1000, rows=20000, pairs="gps", k=56, scaling="strong", e2e_dtype="u8", groups=4, parity_pairs=12),
+    4: dict(label="web collection of {images} images x {rows} descriptors, retrieval-candidate pair list (BASELINE config #4)",
+            images=5000, rows=16384, pairs="retrieval", k=40, scaling="strong", e2e_dtype="u8", groups=4, parity_pairs=12),
+    5: dict(label="aerial survey of {images} images x {rows} descriptors, GPS-neighbour guided pair list (BASELINE config #5)",
+            images=10000, rows=32768, pairs="gps", k=93, scaling="strong", e2e_dtype="u8", groups=8, parity_pairs=6),
+}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -42,11 +63,18 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--images", type=int, default=100, help="images per GPU")
-    ap.add_argument("--rows", type=int, default=8192, help="descriptors per image")
+    ap.add_argument("--workload", type=int, default=2, choices=sorted(WORKLOADS))
+    ap.add_argument("--engine", default="auto", choices=["auto", "ranks", "single"],
+                    help="ranks: one process per GPU (torchrun, NCCL via torch.distributed); single: one process, the C++ multi-GPU engine")
+    ap.add_argument("--images", type=int, default=0, help="override: images per GPU (workload 2) / images in the collection (3-5)")
+    ap.add_argument("--rows", type=int, default=0, help="override: descriptors per image")
+    ap.add_argument("--pairs-k", type=int, default=0, help="override: neighbours / partners per image of the guided pair lists")
     ap.add_argument("--cpu-sample-pairs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-dtype", default="", choices=["", "f32", "u8"])
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--parity-pairs", type=int, default=-1, help="pairs checked against the CPU oracle after the timed regions")
     ap.add_argument("--mutual", type=int, default=1, help="1 = ratio + mutual cross-check (headline), 0 = ratio only")
     ap.add_argument("--no-int8-peak", action="store_true", help="skip the cuBLAS int8 GEMM peak measurement (rank 0, N = 1)")
     return ap.parse_args()
@@ -60,16 +88,18 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def ncu_traffic_bytes(pairs_per_step: int, launches_per_step: float):
-    """DRAM bytes per launch of the matching kernel, scaled from the committed `ncu --set full` capture
-    (profiles/r1_match_kernel_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one forward launch and the
-    number of pairs it covered).  None when no capture is committed."""
-    path = os.path.join(ROOT, "profiles", "r1_match_kernel_traffic.json")
-    if not os.path.exists(path) or launches_per_step <= 0:
-        return None
+def ncu_traffic(workload: int, rows: int, images_per_gpu: int, world: int):
+    """DRAM bytes per launch of the matching kernel from the committed `ncu --set full` capture of THIS configuration
+    (profiles/r2_match_kernel_traffic.json), or None: the figure is never extrapolated to another table size."""
+    path = os.path.join(ROOT, "profiles", "r2_match_kernel_traffic.json")
+    if not os.path.exists(path):
+        return None, "no capture committed"
     with open(path) as f:
         t = json.load(f)
-    return t["dram_bytes_per_pair"] * pairs_per_step / launches_per_step
+    for c in t.get("captures", []):
+        if c.get("workload") == workload and c.get("rows") == rows and c.get("images_per_gpu") == images_per_gpu and c.get("n_gpus", 1) == world:
+            return c["dram_bytes_per_launch"], c.get("source", "profiles/r2_match_kernel_traffic.json")
+    return None, "no ncu capture of this configuration"
 
 
 def measure_int8_peak(dev):
@@ -221,9 +251,10 @@ def run_reference(args):
     if rank != 0:
         return
     from metricsfm_b200 import synth
-    col = synth.Collection(args.rows, seed=0)
+    rows = args.rows or WORKLOADS[args.workload]["rows"]
+    col = synth.Collection(rows, seed=0)
     per_step = 2
-    n_img = min(args.images, 2 * per_step * (args.steps + args.warmup))
+    n_img = min(100, 2 * per_step * (args.steps + args.warmup))
     images = {i: col.image_u8(i) for i in range(n_img)}
     pairs = synth.exhaustive_pairs(n_img)
     vals = []
@@ -239,13 +270,12 @@ def run_reference(args):
     total_s = sum(d for _, d in vals)
     value = total_pairs / total_s
     line = {
-        "impl": "reference", "metric": "image-pairs/sec (8k x 8k SIFT-128)", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": f"image-pairs/sec ({rows} x {rows} SIFT-128)", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / max(args.steps, 1), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"exhaustive {args.images} web images x {args.rows} SIFT-128 (BASELINE config #2), "
-                               f"bounded sample of {per_step} pairs per step"},
+        "scaling": WORKLOADS[args.workload]["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE config #{args.workload} ({rows}-row SIFT-128 images), bounded sample of {per_step} pairs per step"},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind,
-                         "sample": f"{per_step} pairs of {args.rows}x{args.rows} per step x {args.steps} steps: nanoflann exact KD-tree "
+                         "sample": f"{per_step} pairs of {rows}x{rows} per step x {args.steps} steps: nanoflann exact KD-tree "
                                    f"on idx1 + 2-NN of idx2 rows + ratio {RATIO_ALL} (feature_matching.cpp:319-342), OpenMP over queries"},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -253,12 +283,74 @@ def run_reference(args):
     print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
-# ====================================================================================================== native arm
-def run_native(args):
+# ====================================================================================================== workloads
+def build_workload(args, world: int):
+    """Global description of the workload: image count, rows, candidate pair list (identical on every rank)."""
+    from metricsfm_b200 import synth
+    w = dict(WORKLOADS[args.workload])
+    rows = args.rows or w["rows"]
+    if args.workload == 2:
+        ipg = args.images or w["images_per_gpu"]
+        n_images = ipg * world
+        base = synth.exhaustive_pairs(ipg).astype(np.int64)
+        # one collection; class c = {ids = c mod world}: its members sit in every owner block (blocks are contiguous id ranges)
+        pairs = np.concatenate([base * world + c for c in range(world)], axis=0).astype(np.int32)
+        order = np.lexsort((pairs[:, 1], pairs[:, 0]))   # grouped by reference image, like the reference's idx1 loop
+        pairs = pairs[order]
+        label = w["label"].format(ipg=ipg, rows=rows, ppg=len(base))
+    else:
+        n_images = args.images or w["images"]
+        k = args.pairs_k or w["k"]
+        pairs = synth.gps_neighbour_pairs(n_images, k=k) if w["pairs"] == "gps" else synth.retrieval_pairs(n_images, partners=k)
+        label = w["label"].format(images=n_images, rows=rows) + f", {len(pairs)} pairs"
+    return dict(n_images=n_images, rows=rows, pairs=np.ascontiguousarray(pairs, np.int32), label=label, scaling=w["scaling"],
+                e2e_dtype=args.e2e_dtype or w["e2e_dtype"], groups=w["groups"],
+                parity_pairs=w["parity_pairs"] if args.parity_pairs < 0 else args.parity_pairs)
+
+
+def group_layout(n_images: int, world: int, n_groups: int):
+    """Staging layout.  Owner blocks are contiguous id ranges (msfm_sched_image_owner); every block is cut into n_groups
+    slices and the table is laid out group-major — [group 0: slice of rank 0, slice of rank 1, ...][group 1: ...] — so
+    that one group is one contiguous arena range made of `world` equal parts: one in-place all-gather replicates it, and
+    the pairs of groups <= g can be matched while group g + 1 is still being copied.
+    Returns (owner[n_images], group[n_images], slices[g][r] = list of ids)."""
+    from metricsfm_b200 import scheduler
+    owner = scheduler.image_owner(n_images, world)
+    group = np.zeros((n_images,), np.int32)
+    slices = [[[] for _ in range(world)] for _ in range(n_groups)]
+    for r in range(world):
+        ids = np.nonzero(owner == r)[0]
+        per = (len(ids) + n_groups - 1) // n_groups
+        for k, i in enumerate(ids):
+            g = min(k // max(per, 1), n_groups - 1)
+            group[i] = g
+            slices[g][r].append(int(i))
+    return owner, group, slices
+
+
+def parity_check(sampled, regenerate, mutual: bool):
+    """sampled: list of (ref id, query id, matches [n,2], good [n]) — the lists the GPU path produced.  Re-generates the
+    images and compares with the CPU oracle bit for bit.  Returns (checked, ok, first failure or None)."""
+    from oracle import oracle
+    oracle.use_all_host_threads()
+    cache, bad = {}, None
+    for r, q, m, g in sampled:
+        for i in (r, q):
+            if i not in cache:
+                cache[i] = regenerate(i)
+        exp = oracle.match_pair_u8(cache[r], cache[q], RATIO_ALL, mutual=mutual, ratio_good=RATIO_GOOD)
+        if not (np.array_equal(np.asarray(m).reshape(-1, 2), exp["pairs"]) and np.array_equal(np.asarray(g), exp["good"])):
+            bad = bad or (int(r), int(q))
+    return len(sampled), bad is None, bad
+
+
+# ====================================================================================================== native arm: ranks
+def run_native_ranks(args):
     import torch
     import torch.distributed as dist
-    from metricsfm_b200 import distributed as D, scheduler, synth
-    from metricsfm_b200.matcher import Matcher
+    from metricsfm_b200 import distributed as D, scheduler
+    from metricsfm_b200.matcher import Matcher, MatchResult
+    from metricsfm_b200.synth_gpu import GpuCollection
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -272,54 +364,98 @@ def run_native(args):
         numa = D.pin_to_gpu_numa_node(local_rank)   # before the page-locked staging buffers are allocated
         dist.init_process_group("nccl", device_id=dev)
 
-    n_local, rows = args.images, args.rows
-    n_global = n_local * world
+    wl = build_workload(args, world)
+    n_images, rows, pairs = wl["n_images"], wl["rows"], wl["pairs"]
     rows_padded = (rows + 255) // 256 * 256
-    arena_rows = n_global * rows_padded
+    arena_rows = n_images * rows_padded
+    owner, group, slices = group_layout(n_images, world, wl["groups"])
+    n_groups = wl["groups"]
+    my_ids = [i for g in range(n_groups) for i in slices[g][rank]]
+    slot_of = {gid: k for k, gid in enumerate(my_ids)}
 
-    # ---- synthetic inputs (seeded; identical on every rank for a given image id), staged in pinned host memory
-    col = synth.Collection(rows, seed=0)
-    my_ids = list(range(rank * n_local, (rank + 1) * n_local))
-    host_desc = torch.empty((n_local, rows, 128), dtype=torch.uint8).pin_memory()
+    # ---- synthetic descriptors: generated on the GPU, kept in page-locked host memory (the e2e step starts from there)
+    col = GpuCollection(rows, dev, seed=0)
+    host_u8 = torch.empty((len(my_ids), rows, 128), dtype=torch.uint8).pin_memory()
     for k, gid in enumerate(my_ids):
-        host_desc[k].numpy()[:] = col.image_u8(gid)
+        host_u8[k].copy_(col.image_u8(gid))
+    e2e_f32 = wl["e2e_dtype"] == "f32" and not args.no_e2e
+    host_f32 = None
+    if e2e_f32:
+        host_f32 = torch.empty((len(my_ids), rows, 128), dtype=torch.float32).pin_memory()   # CV_32FC1 rows (integer-valued: VLSIFT + rounding)
+        host_f32.copy_(host_u8)
 
-    # ---- global pair list: exhaustive within each rank's block of images (4,950 pairs per block); LPT-sharded
-    base = synth.exhaustive_pairs(n_local)
-    pairs = np.concatenate([base + b * n_local for b in range(world)], axis=0)
-    rows_per_image = np.full((n_global,), rows, np.int64)
+    # ---- pair list: ONE list for the whole job, sharded by cost (C++ scheduler, msfm_sched_shard)
+    rows_per_image = np.full((n_images,), rows, np.int32)
     shards = scheduler.shard_pairs(pairs, rows_per_image, world)
-    my_pairs = pairs[shards[rank]]
+    my_idx = shards[rank]
+    # within the shard: pairs in the order their images land (group of the newer image), reference-grouped inside
+    pg = np.maximum(group[pairs[my_idx, 0]], group[pairs[my_idx, 1]])
+    order = np.argsort(pg, kind="stable")
+    my_idx, pg = my_idx[order], pg[order]
+    my_pairs = np.ascontiguousarray(pairs[my_idx])
+    sub_bounds = [int(np.searchsorted(pg, g, side="left")) for g in range(n_groups)] + [len(my_idx)]
+    foreign_reads = int(np.sum(owner[my_pairs[:, 0]] != rank) + np.sum(owner[my_pairs[:, 1]] != rank))
 
-    # ---- packed table lives in torch-owned memory so NCCL can fill it during replication
+    # ---- packed table in torch-owned memory so NCCL can fill it during replication
     desc_arena = torch.empty((arena_rows, 128), dtype=torch.uint8, device=dev)
     norm_arena = torch.empty((arena_rows,), dtype=torch.int32, device=dev)
-    m = Matcher(device=local_rank, max_images=n_global, arena_rows=arena_rows, external_desc_arena=desc_arena.data_ptr(),
+    m = Matcher(device=local_rank, max_images=n_images, arena_rows=arena_rows, external_desc_arena=desc_arena.data_ptr(),
                 external_norm_arena=norm_arena.data_ptr())
     lib_stream = torch.cuda.ExternalStream(m.cuda_stream(), device=dev)
+    up_stream = torch.cuda.ExternalStream(m.upload_stream(), device=dev)
+    side = torch.cuda.Stream(device=dev)
 
-    owner, ranges = D.block_ranges(n_global, rows_padded, world)
-
-    def stage_table():
-        """Pack + upload this rank's images (H2D), reserve the others, replicate over NCCL.  Returns H2D bytes."""
+    def stage_table(use_f32: bool):
+        """Queue the staging of the whole table, group by group: H2D + pack of this rank's slice on the upload stream, the
+        other ranks' slices reserved, one in-place all-gather per group on a side stream.  Nothing waits on the host.
+        Returns the per-group events matching has to wait for, and the H2D bytes."""
         m.release_all()
-        mine = [gid for gid in range(n_global) if owner[gid] == rank]
-        before = [gid for gid in range(n_global) if gid < mine[0]]
-        after = [gid for gid in range(n_global) if gid > mine[-1]]
-        # identical allocation order on every rank => identical arena offsets; one call per block of foreign images
-        if before:
-            m.reserve_batch(before, [rows] * len(before))
-        # page-locked host rows, no host wait: the transfer overlaps the pair planning of match_pairs
-        m.upload_batch(mine, [host_desc[g - rank * n_local] for g in mine], wait=False)
-        if after:
-            m.reserve_batch(after, [rows] * len(after))
-        if world > 1:
-            lib_stream.synchronize()
-            D.replicate_arena(desc_arena, norm_arena, ranges, dist)   # NCCL broadcast per owner block
-            torch.cuda.synchronize()
-        return n_local * rows * 128
+        events, h2d = [], 0
+        base_row = 0
+        for g in range(n_groups):
+            part = max(len(slices[g][r]) for r in range(world)) * rows_padded
+            equal = all(len(slices[g][r]) * rows_padded == part for r in range(world))
+            for r in range(world):        # identical allocation order on every rank => identical arena offsets
+                ids = slices[g][r]
+                if not ids:
+                    continue
+                if r == rank:
+                    if use_f32:
+                        m.upload_f32_batch_async(ids, [host_f32[slot_of[i]] for i in ids], scale=1.0)
+                        h2d += len(ids) * rows * 512
+                    else:
+                        m.upload_batch(ids, [host_u8[slot_of[i]] for i in ids], wait=False)
+                        h2d += len(ids) * rows * 128
+                else:
+                    m.reserve_batch(ids, [rows] * len(ids), wait=False)
+            n_rows_g = sum(len(slices[g][r]) for r in range(world)) * rows_padded
+            if world > 1:
+                ev_up = torch.cuda.Event()
+                ev_up.record(up_stream)
+                with torch.cuda.stream(side):
+                    side.wait_event(ev_up)
+                    lo = base_row + sum(len(slices[g][r]) for r in range(rank)) * rows_padded
+                    hi = lo + len(slices[g][rank]) * rows_padded
+                    if equal:
+                        w1 = dist.all_gather_into_tensor(desc_arena[base_row:base_row + n_rows_g], desc_arena[lo:hi], async_op=True)
+                        w2 = dist.all_gather_into_tensor(norm_arena[base_row:base_row + n_rows_g], norm_arena[lo:hi], async_op=True)
+                        w1.wait(); w2.wait()
+                    else:                  # ragged slices: one broadcast per owner
+                        off = base_row
+                        for r in range(world):
+                            nr = len(slices[g][r]) * rows_padded
+                            if nr:
+                                dist.broadcast(desc_arena[off:off + nr], src=r)
+                                dist.broadcast(norm_arena[off:off + nr], src=r)
+                            off += nr
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                events.append(ev)
+            else:
+                events.append(None)
+            base_row += n_rows_g
+        return events, h2d
 
-    stage_table()
     kw = dict(ratio_good=RATIO_GOOD, mutual=bool(args.mutual), min_keypoints=20, orientation=0)
     flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -328,14 +464,20 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput ("value")
+    # ---- device-resident throughput ("value"): table staged once, untimed
+    events, _ = stage_table(False)
+    for ev in events:
+        if ev is not None:
+            m.wait_event(ev.cuda_event)
+    m.sync()
+    torch.cuda.synchronize()
     sampler = ClockSampler(local_rank, enabled=(rank == 0))
     sampler.start()
     for _ in range(args.warmup):
         m.match_pairs_resident(my_pairs, RATIO_ALL, **kw)
     barrier()
     sampler.mark_begin()
-    step_ms, kern_ms, launches, match_launches, ops = [], [], 0, 0, 0
+    step_ms, kern_ms, launches, match_launches, ops, twin_pairs = [], [], 0, 0, 0, 0
     n_matches = 0
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
@@ -353,6 +495,7 @@ def run_native(args):
         launches += t["total_launches"]
         match_launches += t["match_launches"]
         ops = t["int8_ops"]
+        twin_pairs = t["twin_pairs"]
     barrier()
     sampler.mark_end()
     wall_s = time.perf_counter() - t_wall0
@@ -362,31 +505,40 @@ def run_native(args):
         tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt.item())
-        cnt = torch.tensor([len(my_pairs) * args.steps], dtype=torch.float64, device=dev)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        pairs_done = float(cnt.item())
-    else:
-        pairs_done = float(len(my_pairs) * args.steps)
+    pairs_done = float(len(pairs) * args.steps)   # all ranks together match the whole list once per step
     value = pairs_done / (total_ms * 1e-3)
 
-    # ---- end to end through the public API from host buffers
-    e2e = None
+    # ---- end to end through the public API from host buffers, staging pipelined against matching
+    e2e, sampled_local = None, []
+    cap = int(min(len(my_pairs) * min(rows, 4096), 1 << 28)) + 1024
+    out = MatchResult(offsets=np.zeros((len(my_pairs) + n_groups + 1,), np.int64), ok=np.zeros((len(my_pairs) + 1,), np.int32),
+                      matches=torch.empty((cap, 2), dtype=torch.int32).pin_memory().numpy(),
+                      good=torch.empty((cap,), dtype=torch.uint8).pin_memory().numpy())
+    list_off = np.zeros((len(my_pairs) + 1,), np.int64)   # absolute offsets of this rank's lists in `out`
+
+    def e2e_step(use_f32: bool):
+        events, h2d = stage_table(use_f32)
+        done, d2h = 0, 0
+        for g in range(n_groups):
+            a, b = sub_bounds[g], sub_bounds[g + 1]
+            if events[g] is not None:
+                m.wait_event(events[g].cuda_event)       # device-side: later launches wait for group g's all-gather
+            if b == a:
+                continue
+            sub = MatchResult(offsets=out.offsets[a + g:b + g + 1], ok=out.ok[a:b], matches=out.matches[done:], good=out.good[done:])
+            res = m.match_pairs(my_pairs[a:b], RATIO_ALL, out=sub, **kw)
+            list_off[a:b + 1] = done + sub.offsets[:b - a + 1]
+            done += len(res.matches)
+            d2h += m.timing()["d2h_bytes"]
+        return h2d + my_pairs.nbytes, d2h, done
+
     if not args.no_e2e:
-        from metricsfm_b200.matcher import MatchResult
-        e2e_steps = max(1, min(args.steps, 3))
-        cap = len(my_pairs) * 2048
-        out = MatchResult(offsets=np.zeros((len(my_pairs) + 1,), np.int64), ok=np.zeros((len(my_pairs),), np.int32),
-                          matches=torch.empty((cap, 2), dtype=torch.int32).pin_memory().numpy(),
-                          good=torch.empty((cap,), dtype=torch.uint8).pin_memory().numpy())
-        d2h = 0
-        h2d = 0
-        for it in range(1 + e2e_steps):
-            if it == 1:
-                barrier()
-                t0 = time.perf_counter()
-            h2d = stage_table() + my_pairs.nbytes
-            res = m.match_pairs(my_pairs, RATIO_ALL, out=out, **kw)
-            d2h = m.timing()["d2h_bytes"]
+        e2e_steps = max(1, args.e2e_steps)
+        e2e_step(e2e_f32)                                   # warm-up (allocations, NCCL channels)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            h2d, d2h, n_e2e = e2e_step(e2e_f32)
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -394,14 +546,65 @@ def run_native(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
         e2e = {"value": (len(pairs) * e2e_steps) / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "steps": e2e_steps, "timer": "host wall clock between barriers + cuda synchronize, max over ranks",
-               "matches_per_step": int(len(res.matches))}
+               "steps": e2e_steps, "host_rows": "float32 (CV_32FC1, the reference's container)" if e2e_f32 else "uint8",
+               "pipeline": f"{n_groups} staging groups on the upload stream" + (" + one NCCL all-gather per group on a side stream" if world > 1 else "")
+                           + "; the pairs of groups <= g are matched while group g+1 is copied",
+               "timer": "host wall clock between barriers + cuda synchronize, max over ranks", "matches_per_step_this_rank": int(n_e2e),
+               "match_lists": "page-locked host buffers of the rank that matched the pair"}
+        if e2e_f32:                                         # the same pipeline fed with pre-quantised uint8 rows, for comparison
+            e2e_step(False)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                h2d_u8, _, _ = e2e_step(False)
+            barrier()
+            dt8 = time.perf_counter() - t0
+            if world > 1:
+                tt = torch.tensor([dt8], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt8 = float(tt.item())
+            e2e["uint8_rows"] = {"value": (len(pairs) * e2e_steps) / dt8, "h2d_bytes_per_step": int(h2d_u8)}
+    else:
+        e2e_step(False)                                     # the parity check below needs lists in host memory
+
+    # ---- parity inside the run: sampled pairs of EVERY rank's shard against the CPU oracle (rank 0 re-generates the images)
+    n_par = wl["parity_pairs"]
+    per_rank = (n_par + world - 1) // world if n_par > 0 else 0
+    rng = np.random.default_rng(1234 + rank)
+    if per_rank and len(my_pairs):
+        # prefer pairs that read rows received over NCCL
+        cand = np.nonzero((owner[my_pairs[:, 0]] != rank) | (owner[my_pairs[:, 1]] != rank))[0] if world > 1 else np.arange(len(my_pairs))
+        if len(cand) == 0:
+            cand = np.arange(len(my_pairs))
+        for k in rng.choice(cand, size=min(per_rank, len(cand)), replace=False):
+            a, b = int(list_off[k]), int(list_off[k + 1])
+            sampled_local.append((int(my_pairs[k, 0]), int(my_pairs[k, 1]), out.matches[a:b].copy(), out.good[a:b].copy()))
+    gathered = [sampled_local]
+    if world > 1:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(sampled_local, gathered, dst=0)
+    parity = None
+    if rank == 0 and n_par > 0:
+        sampled = [s for part in gathered for s in part][:max(n_par, 1)]
+        regen = lambda i: col.image_u8(i).cpu().numpy()     # noqa: E731  (deterministic in the image id)
+        checked, ok, bad = parity_check(sampled, regen, bool(args.mutual))
+        # rows this rank received over NCCL equal the re-generated bytes
+        nccl_ok, nccl_checked = True, 0
+        for i in [i for i in range(n_images) if owner[i] != rank][:: max(1, n_images // 16)][:8]:
+            got, _ = m.download_packed(i)
+            nccl_ok = nccl_ok and np.array_equal(got, regen(i))
+            nccl_checked += 1
+        parity = {"parity_checked": checked, "parity_ok": bool(ok and nccl_ok), "first_mismatch": bad,
+                  "nccl_received_images_checked": nccl_checked, "nccl_received_images_ok": bool(nccl_ok),
+                  "how": "match lists of sampled pairs from every rank's shard (pairs reading NCCL-received rows first) == CPU oracle "
+                         "on the re-generated images, bit for bit"}
 
     # ---- CPU baseline (rank 0, N = 1 only): the reference's exact engine on a bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        images = {i: host_desc[i].numpy() for i in range(min(n_local, 2 * args.cpu_sample_pairs))}
-        sel = [tuple(p) for p in pairs if p[0] in images and p[1] in images][: args.cpu_sample_pairs]
+        need = sorted({int(i) for p in pairs[: args.cpu_sample_pairs] for i in p})
+        images = {i: host_u8[slot_of[i]].numpy() for i in need}
+        sel = [tuple(int(x) for x in p) for p in pairs[: args.cpu_sample_pairs]]
         v, kind, cores, secs = cpu_reference_sample(images, sel, len(sel))
         cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind,
                "sample": f"first {len(sel)} pairs of the workload ({rows}x{rows}), {secs:.1f} s: nanoflann exact KD-tree on idx1 + 2-NN of "
@@ -414,48 +617,202 @@ def run_native(args):
     int8_peak = None
     if rank == 0 and world == 1 and not args.no_int8_peak:
         m.close()                      # the library's scratch is not needed any more
+        del desc_arena, norm_arena
         int8_peak = measure_int8_peak(dev)
     if rank == 0:
-        peaks, peaks_src = measured_peaks()
         kern_avg_ms = float(np.mean(kern_ms))
-        achieved_tops = ops / (kern_avg_ms * 1e-3) / 1e12
-        # int8 dense rate = 2 x the bf16 rate on the same tensor pipes; the driver measures bf16 only.  The kernel is timed
-        # inside a long step, so the sustained figure is the denominator.
-        peak_tops = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
-        line = {
-            "metric": "image-pairs/sec (8k x 8k SIFT-128)", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"exhaustive matching of {n_local} web images x {rows} SIFT-128 descriptors ({len(base)} pairs) per GPU "
-                                   f"(BASELINE config #2); 2-NN + ratio {RATIO_ALL}/{RATIO_GOOD}" + (" + mutual cross-check" if args.mutual else " (no mutual check)"),
-                       "pairs_per_step_all_gpus": int(len(pairs)), "parallelism": f"pair-sharded x{world}, table replicated",
-                       "l2": "flushed between timed steps (256 MiB write)", "matches_per_step_rank0": int(n_matches),
-                       "host_numa_pinning_rank0": numa},
-            "roofline": {"bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TFLOP/s", "frac": achieved_tops / peak_tops,
-                         "traffic": ncu_traffic_bytes(len(my_pairs), match_launches / max(args.steps, 1)),
-                         "kernel": "match_pairs_kernel<4,64,8,1,2> (4 strips x N=64 tiles, 8 B stages, 2 TMEM buffers per strip)",
-                         "note": "int8 tensor ops (2 per MAC), i.e. TOP/s; algorithmic ops = 2*M*N*128 per pair; peak = 2 x "
-                                 f"bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks_src}); spec dense int8 = 4500",
-                         "frac_of_spec_int8": achieved_tops / INT8_SPEC_PEAK_TOPS, "kernel_ms_per_step": kern_avg_ms,
-                         "kernel_share_of_step": kern_avg_ms / (float(np.mean(step_ms)))},
-            "clocks": clocks,
-            "gpu_launches": int(launches),
-            "match_kernel_launches": int(match_launches),
-            "wall_s_timed_region": wall_s,
-        }
-        if int8_peak is not None:
-            line["roofline"]["int8_gemm_measured"] = int8_peak
-            if "sustained_tops" in int8_peak:
-                line["roofline"]["frac_of_measured_int8_sustained"] = achieved_tops / int8_peak["sustained_tops"]
-        if e2e is not None:
-            line["e2e"] = e2e
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
-        print(json.dumps(line), file=JSON_OUT, flush=True)
+        emit_line(args, wl, world, value, total_ms, ops, kern_avg_ms, float(np.mean(step_ms)), clocks, launches, match_launches, wall_s,
+                  e2e, cpu, int8_peak, parity, engine="ranks: one process per GPU, torch.distributed/NCCL",
+                  extra_cfg={"matches_per_step_rank0": int(n_matches), "host_numa_pinning_rank0": numa,
+                             "pairs_rank0": int(len(my_pairs)), "foreign_image_reads_rank0": foreign_reads,
+                             "mutual_pairs_needing_tensor_twin_pass_rank0": int(twin_pairs)})
     m.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def emit_line(args, wl, world, value, total_ms, ops_rank0, kern_avg_ms, step_avg_ms, clocks, launches, match_launches, wall_s, e2e, cpu,
+              int8_peak, parity, engine, extra_cfg):
+    peaks, peaks_src = measured_peaks()
+    achieved_tops = ops_rank0 / (kern_avg_ms * 1e-3) / 1e12 if kern_avg_ms > 0 else 0.0
+    sustained = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    burst = 2.0 * float(peaks.get("bf16_tflops", 1650.0))
+    ipg = (args.images or WORKLOADS[2]["images_per_gpu"]) if args.workload == 2 else wl["n_images"]
+    traffic, traffic_src = ncu_traffic(args.workload, wl["rows"], ipg, world)
+    line = {
+        "metric": f"image-pairs/sec ({wl['rows']} x {wl['rows']} SIFT-128)", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"],
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": wl["label"] + f"; 2-NN + ratio {RATIO_ALL}/{RATIO_GOOD}" + (" + mutual cross-check" if args.mutual else " (no mutual check)"),
+                   "pairs_per_step_all_gpus": int(len(wl["pairs"])), "images": int(wl["n_images"]),
+                   "parallelism": f"ONE pair list sharded x{world} by cost (msfm_sched_shard), table replicated over NCCL", "engine": engine,
+                   "l2": "flushed between timed steps (256 MiB write)", **extra_cfg},
+        "roofline": {"bound": "tensor", "achieved": achieved_tops, "peak": INT8_SPEC_PEAK_TOPS, "unit": "TFLOP/s",
+                     "frac": achieved_tops / INT8_SPEC_PEAK_TOPS, "traffic": traffic, "traffic_source": traffic_src,
+                     "kernel": "match_pairs_kernel<4,64,8,1,2> (4 strips x N=64 tiles, 8 B stages, 2 TMEM buffers per strip), rank 0's launches",
+                     "note": "int8 tensor ops (2 per MAC), i.e. TOP/s; algorithmic ops = 2*M*N*128 per pair; peak = B200 dense int8 spec "
+                             "(north_star's denominator; MEASURED_PEAKS.json has no int8 figure): the fractions of 2 x the measured bf16 "
+                             "rates and of the cuBLAS int8 GEMM measured in this run are given beside it",
+                     "frac_of_2x_bf16_sustained": achieved_tops / sustained, "frac_of_2x_bf16_burst": achieved_tops / burst,
+                     "peaks_file": peaks_src, "kernel_ms_per_step": kern_avg_ms, "kernel_share_of_step": kern_avg_ms / step_avg_ms if step_avg_ms else None},
+        "clocks": clocks,
+        "gpu_launches": int(launches),
+        "match_kernel_launches": int(match_launches),
+        "wall_s_timed_region": wall_s,
+    }
+    if int8_peak is not None:
+        line["roofline"]["int8_gemm_measured"] = int8_peak
+        if "sustained_tops" in int8_peak:
+            line["roofline"]["frac_of_measured_int8_sustained"] = achieved_tops / int8_peak["sustained_tops"]
+    if parity is not None:
+        line.update({"parity_checked": parity["parity_checked"], "parity_ok": parity["parity_ok"], "parity": parity})
+    if e2e is not None:
+        line["e2e"] = e2e
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), file=JSON_OUT, flush=True)
+
+
+# ====================================================================================================== native arm: single process
+def run_native_single(args):
+    """ONE host process, every GPU of the box behind the C ABI of include/msfm_multi.h (no torch.distributed): staging with
+    NCCL broadcast, LPT sharding, per-device matching threads and the stitched result all live in csrc/msfm_multi.cc."""
+    import torch
+    from metricsfm_b200.matcher import MatchResult
+    from metricsfm_b200.multi import MultiMatcher
+    from metricsfm_b200.synth_gpu import GpuCollection
+
+    world = args.gpus
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        raise SystemExit(f"--engine single --gpus {world} needs {world} visible CUDA devices")
+    wl = build_workload(args, world)
+    n_images, rows, pairs = wl["n_images"], wl["rows"], wl["pairs"]
+    rows_padded = (rows + 255) // 256 * 256
+    n_groups = wl["groups"]
+    # every image generated on GPU 0, kept in page-locked host memory (the single process owns all host rows)
+    dev0 = torch.device("cuda", 0)
+    col = GpuCollection(rows, dev0, seed=0)
+    host_u8 = torch.empty((n_images, rows, 128), dtype=torch.uint8).pin_memory()
+    for i in range(n_images):
+        host_u8[i].copy_(col.image_u8(i))
+    e2e_f32 = wl["e2e_dtype"] == "f32" and not args.no_e2e
+    host_f32 = None
+    if e2e_f32:
+        host_f32 = torch.empty((n_images, rows, 128), dtype=torch.float32).pin_memory()
+        host_f32.copy_(host_u8)
+    per = (n_images + n_groups - 1) // n_groups
+    groups = [list(range(g * per, min(n_images, (g + 1) * per))) for g in range(n_groups)]
+    group_of = np.minimum(np.arange(n_images) // per, n_groups - 1)
+    pg = np.maximum(group_of[pairs[:, 0]], group_of[pairs[:, 1]])
+    order = np.argsort(pg, kind="stable")
+    pairs_sorted = np.ascontiguousarray(pairs[order])
+    pg = pg[order]
+    bounds = [int(np.searchsorted(pg, g, side="left")) for g in range(n_groups)] + [len(pairs)]
+
+    mm = MultiMatcher(list(range(world)), max_images=n_images, arena_rows=n_images * rows_padded)
+    kw = dict(ratio_good=RATIO_GOOD, mutual=bool(args.mutual), min_keypoints=20, orientation=0)
+    cap = int(min(len(pairs) * min(rows, 4096), 1 << 28)) + 1024
+    out = MatchResult(offsets=np.zeros((len(pairs) + n_groups + 1,), np.int64), ok=np.zeros((len(pairs) + 1,), np.int32),
+                      matches=torch.empty((cap, 2), dtype=torch.int32).pin_memory().numpy(),
+                      good=torch.empty((cap,), dtype=torch.uint8).pin_memory().numpy())
+
+    def stage(use_f32):
+        mm.release_all()
+        h2d = 0
+        for ids in groups:
+            if use_f32:
+                mm.upload_f32(ids, [host_f32[i] for i in ids], scale=1.0)
+                h2d += len(ids) * rows * 512
+            else:
+                mm.upload_u8(ids, [host_u8[i] for i in ids])
+                h2d += len(ids) * rows * 128
+        return h2d
+
+    # ---- device-resident: table staged once; a step = msfm_multi_match_pairs over the whole list (lists stitched on the host)
+    stage(False)
+    mm.sync()
+    sampler = ClockSampler(0)
+    sampler.start()
+    full = MatchResult(offsets=np.zeros((len(pairs) + 1,), np.int64), ok=np.zeros((len(pairs),), np.int32), matches=out.matches, good=out.good)
+    for _ in range(args.warmup):
+        mm.match_pairs(pairs_sorted, RATIO_ALL, capacity=cap, out=full, **kw)
+    sampler.mark_begin()
+    dev_ms, wall_ms, kern_ms, launches, match_launches, ops0 = [], [], [], 0, 0, 0
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = mm.match_pairs(pairs_sorted, RATIO_ALL, capacity=cap, out=full, **kw)
+        t, per_dev = mm.timing()
+        dev_ms.append(t["device_ms_max"])
+        wall_ms.append(t["wall_ms"])
+        kern_ms.append(per_dev[0]["match_kernel_ms"])
+        ops0 = per_dev[0]["int8_ops"]
+        launches += sum(p["total_launches"] for p in per_dev)
+        match_launches += sum(p["match_launches"] for p in per_dev)
+    sampler.mark_end()
+    wall_s = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    total_ms = float(sum(dev_ms))
+    value = len(pairs) * args.steps / (total_ms * 1e-3)
+    n_matches = len(res.matches)
+
+    list_off = np.zeros((len(pairs) + 1,), np.int64)
+
+    def e2e_step(use_f32):
+        h2d = stage(use_f32)
+        done = 0
+        for g in range(n_groups):
+            a, b = bounds[g], bounds[g + 1]
+            if b == a:
+                continue
+            sub = MatchResult(offsets=out.offsets[a + g:b + g + 1], ok=out.ok[a:b], matches=out.matches[done:], good=out.good[done:])
+            r = mm.match_pairs(pairs_sorted[a:b], RATIO_ALL, capacity=cap, out=sub, **kw)
+            list_off[a:b + 1] = done + sub.offsets[:b - a + 1]
+            done += len(r.matches)
+        return h2d + pairs.nbytes, done * 9, done
+
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(1, args.e2e_steps)
+        e2e_step(e2e_f32)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            h2d, d2h, n_e2e = e2e_step(e2e_f32)
+        mm.sync()
+        dt = time.perf_counter() - t0
+        e2e = {"value": len(pairs) * e2e_steps / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "steps": e2e_steps, "host_rows": "float32 (CV_32FC1, the reference's container)" if e2e_f32 else "uint8",
+               "pipeline": f"{n_groups} staging groups (owner H2D + NCCL broadcast); the pairs of groups <= g are matched while group g+1 lands",
+               "timer": "host wall clock of the single process", "matches_per_step": int(n_e2e),
+               "match_lists": "stitched into ONE result in the caller's pair order (msfm_multi_match_pairs)"}
+    else:
+        e2e_step(False)
+
+    parity = None
+    n_par = wl["parity_pairs"]
+    if n_par > 0:
+        rng = np.random.default_rng(1234)
+        sampled = []
+        for k in rng.choice(len(pairs), size=min(n_par, len(pairs)), replace=False):
+            a, b = int(list_off[k]), int(list_off[k + 1])
+            sampled.append((int(pairs_sorted[k, 0]), int(pairs_sorted[k, 1]), out.matches[a:b].copy(), out.good[a:b].copy()))
+        regen = lambda i: host_u8[i].numpy()     # noqa: E731
+        checked, ok, bad = parity_check(sampled, regen, bool(args.mutual))
+        nccl_ok, nccl_checked = True, 0
+        for d in range(world):
+            for i in (0, n_images // 2, n_images - 1):
+                got, _ = mm.download_packed(d, i)
+                nccl_ok = nccl_ok and np.array_equal(got, host_u8[i].numpy())
+                nccl_checked += 1
+        parity = {"parity_checked": checked, "parity_ok": bool(ok and nccl_ok), "first_mismatch": bad,
+                  "nccl_received_images_checked": nccl_checked, "nccl_received_images_ok": bool(nccl_ok),
+                  "how": "stitched match lists of sampled pairs == CPU oracle, bit for bit; every device's replica of sampled images == host rows"}
+    mm.close()
+    emit_line(args, wl, world, value, total_ms, ops0, float(np.mean(kern_ms)), float(np.mean(dev_ms)), clocks, launches, match_launches, wall_s,
+              e2e, None, None, parity, engine="single: one host process, C++ multi-GPU engine (include/msfm_multi.h), NCCL via ncclCommInitAll",
+              extra_cfg={"matches_per_step": int(n_matches), "host_wall_ms_per_step_incl_stitch": float(np.mean(wall_ms)),
+                         "value_timer": "max over devices of the CUDA-event time of each device's msfm_match_pairs call"})
 
 
 JSON_OUT = sys.stdout
@@ -475,8 +832,16 @@ def main():
     claim_stdout()
     if args.impl == "reference":
         run_reference(args)
+        return
+    under_torchrun = int(os.environ.get("WORLD_SIZE", "1")) > 1
+    engine = args.engine
+    if engine == "auto":
+        engine = "ranks" if (under_torchrun or args.gpus == 1) else "single"
+    if engine == "single":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_native_single(args)
     else:
-        run_native(args)
+        run_native_ranks(args)
 
 
 if __name__ == "__main__":

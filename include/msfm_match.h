@@ -170,6 +170,11 @@ msfm_status msfm_upload_f32_batch_async(msfm_ctx *ctx, int32_t n, const int32_t 
 msfm_status msfm_reserve(msfm_ctx *ctx, int32_t image_id, int32_t rows, int64_t *row_offset);
 /* Several images in one call (row_offsets may be NULL); images before a failing one stay reserved. */
 msfm_status msfm_reserve_batch(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const int32_t *rows, int64_t *row_offsets);
+/* Same without the host wait: pad rows and tensor maps are queued on the upload stream (msfm_get_upload_stream).  A
+ * foreign writer must order itself behind that stream (an event recorded on it after this call) and matching behind
+ * the writer (msfm_wait_event). */
+msfm_status msfm_reserve_batch_async(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const int32_t *rows,
+                                     int64_t *row_offsets);
 msfm_status msfm_release(msfm_ctx *ctx, int32_t image_id);
 msfm_status msfm_release_all(msfm_ctx *ctx);
 msfm_status msfm_image_info(const msfm_ctx *ctx, int32_t image_id, int32_t *rows, int64_t *row_offset);

@@ -5,7 +5,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from .build import LIB_PATH
+from .build import LIB_PATH, SCHED_LIB
 
 _i32p = C.POINTER(C.c_int32)
 _i64p = C.POINTER(C.c_int64)
@@ -25,8 +25,27 @@ EXPORTED_SYMBOLS = [
     "msfm_upload_u8_batch", "msfm_upload_u8_batch_async", "msfm_sync", "msfm_upload_f32", "msfm_reserve", "msfm_reserve_batch", "msfm_release", "msfm_release_all", "msfm_image_info", "msfm_table_ptrs",
     "msfm_download_packed", "msfm_knn2", "msfm_colbest", "msfm_match_pairs", "msfm_match_pairs_resident",
     "msfm_last_timing", "msfm_get_stream", "msfm_knn2_crosscheck", "msfm_geo_verify", "msfm_geo_ransac",
-    "msfm_upload_f32_batch_async", "msfm_get_upload_stream", "msfm_wait_event", "msfm_test_set_band_event_cap", "msfm_test_force_twin_pass",
+    "msfm_upload_f32_batch_async", "msfm_get_upload_stream", "msfm_wait_event", "msfm_test_set_band_event_cap", "msfm_test_force_twin_pass", "msfm_reserve_batch_async",
 ]
+
+
+# include/msfm_sched.h and include/msfm_multi.h (same library)
+SCHED_SYMBOLS = ["msfm_sched_shard", "msfm_sched_image_owner", "msfm_sched_offsets", "msfm_sched_scatter"]
+MULTI_SYMBOLS = [
+    "msfm_multi_create", "msfm_multi_destroy", "msfm_multi_last_error", "msfm_multi_device_count", "msfm_multi_context",
+    "msfm_multi_upload_u8", "msfm_multi_upload_f32", "msfm_multi_release_all", "msfm_multi_sync", "msfm_multi_match_pairs",
+    "msfm_multi_last_timing",
+]
+
+
+class MultiConfig(C.Structure):
+    _fields_ = [("n_devices", C.c_int32), ("devices", C.POINTER(C.c_int32)), ("max_images", C.c_int32), ("arena_rows", C.c_int64),
+                ("reserved", C.c_int32 * 4)]
+
+
+class MultiTiming(C.Structure):
+    _fields_ = [("wall_ms", C.c_float), ("device_ms_max", C.c_float), ("stitch_ms", C.c_float), ("n_devices", C.c_int32),
+                ("int8_ops", C.c_int64), ("bytes_broadcast", C.c_int64)]
 
 
 class Config(C.Structure):
@@ -90,6 +109,7 @@ def load() -> C.CDLL:
     L.msfm_upload_f32.argtypes = [vp, C.c_int32, vp, C.c_int32, C.c_int64, C.c_float]
     L.msfm_reserve.argtypes = [vp, C.c_int32, C.c_int32, _i64p]
     L.msfm_reserve_batch.argtypes = [vp, C.c_int32, vp, vp, vp]
+    L.msfm_reserve_batch_async.argtypes = [vp, C.c_int32, vp, vp, vp]
     L.msfm_release.argtypes = [vp, C.c_int32]
     L.msfm_release_all.argtypes = [vp]
     L.msfm_image_info.argtypes = [vp, C.c_int32, _i32p, _i64p]
@@ -113,5 +133,50 @@ def load() -> C.CDLL:
         fn = getattr(L, name)
         if name not in ("msfm_abi_version", "msfm_status_string", "msfm_last_error"):
             fn.restype = C.c_int
+    _declare_sched(L)
+    L.msfm_multi_create.argtypes = [C.POINTER(MultiConfig), C.POINTER(vp)]
+    L.msfm_multi_destroy.argtypes = [vp]
+    L.msfm_multi_last_error.argtypes = [vp]
+    L.msfm_multi_last_error.restype = C.c_char_p
+    L.msfm_multi_device_count.argtypes = [vp]
+    L.msfm_multi_device_count.restype = C.c_int32
+    L.msfm_multi_context.argtypes = [vp, C.c_int32]
+    L.msfm_multi_context.restype = vp
+    L.msfm_multi_upload_u8.argtypes = [vp, C.c_int32, vp, vp, vp]
+    L.msfm_multi_upload_f32.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_float]
+    L.msfm_multi_release_all.argtypes = [vp]
+    L.msfm_multi_sync.argtypes = [vp]
+    L.msfm_multi_match_pairs.argtypes = [vp, vp, C.c_int64, C.POINTER(Params), C.POINTER(Result)]
+    L.msfm_multi_last_timing.argtypes = [vp, C.POINTER(MultiTiming), vp]
+    for name in MULTI_SYMBOLS:
+        if name not in ("msfm_multi_last_error", "msfm_multi_device_count", "msfm_multi_context"):
+            getattr(L, name).restype = C.c_int
     _lib = L
     return L
+
+
+def _declare_sched(L) -> None:
+    vp = C.c_void_p
+    L.msfm_sched_shard.argtypes = [vp, C.c_int64, vp, C.c_int32, C.c_int32, vp, vp]
+    L.msfm_sched_shard.restype = C.c_int
+    L.msfm_sched_image_owner.argtypes = [C.c_int32, C.c_int32, vp]
+    L.msfm_sched_image_owner.restype = C.c_int
+    L.msfm_sched_offsets.argtypes = [vp, C.c_int64, vp]
+    L.msfm_sched_offsets.restype = C.c_int64
+    L.msfm_sched_scatter.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp]
+    L.msfm_sched_scatter.restype = C.c_int
+
+
+_sched = None
+
+
+def load_sched() -> C.CDLL:
+    """The pair scheduler's host logic (include/msfm_sched.h) from the host-only libmsfm_sched.so: usable by launchers and
+    CPU tests that never touch a GPU.  The same code is linked into libmsfm_match.so."""
+    global _sched
+    if _sched is None:
+        if not os.path.exists(SCHED_LIB):
+            raise RuntimeError(f"{SCHED_LIB} not found: run `python -m metricsfm_b200.build`")
+        _sched = C.CDLL(SCHED_LIB)
+        _declare_sched(_sched)
+    return _sched

@@ -7,45 +7,64 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
+HOST_DIR = os.path.join(PKG_DIR, "host")
+INC = os.path.join(PKG_DIR, "..", "include")
 LIB_PATH = os.path.join(CSRC, "libmsfm_match.so")
-SOURCES = ["msfm_api.cu"]
-HEADERS = ["match_kernel.cuh", "aux_kernels.cuh", "geo_kernels.cuh", "sm100_ptx.cuh", os.path.join("..", "..", "include", "msfm_match.h")]
+OBJ_DIR = os.path.join(CSRC, "_obj")
+PUBLIC_HEADERS = [os.path.join(INC, h) for h in ("msfm_match.h", "msfm_sched.h", "msfm_multi.h")]
+# translation units of libmsfm_match.so: (source, headers it depends on, compiled by nvcc as CUDA?)
+UNITS = [
+    (os.path.join(CSRC, "msfm_api.cu"),
+     [os.path.join(CSRC, h) for h in ("match_kernel.cuh", "aux_kernels.cuh", "geo_kernels.cuh", "sm100_ptx.cuh", "msfm_internal.h")]),
+    (os.path.join(CSRC, "msfm_multi.cc"), [os.path.join(CSRC, "msfm_internal.h")]),   # multi-GPU engine (host code + CUDA runtime API)
+    (os.path.join(HOST_DIR, "msfm_sched.cc"), []),                                    # pair scheduler (pure host)
+]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
     "-ccbin", "/usr/bin/g++",
 ]
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+def _newer(target: str, deps) -> bool:
+    return os.path.exists(target) and all(os.path.getmtime(d) <= os.path.getmtime(target) for d in deps if os.path.exists(d))
 
 
 def build_native(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into csrc/libmsfm_match.so (skipped when up to date).  Returns the library path."""
-    if not force and not _stale():
-        return LIB_PATH
+    """Compile the translation units of csrc/libmsfm_match.so for sm_100a (each object is rebuilt only when its own
+    sources changed) and link them.  Returns the library path."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    extra = os.environ.get("MSFM_NVCC_EXTRA", "").split()  # kernel experiments, e.g. -DMSFM_PRODUCER_AUX=7
-    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed building libmsfm_match.so")
-    with open(os.path.join(CSRC, "ptxas_info.txt"), "w") as f:
-        f.write(proc.stderr)
+    extra = os.environ.get("MSFM_NVCC_EXTRA", "").split()  # kernel experiments, e.g. -DMSFM_EXPERIMENTS
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    me = os.path.abspath(__file__)
+    objs, relink = [], force or not os.path.exists(LIB_PATH)
+    for src, hdrs in UNITS:
+        obj = os.path.join(OBJ_DIR, os.path.splitext(os.path.basename(src))[0] + ".o")
+        objs.append(obj)
+        if not force and _newer(obj, [src, me] + hdrs + PUBLIC_HEADERS):
+            continue
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-x", "cu", "-c", "-o", obj, src]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or proc.returncode != 0:
+            sys.stderr.write(proc.stdout + proc.stderr)
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed compiling {os.path.basename(src)}")
+        if src.endswith("msfm_api.cu"):
+            with open(os.path.join(CSRC, "ptxas_info.txt"), "w") as f:
+                f.write(proc.stderr)
+        relink = True
+    if relink or not _newer(LIB_PATH, objs):
+        proc = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-o", LIB_PATH] + objs + ["-ldl", "-lpthread"],
+                              capture_output=True, text=True)
+        if proc.returncode != 0:
+            sys.stderr.write(proc.stdout + proc.stderr)
+            raise RuntimeError("linking libmsfm_match.so failed")
     return LIB_PATH
 
 
-HOST_DIR = os.path.join(PKG_DIR, "host")
 SHIM_BIN = os.path.join(HOST_DIR, "shim_selftest")
 
 
@@ -62,10 +81,7 @@ def build_host_shim(force: bool = False) -> str:
 
 STORE_LIB = os.path.join(HOST_DIR, "libmsfm_store.so")
 GRAPH_LIB = os.path.join(HOST_DIR, "libmsfm_graph.so")
-
-
-def _newer(target: str, deps) -> bool:
-    return os.path.exists(target) and all(os.path.getmtime(d) <= os.path.getmtime(target) for d in deps if os.path.exists(d))
+SCHED_LIB = os.path.join(HOST_DIR, "libmsfm_sched.so")
 
 
 def build_host_libs(force: bool = False):
@@ -79,7 +95,10 @@ def build_host_libs(force: bool = False):
         subprocess.check_call(common + ["-o", STORE_LIB, store_src])
     if force or not _newer(GRAPH_LIB, [graph_src, store_src, LIB_PATH, os.path.join(inc, "msfm_graph.h"), os.path.abspath(__file__)]):
         subprocess.check_call(common + ["-o", GRAPH_LIB, graph_src, store_src, "-L" + CSRC, "-lmsfm_match", "-Wl,-rpath,$ORIGIN/../csrc"])
-    return STORE_LIB, GRAPH_LIB
+    sched_src = os.path.join(HOST_DIR, "msfm_sched.cc")
+    if force or not _newer(SCHED_LIB, [sched_src, os.path.join(inc, "msfm_sched.h"), os.path.join(inc, "msfm_match.h"), os.path.abspath(__file__)]):
+        subprocess.check_call(common + ["-o", SCHED_LIB, sched_src])   # host-only copy of the pair scheduler (CPU tests, launchers)
+    return STORE_LIB, GRAPH_LIB, SCHED_LIB
 
 
 if __name__ == "__main__":

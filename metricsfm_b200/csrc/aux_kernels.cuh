@@ -426,12 +426,14 @@ __global__ void __launch_bounds__(256) rescore_band_kernel(const BandParams bp, 
 //   (B) rows for which j is not the nearest: then d(q', j) >= d1(q') (j is at best their second neighbour), so only rows
 //       with d1(q') <= d0 can beat or tie the candidate.  A true match has a small d0 and almost no row has a second
 //       neighbour that close: the few "dangerous" rows are listed per pair and their distance to j is computed exactly.
-// A pair whose dangerous sets are large (repetitive structure, near-duplicate rows: more than kDangerPerCand rivals for
-// some candidate or more than kDangerListCap listed rows), and every pair of the float regime with re-scoring, falls
+// A pair whose dangerous sets are large (repetitive structure, near-duplicate rows: more than kDangerWorkCap candidates
+// that have to look at dangerous rows, or more than kDangerEvalBudget exact distances in total), and every pair of the float regime with re-scoring, falls
 // back to the tensor twin pass: the candidates' reference rows are gathered into the candidate scratch image, which the
 // matching kernel then searches against the query image (twin_counts[pair] > 0 routes the pair there).
-constexpr int kDangerPerCand = 64;
-constexpr int kDangerListCap = 4096;
+constexpr int kDangerWorkCap = 2048;     // candidates per pair that have to look at the dangerous rows (shared memory)
+constexpr int kDangerEvalBudget = 32768;  // exact 128-byte distances per pair on CUDA cores (~1/20 of a twin pass)
+constexpr int kSmemTableRows = 20480;    // reference rows whose column table fits in shared memory (160 KiB)
+constexpr size_t kSelectSmemBytes = (size_t)kDangerWorkCap * 16 + (size_t)kSmemTableRows * 8;  // 192 KiB
 constexpr int kCandGood = 1, kCandKilled = 2;  // bits of cand_good[]
 
 struct SelectParams {
@@ -445,7 +447,9 @@ struct SelectParams {
     uint8_t *cand_good;        // kCandGood | kCandKilled
     int32_t *counts;           // [n_pairs] one-way candidates
     int32_t mutual;
-    unsigned long long *colbest;  // [sum of ref rows of the batch] (d0 << 32 | q), initialised to ~0
+    unsigned long long *colbest;  // [sum of ref rows of the batch] (d0 << 32 | q), initialised to ~0: column table of the
+                                  // pairs with more than smem_table_rows reference rows (the others keep it in shared memory)
+    int32_t smem_table_rows;
     int2 *danger;              // [forward kNN rows] per-pair list of (row, d1) of the dangerous rows
     int32_t *twin_counts;      // [n_pairs] candidates routed to the tensor twin pass (0: decided here)
     unsigned int *twin_gate;   // number of pairs routed to the twin pass (the twin launch returns at once when 0)
@@ -478,52 +482,100 @@ __device__ __forceinline__ int sqdist_u8_rows(const uint8_t *__restrict__ a, con
     return na + nb - 2 * (int)ab;
 }
 
+// Block-wide exclusive scan of a small per-thread count (threads in index order); adds the block total to `running`.
+__device__ __forceinline__ int block_scan_excl(int v, int &running, int *warp_excl, int *chunk_total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) warp_excl[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = (lane < nwarps) ? warp_excl[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if (lane >= o) wi += n;
+        }
+        warp_excl[lane] = wi - w;
+        if (lane == 31) *chunk_total = wi;
+    }
+    __syncthreads();
+    const int excl = running + warp_excl[warp] + incl - v;
+    running += *chunk_total;
+    __syncthreads();
+    return excl;
+}
+
+constexpr int kSelRows = 8;  // query rows per thread and chunk: their kNN records are loaded together (one L2 round trip)
+
 __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectParams sp) {
+    // dynamic shared memory (mutual launches only): job list, dangerous-row list, column table of pairs with
+    // <= smem_table_rows reference rows
+    extern __shared__ unsigned long long s_dyn[];
+    int4 *s_work = reinterpret_cast<int4 *>(s_dyn);
+    unsigned long long *s_table = reinterpret_cast<unsigned long long *>(s_work + kDangerWorkCap);
     __shared__ int warp_excl[32];
     __shared__ int chunk_total;
-    __shared__ int s_d0max, s_overflow;
+    __shared__ int s_d0max, s_d1min, s_nd, s_nwork, s_evals;
     const PairDesc pd = sp.pairs[blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int2 *danger = sp.danger + pd.knn_off;  // this pair's dangerous rows (row, d1), unordered; at most one per query row
     // the bound-based check needs integer distances that are final: not in the re-scored float regime
     const bool bounds = sp.mutual && !sp.force_twin && !(sp.float_mutual && pd.fscale2 > 0.0f);
-    if (threadIdx.x == 0) { s_d0max = -1; s_overflow = 0; }
+    unsigned long long *table = sp.colbest + pd.col_off;
+    if (bounds && pd.ref_rows <= sp.smem_table_rows) {
+        table = s_table;
+        for (int j = threadIdx.x; j < pd.ref_rows; j += blockDim.x) s_table[j] = ~0ull;
+    }
+    if (threadIdx.x == 0) { s_d0max = -1; s_d1min = INT_MAX; s_nd = 0; s_nwork = 0; s_evals = 0; }
     __syncthreads();
     int running = 0;
-    for (int base = 0; base < pd.qry_rows; base += blockDim.x) {
-        const int q = base + threadIdx.x;
-        bool keep = false, is_good = false;
-        int nn0 = -1, dist0 = 0;
-        if (q < pd.qry_rows) {
-            const int4 k = merge_knn_shares(sp.knn, pd.knn_off + q, sp.nshare);
-            if (k.x >= 0 && (k.x & kRescoredFlag)) {  // decided on exact fp32 distances by rescore_band_kernel
-                keep = (k.y & 1) != 0;
-                is_good = (k.y & 2) != 0;
-                nn0 = k.x & ~kRescoredFlag;
-                dist0 = k.z;
+    for (int base = 0; base < pd.qry_rows; base += blockDim.x * kSelRows) {
+        const int q0 = base + threadIdx.x * kSelRows;  // this thread's rows are consecutive: thread order = row order
+        int4 k[kSelRows];
+#pragma unroll
+        for (int r = 0; r < kSelRows; ++r)
+            k[r] = (q0 + r < pd.qry_rows) ? merge_knn_shares(sp.knn, pd.knn_off + q0 + r, sp.nshare) : make_int4(-1, -1, INT_MAX, INT_MAX);
+        unsigned keep = 0, good = 0;
+        int d0max = -1;
+#pragma unroll
+        for (int r = 0; r < kSelRows; ++r) {
+            if (k[r].x >= 0 && (k[r].x & kRescoredFlag)) {  // decided on exact fp32 distances by rescore_band_kernel
+                if (k[r].y & 1) keep |= 1u << r;
+                if (k[r].y & 2) good |= 1u << r;
+                k[r].x &= ~kRescoredFlag;
             } else {
-                if (k.x >= 0 && k.y >= 0) {
-                    const float d0 = (float)k.z, d1 = (float)k.w;
-                    const float r = __fdiv_rn(d0, d1);  // IEEE divide; 0/0 = NaN fails every comparison
-                    keep = ratio_accepts(r, sp.ratio, sp.reject_gt);
-                    if (sp.max_dist_sq > 0.0f) keep = keep && (d0 < sp.max_dist_sq);
-                    is_good = keep && sp.ratio_good > 0.0f && ratio_accepts(r, sp.ratio_good, sp.reject_gt);
-                    nn0 = k.x;
-                    dist0 = k.z;
+                if (k[r].x >= 0 && k[r].y >= 0) {
+                    const float d0 = (float)k[r].z, d1 = (float)k[r].w;
+                    const float ratio = __fdiv_rn(d0, d1);  // IEEE divide; 0/0 = NaN fails every comparison
+                    bool kp = ratio_accepts(ratio, sp.ratio, sp.reject_gt);
+                    if (sp.max_dist_sq > 0.0f) kp = kp && (d0 < sp.max_dist_sq);
+                    if (kp) keep |= 1u << r;
+                    if (kp && sp.ratio_good > 0.0f && ratio_accepts(ratio, sp.ratio_good, sp.reject_gt)) good |= 1u << r;
                 }
                 // rival kind (A): every row, accepted or not, claims its nearest reference row
-                if (bounds && k.x >= 0) atomicMin(sp.colbest + pd.col_off + k.x, colbest_key(k.z, q));
+                if (bounds && k[r].x >= 0) atomicMin(table + k[r].x, colbest_key(k[r].z, q0 + r));
             }
+            if (keep & (1u << r)) d0max = max(d0max, k[r].z);
         }
-        const int slot = block_rank(keep, running, warp_excl, &chunk_total);
-        if (keep) {
-            sp.cand_q[pd.knn_off + slot] = q;
-            sp.cand_j[pd.knn_off + slot] = nn0;
-            sp.cand_good[pd.knn_off + slot] = is_good ? kCandGood : 0;
-            // float regime: a query row that is a few 1e-3 farther in quantised units may be the nearer one in fp32,
-            // so the mutual search keeps every row within ~3 % of the candidate's distance (see emit_matches_kernel)
-            sp.cand_d0[pd.knn_off + slot] = (sp.float_mutual && pd.fscale2 > 0.0f) ? dist0 + (dist0 >> 5) + 256 : dist0;
-            if (bounds) atomicMax(&s_d0max, dist0);
-        }
+        int slot = block_scan_excl(__popc(keep), running, warp_excl, &chunk_total);
+#pragma unroll
+        for (int r = 0; r < kSelRows; ++r)
+            if (keep & (1u << r)) {
+                sp.cand_q[pd.knn_off + slot] = q0 + r;
+                sp.cand_j[pd.knn_off + slot] = k[r].x;
+                sp.cand_good[pd.knn_off + slot] = (good >> r) & 1u ? kCandGood : 0;
+                // float regime: a query row that is a few 1e-3 farther in quantised units may be the nearer one in fp32,
+                // so the mutual search keeps every row within ~3 % of the candidate's distance (see emit_matches_kernel)
+                sp.cand_d0[pd.knn_off + slot] = (sp.float_mutual && pd.fscale2 > 0.0f) ? k[r].z + (k[r].z >> 5) + 256 : k[r].z;
+                ++slot;
+            }
+        if (bounds && d0max >= 0) atomicMax(&s_d0max, d0max);
     }
     if (threadIdx.x == 0) sp.counts[blockIdx.x] = running;
     if (!sp.mutual) return;
@@ -531,54 +583,63 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
     bool overflow = !bounds;
     if (bounds && running > 0) {
         // ---- rival kind (B): rows whose second neighbour is at least as close as the weakest candidate's match
+        //      (unordered list in the pair's scratch region; no block-wide synchronisation inside the loop)
         const int d0max = s_d0max;
-        int nd = 0;
-        for (int base = 0; base < pd.qry_rows; base += blockDim.x) {
-            const int q = base + threadIdx.x;
-            bool dang = false;
-            int d1v = 0;
-            if (q < pd.qry_rows) {
-                const int4 k = merge_knn_shares(sp.knn, pd.knn_off + q, sp.nshare);
-                if (k.y >= 0) { d1v = k.w; dang = d1v <= d0max; }
-            }
-            const int slot = block_rank(dang, nd, warp_excl, &chunk_total);
-            if (dang && slot < kDangerListCap) sp.danger[pd.knn_off + slot] = make_int2(q, d1v);
-        }
-        overflow = nd > kDangerListCap;
-        if (!overflow) {
-            __syncthreads();  // the dangerous list is read by other warps
-            const int2 *dl = sp.danger + pd.knn_off;
-            for (int i = warp; i < running; i += nwarps) {
-                const int q = sp.cand_q[pd.knn_off + i], j = sp.cand_j[pd.knn_off + i], d0 = sp.cand_d0[pd.knn_off + i];
-                bool kill = __ldcg(sp.colbest + pd.col_off + j) != colbest_key(d0, q);  // a kind-(A) rival is closer
-                if (!kill && nd > 0) {
-                    int cnt = 0;
-                    for (int e = lane; e < nd; e += 32) {
-                        const int2 r = dl[e];
-                        cnt += (r.y <= d0 && r.x != q) ? 1 : 0;
-                    }
-                    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-                    if (cnt > kDangerPerCand) {
-                        if (lane == 0) s_overflow = 1;  // too ambiguous for CUDA cores: the whole pair takes the tensor pass
-                    } else if (cnt > 0) {
-                        const uint8_t *rj = sp.desc_arena + (pd.ref_off + j) * kDim;
-                        const int nb = ckey_to_norm(sp.ckeys[pd.ref_off + j]);
-                        bool closer = false;
-                        for (int e = lane; e < nd; e += 32) {
-                            const int2 r = dl[e];
-                            if (r.y <= d0 && r.x != q) {
-                                const int d = sqdist_u8_rows(sp.desc_arena + (pd.qry_off + r.x) * kDim, rj,
-                                                             ckey_to_norm(sp.ckeys[pd.qry_off + r.x]), nb);
-                                closer = closer || d < d0 || (d == d0 && r.x < q);
-                            }
-                        }
-                        kill = __any_sync(0xFFFFFFFFu, closer);
-                    }
+        for (int base = 0; base < pd.qry_rows; base += blockDim.x * kSelRows) {
+            int2 v[kSelRows];  // (id1, d1): the loads of a chunk fly together
+#pragma unroll
+            for (int r = 0; r < kSelRows; ++r) {
+                const int q = base + r * blockDim.x + threadIdx.x;
+                v[r] = make_int2(-1, 0);
+                if (q < pd.qry_rows) {
+                    const int4 k = merge_knn_shares(sp.knn, pd.knn_off + q, sp.nshare);
+                    v[r] = make_int2(k.y, k.w);
                 }
-                if (lane == 0 && kill) sp.cand_good[pd.knn_off + i] |= kCandKilled;
+            }
+#pragma unroll
+            for (int r = 0; r < kSelRows; ++r)
+                if (v[r].x >= 0 && v[r].y <= d0max) {
+                    danger[atomicAdd(&s_nd, 1)] = make_int2(base + r * blockDim.x + threadIdx.x, v[r].y);
+                    atomicMin(&s_d1min, v[r].y);
+                }
+        }
+        __syncthreads();
+        const int nd = s_nd;
+        {
+            // ---- verdicts.  One thread per candidate: the column table decides kind (A); a candidate whose match is
+            //      closer than every dangerous row's second neighbour (the usual case) is done, the others are listed.
+            const int d1min = s_d1min;
+            for (int i = threadIdx.x; i < running; i += blockDim.x) {
+                const int q = sp.cand_q[pd.knn_off + i], j = sp.cand_j[pd.knn_off + i], d0 = sp.cand_d0[pd.knn_off + i];
+                const unsigned long long best = (table == s_table) ? s_table[j] : __ldcg(table + j);
+                if (best != colbest_key(d0, q)) {  // a kind-(A) rival is closer
+                    sp.cand_good[pd.knn_off + i] |= kCandKilled;
+                } else if (nd > 0 && d0 >= d1min) {
+                    const int slot = atomicAdd(&s_nwork, 1);
+                    if (slot < kDangerWorkCap) s_work[slot] = make_int4(i, q, j, d0);
+                }
             }
             __syncthreads();
-            overflow = s_overflow != 0;
+            const int nwork = s_nwork;
+            overflow = nwork > kDangerWorkCap;
+            if (!overflow && nwork > 0) {
+                // (listed candidate) x (dangerous row), spread evenly over the CTA; a hit costs one exact 128-byte distance
+                const unsigned total = (unsigned)nwork * (unsigned)nd;  // <= 2048 x 1,000,000 < 2^31
+                for (unsigned t = threadIdx.x; t < total; t += blockDim.x) {
+                    const int w = (int)(t / (unsigned)nd), e = (int)(t - (unsigned)w * (unsigned)nd);
+                    const int4 c = s_work[w];  // (candidate, q, j, d0)
+                    const int2 r = danger[e];
+                    if (r.y <= c.w && r.x != c.y) {
+                        if (atomicAdd(&s_evals, 1) >= kDangerEvalBudget) break;  // too ambiguous for CUDA cores
+                        const int d = sqdist_u8_rows(sp.desc_arena + (pd.qry_off + r.x) * kDim, sp.desc_arena + (pd.ref_off + c.z) * kDim,
+                                                     ckey_to_norm(sp.ckeys[pd.qry_off + r.x]), ckey_to_norm(sp.ckeys[pd.ref_off + c.z]));
+                        // several rivals may kill the same candidate: they all set the same bit, the other bits are final
+                        if (d < c.w || (d == c.w && r.x < c.y)) sp.cand_good[pd.knn_off + c.x] |= kCandKilled;
+                    }
+                }
+                __syncthreads();
+                overflow = s_evals >= kDangerEvalBudget;
+            }
         }
     }
     if (threadIdx.x == 0) {
@@ -587,6 +648,7 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
     }
     if (!overflow) return;
     // ---- tensor twin pass for this pair: gather the candidates' reference rows (+ column keys) into the scratch image
+    __syncthreads();
     for (int i = warp; i < running; i += nwarps) {
         const int j = sp.cand_j[pd.knn_off + i];
         const uint32_t w = reinterpret_cast<const uint32_t *>(sp.desc_arena + (pd.ref_off + j) * kDim)[lane];

@@ -21,6 +21,7 @@
 #include "aux_kernels.cuh"
 #include "geo_kernels.cuh"
 #include "match_kernel.cuh"
+#include "msfm_internal.h"
 
 namespace {
 
@@ -232,14 +233,15 @@ void recycle_marks(msfm_ctx *ctx) {
     ctx->waited_seq = ctx->upload_seq;
 }
 
-// Order the main stream behind the upload mark `need` (and with it behind every older one: marks complete in order).
+// Order the main stream behind the upload mark `need` and every older one.
 msfm_status wait_for_uploads(msfm_ctx *ctx, uint64_t need) {
     if (need <= ctx->waited_seq) return MSFM_OK;
     size_t k = 0;
     for (; k < ctx->marks.size(); ++k) {
         if (ctx->marks[k].seq > need) break;
-        if (ctx->marks[k].seq == need) MSFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->marks[k].ev, 0));
-        ctx->event_pool.push_back(ctx->marks[k].ev);  // recorded and (where needed) waited for: reusable in stream order
+        // marks can sit on different streams (uploads, a collective's stream): wait for each one not yet ordered
+        MSFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->marks[k].ev, 0));
+        ctx->event_pool.push_back(ctx->marks[k].ev);  // recorded and waited for: reusable in stream order
     }
     ctx->marks.erase(ctx->marks.begin(), ctx->marks.begin() + k);
     ctx->waited_seq = need;
@@ -283,6 +285,7 @@ struct BatchPlan {
     int64_t query_rows = 0;          // forward kNN rows (= candidate / match scratch rows)
     int64_t ref_rows = 0;            // sum of reference rows (= entries of the mutual check's column table)
     uint64_t need_seq = 0;           // newest upload mark among the batch's images
+    bool big_ref = false;            // some reference image's column table does not fit in shared memory
     int64_t ops = 0;
     bool mutual = false;
     bool has_empty = false;          // some pair has no work items: its kNN rows must read "absent"
@@ -452,6 +455,7 @@ void plan_add_pair(msfm_ctx *ctx, BatchPlan &plan, int64_t src, int32_t ref, int
     pd.fscale2 = (r.has_float && q.has_float && r.scale == q.scale) ? r.scale * r.scale : 0.0f;
     pd.pad_ = 0;
     pd.col_off = plan.ref_rows;
+    if (r.rows > msfm::kSmemTableRows) plan.big_ref = true;
     plan.need_seq = std::max(plan.need_seq, std::max(r.ready_seq, q.ready_seq));
     if (pd.fscale2 > 0.0f) plan.any_float = true;
     const int32_t pidx = (int32_t)plan.pairs.size();
@@ -485,12 +489,35 @@ msfm_status knn_single(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, BatchPla
     return run_match_stage(ctx, plan);  // a pair without work items leaves "absent" rows (memset)
 }
 
-msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const msfm_params *params, msfm_result *out,
+// Where a call's results go: per-pair offsets / ok flags in host arrays, the match lists through a sink (see msfm_internal.h).
+struct OutSpec {
+    int64_t *offsets = nullptr;
+    int32_t *ok = nullptr;
+    bool has_good = false;
+    msfm_sink_fn sink = nullptr;
+    void *user = nullptr;
+};
+
+// The public entry point's sink: the caller's msfm_result buffers.
+struct CallerBuffers {
+    int32_t (*matches)[2];
+    uint8_t *good;
+    int64_t capacity;
+};
+int caller_sink(void *user, int64_t first, int64_t n, int32_t (**m)[2], uint8_t **g) {
+    const CallerBuffers *cb = static_cast<const CallerBuffers *>(user);
+    if (first + n > cb->capacity) return 1;
+    *m = cb->matches + first;
+    *g = cb->good ? cb->good + first : nullptr;
+    return 0;
+}
+
+msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const msfm_params *params, const OutSpec *out,
                              bool resident, int64_t *n_matches_total) {
     if (!ctx) return MSFM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (n_pairs < 0 || (n_pairs > 0 && !pairs) || !params) return fail(ctx, MSFM_ERR_INVALID_ARG, "null pair list / params or negative n_pairs");
-    if (!resident && (!out || !out->offsets || !out->ok || (!out->matches && out->match_capacity > 0)))
+    if (!resident && (!out || !out->offsets || !out->ok || !out->sink))
         return fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_result needs offsets, ok and matches buffers");
     if (!(params->ratio > 0.0f)) return fail(ctx, MSFM_ERR_INVALID_ARG, "ratio must be > 0");
     msfm_status st;
@@ -501,7 +528,7 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
     ctx->timing = msfm_timing{};
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
     const bool mutual = params->mutual != 0;
-    const bool want_good = params->ratio_good > 0.0f && (resident || out->good);
+    const bool want_good = params->ratio_good > 0.0f && (resident || out->has_good);
     const int64_t max_rows = mutual ? kBatchMaxQueryRowsMutual : kBatchMaxQueryRows;
     int64_t written = 0;  // matches written to the caller so far
     int64_t total = 0;
@@ -604,10 +631,10 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             // ---- ratio test -> one-way candidates; mutual check from the forward results (column table + dangerous rows),
             //      pairs too ambiguous for that are routed to the tensor twin pass
             if (mutual) {
-                if ((st = ensure(ctx, ctx->colbest, (size_t)std::max<int64_t>(plan.ref_rows, 1) * 8)) != MSFM_OK) return st;
+                if ((st = ensure(ctx, ctx->colbest, plan.big_ref ? (size_t)std::max<int64_t>(plan.ref_rows, 1) * 8 : 256)) != MSFM_OK) return st;
                 if ((st = ensure(ctx, ctx->twin_counts, (size_t)(nb + 1) * 4)) != MSFM_OK) return st;
                 ctx->twin_gate_index = nb;
-                MSFM_CUDA(ctx, cudaMemsetAsync(ctx->colbest.ptr, 0xFF, (size_t)plan.ref_rows * 8, ctx->stream));
+                if (plan.big_ref) MSFM_CUDA(ctx, cudaMemsetAsync(ctx->colbest.ptr, 0xFF, (size_t)plan.ref_rows * 8, ctx->stream));
                 MSFM_CUDA(ctx, cudaMemsetAsync(static_cast<int32_t *>(ctx->twin_counts.ptr) + nb, 0, 4, ctx->stream));
             }
             msfm::SelectParams sp;
@@ -627,6 +654,7 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             sp.mutual = mutual ? 1 : 0;
             sp.force_twin = ctx->force_twin ? 1 : 0;
             sp.colbest = static_cast<unsigned long long *>(ctx->colbest.ptr);
+            sp.smem_table_rows = msfm::kSmemTableRows;
             sp.danger = static_cast<int2 *>(ctx->matches.ptr);  // the match scratch is written by the emission afterwards
             sp.twin_counts = static_cast<int32_t *>(ctx->twin_counts.ptr);
             sp.twin_gate = reinterpret_cast<unsigned int *>(static_cast<int32_t *>(ctx->twin_counts.ptr) + nb);
@@ -634,7 +662,7 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             sp.ckeys = ctx->norms;
             sp.cand_desc = static_cast<uint8_t *>(ctx->cand_desc.ptr);
             sp.cand_ckeys = static_cast<int32_t *>(ctx->cand_ckeys.ptr);
-            msfm::select_candidates_kernel<<<nb, 1024, 0, ctx->stream>>>(sp);
+            msfm::select_candidates_kernel<<<nb, 1024, mutual ? msfm::kSelectSmemBytes : 0, ctx->stream>>>(sp);
             MSFM_CUDA(ctx, cudaGetLastError());
             ctx->timing.total_launches += 1;
             // ---- tensor twin pass (nearest query row of every candidate's reference row) for the routed pairs only
@@ -692,22 +720,23 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             const int64_t bt = batch_offsets[nb];
             total += bt;
             if (!resident && bt > 0) {
-                if (written + bt > out->match_capacity)
-                    return fail(ctx, MSFM_ERR_CAPACITY, "match buffer too small: need at least %lld entries, capacity %lld",
-                                (long long)(written + bt), (long long)out->match_capacity);
+                int32_t (*dst_m)[2] = nullptr;
+                uint8_t *dst_g = nullptr;
+                if (out->sink(out->user, written, bt, &dst_m, &dst_g) != 0 || !dst_m)
+                    return fail(ctx, MSFM_ERR_CAPACITY, "match buffer too small: need at least %lld entries", (long long)(written + bt));
                 cudaEvent_t d0 = ctx->ev_k0, d1 = ctx->ev_k1;  // reuse as D2H brackets (kernel time already read)
                 MSFM_CUDA(ctx, cudaEventRecord(d0, ctx->stream));
-                MSFM_CUDA(ctx, cudaMemcpyAsync(out->matches + written, ctx->tight_matches.ptr, (size_t)bt * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
-                if (out->good) {
-                    if (want_good) MSFM_CUDA(ctx, cudaMemcpyAsync(out->good + written, ctx->tight_good.ptr, (size_t)bt, cudaMemcpyDeviceToHost, ctx->stream));
-                    else memset(out->good + written, 0, (size_t)bt);
+                MSFM_CUDA(ctx, cudaMemcpyAsync(dst_m, ctx->tight_matches.ptr, (size_t)bt * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
+                if (dst_g) {
+                    if (want_good) MSFM_CUDA(ctx, cudaMemcpyAsync(dst_g, ctx->tight_good.ptr, (size_t)bt, cudaMemcpyDeviceToHost, ctx->stream));
+                    else memset(dst_g, 0, (size_t)bt);
                 }
                 MSFM_CUDA(ctx, cudaEventRecord(d1, ctx->stream));
                 MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
                 float ms = 0.f;
                 MSFM_CUDA(ctx, cudaEventElapsedTime(&ms, d0, d1));
                 ctx->timing.d2h_ms += ms;
-                ctx->timing.d2h_bytes += bt * (int64_t)(sizeof(int2) + (out->good && want_good ? 1 : 0));
+                ctx->timing.d2h_bytes += bt * (int64_t)(sizeof(int2) + (dst_g && want_good ? 1 : 0));
             }
         }
         // ---- host bookkeeping for pairs [first, last)
@@ -830,7 +859,8 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
         cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, true>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::kSmemAlloc) != cudaSuccess ||
         cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, false, 1>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::kSmemAlloc) != cudaSuccess)
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::kSmemAlloc) != cudaSuccess ||
+        cudaFuncSetAttribute(msfm::select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msfm::kSelectSmemBytes) != cudaSuccess)
         return bail(MSFM_ERR_CUDA);
     if (ctx->debug_flags & 8u) {
         if (cudaMalloc(&ctx->dbg_stats.ptr, 512) != cudaSuccess) return bail(MSFM_ERR_OUT_OF_MEMORY);
@@ -895,12 +925,12 @@ static msfm_status finish_upload_sync(msfm_ctx *ctx) {
     return MSFM_OK;
 }
 
-static msfm_status leave_upload_mark(msfm_ctx *ctx, const std::vector<int32_t> &ids) {
+static msfm_status leave_upload_mark(msfm_ctx *ctx, const std::vector<int32_t> &ids, cudaStream_t on = nullptr) {
     if (ids.empty()) return MSFM_OK;
     cudaEvent_t ev = nullptr;
     if (!ctx->event_pool.empty()) { ev = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
     else MSFM_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    const cudaError_t e = cudaEventRecord(ev, ctx->upload_stream);
+    const cudaError_t e = cudaEventRecord(ev, on ? on : ctx->upload_stream);
     if (e != cudaSuccess) {
         ctx->event_pool.push_back(ev);
         return fail(ctx, MSFM_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e));
@@ -937,9 +967,7 @@ msfm_status msfm_reserve(msfm_ctx *ctx, int32_t image_id, int32_t rows, int64_t 
     return msfm_reserve_batch(ctx, 1, &image_id, &rows, row_offset);
 }
 
-msfm_status msfm_reserve_batch(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const int32_t *rows, int64_t *row_offsets) {
-    if (!ctx) return MSFM_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+static msfm_status reserve_batch_locked(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const int32_t *rows, int64_t *row_offsets) {
     if (n < 0 || (n > 0 && (!image_ids || !rows))) return fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_reserve_batch: null argument");
     MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
     msfm_status st = MSFM_OK;
@@ -954,6 +982,13 @@ msfm_status msfm_reserve_batch(msfm_ctx *ctx, int32_t n, const int32_t *image_id
         }
         if (row_offsets) row_offsets[i] = off;
     }
+    return st;
+}
+
+msfm_status msfm_reserve_batch(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const int32_t *rows, int64_t *row_offsets) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const msfm_status st = reserve_batch_locked(ctx, n, image_ids, rows, row_offsets);
     // pad rows and tensor maps are in place when the call returns: a foreign writer (a collective) may fill the rows at once
     const msfm_status fin = finish_upload_sync(ctx);
     return st != MSFM_OK ? st : fin;
@@ -1276,7 +1311,58 @@ msfm_status msfm_colbest(msfm_ctx *ctx, int32_t ref_id, int32_t query_id, int32_
 msfm_status msfm_match_pairs(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const msfm_params *params, msfm_result *out) {
     if (!ctx) return MSFM_ERR_INVALID_ARG;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return MSFM_ERR_CUDA;
-    return match_pairs_impl(ctx, pairs, n_pairs, params, out, false, nullptr);
+    if (!out || (!out->matches && out->match_capacity > 0)) return match_pairs_impl(ctx, pairs, n_pairs, params, nullptr, false, nullptr);
+    CallerBuffers cb{out->matches, out->good, out->match_capacity};
+    OutSpec spec;
+    spec.offsets = out->offsets;
+    spec.ok = out->ok;
+    spec.has_good = out->good != nullptr;
+    spec.sink = caller_sink;
+    spec.user = &cb;
+    return match_pairs_impl(ctx, pairs, n_pairs, params, &spec, false, nullptr);
+}
+
+msfm_status msfm_internal_match_pairs_sink(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const msfm_params *params, int64_t *offsets,
+                                           int32_t *ok, int want_good, msfm_sink_fn sink, void *user) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return MSFM_ERR_CUDA;
+    OutSpec spec;
+    spec.offsets = offsets;
+    spec.ok = ok;
+    spec.has_good = want_good != 0;
+    spec.sink = sink;
+    spec.user = user;
+    return match_pairs_impl(ctx, pairs, n_pairs, params, &spec, false, nullptr);
+}
+
+msfm_status msfm_reserve_batch_async(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const int32_t *rows, int64_t *row_offsets) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const msfm_status st = reserve_batch_locked(ctx, n, image_ids, rows, row_offsets);
+    // tensor maps and pad rows are queued on the upload stream: matching launches that touch these images wait for them
+    std::vector<int32_t> ids;
+    for (int32_t i = 0; i < n && image_ids; ++i)
+        if (image_ids[i] >= 0 && image_ids[i] < ctx->max_images && ctx->images[image_ids[i]].present) ids.push_back(image_ids[i]);
+    const msfm_status mk = (st == MSFM_OK) ? leave_upload_mark(ctx, ids) : MSFM_OK;
+    return st != MSFM_OK ? st : mk;
+}
+
+msfm_status msfm_internal_reserve_batch_nosync(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const int32_t *rows) {
+    return msfm_reserve_batch_async(ctx, n, image_ids, rows, nullptr);
+}
+
+msfm_status msfm_internal_mark_on_stream(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, cudaStream_t stream) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (n < 0 || (n > 0 && !image_ids)) return fail(ctx, MSFM_ERR_INVALID_ARG, "null image list");
+    MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<int32_t> ids;
+    for (int32_t i = 0; i < n; ++i) {
+        const msfm_status st = check_image_id(ctx, image_ids[i], true);
+        if (st != MSFM_OK) return st;
+        ids.push_back(image_ids[i]);
+    }
+    return leave_upload_mark(ctx, ids, stream);
 }
 
 msfm_status msfm_match_pairs_resident(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pairs, const msfm_params *params,

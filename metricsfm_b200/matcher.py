@@ -179,14 +179,16 @@ class Matcher:
         self._check(self._L.msfm_reserve(self._h, image_id, rows, C.byref(off)))
         return off.value
 
-    def reserve_batch(self, image_ids, rows) -> np.ndarray:
-        """msfm_reserve for several images in one call; returns their row offsets."""
+    def reserve_batch(self, image_ids, rows, wait: bool = True) -> np.ndarray:
+        """msfm_reserve for several images in one call; returns their row offsets.  wait=False
+        (msfm_reserve_batch_async): pad rows / tensor maps are only queued on the upload stream."""
         ids = np.ascontiguousarray(image_ids, np.int32)
         r = np.ascontiguousarray(rows, np.int32)
         if ids.shape != r.shape:
             raise ValueError("image_ids and rows must have the same length")
         offs = np.zeros(ids.shape, np.int64)
-        self._check(self._L.msfm_reserve_batch(self._h, len(ids), ids.ctypes.data, r.ctypes.data, offs.ctypes.data))
+        fn = self._L.msfm_reserve_batch if wait else self._L.msfm_reserve_batch_async
+        self._check(fn(self._h, len(ids), ids.ctypes.data, r.ctypes.data, offs.ctypes.data))
         return offs
 
     def release(self, image_id: int) -> None:

@@ -11,15 +11,33 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "msfm_match.h")
 
 
-def header_functions():
-    src = open(HEADER).read()
+def header_functions(name="msfm_match.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
     return sorted(set(re.findall(r"\b(msfm_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_and_binding_agree(native_lib):
     from metricsfm_b200 import _lib
     assert header_functions() == sorted(_lib.EXPORTED_SYMBOLS)
+    assert header_functions("msfm_sched.h") == sorted(_lib.SCHED_SYMBOLS)
+    assert header_functions("msfm_multi.h") == sorted(_lib.MULTI_SYMBOLS)
+
+
+def test_scheduler_and_multi_gpu_engine_are_exported(native_lib):
+    """include/msfm_sched.h + msfm_multi.h: exported by the CUDA library; the scheduler also by the host-only library."""
+    from metricsfm_b200 import _lib
+    from metricsfm_b200.build import LIB_PATH, SCHED_LIB, build_host_libs
+    build_host_libs()
+    out = subprocess.check_output(["nm", "-D", "--defined-only", LIB_PATH], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    for name in _lib.SCHED_SYMBOLS + _lib.MULTI_SYMBOLS:
+        assert name in exported, name
+    assert not [s for s in exported if "internal" in s]          # the inter-unit helpers stay hidden
+    host = subprocess.check_output(["nm", "-D", "--defined-only", SCHED_LIB], text=True)
+    for name in _lib.SCHED_SYMBOLS:
+        assert f" T {name}" in host
 
 
 def test_library_exports_every_declared_symbol(native_lib):
