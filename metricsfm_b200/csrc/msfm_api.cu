@@ -79,7 +79,12 @@ struct msfm_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;         // matching: plans, kernels, result copies
-    cudaStream_t upload_stream = nullptr;  // table changes: host->device copies, packer, tensor maps (overlaps matching)
+    cudaStream_t upload_stream = nullptr;  // table changes: packer launches, tensor maps, pad rows (overlaps matching)
+    cudaStream_t copy_stream = nullptr;    // host->device copies of the asynchronous batch uploads: they never queue behind a
+                                           // packer launch that is waiting for an SM (the matching kernel is persistent)
+    cudaEvent_t ev_copy = nullptr;
+    struct StageBuf { void *ptr; size_t bytes; cudaEvent_t done; bool used; };
+    std::vector<StageBuf> stage_pool;      // float staging of msfm_upload_f32_batch_async calls still in flight
     std::vector<UploadMark> marks;         // asynchronous uploads still to be ordered before matching launches
     std::vector<cudaEvent_t> event_pool;
     uint64_t upload_seq = 0, waited_seq = 0;
@@ -834,6 +839,8 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
     ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MSFM_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MSFM_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MSFM_ERR_CUDA);
+    if (cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming) != cudaSuccess) return bail(MSFM_ERR_CUDA);
     cudaEvent_t *evs[] = {&ctx->ev_begin, &ctx->ev_end, &ctx->ev_k0, &ctx->ev_k1, &ctx->ev_k2, &ctx->ev_k3, &ctx->ev_f1};
     for (cudaEvent_t *e : evs)
         if (cudaEventCreate(e) != cudaSuccess) return bail(MSFM_ERR_CUDA);
@@ -874,8 +881,14 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
 msfm_status msfm_destroy(msfm_ctx *ctx) {
     if (!ctx) return MSFM_OK;
     cudaSetDevice(ctx->device);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->upload_stream) cudaStreamSynchronize(ctx->upload_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (const msfm_ctx::StageBuf &b : ctx->stage_pool) {
+        cudaFree(b.ptr);
+        cudaEventDestroy(b.done);
+    }
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     if (ctx->dbg_stats.ptr) {
         unsigned long long h[64] = {0};
         cudaMemcpy(h, ctx->dbg_stats.ptr, 512, cudaMemcpyDeviceToHost);
@@ -909,6 +922,7 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
     for (const UploadMark &m : ctx->marks) cudaEventDestroy(m.ev);
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MSFM_OK;
@@ -1074,8 +1088,13 @@ static msfm_status upload_u8_batch_locked(msfm_ctx *ctx, int32_t n, const int32_
     }
     // On an argument error the images before the failing one stay uploaded (documented); a CUDA failure below rolls back
     // every image whose rows this call has not provably written.
-    for (const Run &r : runs)  // copies back to back, so the copy engine is not held up by the keying kernels
-        if (r.rows > 0) MSFM_CUDA_UPLOAD(ctx, in_runs, cudaMemcpyAsync(ctx->desc + r.off * kDim, r.src, (size_t)r.rows * kDim, cudaMemcpyHostToDevice, ctx->upload_stream));
+    // copies back to back on the copy stream (never held up by a keying kernel that waits for an SM), keys afterwards
+    for (const Run &r : runs)
+        if (r.rows > 0) MSFM_CUDA_UPLOAD(ctx, in_runs, cudaMemcpyAsync(ctx->desc + r.off * kDim, r.src, (size_t)r.rows * kDim, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (!runs.empty()) {
+        MSFM_CUDA_UPLOAD(ctx, in_runs, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+        MSFM_CUDA_UPLOAD(ctx, in_runs, cudaStreamWaitEvent(ctx->upload_stream, ctx->ev_copy, 0));
+    }
     for (const Run &r : runs) {    // keys + pad rows, in place
         if (r.rows_padded == 0) continue;
         const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(8 * ctx->num_sms, (r.rows_padded + 7) / 8));
@@ -1163,8 +1182,9 @@ msfm_status msfm_upload_f32(msfm_ctx *ctx, int32_t image_id, const float *desc, 
 }
 
 // Several float images (dense 128-float rows) without a host wait: the rows must sit in page-locked memory and stay
-// valid until msfm_sync() or a later call that returns results.  The staging buffer is used as a ring: every copy into
-// it is queued behind the packer launch that consumed the bytes it overwrites (one stream), so no wait is needed.
+// valid until msfm_sync() or a later call that returns results.  All host->device copies of the call are queued back to
+// back on the copy stream — into a staging buffer that belongs to this call until its packer launches have run, or
+// straight into the retained float rows — and the packer launches follow on the upload stream.
 msfm_status msfm_upload_f32_batch_async(msfm_ctx *ctx, int32_t n, const int32_t *image_ids, const float *const *descs, const int32_t *rows,
                                         float scale) {
     if (!ctx) return MSFM_ERR_INVALID_ARG;
@@ -1172,24 +1192,56 @@ msfm_status msfm_upload_f32_batch_async(msfm_ctx *ctx, int32_t n, const int32_t 
     if (n < 0 || (n > 0 && (!image_ids || !descs || !rows)) || !(scale > 0.0f))
         return fail(ctx, MSFM_ERR_INVALID_ARG, "msfm_upload_f32_batch_async: null argument or scale <= 0");
     MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
-    size_t largest = 0;
+    size_t total = 0;
     for (int32_t i = 0; i < n; ++i)
-        if (rows[i] > 0) largest = std::max(largest, (size_t)rows[i] * kDim * sizeof(float));
+        if (rows[i] > 0) total += (size_t)rows[i] * kDim * sizeof(float);
     msfm_status st = MSFM_OK;
-    const size_t ring = ctx->fdesc ? 0 : std::max<size_t>(largest, std::min<size_t>((size_t)64 << 20, largest * (size_t)std::max(n, 1)));
-    if (ring && (st = ensure(ctx, ctx->staging, ring, ctx->upload_stream)) != MSFM_OK) return st;
+    msfm_ctx::StageBuf *stage = nullptr;
+    if (!ctx->fdesc && total > 0) {
+        for (msfm_ctx::StageBuf &b : ctx->stage_pool)
+            if (b.bytes >= total && (!b.used || cudaEventQuery(b.done) == cudaSuccess)) { stage = &b; break; }
+        if (!stage) {
+            msfm_ctx::StageBuf nb{nullptr, std::max<size_t>(total, (size_t)64 << 20), nullptr, false};
+            MSFM_CUDA(ctx, cudaMalloc(&nb.ptr, nb.bytes));
+            if (cudaEventCreateWithFlags(&nb.done, cudaEventDisableTiming) != cudaSuccess) {
+                cudaFree(nb.ptr);
+                return fail(ctx, MSFM_ERR_CUDA, "cudaEventCreate failed");
+            }
+            ctx->stage_pool.push_back(nb);
+            stage = &ctx->stage_pool.back();
+        }
+        stage->used = true;
+    }
+    struct Job { int32_t id; int32_t rows; const float *src; };
+    std::vector<Job> jobs;
     std::vector<int32_t> uploaded;
     size_t pos = 0;
-    for (int32_t i = 0; i < n && st == MSFM_OK; ++i) {
+    for (int32_t i = 0; i < n && st == MSFM_OK; ++i) {  // reserve + copies
         if (rows[i] > 0 && !descs[i]) { st = fail(ctx, MSFM_ERR_INVALID_ARG, "null descriptors"); break; }
         int64_t off = 0;
         if ((st = reserve_locked(ctx, image_ids[i], rows[i], &off)) != MSFM_OK) break;
-        const size_t bytes = ctx->fdesc ? 0 : (size_t)std::max(rows[i], 0) * kDim * sizeof(float);
-        if (pos + bytes > ctx->staging.bytes) pos = 0;
-        st = upload_f32_enqueue(ctx, image_ids[i], descs[i], rows[i], kDim, scale,
-                                reinterpret_cast<float *>(static_cast<char *>(ctx->staging.ptr) + pos));
-        if (st == MSFM_OK) { uploaded.push_back(image_ids[i]); pos += bytes; }
+        uploaded.push_back(image_ids[i]);
+        const size_t bytes = (size_t)std::max(rows[i], 0) * kDim * sizeof(float);
+        float *dst = ctx->fdesc ? ctx->fdesc + off * kDim : reinterpret_cast<float *>(static_cast<char *>(stage ? stage->ptr : nullptr) + pos);
+        if (bytes) MSFM_CUDA_UPLOAD(ctx, uploaded, cudaMemcpyAsync(dst, descs[i], bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (ctx->fdesc && rows[i] > 0) {
+            ctx->images[image_ids[i]].has_float = true;
+            ctx->images[image_ids[i]].scale = scale;
+        }
+        jobs.push_back({image_ids[i], rows[i], dst});
+        if (!ctx->fdesc) pos += bytes;
     }
+    if (!jobs.empty()) {
+        MSFM_CUDA_UPLOAD(ctx, uploaded, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+        MSFM_CUDA_UPLOAD(ctx, uploaded, cudaStreamWaitEvent(ctx->upload_stream, ctx->ev_copy, 0));
+    }
+    for (const Job &j : jobs) {  // quantise + key
+        const ImageSlot &sl = ctx->images[j.id];
+        const int blocks = std::max(1, std::min(4 * ctx->num_sms, (sl.rows_padded + 7) / 8));
+        msfm::pack_f32_kernel<<<blocks, 256, 0, ctx->upload_stream>>>(j.src, kDim, j.rows, sl.rows_padded, scale, ctx->desc + sl.off * kDim, ctx->norms + sl.off);
+        MSFM_CUDA_UPLOAD(ctx, uploaded, cudaGetLastError());
+    }
+    if (stage) MSFM_CUDA_UPLOAD(ctx, uploaded, cudaEventRecord(stage->done, ctx->upload_stream));
     const msfm_status mk = leave_upload_mark(ctx, uploaded);
     return st != MSFM_OK ? st : mk;
 }

@@ -55,29 +55,31 @@ def block_ranges(n_images: int, rows_padded_per_image, world_size: int):
 
 
 def replicate_arena(desc_arena, side_arena, ranges, dist) -> int:
-    """Broadcast every owner's block of the packed table to all ranks.  Returns the bytes this rank received."""
-    received = 0
+    """Replicate every owner's block of the packed table on all ranks.  Returns the bytes this rank received.
+
+    The collective is chosen from facts every rank agrees on (backend name, block layout) BEFORE anything is issued, so all
+    ranks always issue the same sequence; errors of the collectives themselves propagate."""
     rank = dist.get_rank()
     world = dist.get_world_size()
-    # Equal, contiguous owner blocks in rank order (the usual case: equally sized images): ONE in-place all-gather per
-    # arena (ncclAllGather over NVLink/NVSwitch; the input is this rank's own slice of the output).
+    row_bytes = desc_arena.shape[1] * desc_arena.element_size() + side_arena.element_size()
+    # Equal, contiguous owner blocks in rank order (the usual case: equally sized images) on NCCL: ONE in-place all-gather
+    # per arena over NVLink/NVSwitch (the input is this rank's own slice of the output).
     block = ranges[0][1] - ranges[0][0]
-    if world > 1 and block > 0 and all(r == (i * block + ranges[0][0], (i + 1) * block + ranges[0][0]) for i, r in enumerate(ranges)):
-        try:
-            base = ranges[0][0]
-            lo, hi = ranges[rank]
-            dist.all_gather_into_tensor(desc_arena[base:base + world * block], desc_arena[lo:hi])
-            dist.all_gather_into_tensor(side_arena[base:base + world * block], side_arena[lo:hi])
-            return (world - 1) * block * (desc_arena.shape[1] * desc_arena.element_size() + side_arena.element_size())
-        except (RuntimeError, NotImplementedError):
-            pass  # backend without all_gather_into_tensor: fall back to the broadcasts below
-    for src, (lo, hi) in enumerate(ranges):
+    equal_blocks = block > 0 and all(r == (i * block + ranges[0][0], (i + 1) * block + ranges[0][0]) for i, r in enumerate(ranges))
+    if world > 1 and equal_blocks and str(dist.get_backend()).lower() == "nccl":
+        base = ranges[0][0]
+        lo, hi = ranges[rank]
+        dist.all_gather_into_tensor(desc_arena[base:base + world * block], desc_arena[lo:hi])
+        dist.all_gather_into_tensor(side_arena[base:base + world * block], side_arena[lo:hi])
+        return (world - 1) * block * row_bytes
+    received = 0
+    for src, (lo, hi) in enumerate(ranges):     # ragged blocks, or a backend without in-place all-gather (gloo in the CPU tests)
         if hi <= lo:
             continue
         dist.broadcast(desc_arena[lo:hi], src=src)
         dist.broadcast(side_arena[lo:hi], src=src)
         if src != rank:
-            received += (hi - lo) * (desc_arena.shape[1] * desc_arena.element_size() + side_arena.element_size())
+            received += (hi - lo) * row_bytes
     return received
 
 

@@ -31,8 +31,9 @@ FeatureMatchingB200::FeatureMatchingB200(const MatcherB200Options &opt) : opt_(o
     msfm_config cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.device = opt.device;
-    cfg.max_images = 2;
-    cfg.arena_rows = 2 * 1000192;  // two images of up to idx_max_per_image rows (basic_structs.h:171)
+    cfg.max_images = 2 + (opt.max_indices > 0 ? opt.max_indices : 0);  // slots 0/1: the transient images of a call; 2..: indices
+    cfg.arena_rows = opt.arena_rows;
+    indices_.assign(opt.max_indices > 0 ? opt.max_indices : 0, nullptr);
     msfm_status st = msfm_create(&cfg, &ctx_);
     if (st != MSFM_OK) {
         ctx_ = nullptr;
@@ -40,26 +41,35 @@ FeatureMatchingB200::FeatureMatchingB200(const MatcherB200Options &opt) : opt_(o
     }
 }
 
-FeatureMatchingB200::~FeatureMatchingB200() { msfm_destroy(ctx_); }
+FeatureMatchingB200::~FeatureMatchingB200() {
+    for (KDIndexB200 *k : indices_) delete k;
+    msfm_destroy(ctx_);
+}
 
-bool FeatureMatchingB200::Upload(int slot, cv::Mat &d) { return upload_mat(ctx_, slot, d, opt_.descriptor_scale, err_); }
+// A transient image of one call: replaces whatever the slot held (the persistent indices keep their rows).
+bool FeatureMatchingB200::Upload(int slot, cv::Mat &d) {
+    if (transient_[slot]) msfm_release(ctx_, slot);
+    transient_[slot] = upload_mat(ctx_, slot, d, opt_.descriptor_scale, err_);
+    return transient_[slot];
+}
 
 bool FeatureMatchingB200::Match(cv::Mat &d1, cv::Mat &d2, bool mutual, std::vector<std::pair<int, int>> &matches) {
     if (!ctx_) return false;
-    msfm_release_all(ctx_);
     if (!Upload(0, d1) || !Upload(1, d2)) return false;
-    // index on image 2, queries = rows of image 1 (feature_matching.cpp:35-44)
-    msfm_pair pair = {1, 0};
+    // index on image 2, queries = rows of image 1, (i1, i2) ascending i1 (feature_matching.cpp:35-64)
+    return MatchSlots(1, 0, d1.rows, mutual, 1, matches);
+}
+
+bool FeatureMatchingB200::MatchSlots(int ref_slot, int qry_slot, int qry_rows, bool mutual, int orientation,
+                                     std::vector<std::pair<int, int>> &matches) {
+    msfm_pair pair = {ref_slot, qry_slot};
     msfm_params prm;
     memset(&prm, 0, sizeof prm);
     prm.ratio = opt_.th_ratio;
-    prm.ratio_good = 0.f;
-    prm.max_dist_sq = 0.f;
     prm.mutual = mutual ? 1 : 0;
     prm.min_keypoints = opt_.th_reject;
-    prm.orientation = 1;  // (i1, i2), ascending i1 (feature_matching.cpp:56-64)
-    prm.rescore_band = 0.f;
-    std::vector<int32_t> buf((size_t)(d1.rows > 0 ? d1.rows : 1) * 2);
+    prm.orientation = orientation;
+    std::vector<int32_t> buf((size_t)(qry_rows > 0 ? qry_rows : 1) * 2);
     int64_t offsets[2] = {0, 0};
     int32_t okflag = 0;
     msfm_result res;
@@ -67,7 +77,7 @@ bool FeatureMatchingB200::Match(cv::Mat &d1, cv::Mat &d2, bool mutual, std::vect
     res.ok = &okflag;
     res.matches = reinterpret_cast<int32_t(*)[2]>(buf.data());
     res.good = nullptr;
-    res.match_capacity = d1.rows;
+    res.match_capacity = qry_rows;
     msfm_status st = msfm_match_pairs(ctx_, &pair, 1, &prm, &res);
     if (st != MSFM_OK) {
         err_ = msfm_last_error(ctx_);
@@ -154,6 +164,12 @@ bool FeatureMatchingB200::KNNMatchingWithGeoVerify(std::vector<cv::KeyPoint> &kp
     if ((int)kp1.size() < opt_.th_reject || (int)kp2.size() < opt_.th_reject) return false;  // feature_matching.cpp:74-77
     std::vector<std::pair<int, int>> cur;
     if (!Match(descriptors1, descriptors2, opt_.mutual, cur)) return false;                   // ratio matches (i1, i2)
+    return Verify(kp1, kp2, cur, matches);
+}
+
+// The verification passes every KNNMatchingWithGeoVerify overload shares (feature_matching.cpp:94-147 and its copies).
+bool FeatureMatchingB200::Verify(std::vector<cv::KeyPoint> &kp1, std::vector<cv::KeyPoint> &kp2, std::vector<std::pair<int, int>> &cur,
+                                 std::vector<std::pair<int, int>> &matches) {
     std::vector<float> xy1(kp1.size() * 2), xy2(kp2.size() * 2);
     for (size_t i = 0; i < kp1.size(); ++i) { xy1[2 * i] = kp1[i].pt.x; xy1[2 * i + 1] = kp1[i].pt.y; }
     for (size_t i = 0; i < kp2.size(); ++i) { xy2[2 * i] = kp2[i].pt.x; xy2[2 * i + 1] = kp2[i].pt.y; }
@@ -197,9 +213,74 @@ bool FeatureMatchingB200::KNNMatchingWithGeoVerify(std::vector<cv::KeyPoint> &kp
     return true;  // the reference falls off the end here; its callers treat the call as successful
 }
 
+// ---------------------------------------------------------------------------------------------------- persistent indices
+bool FeatureMatchingB200::GenerateKDIndex(cv::Mat &descriptors, KDIndexB200 **kdindex) {
+    if (!ctx_ || !kdindex) return false;
+    *kdindex = nullptr;
+    for (size_t k = 0; k < indices_.size(); ++k) {
+        if (indices_[k]) continue;
+        const int slot = 2 + (int)k;
+        if (!upload_mat(ctx_, slot, descriptors, opt_.descriptor_scale, err_)) return false;  // packed once; stays in HBM
+        KDIndexB200 *idx = new KDIndexB200();
+        idx->slot_ = slot;
+        idx->rows_ = descriptors.rows;
+        indices_[k] = idx;
+        *kdindex = idx;
+        return true;
+    }
+    err_ = "no free index slot (MatcherB200Options::max_indices)";
+    return false;
+}
+
+void FeatureMatchingB200::ReleaseKDIndex(KDIndexB200 *kdindex) {
+    if (!ctx_ || !kdindex) return;
+    for (size_t k = 0; k < indices_.size(); ++k)
+        if (indices_[k] == kdindex) {
+            msfm_release(ctx_, kdindex->slot_);
+            delete kdindex;
+            indices_[k] = nullptr;
+        }
+}
+
+bool FeatureMatchingB200::MatchAgainstIndex(KDIndexB200 *kdindex, cv::Mat &descriptors_other, bool index_is_image1,
+                                            std::vector<std::pair<int, int>> &matches) {
+    if (!ctx_ || !kdindex || kdindex->slot_ < 2) return false;
+    if (!Upload(0, descriptors_other)) return false;  // only the partner is staged; the index stays where it is
+    // index on image 1: pairs (i1, i2) ascending i2 = (ref, query) = orientation 0; index on image 2: (i1, i2) ascending
+    // i1 = (query, ref) = orientation 1
+    return MatchSlots(kdindex->slot_, 0, descriptors_other.rows, opt_.mutual, index_is_image1 ? 0 : 1, matches);
+}
+
+bool FeatureMatchingB200::KNNMatchingWithGeoVerify(std::vector<cv::KeyPoint> &kp1, cv::Mat &descriptors1, std::vector<cv::KeyPoint> &kp2,
+                                                   KDIndexB200 *kdindex2, std::vector<std::pair<int, int>> &matches) {
+    if ((int)kp1.size() < opt_.th_reject || (int)kp2.size() < opt_.th_reject) return false;  // feature_matching.cpp:157-160
+    std::vector<std::pair<int, int>> cur;
+    if (!MatchAgainstIndex(kdindex2, descriptors1, false, cur)) return false;
+    return Verify(kp1, kp2, cur, matches);
+}
+
+bool FeatureMatchingB200::KNNMatchingWithGeoVerify(std::vector<cv::KeyPoint> &kp1, KDIndexB200 *kdindex1, std::vector<cv::KeyPoint> &kp2,
+                                                   cv::Mat &descriptors2, std::vector<std::pair<int, int>> &matches) {
+    if ((int)kp1.size() < opt_.th_reject || (int)kp2.size() < opt_.th_reject) return false;  // feature_matching.cpp:239-242,325-328
+    std::vector<std::pair<int, int>> cur;
+    if (!MatchAgainstIndex(kdindex1, descriptors2, true, cur)) return false;
+    return Verify(kp1, kp2, cur, matches);
+}
+
+bool FeatureMatchingB200::KNNMatchingWithGeoVerify(std::vector<cv::KeyPoint> &kp1, std::vector<cv::KeyPoint> &kp2, int *id, float *dis,
+                                                   std::vector<std::pair<int, int>> &matches) {
+    if (!ctx_ || !id || !dis) return false;
+    if ((int)kp1.size() < opt_.th_reject || (int)kp2.size() < opt_.th_reject) return false;  // feature_matching.cpp:483-486
+    std::vector<std::pair<int, int>> cur;
+    for (size_t i = 0; i < kp2.size(); ++i) {                                                   // :488-500
+        const float ratio = dis[2 * i + 0] / dis[2 * i + 1];
+        if (ratio < opt_.th_ratio) cur.push_back(std::pair<int, int>(id[2 * i + 0], (int)i));
+    }
+    return Verify(kp1, kp2, cur, matches);
+}
+
 bool FeatureMatchingB200::KNN2(cv::Mat &descriptors1, cv::Mat &descriptors2, int *id, float *dis) {
     if (!ctx_) return false;
-    msfm_release_all(ctx_);
     if (!Upload(0, descriptors1) || !Upload(1, descriptors2)) return false;
     msfm_status st = msfm_knn2(ctx_, 0, 1, id, dis);
     if (st != MSFM_OK) err_ = msfm_last_error(ctx_);
@@ -288,6 +369,72 @@ bool MatchGraphB200::MatchPairs(const std::vector<std::vector<int>> &match_graph
         }
     }
     return true;
+}
+
+// ---------------------------------------------------------------------------------------------------- SiftMatchGPU shape
+SiftMatchB200::SiftMatchB200(int max_sift, int device) : device_(device), max_sift_(max_sift > 0 ? max_sift : 4096) { SetMaxSift(max_sift_); }
+
+SiftMatchB200::~SiftMatchB200() { msfm_destroy(ctx_); }
+
+void SiftMatchB200::SetMaxSift(int max_sift) {
+    if (max_sift <= 0) return;
+    if (ctx_ && max_sift <= max_sift_) { max_sift_ = max_sift; return; }  // shrinking keeps the table
+    msfm_destroy(ctx_);
+    ctx_ = nullptr;
+    max_sift_ = max_sift;
+    set_[0] = set_[1] = false;
+    msfm_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.device = device_;
+    cfg.max_images = 2;
+    cfg.arena_rows = 2ll * ((max_sift + 255) / 256 * 256);
+    if (msfm_create(&cfg, &ctx_) != MSFM_OK) ctx_ = nullptr;
+}
+
+void SiftMatchB200::SetDescriptors(int index, int num, const float *descriptors, int id) {
+    if (!ctx_ || index < 0 || index > 1 || num < 0 || (num > 0 && !descriptors)) return;
+    if (id >= 0 && set_[index] && id_[index] == id) return;  // same feature set as last time (SiftGPU.h: "id" caching)
+    num = num < max_sift_ ? num : max_sift_;                 // SiftGPU keeps at most max_sift features per set
+    if (set_[index]) msfm_release(ctx_, index);
+    set_[index] = msfm_upload_f32(ctx_, index, descriptors, num, MSFM_DIM, 512.0f) == MSFM_OK;  // "normalized to 1.0"
+    num_[index] = set_[index] ? num : 0;
+    id_[index] = id;
+}
+
+void SiftMatchB200::SetDescriptors(int index, int num, const unsigned char *descriptors, int id) {
+    if (!ctx_ || index < 0 || index > 1 || num < 0 || (num > 0 && !descriptors)) return;
+    if (id >= 0 && set_[index] && id_[index] == id) return;
+    num = num < max_sift_ ? num : max_sift_;
+    if (set_[index]) msfm_release(ctx_, index);
+    set_[index] = msfm_upload_u8(ctx_, index, descriptors, num, MSFM_DIM) == MSFM_OK;            // "normalized to 512"
+    num_[index] = set_[index] ? num : 0;
+    id_[index] = id;
+}
+
+int SiftMatchB200::GetSiftMatch(int max_match, int match_buffer[][2], float distmax, float ratiomax, int mutual_best_match) {
+    if (!ctx_ || !set_[0] || !set_[1] || max_match <= 0 || !match_buffer || num_[0] == 0 || num_[1] == 0) return 0;
+    msfm_pair pair = {1, 0};  // set 1 is searched, the rows of set 0 are the queries
+    msfm_params prm;
+    memset(&prm, 0, sizeof prm);
+    prm.ratio = ratiomax;
+    // acos(d1.d2) < distmax  <=>  |d1 - d2|^2 < 2 - 2 cos(distmax) for unit vectors; rows are 512-scaled
+    prm.max_dist_sq = distmax > 0.0f ? (float)(512.0 * 512.0 * (2.0 - 2.0 * std::cos((double)distmax))) : 0.0f;
+    prm.mutual = mutual_best_match ? 1 : 0;
+    prm.min_keypoints = 0;  // SiftMatchGPU has no keypoint gate
+    prm.orientation = 1;    // (index in set 0, index in set 1), ascending set-0 index
+    std::vector<int32_t> buf((size_t)num_[0] * 2);
+    int64_t offsets[2] = {0, 0};
+    int32_t okflag = 0;
+    msfm_result res;
+    res.offsets = offsets;
+    res.ok = &okflag;
+    res.matches = reinterpret_cast<int32_t(*)[2]>(buf.data());
+    res.good = nullptr;
+    res.match_capacity = num_[0];
+    if (msfm_match_pairs(ctx_, &pair, 1, &prm, &res) != MSFM_OK) return 0;
+    const int n = (int)(offsets[1] < max_match ? offsets[1] : max_match);  // "max_match: the length of the match_buffer"
+    for (int k = 0; k < n; ++k) { match_buffer[k][0] = buf[2 * k]; match_buffer[k][1] = buf[2 * k + 1]; }
+    return n;
 }
 
 }  // namespace objectsfm

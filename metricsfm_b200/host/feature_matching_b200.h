@@ -33,6 +33,23 @@ struct MatcherB200Options {
     float th_ratio = 0.5f;   // feature_matching.cpp:27
     int th_reject = 20;      // feature_matching.cpp:28
     bool mutual = false;     // the CPU paths have none; SiftMatchGPU::GetSiftMatch defaults to 1 (SiftGPU.h:308)
+    int max_indices = 14;    // persistent indices (GenerateKDIndex) that can be alive at once
+    long long arena_rows = 1ll << 20;  // descriptor rows the matcher's table holds (two transient images + the indices);
+                                       // 128 MiB of HBM at the default; idx_max_per_image is 1,000,000 (basic_structs.h:171)
+};
+
+class FeatureMatchingB200;
+
+// Stand-in for the reference's persistent kNN indices — cv::flann::Index* (feature_matching.h:41-47, GenerateKDIndex :63),
+// my_kd_tree_t* (:49-51), flann_index_t (:53-55): the image's descriptors, packed ONCE into the matcher's table in HBM.
+// Build it once per image and match any number of partners against it (fine_matching_graph.cc:72-101 does exactly that
+// per idx1); nothing is re-uploaded per pair.
+class KDIndexB200 {
+public:
+    int rows() const { return rows_; }
+private:
+    friend class FeatureMatchingB200;
+    int slot_ = -1, rows_ = 0;
 };
 
 class FeatureMatchingB200 {
@@ -64,12 +81,66 @@ public:
     // arrays KNNMatchingWithGeoVerify(kp1, kp2, id, dis, matches) and fine_matching_graph.cc:96-99 consume.
     bool KNN2(cv::Mat &descriptors1, cv::Mat &descriptors2, int *id, float *dis);
 
+    // ---- persistent-index overloads (feature_matching.h:41-55, :63) --------------------------------------------------
+    // FeatureMatching::GenerateKDIndex(descriptors, &kdindex): pack the image once.  ReleaseKDIndex frees its table rows.
+    bool GenerateKDIndex(cv::Mat &descriptors, KDIndexB200 **kdindex);
+    void ReleaseKDIndex(KDIndexB200 *kdindex);
+    // KNNMatchingWithGeoVerify(kp1, descriptors1, kp2, kdindex2, matches) (feature_matching.cpp:152-233): index on image 2,
+    // every row of image 1 queried, ratio < th_ratio, pairs (i1, i2) ascending i1, then the verification passes.
+    bool KNNMatchingWithGeoVerify(std::vector<cv::KeyPoint> &kp1, cv::Mat &descriptors1, std::vector<cv::KeyPoint> &kp2,
+                                  KDIndexB200 *kdindex2, std::vector<std::pair<int, int>> &matches);
+    // KNNMatchingWithGeoVerify(kp1, kdindex1 | kd_tree1 | flann kd_tree1, kp2, descriptors2, matches)
+    // (feature_matching.cpp:235-475): index on image 1, every row of image 2 queried, pairs (i1, i2) ascending i2.
+    bool KNNMatchingWithGeoVerify(std::vector<cv::KeyPoint> &kp1, KDIndexB200 *kdindex1, std::vector<cv::KeyPoint> &kp2,
+                                  cv::Mat &descriptors2, std::vector<std::pair<int, int>> &matches);
+    // The kNN + ratio part of the two overloads above without the verification passes (what FineMatchingGraph's loops do
+    // per partner, fine_matching_graph.cc:96-133): index_is_image1 selects the orientation.
+    bool MatchAgainstIndex(KDIndexB200 *kdindex, cv::Mat &descriptors_other, bool index_is_image1,
+                           std::vector<std::pair<int, int>> &matches);
+    // KNNMatchingWithGeoVerify(kp1, kp2, id, dis, matches) (feature_matching.cpp:477-553): the caller supplies the kNN
+    // arrays (index on image 1, [2*N2] FLANN layout — e.g. from KNN2 or msfm_knn2); ratio < th_ratio on them, then the
+    // verification passes.
+    bool KNNMatchingWithGeoVerify(std::vector<cv::KeyPoint> &kp1, std::vector<cv::KeyPoint> &kp2, int *id, float *dis,
+                                  std::vector<std::pair<int, int>> &matches);
+
 private:
     bool Match(cv::Mat &d1, cv::Mat &d2, bool mutual, std::vector<std::pair<int, int>> &matches);
+    bool MatchSlots(int ref_slot, int qry_slot, int qry_rows, bool mutual, int orientation, std::vector<std::pair<int, int>> &matches);
+    bool Verify(std::vector<cv::KeyPoint> &kp1, std::vector<cv::KeyPoint> &kp2, std::vector<std::pair<int, int>> &cur,
+                std::vector<std::pair<int, int>> &matches);
     bool Upload(int slot, cv::Mat &d);
     msfm_ctx *ctx_ = nullptr;
     MatcherB200Options opt_;
+    std::vector<KDIndexB200 *> indices_;  // slot 2 + k
+    bool transient_[2] = {false, false};
     std::string err_;
+};
+
+// SiftMatchGPU-shaped front end (thirdparty/siftgpu/include/siftgpu/SiftGPU.h:255-336; declared in the reference, no call
+// sites, shipped as a binary): two descriptor sets, then GetSiftMatch.  Set 0 rows are the queries, set 1 the reference
+// set; matches come back as (index in set 0, index in set 1), ascending set-0 index, truncated to max_match.
+//   * descriptors: unsigned char rows "normalized to 512" (SiftGPU.h:298) are taken as they are; float rows "normalized
+//     to 1.0" (:296) are quantised with scale 512
+//   * distmax is SiftGPU's angular bound acos(d1.d2) < distmax; it becomes the equivalent squared-L2 gate
+//     d^2 < 512^2 * (2 - 2 cos(distmax)) (exact for unit-norm rows)
+//   * ratiomax applies to squared L2 distances, strict '<' (north_star fixes the metric; SiftGPU compares angles)
+//   * mutual_best_match: lowest index wins ties in both directions, like the recovered s_row_max / s_col_max shaders
+class SiftMatchB200 {
+public:
+    explicit SiftMatchB200(int max_sift = 4096, int device = 0);  // SiftMatchGPU(int max_sift = 4096)
+    ~SiftMatchB200();
+    SiftMatchB200(const SiftMatchB200 &) = delete;
+    SiftMatchB200 &operator=(const SiftMatchB200 &) = delete;
+    bool ok() const { return ctx_ != nullptr; }
+    void SetMaxSift(int max_sift);
+    void SetDescriptors(int index, int num, const float *descriptors, int id = -1);
+    void SetDescriptors(int index, int num, const unsigned char *descriptors, int id = -1);
+    int GetSiftMatch(int max_match, int match_buffer[][2], float distmax = 0.7f, float ratiomax = 0.8f, int mutual_best_match = 1);
+
+private:
+    msfm_ctx *ctx_ = nullptr;
+    int device_, max_sift_, num_[2] = {0, 0}, id_[2] = {-1, -1};
+    bool set_[2] = {false, false};
 };
 
 // Least-squares homography pt2 ~ H pt1 (normalised DLT, smallest eigenvector of A^T A by Jacobi sweeps), scaled so that

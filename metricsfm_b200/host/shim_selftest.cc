@@ -71,6 +71,44 @@ int main(int argc, char **argv) {
         printf("\n");
     }
 
+    {   // FeatureMatchingCudaSift::Run-shaped entry (mutual best match) and the persistent-index overloads
+        std::vector<std::pair<int, int>> rm;
+        const bool okr = matcher.Run(kp1, d1, kp2, d2, rm);
+        printf("Run %d %zu\n", okr ? 1 : 0, rm.size());
+        for (auto &m : rm) printf("%d %d\n", m.first, m.second);
+        objectsfm::KDIndexB200 *idx1 = nullptr, *idx2 = nullptr;
+        const bool okg = matcher.GenerateKDIndex(d1, &idx1) && matcher.GenerateKDIndex(d2, &idx2);
+        for (int rep = 0; rep < 2; ++rep) {  // the index is built once and queried again: nothing is re-uploaded for it
+            std::vector<std::pair<int, int>> m1, m2;
+            const bool ok1 = okg && matcher.MatchAgainstIndex(idx1, d2, true, m1);   // index on image 1, queries = image 2
+            const bool ok2i = okg && matcher.MatchAgainstIndex(idx2, d1, false, m2);  // index on image 2, queries = image 1
+            printf("Index1 %d %zu\n", ok1 ? 1 : 0, m1.size());
+            for (auto &m : m1) printf("%d %d\n", m.first, m.second);
+            printf("Index2 %d %zu\n", ok2i ? 1 : 0, m2.size());
+            for (auto &m : m2) printf("%d %d\n", m.first, m.second);
+        }
+        matcher.ReleaseKDIndex(idx1);
+        matcher.ReleaseKDIndex(idx2);
+        // SiftMatchGPU-shaped front end: u8 rows, distmax off-by-default semantics checked with a wide bound
+        objectsfm::SiftMatchB200 sm(4096);
+        std::vector<unsigned char> u1((size_t)n1 * 128), u2((size_t)n2 * 128);
+        for (size_t i = 0; i < u1.size(); ++i) u1[i] = (unsigned char)buf[i];
+        for (size_t i = 0; i < u2.size(); ++i) u2[i] = (unsigned char)buf[(size_t)n1 * 128 + i];
+        sm.SetDescriptors(0, n1, u1.data(), 7);
+        sm.SetDescriptors(1, n2, u2.data(), 8);
+        sm.SetDescriptors(1, n2, u1.data(), 8);  // same id: ignored, set 1 keeps image 2
+        std::vector<int> mb((size_t)n1 * 2);
+        const int full = sm.ok() ? sm.GetSiftMatch(n1, reinterpret_cast<int(*)[2]>(mb.data()), 3.2f, 0.8f, 1) : -1;
+        printf("SiftMatch %d\n", full);
+        for (int k = 0; k < full; ++k) printf("%d %d\n", mb[2 * k], mb[2 * k + 1]);
+        const int capped = sm.ok() ? sm.GetSiftMatch(5, reinterpret_cast<int(*)[2]>(mb.data()), 3.2f, 0.8f, 0) : -1;
+        printf("SiftMatchCapped %d\n", capped);
+        for (int k = 0; k < capped; ++k) printf("%d %d\n", mb[2 * k], mb[2 * k + 1]);
+        const int gated = sm.ok() ? sm.GetSiftMatch(n1, reinterpret_cast<int(*)[2]>(mb.data()), 0.35f, 0.8f, 0) : -1;
+        printf("SiftMatchGated %d\n", gated);
+        for (int k = 0; k < gated; ++k) printf("%d %d\n", mb[2 * k], mb[2 * k + 1]);
+    }
+
     objectsfm::MatchGraphB200 graph(0, 2, n1 + n2);
     std::vector<std::vector<int>> init = {{1}, {0}};
     std::vector<std::vector<objectsfm::MatchGraphB200::PairMatches>> out;

@@ -262,6 +262,36 @@ def test_cpp_host_shim_matches_oracle(oracle_mod, native_lib, tmp_path):
     oids, odists = oracle_mod.knn2_u8(d1, d2)
     np.testing.assert_array_equal(rows[:, :2].astype(np.int32), oids)
     np.testing.assert_array_equal(rows[:, 2:].astype(np.float32), odists)
+
+    def block(name):
+        head = next(it).split()
+        assert head[0] == name, head
+        n = int(head[-1])
+        return head, np.array([next(it).split() for _ in range(max(n, 0))], dtype=np.int32).reshape(-1, 2)
+
+    head, got = block("Run")                                               # FeatureMatchingCudaSift::Run: mutual best match
+    assert head[1] == "1"
+    np.testing.assert_array_equal(got, oracle_mod.match_pair_u8(d2, d1, 0.5, orientation=1, mutual=True)["pairs"])
+    for _ in range(2):                                                     # persistent indices, queried twice
+        head, got = block("Index1")                                        # index on image 1, (i1, i2) ascending i2
+        assert head[1] == "1"
+        np.testing.assert_array_equal(got, oracle_mod.match_pair_u8(d1, d2, 0.5, orientation=0)["pairs"])
+        head, got = block("Index2")                                        # index on image 2, (i1, i2) ascending i1
+        assert head[1] == "1"
+        np.testing.assert_array_equal(got, exp)
+    # SiftMatchGPU shape: set 0 = queries (image 1), set 1 = image 2; ratio 0.8 on squared L2, mutual, no keypoint gate
+    head, got = block("SiftMatch")
+    full = oracle_mod.match_pair_u8(d2, d1, 0.8, orientation=1, mutual=True, min_keypoints=0)["pairs"]
+    np.testing.assert_array_equal(got, full)
+    head, got = block("SiftMatchCapped")                                   # max_match truncates the one-way list
+    oneway = oracle_mod.match_pair_u8(d2, d1, 0.8, orientation=1, min_keypoints=0)["pairs"]
+    assert len(oneway) > 5
+    np.testing.assert_array_equal(got, oneway[:5])
+    head, got = block("SiftMatchGated")                                    # distmax 0.35 rad -> squared-L2 gate
+    gate = float(np.float32(512.0 * 512.0 * (2.0 - 2.0 * np.cos(np.float64(np.float32(0.35))))))
+    gated = oracle_mod.match_pair_u8(d2, d1, 0.8, orientation=1, min_keypoints=0, max_dist_sq=gate)["pairs"]
+    np.testing.assert_array_equal(got, gated)
+    assert 0 < len(gated) < len(oneway)
     assert next(it).split() == ["MatchPairs", "1"]
     for ref, qry in ((d1, d2), (d2, d1)):
         head = next(it).split()
