@@ -40,6 +40,9 @@ typedef struct msfm_graph_options {
     int64_t max_batch_rows;  /* the missing images are processed in chunks of consecutive idx1 whose pair lists need at most
                                 this many match slots (sum of query rows) on the host; match_index.txt advances per chunk.
                                 0 = 32 Mi.  Results do not depend on the chunking. */
+    int32_t n_devices;       /* > 1: the pair list is matched on devices 0 .. n_devices-1 by the single-process multi-GPU
+                                engine (msfm_multi.h); `device` is then ignored.  0 / 1 = one GPU (`device`) */
+    int32_t reserved;        /* must be zero */
 } msfm_graph_options;
 
 /* Geo-verification seam.  xy1/xy2: centred keypoints of both images as stored in the feature files; matches: the

@@ -133,6 +133,12 @@ typedef struct msfm_timing {
 int32_t msfm_abi_version(void);
 const char *msfm_status_string(msfm_status s);
 
+/* Page-locked host memory for the staging buffers of the *_async uploads and for result buffers (a host that does not
+ * link the CUDA runtime itself, like the graph driver, gets it from here).  msfm_device_memory: free / total HBM bytes. */
+msfm_status msfm_host_alloc(size_t bytes, void **out);
+msfm_status msfm_host_free(void *ptr);
+msfm_status msfm_device_memory(int32_t device, int64_t *free_bytes, int64_t *total_bytes);
+
 msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out);
 msfm_status msfm_destroy(msfm_ctx *ctx);
 /* Last error text of this context (valid until the next call on it); never NULL. */

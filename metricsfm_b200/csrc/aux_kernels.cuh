@@ -73,6 +73,18 @@ __global__ void init_pad_kernel(int rows, int rows_padded, uint8_t *__restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------------ plan upload
+// The per-batch plan (pair descriptors + work items, a few hundred KB in page-locked host memory) is PULLED by the SMs over
+// PCIe instead of being copied by the host->device copy engine: that engine is a FIFO, and a plan copy queued behind the
+// bulk descriptor uploads of later image groups would hold back the matching launch until all of them had finished.
+__global__ void pull_plan_kernel(const uint4 *__restrict__ host_src, uint4 *__restrict__ dst0, size_t n0, uint4 *__restrict__ dst1, size_t n1) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = host_src[i];
+        if (i < n0) dst0[i] = v;
+        else dst1[i - n0] = v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ kNN shares
 // The matching kernel leaves `nshare` partial results per query row (one per column share).  Each is sorted
 // (d0,id0) <= (d1,id1); absent entries are (INT_MAX, -1).  The row's result is the two smallest (d, id) pairs.

@@ -420,23 +420,31 @@ msfm_status run_match_stage(msfm_ctx *ctx, const BatchPlan &plan) {
     const size_t pd_bytes = fw_bytes + tw_bytes + bt_bytes;
     const size_t it_fw = plan.items.size() * sizeof(WorkItem);
     const size_t it_tw = (plan.twin_items.size() + plan.band_items.size()) * sizeof(WorkItem);
-    if ((st = ensure(ctx, ctx->pairdesc, pd_bytes)) != MSFM_OK) return st;
-    if ((st = ensure(ctx, ctx->items, it_fw + it_tw)) != MSFM_OK) return st;
+    // both parts padded to whole 16-byte words for the pull kernel
+    const size_t pd_pad = (pd_bytes + 15) / 16 * 16, it_pad = (it_fw + it_tw + 15) / 16 * 16;
+    if ((st = ensure(ctx, ctx->pairdesc, pd_pad)) != MSFM_OK) return st;
+    if ((st = ensure(ctx, ctx->items, it_pad)) != MSFM_OK) return st;
     if ((st = ensure(ctx, ctx->knn, (size_t)plan.knn_rows() * kCsplit * sizeof(int4))) != MSFM_OK) return st;
     if ((st = ensure(ctx, ctx->cand_counts, plan.pairs.size() * 4)) != MSFM_OK) return st;
-    if ((st = ensure_pinned(ctx, pd_bytes + it_fw + it_tw + 64)) != MSFM_OK) return st;
+    if ((st = ensure_pinned(ctx, pd_pad + it_pad + 64)) != MSFM_OK) return st;
     if ((st = wait_for_uploads(ctx, plan.need_seq)) != MSFM_OK) return st;  // asynchronous uploads of the batch's images
     // the pinned staging area is reused per batch: the previous batch has been synchronised by its D2H
     char *hp = static_cast<char *>(ctx->h_pinned);
     memcpy(hp, plan.pairs.data(), fw_bytes);
     if (tw_bytes) memcpy(hp + fw_bytes, plan.twins.data(), tw_bytes);
     if (bt_bytes) memcpy(hp + fw_bytes + tw_bytes, plan.band_twins.data(), bt_bytes);
-    memcpy(hp + pd_bytes, plan.items.data(), it_fw);
-    if (!plan.twin_items.empty()) memcpy(hp + pd_bytes + it_fw, plan.twin_items.data(), plan.twin_items.size() * sizeof(WorkItem));
+    memcpy(hp + pd_pad, plan.items.data(), it_fw);
+    if (!plan.twin_items.empty()) memcpy(hp + pd_pad + it_fw, plan.twin_items.data(), plan.twin_items.size() * sizeof(WorkItem));
     if (!plan.band_items.empty())
-        memcpy(hp + pd_bytes + it_fw + plan.twin_items.size() * sizeof(WorkItem), plan.band_items.data(), plan.band_items.size() * sizeof(WorkItem));
-    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->pairdesc.ptr, hp, pd_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    MSFM_CUDA(ctx, cudaMemcpyAsync(ctx->items.ptr, hp + pd_bytes, it_fw + it_tw, cudaMemcpyHostToDevice, ctx->stream));
+        memcpy(hp + pd_pad + it_fw + plan.twin_items.size() * sizeof(WorkItem), plan.band_items.data(), plan.band_items.size() * sizeof(WorkItem));
+    {   // pulled by the SMs, not queued on the copy engine behind bulk uploads (see pull_plan_kernel)
+        const size_t n16 = (pd_pad + it_pad) / 16;
+        const int blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->num_sms, (n16 + 255) / 256));
+        msfm::pull_plan_kernel<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const uint4 *>(hp), static_cast<uint4 *>(ctx->pairdesc.ptr), pd_pad / 16,
+                                                               static_cast<uint4 *>(ctx->items.ptr), it_pad / 16);
+        MSFM_CUDA(ctx, cudaGetLastError());
+        ctx->timing.total_launches += 1;
+    }
     if (plan.has_empty) MSFM_CUDA(ctx, cudaMemsetAsync(ctx->knn.ptr, 0xFF, (size_t)plan.query_rows * kCsplit * sizeof(int4), ctx->stream));
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
     if (!plan.items.empty() && (st = launch_match_kernel(ctx, 0, plan.items.size())) != MSFM_OK) return st;
@@ -796,6 +804,26 @@ const char *msfm_status_string(msfm_status s) {
 }
 
 const char *msfm_last_error(const msfm_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+msfm_status msfm_host_alloc(size_t bytes, void **out) {
+    if (!out) return MSFM_ERR_INVALID_ARG;
+    *out = nullptr;
+    const cudaError_t e = cudaHostAlloc(out, bytes > 0 ? bytes : 1, cudaHostAllocPortable);
+    return e == cudaSuccess ? MSFM_OK : (e == cudaErrorMemoryAllocation ? MSFM_ERR_OUT_OF_MEMORY : MSFM_ERR_CUDA);
+}
+
+msfm_status msfm_host_free(void *ptr) {
+    if (!ptr) return MSFM_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? MSFM_OK : MSFM_ERR_CUDA;
+}
+
+msfm_status msfm_device_memory(int32_t device, int64_t *free_bytes, int64_t *total_bytes) {
+    size_t f = 0, t = 0;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMemGetInfo(&f, &t) != cudaSuccess) return MSFM_ERR_CUDA;
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    return MSFM_OK;
+}
 
 msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
     if (!cfg || !out) return MSFM_ERR_INVALID_ARG;

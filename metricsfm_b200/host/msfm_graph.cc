@@ -4,11 +4,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
 #include "../../include/msfm_graph.h"
 #include "../../include/msfm_match.h"
+#include "../../include/msfm_multi.h"
 #include "../../include/msfm_store.h"
 
 namespace {
@@ -88,35 +90,100 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
     }
     clk.lap("feature headers");
 
-    // ---- stage every needed image in HBM once (replaces the per-idx1 flann_build_index and the per-pair re-reads)
+    // ---- stage every needed image in HBM once (replaces the per-idx1 flann_build_index and the per-pair re-reads):
+    //      feature files are read into page-locked staging, one chunk while the previous chunk's host->device copies run
+    const int n_dev = opt->n_devices > 1 ? opt->n_devices : 1;
     msfm_ctx *ctx = nullptr;
+    msfm_multi *mm = nullptr;
     if (any_pair) {
-        msfm_config cfg;
-        memset(&cfg, 0, sizeof cfg);
-        cfg.device = opt->device;
-        cfg.max_images = num_imgs;
-        cfg.arena_rows = arena_rows > 0 ? arena_rows : 256;
-        cfg.keep_float = opt->rescore_band > 0.0f ? 1 : 0;
-        msfm_status st = msfm_create(&cfg, &ctx);
-        if (st != MSFM_OK) return fail(err, err_cap, -4, "msfm_create: %s", msfm_status_string(st));
+        // each row costs 132 B packed (+ 512 B when the float rows are retained for re-scoring)
+        const int64_t need = arena_rows * (132 + (opt->rescore_band > 0.0f ? 512 : 0));
+        int64_t free_b = 0, total_b = 0;
+        if (msfm_device_memory(opt->device, &free_b, &total_b) == MSFM_OK && need > free_b)
+            return fail(err, err_cap, -4, "the descriptor table of this run needs %.1f GB of HBM (%lld rows), device %d has %.1f GB free: "
+                                          "match the collection in several runs over subsets of match_graph_init (resume keeps what is done)",
+                        need / 1e9, (long long)arena_rows, opt->device, free_b / 1e9);
+        if (n_dev > 1) {
+            if (opt->rescore_band > 0.0f) return fail(err, err_cap, -1, "rescore_band (retained float rows) is single-GPU only");
+            msfm_multi_config mc;
+            memset(&mc, 0, sizeof mc);
+            mc.n_devices = n_dev;
+            mc.max_images = num_imgs;
+            mc.arena_rows = arena_rows > 0 ? arena_rows : 256;
+            msfm_status st = msfm_multi_create(&mc, &mm);
+            if (st != MSFM_OK) return fail(err, err_cap, -4, "msfm_multi_create: %s", msfm_status_string(st));
+            ctx = msfm_multi_context(mm, 0);  // geo-verification runs on the first device
+        } else {
+            msfm_config cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.device = opt->device;
+            cfg.max_images = num_imgs;
+            cfg.arena_rows = arena_rows > 0 ? arena_rows : 256;
+            cfg.keep_float = opt->rescore_band > 0.0f ? 1 : 0;
+            msfm_status st = msfm_create(&cfg, &ctx);
+            if (st != MSFM_OK) return fail(err, err_cap, -4, "msfm_create: %s", msfm_status_string(st));
+        }
     }
+    void *stage[2] = {nullptr, nullptr};
     auto bail = [&](int code, const std::string &msg) {
-        if (ctx) msfm_destroy(ctx);
+        if (mm) msfm_multi_destroy(mm);
+        else if (ctx) msfm_destroy(ctx);
+        msfm_host_free(stage[0]);
+        msfm_host_free(stage[1]);
         return fail(err, err_cap, code, "%s", msg.c_str());
     };
-    std::vector<char> staging;
-    for (int32_t i = 0; ctx && i < num_imgs; ++i) {
-        if (!imgs[i].needed) continue;
-        const msfm_feature_info &fi = imgs[i].info;
-        imgs[i].xy.resize((size_t)fi.num_pts * 2);
-        staging.resize((size_t)fi.desc_rows * 128 * fi.desc_elem_size + 16);
-        msfm_feature_path(fold, i, path, sizeof path);
-        if (msfm_feature_read(path, &fi, nullptr, nullptr, imgs[i].xy.data(), staging.data(), (int64_t)128 * fi.desc_elem_size) != 0)
-            return bail(-2, "feature file of image " + std::to_string(i) + " truncated");
-        msfm_status st = fi.desc_type == 0
-                             ? msfm_upload_u8(ctx, i, reinterpret_cast<const uint8_t *>(staging.data()), fi.desc_rows, 128)
-                             : msfm_upload_f32(ctx, i, reinterpret_cast<const float *>(staging.data()), fi.desc_rows, 128, opt->descriptor_scale);
-        if (st != MSFM_OK) return bail(-4, std::string("upload: ") + msfm_last_error(ctx));
+    auto sync_uploads = [&]() { return mm ? msfm_multi_sync(mm) : msfm_sync(ctx); };
+    if (ctx) {
+        const size_t kStageBytes = (size_t)256 << 20;
+        size_t largest = 0;
+        for (int32_t i = 0; i < num_imgs; ++i)
+            if (imgs[i].needed) largest = std::max(largest, (size_t)imgs[i].info.desc_rows * 128 * imgs[i].info.desc_elem_size);
+        const size_t cap = std::max(kStageBytes, largest + 16);
+        for (void *&p : stage)
+            if (msfm_host_alloc(cap, &p) != MSFM_OK) return bail(-4, "cannot allocate page-locked staging memory");
+        int which = 0;
+        int32_t i = 0;
+        while (i < num_imgs) {
+            // fill one staging buffer with as many consecutive needed images of one descriptor type as fit
+            char *base = static_cast<char *>(stage[which]);
+            size_t used = 0;
+            std::vector<int32_t> ids, nrows;
+            std::vector<const void *> ptrs;
+            int type = -1;
+            while (i < num_imgs) {
+                if (!imgs[i].needed) { ++i; continue; }
+                const msfm_feature_info &fi = imgs[i].info;
+                const size_t bytes = (size_t)fi.desc_rows * 128 * fi.desc_elem_size;
+                if (type >= 0 && (fi.desc_type != type || used + bytes > cap)) break;
+                type = fi.desc_type;
+                imgs[i].xy.resize((size_t)fi.num_pts * 2);
+                msfm_feature_path(fold, i, path, sizeof path);
+                if (msfm_feature_read(path, &fi, nullptr, nullptr, imgs[i].xy.data(), base + used, (int64_t)128 * fi.desc_elem_size) != 0)
+                    return bail(-2, "feature file of image " + std::to_string(i) + " truncated");
+                ids.push_back(i);
+                nrows.push_back(fi.desc_rows);
+                ptrs.push_back(base + used);
+                used += (bytes + 255) / 256 * 256;
+                ++i;
+            }
+            if (ids.empty()) break;
+            msfm_status st;
+            const int32_t n = (int32_t)ids.size();
+            if (type == 0)
+                st = mm ? msfm_multi_upload_u8(mm, n, ids.data(), reinterpret_cast<const uint8_t *const *>(ptrs.data()), nrows.data())
+                        : msfm_upload_u8_batch_async(ctx, n, ids.data(), reinterpret_cast<const uint8_t *const *>(ptrs.data()), nrows.data(), nullptr);
+            else
+                st = mm ? msfm_multi_upload_f32(mm, n, ids.data(), reinterpret_cast<const float *const *>(ptrs.data()), nrows.data(), opt->descriptor_scale)
+                        : msfm_upload_f32_batch_async(ctx, n, ids.data(), reinterpret_cast<const float *const *>(ptrs.data()), nrows.data(), opt->descriptor_scale);
+            if (st != MSFM_OK) return bail(-4, std::string("upload: ") + (mm ? msfm_multi_last_error(mm) : msfm_last_error(ctx)));
+            which ^= 1;
+            // the other buffer is filled next: its copies (queued one round ago) must have left it
+            if (sync_uploads() != MSFM_OK) return bail(-4, "upload synchronisation failed");
+        }
+        if (sync_uploads() != MSFM_OK) return bail(-4, "upload synchronisation failed");
+        msfm_host_free(stage[0]);
+        msfm_host_free(stage[1]);
+        stage[0] = stage[1] = nullptr;
     }
     clk.lap("create + read + upload");
 
@@ -165,8 +232,9 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
             res.matches = reinterpret_cast<int32_t(*)[2]>(mbuf.data());
             res.good = gbuf.data();
             res.match_capacity = capacity;
-            msfm_status st = msfm_match_pairs(ctx, pairs.data(), (int64_t)pairs.size(), &prm, &res);
-            if (st != MSFM_OK) return bail(-4, std::string("msfm_match_pairs: ") + msfm_last_error(ctx));
+            msfm_status st = mm ? msfm_multi_match_pairs(mm, pairs.data(), (int64_t)pairs.size(), &prm, &res)
+                                : msfm_match_pairs(ctx, pairs.data(), (int64_t)pairs.size(), &prm, &res);
+            if (st != MSFM_OK) return bail(-4, std::string("msfm_match_pairs: ") + (mm ? msfm_multi_last_error(mm) : msfm_last_error(ctx)));
         }
         clk.lap("msfm_match_pairs");
         // ---- GeoVerificationFundamental for the chunk on the GPU (fine_matching_graph.cc:137-153)
@@ -228,7 +296,8 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
         pair_base += (int64_t)pairs.size();
         clk.lap("verify seam + match files");
     }
-    if (ctx) msfm_destroy(ctx);
+    if (mm) msfm_multi_destroy(mm);
+    else if (ctx) msfm_destroy(ctx);
     clk.lap("msfm_destroy");
     if (msfm_graph_write(fold, num_imgs, graph.data()) != 0) return fail(err, err_cap, -2, "cannot write graph_matching.txt");
     return 0;

@@ -104,7 +104,7 @@ int main(int argc, char **argv) {
         const int capped = sm.ok() ? sm.GetSiftMatch(5, reinterpret_cast<int(*)[2]>(mb.data()), 3.2f, 0.8f, 0) : -1;
         printf("SiftMatchCapped %d\n", capped);
         for (int k = 0; k < capped; ++k) printf("%d %d\n", mb[2 * k], mb[2 * k + 1]);
-        const int gated = sm.ok() ? sm.GetSiftMatch(n1, reinterpret_cast<int(*)[2]>(mb.data()), 0.35f, 0.8f, 0) : -1;
+        const int gated = sm.ok() ? sm.GetSiftMatch(n1, reinterpret_cast<int(*)[2]>(mb.data()), 0.2f, 0.8f, 0) : -1;
         printf("SiftMatchGated %d\n", gated);
         for (int k = 0; k < gated; ++k) printf("%d %d\n", mb[2 * k], mb[2 * k + 1]);
     }

@@ -29,7 +29,8 @@ class FeatureInfo(C.Structure):
 class GraphOptions(C.Structure):
     _fields_ = [("device", C.c_int32), ("th_good", C.c_float), ("th_all", C.c_float), ("mutual", C.c_int32),
                 ("min_keypoints", C.c_int32), ("min_good", C.c_int32), ("descriptor_scale", C.c_float), ("rescore_band", C.c_float),
-                ("geo_verify", C.c_int32), ("geo_seed", C.c_uint32), ("max_batch_rows", C.c_int64)]
+                ("geo_verify", C.c_int32), ("geo_seed", C.c_uint32), ("max_batch_rows", C.c_int64), ("n_devices", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 VERIFY_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_float), C.c_int32,
@@ -211,13 +212,13 @@ def init_graph_read(fold: str):
 # ---------------------------------------------------------------------------------------------------- driver
 def build_match_graph(fold: str, offsets: np.ndarray, lst: np.ndarray, *, device=0, th_good=0.6, th_all=0.85, mutual=False,
                       min_keypoints=0, min_good=0, descriptor_scale=1.0, rescore_band=0.0, verify=None, geo_verify=False,
-                      geo_seed=0, max_batch_rows=0) -> None:
+                      geo_seed=0, max_batch_rows=0, n_devices=1) -> None:
     """FineMatchingGraph::BuildMatchGraph on the GPU matcher (see include/msfm_graph.h).  `verify(idx1, idx2, xy1, xy2,
     matches, good)` -> (accept, keep_indices) is the geo-verification seam."""
     offsets = np.ascontiguousarray(offsets, np.int64)
     lst = np.ascontiguousarray(lst, np.int32)
     opt = GraphOptions(device, th_good, th_all, int(bool(mutual)), min_keypoints, min_good, descriptor_scale, rescore_band,
-                       int(bool(geo_verify)), geo_seed, max_batch_rows)
+                       int(bool(geo_verify)), geo_seed, max_batch_rows, int(n_devices), 0)
     cb = None
     if verify is not None:
         def _trampoline(_user, idx1, idx2, xy1, n1, xy2, n2, m, g, n, keep, n_keep):
