@@ -92,6 +92,29 @@ int msfm_pairs_all(int32_t num_imgs, int64_t *offsets, int32_t *list);
  * (initial_matching_graph.cc:114-162).  Ties in distance are broken by the lower image index (the reference's
  * std::sort leaves them unspecified).  list capacity num_imgs*k. */
 int msfm_pairs_priori_xy(int32_t num_imgs, const double *xy, int32_t knn, int64_t *offsets, int32_t *list);
+
+/* "feature" (BoW retrieval) route, InitialMatchingGraph::match_graph_feature (initial_matching_graph.cc:164-294) on top of
+ * SimilarityGraph::SimilarityGraphInvFile (similarity_graph.cc:47-117).  Visual-word ids per image come from the
+ * reference's <idx>_words files (fbow, out of scope here) in adjacency form: words of image i are
+ * word_ids[word_offsets[i] .. word_offsets[i+1]), one per keypoint.
+ *
+ * msfm_similarity_invfile: inverted file over each image's "unique" words as math::keep_unique_vector leaves them
+ *   (utils/basic_funcs.h:126-151: the ids that occur exactly once in the image, without the image's smallest and largest
+ *   id), words listed by more than num_words/100 images dropped (:107-116), similarity[i][j] = number of shared words. */
+int msfm_similarity_invfile(int32_t num_imgs, const int64_t *word_offsets, const int32_t *word_ids, int32_t num_words,
+                            float *similarity /* [num_imgs * num_imgs] */);
+/* Hypotheses of image i: the th_num_match most similar images, similarity descending (ties: lower image index; the
+ * reference's std::sort leaves them unspecified).  th_num_match = 0 takes the reference's rule
+ * min(max(200, num_imgs/10), num_imgs-1), capped at 500 (:166-168).  list capacity num_imgs * th_num_match. */
+int msfm_pairs_similarity_topk(int32_t num_imgs, const float *similarity, int32_t th_num_match, int64_t *offsets,
+                               int32_t *list);
+/* Word-collision matches of two images (:239-251): pt_word_map of each image from math::keep_unique_idx_vector
+ * (utils/basic_funcs.cc:380-406: word -> keypoint index, for the word groups that FOLLOW a singleton group in sorted
+ * order; first element of the group, the lower keypoint index among equals), then (pt1, pt2) for every word in both maps,
+ * ascending word id.  Returns the number of matches (written up to `cap`), or a negative error.  The reference keeps a
+ * hypothesis when it has >= 30 such matches and F-RANSAC leaves > 20 inliers (msfm_geo_ransac on the GPU). */
+int msfm_word_matches(const int32_t *words1, int32_t n1, const int32_t *words2, int32_t n2, int32_t (*matches)[2],
+                      int32_t cap);
 /* init_match_graph.txt */
 int msfm_init_graph_write(const char *fold, int32_t num_imgs, int32_t id_last, const int64_t *offsets, const int32_t *list);
 int msfm_init_graph_read(const char *fold, int32_t *num_imgs, int32_t *id_last, int64_t *offsets, int32_t offsets_cap,

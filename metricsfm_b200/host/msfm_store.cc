@@ -284,6 +284,112 @@ int msfm_pairs_priori_xy(int32_t num_imgs, const double *xy, int32_t knn, int64_
     return MSFM_STORE_OK;
 }
 
+// ---- BoW retrieval route -------------------------------------------------------------------------------------------
+namespace {
+// math::keep_unique_vector (utils/basic_funcs.h:126-151) as it behaves: after sorting, a value is kept when its run has
+// length one, except that the first run is never "unique" (the loop starts by comparing data[0] with itself) and the last
+// run is never flushed.
+std::vector<int32_t> unique_words_of_image(const int32_t *w, int64_t n) {
+    std::vector<int32_t> data(w, w + n), kept;
+    if (data.empty()) return kept;
+    std::sort(data.begin(), data.end());
+    int32_t v = data[0];
+    bool is_unique = true;
+    for (int32_t x : data) {
+        if (x != v) {
+            if (is_unique) kept.push_back(v);
+            v = x;
+            is_unique = true;
+        } else {
+            is_unique = false;
+        }
+    }
+    return kept;
+}
+
+// math::keep_unique_idx_vector (utils/basic_funcs.cc:380-406) + the pt_word_map insertion of
+// initial_matching_graph.cc:194-201: (word, keypoint index) sorted by word; whenever the value changes and the run that
+// just ended was a singleton (and not the first run), the FIRST element of the new run is recorded.
+std::vector<std::pair<int32_t, int32_t>> pt_word_map(const int32_t *w, int32_t n) {
+    std::vector<std::pair<int32_t, int32_t>> d((size_t)n), out;  // (index, word)
+    for (int32_t i = 0; i < n; ++i) d[i] = {i, w[i]};
+    std::stable_sort(d.begin(), d.end(), [](const std::pair<int32_t, int32_t> &l, const std::pair<int32_t, int32_t> &r) { return l.second < r.second; });
+    if (d.empty()) return out;
+    bool is_unique = true;
+    int32_t v = d[0].second;
+    for (const auto &e : d) {
+        if (e.second != v) {
+            if (is_unique) out.push_back({e.second, e.first});  // map key = the new run's word, value = its first keypoint
+            v = e.second;
+            is_unique = true;
+        } else {
+            is_unique = false;
+        }
+    }
+    return out;  // ascending word id, each word at most once
+}
+}  // namespace
+
+int msfm_similarity_invfile(int32_t num_imgs, const int64_t *word_offsets, const int32_t *word_ids, int32_t num_words, float *similarity) {
+    if (num_imgs < 0 || num_words < 0 || !word_offsets || !similarity || (word_offsets[num_imgs] > 0 && !word_ids)) return MSFM_STORE_ERR_ARG;
+    std::vector<std::vector<int32_t>> inverted((size_t)num_words);
+    for (int32_t i = 0; i < num_imgs; ++i) {
+        const int64_t a = word_offsets[i], n = word_offsets[i + 1] - a;
+        if (n <= 0) continue;
+        for (int32_t id : unique_words_of_image(word_ids + a, n)) {
+            if (id < 0 || id >= num_words) return MSFM_STORE_ERR_ARG;
+            inverted[id].push_back(i);
+        }
+    }
+    const int32_t th_bin_size = num_words / 100;  // similarity_graph.cc:108
+    std::fill(similarity, similarity + (size_t)num_imgs * num_imgs, 0.0f);
+    for (const std::vector<int32_t> &bin : inverted) {
+        if (bin.empty() || (int64_t)bin.size() > th_bin_size) continue;
+        for (size_t m = 0; m + 1 < bin.size(); ++m)
+            for (size_t n = m + 1; n < bin.size(); ++n) {
+                similarity[(size_t)bin[m] * num_imgs + bin[n]] += 1.0f;
+                similarity[(size_t)bin[n] * num_imgs + bin[m]] += 1.0f;
+            }
+    }
+    return MSFM_STORE_OK;
+}
+
+int msfm_pairs_similarity_topk(int32_t num_imgs, const float *similarity, int32_t th_num_match, int64_t *offsets, int32_t *list) {
+    if (num_imgs < 0 || !offsets || (num_imgs > 0 && (!similarity || !list))) return MSFM_STORE_ERR_ARG;
+    if (th_num_match <= 0) {
+        th_num_match = std::min(std::max(200, num_imgs / 10), num_imgs - 1);  // initial_matching_graph.cc:166-168
+        if (th_num_match > 500) th_num_match = 500;
+    }
+    int64_t n = 0;
+    std::vector<std::pair<int32_t, float>> sim_sort;
+    for (int32_t i = 0; i < num_imgs; ++i) {
+        offsets[i] = n;
+        sim_sort.clear();
+        for (int32_t j = 0; j < num_imgs; ++j)
+            if (j != i && !(similarity[(size_t)i * num_imgs + j] < 0)) sim_sort.push_back({j, similarity[(size_t)i * num_imgs + j]});
+        std::stable_sort(sim_sort.begin(), sim_sort.end(), [](const std::pair<int32_t, float> &l, const std::pair<int32_t, float> &r) { return l.second > r.second; });
+        const int32_t t = std::min<int32_t>((int32_t)sim_sort.size(), std::max(th_num_match, 0));
+        for (int32_t j = 0; j < t; ++j) list[n++] = sim_sort[j].first;
+    }
+    offsets[num_imgs] = n;
+    return MSFM_STORE_OK;
+}
+
+int msfm_word_matches(const int32_t *words1, int32_t n1, const int32_t *words2, int32_t n2, int32_t (*matches)[2], int32_t cap) {
+    if (n1 < 0 || n2 < 0 || (n1 > 0 && !words1) || (n2 > 0 && !words2) || cap < 0 || (cap > 0 && !matches)) return MSFM_STORE_ERR_ARG;
+    const auto m1 = pt_word_map(words1, n1), m2 = pt_word_map(words2, n2);
+    int32_t n = 0;
+    size_t b = 0;
+    for (const auto &e : m1) {  // both ascending by word: a merge instead of the reference's std::map lookups
+        while (b < m2.size() && m2[b].first < e.first) ++b;
+        if (b < m2.size() && m2[b].first == e.first) {
+            if (n < cap) { matches[n][0] = e.second; matches[n][1] = m2[b].second; }
+            ++n;
+        }
+    }
+    return n;
+}
+
 // WriteOutInitMatchGraph, initial_matching_graph.cc:324-344.
 int msfm_init_graph_write(const char *fold, int32_t num_imgs, int32_t id_last, const int64_t *offsets, const int32_t *list) {
     if (!fold || num_imgs < 0 || !offsets) return MSFM_STORE_ERR_ARG;

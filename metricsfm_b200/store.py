@@ -14,6 +14,7 @@ STORE_SYMBOLS = [
     "msfm_feature_path", "msfm_feature_stat", "msfm_feature_read", "msfm_feature_write", "msfm_match_path", "msfm_match_append",
     "msfm_match_read", "msfm_match_index_missing", "msfm_match_index_append", "msfm_graph_write", "msfm_graph_read",
     "msfm_graph_recover", "msfm_pairs_all", "msfm_pairs_priori_xy", "msfm_init_graph_write", "msfm_init_graph_read",
+    "msfm_similarity_invfile", "msfm_pairs_similarity_topk", "msfm_word_matches",
 ]
 GRAPH_SYMBOLS = ["msfm_build_match_graph"]
 ERR_CAPACITY = -4
@@ -188,6 +189,48 @@ def pairs_priori_xy(xy: np.ndarray, knn: int = 50):
     _chk(lib().msfm_pairs_priori_xy(n, xy.ctypes.data_as(C.c_void_p), knn, offs.ctypes.data_as(C.c_void_p), lst.ctypes.data_as(C.c_void_p)),
          "msfm_pairs_priori_xy")
     return offs, lst[:offs[-1]]
+
+
+def _words_csr(words_per_image):
+    offs = np.zeros((len(words_per_image) + 1,), np.int64)
+    for i, w in enumerate(words_per_image):
+        offs[i + 1] = offs[i] + len(w)
+    flat = np.concatenate([np.asarray(w, np.int32).reshape(-1) for w in words_per_image]) if len(words_per_image) and offs[-1] else np.zeros((0,), np.int32)
+    return offs, np.ascontiguousarray(flat, np.int32)
+
+
+def similarity_invfile(words_per_image, num_words: int) -> np.ndarray:
+    """SimilarityGraph::SimilarityGraphInvFile (similarity_graph.cc:47-117): [n, n] float32 counts of shared words."""
+    offs, flat = _words_csr(words_per_image)
+    n = len(words_per_image)
+    sim = np.zeros((n, n), np.float32)
+    _chk(lib().msfm_similarity_invfile(n, offs.ctypes.data_as(C.c_void_p), flat.ctypes.data_as(C.c_void_p), int(num_words),
+                                       sim.ctypes.data_as(C.c_void_p)), "msfm_similarity_invfile")
+    return sim
+
+
+def pairs_similarity_topk(similarity: np.ndarray, th_num_match: int = 0):
+    """Hypotheses of InitialMatchingGraph::match_graph_feature (initial_matching_graph.cc:166-168, 212-231)."""
+    sim = np.ascontiguousarray(similarity, np.float32)
+    n = sim.shape[0]
+    k = th_num_match if th_num_match > 0 else min(min(max(200, n // 10), n - 1), 500)
+    offs = np.zeros((n + 1,), np.int64)
+    lst = np.empty((max(n * max(k, 0), 1),), np.int32)
+    _chk(lib().msfm_pairs_similarity_topk(n, sim.ctypes.data_as(C.c_void_p), int(th_num_match), offs.ctypes.data_as(C.c_void_p),
+                                          lst.ctypes.data_as(C.c_void_p)), "msfm_pairs_similarity_topk")
+    return offs, lst[:offs[-1]]
+
+
+def word_matches(words1, words2) -> np.ndarray:
+    """Word-collision matches (pt1, pt2) of two images (initial_matching_graph.cc:239-251)."""
+    w1 = np.ascontiguousarray(words1, np.int32).reshape(-1)
+    w2 = np.ascontiguousarray(words2, np.int32).reshape(-1)
+    cap = max(min(len(w1), len(w2)), 1)
+    out = np.empty((cap, 2), np.int32)
+    n = lib().msfm_word_matches(w1.ctypes.data_as(C.c_void_p), len(w1), w2.ctypes.data_as(C.c_void_p), len(w2), out.ctypes.data_as(C.c_void_p), cap)
+    if n < 0:
+        raise StoreError(f"msfm_word_matches failed with status {n}")
+    return out[:n].copy()
 
 
 def init_graph_write(fold: str, offsets: np.ndarray, lst: np.ndarray, id_last: int) -> None:

@@ -147,3 +147,86 @@ def build_match_graph_files(fold: str, adj, match_fn, *, min_good: int = 0) -> N
             f.write(f"{idx1}\n")
     with open(join(fold, "graph_matching.txt"), "wb") as f:
         f.write(graph_text(graph))
+
+
+# ---------------------------------------------------------------------------------------------------- BoW retrieval route
+def keep_unique_vector(data):
+    """math::keep_unique_vector, SfM/src/utils/basic_funcs.h:126-151, line by line (including what its loop really does:
+    the first run is never flagged unique, the last run is never flushed)."""
+    data = sorted(int(x) for x in data)
+    out = []
+    if not data:
+        return out
+    v, is_unique = data[0], True
+    for x in data:
+        if x != v:
+            if is_unique:
+                out.append(v)
+            v, is_unique = x, True
+        else:
+            is_unique = False
+    return out
+
+
+def keep_unique_idx_vector(data):
+    """math::keep_unique_idx_vector, SfM/src/utils/basic_funcs.cc:380-406 (stable sort where the reference's std::sort
+    leaves the order of equal words unspecified)."""
+    d = sorted(((i, int(w)) for i, w in enumerate(data)), key=lambda t: t[1])
+    out = []
+    if not d:
+        return out
+    is_unique, v = True, d[0][1]
+    for i, w in d:
+        if w != v:
+            if is_unique:
+                out.append(i)
+            v, is_unique = w, True
+        else:
+            is_unique = False
+    return out
+
+
+def similarity_invfile(words_per_image, num_words):
+    """SimilarityGraph::SimilarityGraphInvFile + GenerateInvertedFile, SfM/src/graph/similarity_graph.cc:47-117."""
+    import numpy as np
+    n = len(words_per_image)
+    inverted = [[] for _ in range(num_words)]
+    for i, w in enumerate(words_per_image):
+        if len(w):
+            for wid in keep_unique_vector(w):
+                inverted[wid].append(i)
+    th_bin_size = num_words // 100
+    sim = np.zeros((n, n), np.float32)
+    for b in inverted:
+        if b and len(b) > th_bin_size:
+            continue
+        for m in range(len(b) - 1):
+            for k in range(m + 1, len(b)):
+                sim[b[m], b[k]] += 1
+                sim[b[k], b[m]] += 1
+    return sim
+
+
+def pairs_similarity_topk(sim, th_num_match=0):
+    """initial_matching_graph.cc:166-168 and :212-231 (ties: lower index first)."""
+    n = sim.shape[0]
+    if th_num_match <= 0:
+        th_num_match = min(min(max(200, n // 10), n - 1), 500)
+    out = []
+    for i in range(n):
+        cand = [(j, float(sim[i, j])) for j in range(n) if j != i and not sim[i, j] < 0]
+        cand.sort(key=lambda t: -t[1])
+        out.append([j for j, _ in cand[:th_num_match]])
+    return out
+
+
+def word_matches(words1, words2):
+    """initial_matching_graph.cc:190-201 (pt_word_map) and :239-251 (collisions, ascending word id like std::map)."""
+    def pt_word_map(w):
+        m = {}
+        for idx in keep_unique_idx_vector(w):
+            m.setdefault(int(w[idx]), idx)      # std::map::insert keeps the first entry of a key
+        return m
+    m1, m2 = pt_word_map(words1), pt_word_map(words2)
+    return [(m1[w], m2[w]) for w in sorted(m1) if w in m2]
+

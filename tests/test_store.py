@@ -138,3 +138,41 @@ def test_product_tree_does_not_touch_the_store_oracle():
         for f in files:
             if f.endswith((".py", ".cc", ".cu", ".cuh", ".h")):
                 assert "store_oracle" not in open(os.path.join(dirpath, f), errors="ignore").read(), f
+
+
+def test_bow_retrieval_route_matches_restatement():
+    """InitialMatchingGraph::match_graph_feature's candidate generation (inverted-file similarity -> top-k hypotheses ->
+    word-collision matches) against the line-by-line restatement in oracle/store_oracle.py, including the quirks of the
+    reference's keep_unique helpers."""
+    from oracle import store_oracle as so
+    rng = np.random.default_rng(5)
+    num_words, n = 3000, 40
+    shared = rng.integers(0, num_words, size=600)
+    words = []
+    for i in range(n):
+        own = rng.integers(0, num_words, size=rng.integers(300, 900))
+        take = shared[rng.random(len(shared)) < (0.5 if i % 3 == 0 else 0.1)]
+        w = np.concatenate([own, take]).astype(np.int32)
+        rng.shuffle(w)
+        words.append(w)
+    words[7] = np.zeros((0,), np.int32)                      # an image without words
+    words[8] = np.array([5, 5, 5, 9], np.int32)               # duplicates only + the largest id: nothing survives
+    sim = store.similarity_invfile(words, num_words)
+    np.testing.assert_array_equal(sim, so.similarity_invfile(words, num_words))
+    assert sim.sum() > 0 and np.array_equal(sim, sim.T) and sim[7].sum() == 0 and sim[8].sum() == 0
+    for k in (0, 5):
+        offs, lst = store.pairs_similarity_topk(sim, k)
+        exp = so.pairs_similarity_topk(sim, k)
+        for i in range(n):
+            assert list(lst[offs[i]:offs[i + 1]]) == exp[i]
+    # hand-checked quirk: ids sorted = [1, 2, 2, 3, 4, 9] -> keep_unique_vector keeps 3 and 4 (1 is the first run, 9 the last)
+    assert so.keep_unique_vector([2, 9, 1, 4, 2, 3]) == [3, 4]
+    tot = 0
+    for a, b in [(0, 3), (3, 6), (1, 2), (7, 0), (8, 0), (9, 12)]:
+        got = store.word_matches(words[a], words[b])
+        exp = np.array(so.word_matches(words[a], words[b]), np.int32).reshape(-1, 2)
+        np.testing.assert_array_equal(got, exp)
+        for p1, p2 in got:
+            assert words[a][p1] == words[b][p2]
+        tot += len(got)
+    assert tot > 30
