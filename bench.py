@@ -403,18 +403,15 @@ def run_native_ranks(args):
                 external_norm_arena=norm_arena.data_ptr())
     lib_stream = torch.cuda.ExternalStream(m.cuda_stream(), device=dev)
     up_stream = torch.cuda.ExternalStream(m.upload_stream(), device=dev)
-    side = torch.cuda.Stream(device=dev)
 
     def stage_table(use_f32: bool):
-        """Queue the staging of the whole table, group by group: H2D + pack of this rank's slice on the upload stream, the
-        other ranks' slices reserved, one in-place all-gather per group on a side stream.  Nothing waits on the host.
-        Returns the per-group events matching has to wait for, and the H2D bytes."""
+        """Queue the staging of the whole table, group by group: H2D + pack of this rank's slice on the library's upload
+        streams, the other ranks' slices reserved.  Nothing waits on the host.  Returns, per group, what replicate_group()
+        needs (the event after the group's uploads and its arena range), and the H2D bytes."""
         m.release_all()
-        events, h2d = [], 0
+        groups_meta, h2d = [], 0
         base_row = 0
         for g in range(n_groups):
-            part = max(len(slices[g][r]) for r in range(world)) * rows_padded
-            equal = all(len(slices[g][r]) * rows_padded == part for r in range(world))
             for r in range(world):        # identical allocation order on every rank => identical arena offsets
                 ids = slices[g][r]
                 if not ids:
@@ -429,32 +426,39 @@ def run_native_ranks(args):
                 else:
                     m.reserve_batch(ids, [rows] * len(ids), wait=False)
             n_rows_g = sum(len(slices[g][r]) for r in range(world)) * rows_padded
+            ev_up = None
             if world > 1:
                 ev_up = torch.cuda.Event()
                 ev_up.record(up_stream)
-                with torch.cuda.stream(side):
-                    side.wait_event(ev_up)
-                    lo = base_row + sum(len(slices[g][r]) for r in range(rank)) * rows_padded
-                    hi = lo + len(slices[g][rank]) * rows_padded
-                    if equal:
-                        w1 = dist.all_gather_into_tensor(desc_arena[base_row:base_row + n_rows_g], desc_arena[lo:hi], async_op=True)
-                        w2 = dist.all_gather_into_tensor(norm_arena[base_row:base_row + n_rows_g], norm_arena[lo:hi], async_op=True)
-                        w1.wait(); w2.wait()
-                    else:                  # ragged slices: one broadcast per owner
-                        off = base_row
-                        for r in range(world):
-                            nr = len(slices[g][r]) * rows_padded
-                            if nr:
-                                dist.broadcast(desc_arena[off:off + nr], src=r)
-                                dist.broadcast(norm_arena[off:off + nr], src=r)
-                            off += nr
-                    ev = torch.cuda.Event()
-                    ev.record(side)
-                events.append(ev)
-            else:
-                events.append(None)
+            groups_meta.append((ev_up, base_row, n_rows_g))
             base_row += n_rows_g
-        return events, h2d
+        return groups_meta, h2d
+
+    def replicate_group(g: int, meta):
+        """One in-place all-gather of group g (descriptor rows + side words) over NCCL, queued on the library's MAIN stream:
+        it runs between two matching launches, never next to one — the matching kernel is persistent (one CTA per SM,
+        statically partitioned work), and a collective kernel that sits on a few SMs waiting for a peer that is still
+        matching would stall the CTAs that cannot be placed.  The next matching launch is ordered behind it by the stream."""
+        if world == 1:
+            return
+        ev_up, base_row, n_rows_g = meta
+        part = max(len(slices[g][r]) for r in range(world)) * rows_padded
+        equal = all(len(slices[g][r]) * rows_padded == part for r in range(world))
+        with torch.cuda.stream(lib_stream):
+            lib_stream.wait_event(ev_up)
+            lo = base_row + sum(len(slices[g][r]) for r in range(rank)) * rows_padded
+            hi = lo + len(slices[g][rank]) * rows_padded
+            if equal:
+                dist.all_gather_into_tensor(desc_arena[base_row:base_row + n_rows_g], desc_arena[lo:hi])
+                dist.all_gather_into_tensor(norm_arena[base_row:base_row + n_rows_g], norm_arena[lo:hi])
+            else:                  # ragged slices: one broadcast per owner
+                off = base_row
+                for r in range(world):
+                    nr = len(slices[g][r]) * rows_padded
+                    if nr:
+                        dist.broadcast(desc_arena[off:off + nr], src=r)
+                        dist.broadcast(norm_arena[off:off + nr], src=r)
+                    off += nr
 
     kw = dict(ratio_good=RATIO_GOOD, mutual=bool(args.mutual), min_keypoints=20, orientation=0)
     flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -465,10 +469,9 @@ def run_native_ranks(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value"): table staged once, untimed
-    events, _ = stage_table(False)
-    for ev in events:
-        if ev is not None:
-            m.wait_event(ev.cuda_event)
+    metas, _ = stage_table(False)
+    for g, meta in enumerate(metas):
+        replicate_group(g, meta)
     m.sync()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank, enabled=(rank == 0))
@@ -516,13 +519,16 @@ def run_native_ranks(args):
                       good=torch.empty((cap,), dtype=torch.uint8).pin_memory().numpy())
     list_off = np.zeros((len(my_pairs) + 1,), np.int64)   # absolute offsets of this rank's lists in `out`
 
+    trace = os.environ.get("BENCH_TRACE") is not None
+
     def e2e_step(use_f32: bool):
-        events, h2d = stage_table(use_f32)
+        t_begin = time.perf_counter()
+        metas, h2d = stage_table(use_f32)
+        stamps = [time.perf_counter() - t_begin]
         done, d2h = 0, 0
         for g in range(n_groups):
             a, b = sub_bounds[g], sub_bounds[g + 1]
-            if events[g] is not None:
-                m.wait_event(events[g].cuda_event)       # device-side: later launches wait for group g's all-gather
+            replicate_group(g, metas[g])                 # queued on the main stream: runs before sub-list g's launches
             if b == a:
                 continue
             sub = MatchResult(offsets=out.offsets[a + g:b + g + 1], ok=out.ok[a:b], matches=out.matches[done:], good=out.good[done:])
@@ -530,6 +536,10 @@ def run_native_ranks(args):
             list_off[a:b + 1] = done + sub.offsets[:b - a + 1]
             done += len(res.matches)
             d2h += m.timing()["d2h_bytes"]
+            stamps.append(time.perf_counter() - t_begin)
+        if trace:
+            print(f"[trace rank {rank}] f32={use_f32} staging enqueued at {1e3 * stamps[0]:.2f} ms, sub-lists done at "
+                  + ", ".join(f"{1e3 * t:.2f}" for t in stamps[1:]) + " ms", file=sys.stderr, flush=True)
         return h2d + my_pairs.nbytes, d2h, done
 
     if not args.no_e2e:
@@ -547,7 +557,7 @@ def run_native_ranks(args):
             dt = float(tt.item())
         e2e = {"value": (len(pairs) * e2e_steps) / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "steps": e2e_steps, "host_rows": "float32 (CV_32FC1, the reference's container)" if e2e_f32 else "uint8",
-               "pipeline": f"{n_groups} staging groups on the upload stream" + (" + one NCCL all-gather per group on a side stream" if world > 1 else "")
+               "pipeline": f"{n_groups} staging groups on the upload streams" + (" + one NCCL all-gather per group between matching launches" if world > 1 else "")
                            + "; the pairs of groups <= g are matched while group g+1 is copied",
                "timer": "host wall clock between barriers + cuda synchronize, max over ranks", "matches_per_step_this_rank": int(n_e2e),
                "match_lists": "page-locked host buffers of the rank that matched the pair"}

@@ -84,8 +84,8 @@ struct DeviceSlot {
     int device = 0;
     msfm_ctx *ctx = nullptr;
     nccl_comm_t comm = nullptr;
-    cudaStream_t nccl_stream = nullptr, upload_stream = nullptr;
-    cudaEvent_t ev_up = nullptr;
+    cudaStream_t main_stream = nullptr, upload_stream = nullptr;
+    std::vector<cudaEvent_t> event_pool;
     uint8_t *desc = nullptr;
     int32_t *norms = nullptr;
     std::vector<Block> blocks;
@@ -124,9 +124,21 @@ int sink_fn(void *user, int64_t first, int64_t n, int32_t (**m)[2], uint8_t **g)
 
 }  // namespace
 
+// A staged group whose rows sit on their owner devices only: the broadcast to the other devices is issued lazily, between
+// two matching launches (see flush_pending).
+struct ArenaRange { int64_t off, rows; int owner; };
+struct PendingGroup {
+    uint64_t serial;
+    std::vector<ArenaRange> ranges;
+    std::vector<cudaEvent_t> uploaded;  // per device: recorded on its upload stream after the group's uploads / reserves
+};
+
 struct msfm_multi {
     std::vector<DeviceSlot> dev;
     std::vector<int32_t> rows;  // per image id; -1 = not staged
+    std::vector<uint64_t> group_of;  // per image id: serial of the staging group that brought it
+    std::vector<PendingGroup> pending;
+    uint64_t next_serial = 1;
     int32_t max_images = 0;
     std::string err;
     std::mutex mu;
@@ -180,6 +192,7 @@ msfm_status stage_group(msfm_multi *mm, int32_t n, const int32_t *ids, const int
         else runs.back().b = i + 1;
     }
     // identical allocation order on every device => identical arena offsets
+    std::vector<cudaEvent_t> uploaded;
     for (int d = 0; d < W; ++d) {
         DeviceSlot &ds = mm->dev[d];
         for (const Run &r : runs) {
@@ -188,43 +201,65 @@ msfm_status stage_group(msfm_multi *mm, int32_t n, const int32_t *ids, const int
         }
         if (W > 1) {
             MM_CUDA(mm, cudaSetDevice(ds.device));
-            MM_CUDA(mm, cudaEventRecord(ds.ev_up, ds.upload_stream));
-            MM_CUDA(mm, cudaStreamWaitEvent(ds.nccl_stream, ds.ev_up, 0));  // packed rows / pad rows / tensor maps first
+            cudaEvent_t ev = nullptr;
+            if (!ds.event_pool.empty()) { ev = ds.event_pool.back(); ds.event_pool.pop_back(); }
+            else MM_CUDA(mm, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            MM_CUDA(mm, cudaEventRecord(ev, ds.upload_stream));  // packed rows / pad rows / tensor maps of this group
+            uploaded.push_back(ev);
         }
     }
+    const uint64_t serial = mm->next_serial++;
     if (W > 1) {
-        // one broadcast per owner block and arena (adjacent images are coalesced into one range)
-        struct Range { int64_t off, rows; int owner; };
-        std::vector<Range> ranges;
+        // the broadcast itself is issued lazily (flush_pending): one range per owner block and arena, adjacent images coalesced
+        PendingGroup pg;
+        pg.serial = serial;
+        pg.uploaded = uploaded;
         for (const Run &r : runs)
             for (int32_t i = r.a; i < r.b; ++i) {
                 int32_t rr = 0;
                 int64_t off = 0;
                 MM_CTX(mm, mm->dev[0], msfm_image_info(mm->dev[0].ctx, ids[i], &rr, &off));
                 const int64_t padded = ((int64_t)std::max(rr, 1) + 255) / 256 * 256;
-                if (!ranges.empty() && ranges.back().owner == r.owner && ranges.back().off + ranges.back().rows == off) ranges.back().rows += padded;
-                else ranges.push_back({off, padded, r.owner});
+                if (!pg.ranges.empty() && pg.ranges.back().owner == r.owner && pg.ranges.back().off + pg.ranges.back().rows == off) pg.ranges.back().rows += padded;
+                else pg.ranges.push_back({off, padded, r.owner});
             }
+        mm->pending.push_back(pg);
+    }
+    for (int32_t i = 0; i < n; ++i) {
+        mm->rows[ids[i]] = rows[i];
+        mm->group_of[ids[i]] = serial;
+    }
+    return MSFM_OK;
+}
+
+// Replicate the staged groups up to `serial` on every device: grouped ncclBroadcast per owner block (descriptor rows and
+// side words), queued on each device's MAIN stream behind the group's uploads.  Running the collective on the stream the
+// matching launches use keeps it BETWEEN launches: the matching kernel is persistent (one CTA per SM, statically
+// partitioned work), and a collective kernel parked on a few SMs while a peer device is still matching would stall the
+// CTAs that cannot be placed next to it.
+msfm_status flush_pending(msfm_multi *mm, uint64_t serial) {
+    const int W = (int)mm->dev.size();
+    size_t done = 0;
+    for (PendingGroup &pg : mm->pending) {
+        if (pg.serial > serial) break;
+        for (int d = 0; d < W; ++d) {
+            MM_CUDA(mm, cudaSetDevice(mm->dev[d].device));
+            MM_CUDA(mm, cudaStreamWaitEvent(mm->dev[d].main_stream, pg.uploaded[d], 0));
+            mm->dev[d].event_pool.push_back(pg.uploaded[d]);
+        }
         NcclApi &nc = nccl();
         MM_NCCL(mm, nc.GroupStart());
-        for (const Range &rg : ranges)
+        for (const ArenaRange &rg : pg.ranges)
             for (int d = 0; d < W; ++d) {
                 DeviceSlot &ds = mm->dev[d];
-                MM_NCCL(mm, nc.Broadcast(ds.desc + rg.off * MSFM_DIM, ds.desc + rg.off * MSFM_DIM, (size_t)rg.rows * MSFM_DIM, kNcclUint8, rg.owner, ds.comm, ds.nccl_stream));
-                MM_NCCL(mm, nc.Broadcast(ds.norms + rg.off, ds.norms + rg.off, (size_t)rg.rows * 4, kNcclUint8, rg.owner, ds.comm, ds.nccl_stream));
+                MM_NCCL(mm, nc.Broadcast(ds.desc + rg.off * MSFM_DIM, ds.desc + rg.off * MSFM_DIM, (size_t)rg.rows * MSFM_DIM, kNcclUint8, rg.owner, ds.comm, ds.main_stream));
+                MM_NCCL(mm, nc.Broadcast(ds.norms + rg.off, ds.norms + rg.off, (size_t)rg.rows * 4, kNcclUint8, rg.owner, ds.comm, ds.main_stream));
             }
         MM_NCCL(mm, nc.GroupEnd());
-        for (const Range &rg : ranges) mm->timing.bytes_broadcast += rg.rows * (MSFM_DIM + 4);
-        // the received images become usable when the collective has written them
-        std::vector<int32_t> foreign;
-        for (int d = 0; d < W; ++d) {
-            foreign.clear();
-            for (int32_t i = 0; i < n; ++i)
-                if (owner[i] != d) foreign.push_back(ids[i]);
-            MM_CTX(mm, mm->dev[d], msfm_internal_mark_on_stream(mm->dev[d].ctx, (int32_t)foreign.size(), foreign.data(), mm->dev[d].nccl_stream));
-        }
+        for (const ArenaRange &rg : pg.ranges) mm->timing.bytes_broadcast += rg.rows * (MSFM_DIM + 4);
+        ++done;
     }
-    for (int32_t i = 0; i < n; ++i) mm->rows[ids[i]] = rows[i];
+    mm->pending.erase(mm->pending.begin(), mm->pending.begin() + done);
     return MSFM_OK;
 }
 
@@ -246,6 +281,7 @@ msfm_status msfm_multi_create(const msfm_multi_config *cfg, msfm_multi **out) {
     if (!mm) return MSFM_ERR_OUT_OF_MEMORY;
     mm->max_images = cfg->max_images;
     mm->rows.assign((size_t)cfg->max_images, -1);
+    mm->group_of.assign((size_t)cfg->max_images, 0);
     mm->dev.resize((size_t)cfg->n_devices);
     auto bail = [&](msfm_status st) {
         msfm_multi_destroy(mm);
@@ -263,15 +299,14 @@ msfm_status msfm_multi_create(const msfm_multi_config *cfg, msfm_multi **out) {
         c.arena_rows = cfg->arena_rows;
         const msfm_status st = msfm_create(&c, &ds.ctx);
         if (st != MSFM_OK) return bail(st);
-        void *dp = nullptr, *np = nullptr, *us = nullptr;
+        void *dp = nullptr, *np = nullptr, *us = nullptr, *ms = nullptr;
         msfm_table_ptrs(ds.ctx, &dp, &np, nullptr, nullptr);
         msfm_get_upload_stream(ds.ctx, &us);
+        msfm_get_stream(ds.ctx, &ms);
         ds.desc = static_cast<uint8_t *>(dp);
         ds.norms = static_cast<int32_t *>(np);
         ds.upload_stream = static_cast<cudaStream_t>(us);
-        if (cudaSetDevice(ds.device) != cudaSuccess || cudaStreamCreateWithFlags(&ds.nccl_stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ds.ev_up, cudaEventDisableTiming) != cudaSuccess)
-            return bail(MSFM_ERR_CUDA);
+        ds.main_stream = static_cast<cudaStream_t>(ms);
     }
     if (cfg->n_devices > 1) {
         std::vector<nccl_comm_t> comms((size_t)cfg->n_devices, nullptr);
@@ -291,14 +326,15 @@ msfm_status msfm_multi_destroy(msfm_multi *mm) {
     if (!mm) return MSFM_OK;
     for (DeviceSlot &ds : mm->dev) {
         cudaSetDevice(ds.device);
-        if (ds.nccl_stream) cudaStreamSynchronize(ds.nccl_stream);
+        if (ds.main_stream) cudaStreamSynchronize(ds.main_stream);
     }
+    for (PendingGroup &pg : mm->pending)
+        for (size_t d = 0; d < pg.uploaded.size() && d < mm->dev.size(); ++d) mm->dev[d].event_pool.push_back(pg.uploaded[d]);
     for (DeviceSlot &ds : mm->dev) {
         cudaSetDevice(ds.device);
         if (ds.comm) nccl().CommDestroy(ds.comm);
+        for (cudaEvent_t e : ds.event_pool) cudaEventDestroy(e);
         if (ds.ctx) msfm_destroy(ds.ctx);
-        if (ds.nccl_stream) cudaStreamDestroy(ds.nccl_stream);
-        if (ds.ev_up) cudaEventDestroy(ds.ev_up);
         for (Block &b : ds.blocks) {
             cudaFreeHost(b.m);
             cudaFreeHost(b.g);
@@ -334,22 +370,18 @@ msfm_status msfm_multi_upload_f32(msfm_multi *mm, int32_t n, const int32_t *imag
 msfm_status msfm_multi_sync(msfm_multi *mm) {
     if (!mm) return MSFM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(mm->mu);
-    for (DeviceSlot &ds : mm->dev) {
-        MM_CUDA(mm, cudaSetDevice(ds.device));
-        MM_CTX(mm, ds, msfm_sync(ds.ctx));  // the upload stream first: the collective is queued behind it
-        MM_CUDA(mm, cudaStreamSynchronize(ds.nccl_stream));
-    }
+    const msfm_status st = flush_pending(mm, ~0ull);  // every staged group is replicated
+    if (st != MSFM_OK) return st;
+    for (DeviceSlot &ds : mm->dev) MM_CTX(mm, ds, msfm_sync(ds.ctx));  // upload streams and main streams (the collectives)
     return MSFM_OK;
 }
 
 msfm_status msfm_multi_release_all(msfm_multi *mm) {
     if (!mm) return MSFM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(mm->mu);
-    for (DeviceSlot &ds : mm->dev) {
-        MM_CUDA(mm, cudaSetDevice(ds.device));
-        MM_CTX(mm, ds, msfm_sync(ds.ctx));
-        MM_CUDA(mm, cudaStreamSynchronize(ds.nccl_stream));
-    }
+    const msfm_status st = flush_pending(mm, ~0ull);  // keeps the devices' collective sequences in step
+    if (st != MSFM_OK) return st;
+    for (DeviceSlot &ds : mm->dev) MM_CTX(mm, ds, msfm_sync(ds.ctx));
     for (DeviceSlot &ds : mm->dev) MM_CTX(mm, ds, msfm_release_all(ds.ctx));
     std::fill(mm->rows.begin(), mm->rows.end(), -1);
     mm->timing.bytes_broadcast = 0;
@@ -366,6 +398,13 @@ msfm_status msfm_multi_match_pairs(msfm_multi *mm, const msfm_pair *pairs, int64
     for (int64_t i = 0; i < n_pairs; ++i)
         for (int32_t id : {pairs[i].ref, pairs[i].query})
             if (id < 0 || id >= mm->max_images || mm->rows[id] < 0) return mfail(mm, MSFM_ERR_NOT_FOUND, "pair %lld names image %d, which is not staged", (long long)i, id);
+    // replicate what the pair list needs: the staged groups up to the newest one it touches (later groups stay in flight)
+    uint64_t need = 0;
+    for (int64_t i = 0; i < n_pairs; ++i) need = std::max(need, std::max(mm->group_of[pairs[i].ref], mm->group_of[pairs[i].query]));
+    if (W > 1) {
+        const msfm_status fst = flush_pending(mm, need);
+        if (fst != MSFM_OK) return fst;
+    }
     // rows of unstaged images are irrelevant to the scheduler (no pair names them)
     std::vector<int32_t> rows(mm->rows);
     for (int32_t &r : rows) r = std::max(r, 0);
