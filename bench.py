@@ -513,7 +513,7 @@ def run_native_ranks(args):
 
     # ---- end to end through the public API from host buffers, staging pipelined against matching
     e2e, sampled_local = None, []
-    cap = int(min(len(my_pairs) * min(rows, 4096), 1 << 28)) + 1024
+    cap = int(min(len(my_pairs) * min(rows, 4096), 1 << 29)) + 1024
     out = MatchResult(offsets=np.zeros((len(my_pairs) + n_groups + 1,), np.int64), ok=np.zeros((len(my_pairs) + 1,), np.int32),
                       matches=torch.empty((cap, 2), dtype=torch.int32).pin_memory().numpy(),
                       good=torch.empty((cap,), dtype=torch.uint8).pin_memory().numpy())

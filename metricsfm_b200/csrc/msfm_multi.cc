@@ -454,15 +454,18 @@ msfm_status msfm_multi_match_pairs(msfm_multi *mm, const msfm_pair *pairs, int64
     auto scatter_device = [&](DeviceSlot &ds) {
         size_t k = 0;
         for (const Segment &sg : ds.segments) {  // a batch holds whole pairs, in local order
+            // consecutive local pairs that are also consecutive in the caller's list (a run sharing the reference image)
+            // are contiguous on both sides: one copy per run
             while (k < ds.pairs.size() && ds.offsets[k + 1] <= sg.first + sg.n) {
-                const int64_t a = ds.offsets[k], cnt = ds.offsets[k + 1] - a;
+                size_t e = k + 1;
+                while (e < ds.pairs.size() && ds.offsets[e + 1] <= sg.first + sg.n && ds.pair_index[e] == ds.pair_index[e - 1] + 1) ++e;
+                const int64_t a = ds.offsets[k], cnt = ds.offsets[e] - a;
                 if (cnt > 0) {
-                    if (a < sg.first) break;  // belongs to an earlier segment (cannot happen: segments are in order)
                     const int64_t dst = out->offsets[ds.pair_index[k]];
                     memcpy(out->matches + dst, sg.m + (a - sg.first), (size_t)cnt * 8);
                     if (out->good) memcpy(out->good + dst, sg.g + (a - sg.first), (size_t)cnt);
                 }
-                ++k;
+                k = e;
             }
         }
     };
