@@ -526,6 +526,17 @@ def run_native_ranks(args):
         metas, h2d = stage_table(use_f32)
         stamps = [time.perf_counter() - t_begin]
         done, d2h = 0, 0
+        if world == 1:
+            # ONE call over the whole list (ordered by staging group): the library cuts its batches where the next pair's
+            # images have not landed yet, so matching starts on group 0 while the later groups are still being copied
+            sub = MatchResult(offsets=out.offsets[:len(my_pairs) + 1], ok=out.ok[:len(my_pairs)], matches=out.matches, good=out.good)
+            res = m.match_pairs(my_pairs, RATIO_ALL, out=sub, **kw)
+            list_off[:] = sub.offsets[:len(my_pairs) + 1]
+            stamps.append(time.perf_counter() - t_begin)
+            if trace:
+                print(f"[trace rank {rank}] f32={use_f32} staging enqueued at {1e3 * stamps[0]:.2f} ms, done at {1e3 * stamps[1]:.2f} ms, "
+                      f"{m.timing()['match_launches']} matching launches", file=sys.stderr, flush=True)
+            return h2d + my_pairs.nbytes, m.timing()["d2h_bytes"], len(res.matches)
         for g in range(n_groups):
             a, b = sub_bounds[g], sub_bounds[g + 1]
             replicate_group(g, metas[g])                 # queued on the main stream: runs before sub-list g's launches
@@ -557,7 +568,9 @@ def run_native_ranks(args):
             dt = float(tt.item())
         e2e = {"value": (len(pairs) * e2e_steps) / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "steps": e2e_steps, "host_rows": "float32 (CV_32FC1, the reference's container)" if e2e_f32 else "uint8",
-               "pipeline": f"{n_groups} staging groups on the upload streams" + (" + one NCCL all-gather per group between matching launches" if world > 1 else "")
+               "pipeline": f"{n_groups} staging groups on the upload streams" + (" + one NCCL all-gather per group between matching launches; one "
+                                                                                      "msfm_match_pairs call per group" if world > 1 else
+                                                                                      "; ONE msfm_match_pairs call, batches cut where uploads have not landed")
                            + "; the pairs of groups <= g are matched while group g+1 is copied",
                "timer": "host wall clock between barriers + cuda synchronize, max over ranks", "matches_per_step_this_rank": int(n_e2e),
                "match_lists": "page-locked host buffers of the rank that matched the pair"}

@@ -253,6 +253,14 @@ msfm_status wait_for_uploads(msfm_ctx *ctx, uint64_t need) {
     return MSFM_OK;
 }
 
+// Have the asynchronous uploads up to mark `need` finished?  (Host-side query; used to size batches, never for ordering.)
+bool uploads_landed(msfm_ctx *ctx, uint64_t need) {
+    if (need <= ctx->waited_seq) return true;
+    for (const UploadMark &m : ctx->marks)
+        if (m.seq <= need && cudaEventQuery(m.ev) != cudaSuccess) return false;
+    return true;
+}
+
 msfm_status reserve_locked(msfm_ctx *ctx, int32_t image_id, int32_t rows, int64_t *row_offset) {
     msfm_status st = check_image_id(ctx, image_id, false);
     if (st != MSFM_OK) return st;
@@ -560,6 +568,11 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             const bool gated = r.rows < params->min_keypoints || q.rows < params->min_keypoints;
             if (!gated) {
                 if (!c.plan.pairs.empty() && (c.plan.query_rows + q.rows > max_rows || (mutual && c.plan.ref_rows + r.rows > kBatchMaxRefRows))) break;
+                // A pair whose images are still being uploaded does not hold back the pairs before it: the batch is cut
+                // there, runs on what has landed, and the transfer goes on underneath (the caller orders the list by the
+                // newest image a pair needs, e.g. by staging group).
+                const uint64_t need = std::max(r.ready_seq, q.ready_seq);
+                if (!c.plan.pairs.empty() && need > c.plan.need_seq && !uploads_landed(ctx, need)) break;
                 plan_add_pair(ctx, c.plan, next, pairs[next].ref, pairs[next].query);
             }
             ++next;
