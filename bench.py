@@ -384,14 +384,21 @@ def run_native_ranks(args):
         host_f32 = torch.empty((len(my_ids), rows, 128), dtype=torch.float32).pin_memory()   # CV_32FC1 rows (integer-valued: VLSIFT + rounding)
         host_f32.copy_(host_u8)
 
-    # ---- pair list: ONE list for the whole job, sharded by cost (C++ scheduler, msfm_sched_shard)
+    # ---- pair list: ONE list for the whole job, sharded by cost (C++ scheduler, msfm_sched_shard).  The pairs are taken in
+    #      the order their images land (staging group of the newer image) and every group's sub-list is sharded on its
+    #      own, so that all ranks finish a sub-list together: the all-gather of the next group is a rendezvous of the ranks.
     rows_per_image = np.full((n_images,), rows, np.int32)
-    shards = scheduler.shard_pairs(pairs, rows_per_image, world)
-    my_idx = shards[rank]
-    # within the shard: pairs in the order their images land (group of the newer image), reference-grouped inside
-    pg = np.maximum(group[pairs[my_idx, 0]], group[pairs[my_idx, 1]])
-    order = np.argsort(pg, kind="stable")
-    my_idx, pg = my_idx[order], pg[order]
+    pg_all = np.maximum(group[pairs[:, 0]], group[pairs[:, 1]])
+    my_parts, pg_parts = [], []
+    for g in range(n_groups):
+        idx_g = np.nonzero(pg_all == g)[0]
+        if len(idx_g) == 0:
+            continue
+        mine = idx_g[scheduler.shard_pairs(pairs[idx_g], rows_per_image, world)[rank]]
+        my_parts.append(mine)
+        pg_parts.append(np.full((len(mine),), g, np.int64))
+    my_idx = np.concatenate(my_parts) if my_parts else np.zeros((0,), np.int64)
+    pg = np.concatenate(pg_parts) if pg_parts else np.zeros((0,), np.int64)
     my_pairs = np.ascontiguousarray(pairs[my_idx])
     sub_bounds = [int(np.searchsorted(pg, g, side="left")) for g in range(n_groups)] + [len(my_idx)]
     foreign_reads = int(np.sum(owner[my_pairs[:, 0]] != rank) + np.sum(owner[my_pairs[:, 1]] != rank))
