@@ -258,6 +258,9 @@ msfm_status msfm_knn2_crosscheck(msfm_ctx *ctx, int32_t ref_id, int32_t query_id
 msfm_status msfm_test_set_band_event_cap(msfm_ctx *ctx, int64_t cap);
 /* Test hook: 1 routes every pair's mutual check through the tensor twin pass (the fallback of the bound-based check). */
 msfm_status msfm_test_force_twin_pass(msfm_ctx *ctx, int32_t on);
+/* Test hook: 1 switches off the forward pass's dead-row rule (rows whose two nearest neighbours already violate every
+ * ratio the call tests follow only their nearest neighbour exactly); the match lists must not change. */
+msfm_status msfm_test_disable_pruning(msfm_ctx *ctx, int32_t on);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "msfm_upload_u8_batch", "msfm_upload_u8_batch_async", "msfm_sync", "msfm_upload_f32", "msfm_reserve", "msfm_reserve_batch", "msfm_release", "msfm_release_all", "msfm_image_info", "msfm_table_ptrs",
     "msfm_download_packed", "msfm_knn2", "msfm_colbest", "msfm_match_pairs", "msfm_match_pairs_resident",
     "msfm_last_timing", "msfm_get_stream", "msfm_knn2_crosscheck", "msfm_geo_verify", "msfm_geo_ransac",
-    "msfm_upload_f32_batch_async", "msfm_get_upload_stream", "msfm_wait_event", "msfm_test_set_band_event_cap", "msfm_test_force_twin_pass", "msfm_reserve_batch_async", "msfm_host_alloc", "msfm_host_free", "msfm_device_memory",
+    "msfm_upload_f32_batch_async", "msfm_get_upload_stream", "msfm_wait_event", "msfm_test_set_band_event_cap", "msfm_test_force_twin_pass", "msfm_test_disable_pruning", "msfm_reserve_batch_async", "msfm_host_alloc", "msfm_host_free", "msfm_device_memory",
 ]
 
 
@@ -128,6 +128,7 @@ def load() -> C.CDLL:
     L.msfm_wait_event.argtypes = [vp, vp]
     L.msfm_test_set_band_event_cap.argtypes = [vp, C.c_int64]
     L.msfm_test_force_twin_pass.argtypes = [vp, C.c_int32]
+    L.msfm_test_disable_pruning.argtypes = [vp, C.c_int32]
     L.msfm_upload_f32_batch_async.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_float]
     L.msfm_knn2_crosscheck.argtypes = [vp, C.c_int32, C.c_int32, vp, vp]
     L.msfm_geo_verify.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp, C.c_int32, C.POINTER(GeoParams), vp, vp, vp, vp]

@@ -443,9 +443,11 @@ __global__ void __launch_bounds__(256) rescore_band_kernel(const BandParams bp, 
 // back to the tensor twin pass: the candidates' reference rows are gathered into the candidate scratch image, which the
 // matching kernel then searches against the query image (twin_counts[pair] > 0 routes the pair there).
 constexpr int kDangerWorkCap = 2048;     // candidates per pair that have to look at the dangerous rows (shared memory)
-constexpr int kDangerEvalBudget = 32768;  // exact 128-byte distances per pair on CUDA cores (~1/20 of a twin pass)
+constexpr int kDangerEvalBudget = 65536;  // exact 128-byte distances per pair on CUDA cores
 constexpr int kSmemTableRows = 20480;    // reference rows whose column table fits in shared memory (160 KiB)
-constexpr size_t kSelectSmemBytes = (size_t)kDangerWorkCap * 16 + (size_t)kSmemTableRows * 8;  // 192 KiB
+constexpr int kDangerChunk = 256;        // list rows per work unit of the exact evaluation (= entries of a warp's hit queue)
+constexpr int kDangerFlight = 8;         // row loads in flight per lane while scoring hits (4 x this many hits per warp and round)
+constexpr size_t kSelectSmemBytes = (size_t)kDangerWorkCap * 16 + 32 * kDangerChunk * 4 + (size_t)kSmemTableRows * 8;  // 224 KiB
 constexpr int kCandGood = 1, kCandKilled = 2;  // bits of cand_good[]
 
 struct SelectParams {
@@ -530,10 +532,11 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
     // <= smem_table_rows reference rows
     extern __shared__ unsigned long long s_dyn[];
     int4 *s_work = reinterpret_cast<int4 *>(s_dyn);
-    unsigned long long *s_table = reinterpret_cast<unsigned long long *>(s_work + kDangerWorkCap);
+    int *s_hitq = reinterpret_cast<int *>(s_work + kDangerWorkCap);  // [32 warps][kDangerChunk]
+    unsigned long long *s_table = reinterpret_cast<unsigned long long *>(s_hitq + 32 * kDangerChunk);
     __shared__ int warp_excl[32];
     __shared__ int chunk_total;
-    __shared__ int s_d0max, s_d1min, s_nd, s_nwork, s_evals;
+    __shared__ int s_d0max, s_d1min, s_nd, s_nwork, s_evals, s_unit;
     const PairDesc pd = sp.pairs[blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     int2 *danger = sp.danger + pd.knn_off;  // this pair's dangerous rows (row, d1), unordered; at most one per query row
@@ -544,12 +547,12 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
         table = s_table;
         for (int j = threadIdx.x; j < pd.ref_rows; j += blockDim.x) s_table[j] = ~0ull;
     }
-    if (threadIdx.x == 0) { s_d0max = -1; s_d1min = INT_MAX; s_nd = 0; s_nwork = 0; s_evals = 0; }
+    if (threadIdx.x == 0) { s_d0max = -1; s_d1min = INT_MAX; s_nd = 0; s_nwork = 0; s_evals = 0; s_unit = 0; }
     __syncthreads();
     int running = 0;
+    int4 k[kSelRows];  // kNN records of this thread's rows in the current chunk (pass 2 re-uses them when there is only one)
     for (int base = 0; base < pd.qry_rows; base += blockDim.x * kSelRows) {
         const int q0 = base + threadIdx.x * kSelRows;  // this thread's rows are consecutive: thread order = row order
-        int4 k[kSelRows];
 #pragma unroll
         for (int r = 0; r < kSelRows; ++r)
             k[r] = (q0 + r < pd.qry_rows) ? merge_knn_shares(sp.knn, pd.knn_off + q0 + r, sp.nshare) : make_int4(-1, -1, INT_MAX, INT_MAX);
@@ -597,22 +600,19 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
         // ---- rival kind (B): rows whose second neighbour is at least as close as the weakest candidate's match
         //      (unordered list in the pair's scratch region; no block-wide synchronisation inside the loop)
         const int d0max = s_d0max;
+        const bool single = pd.qry_rows <= (int)blockDim.x * kSelRows;  // pass 1's records are still in registers
         for (int base = 0; base < pd.qry_rows; base += blockDim.x * kSelRows) {
-            int2 v[kSelRows];  // (id1, d1): the loads of a chunk fly together
+            const int q0 = base + threadIdx.x * kSelRows;
+            if (!single) {
 #pragma unroll
-            for (int r = 0; r < kSelRows; ++r) {
-                const int q = base + r * blockDim.x + threadIdx.x;
-                v[r] = make_int2(-1, 0);
-                if (q < pd.qry_rows) {
-                    const int4 k = merge_knn_shares(sp.knn, pd.knn_off + q, sp.nshare);
-                    v[r] = make_int2(k.y, k.w);
-                }
+                for (int r = 0; r < kSelRows; ++r)
+                    k[r] = (q0 + r < pd.qry_rows) ? merge_knn_shares(sp.knn, pd.knn_off + q0 + r, sp.nshare) : make_int4(-1, -1, INT_MAX, INT_MAX);
             }
 #pragma unroll
             for (int r = 0; r < kSelRows; ++r)
-                if (v[r].x >= 0 && v[r].y <= d0max) {
-                    danger[atomicAdd(&s_nd, 1)] = make_int2(base + r * blockDim.x + threadIdx.x, v[r].y);
-                    atomicMin(&s_d1min, v[r].y);
+                if (k[r].y >= 0 && k[r].w <= d0max) {  // (id1, d1)
+                    danger[atomicAdd(&s_nd, 1)] = make_int2(q0 + r, k[r].w);
+                    atomicMin(&s_d1min, k[r].w);
                 }
         }
         __syncthreads();
@@ -634,20 +634,79 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
             __syncthreads();
             const int nwork = s_nwork;
             overflow = nwork > kDangerWorkCap;
+            if (!overflow && nwork > 0 && nd <= sp.smem_table_rows) {
+                // the column table has done its job (verdicts above): its shared memory now holds the dangerous-row list, so
+                // that the bound tests below are shared-memory reads instead of dependent L2 round trips
+                int2 *s_danger = reinterpret_cast<int2 *>(s_table);
+                for (int e = threadIdx.x; e < nd; e += blockDim.x) s_danger[e] = danger[e];
+                __syncthreads();
+                danger = s_danger;
+            }
             if (!overflow && nwork > 0) {
-                // (listed candidate) x (dangerous row), spread evenly over the CTA; a hit costs one exact 128-byte distance
-                const unsigned total = (unsigned)nwork * (unsigned)nd;  // <= 2048 x 1,000,000 < 2^31
-                for (unsigned t = threadIdx.x; t < total; t += blockDim.x) {
-                    const int w = (int)(t / (unsigned)nd), e = (int)(t - (unsigned)w * (unsigned)nd);
+                // (listed candidate) x (dangerous row).  The bound test is one compare per combination; the few that pass
+                // ("hits", ~1e4 per 8192 x 8192 pair) cost an exact 128-byte distance each and are latency-bound L2 reads.
+                // Work unit = (candidate, chunk of kDangerChunk list rows), dealt round-robin to the warps: the warp keeps
+                // its 16-byte share of the candidate's reference row in registers, queues the chunk's hits in shared memory
+                // and scores them 16 at a time — eight lanes per distance, four independent row loads in flight per lane.
+                const int nchunks = (nd + kDangerChunk - 1) / kDangerChunk;
+                const int units = nwork * nchunks;
+                const int sub = lane >> 3, part = lane & 7;  // which of the warp's 4 concurrent distances, which 16 bytes
+                int *hitq = s_hitq + warp * kDangerChunk;
+                for (;;) {
+                    int u = 0;
+                    if (lane == 0) u = atomicAdd(&s_unit, 1);  // units differ widely in hits: dealt on demand
+                    u = __shfl_sync(0xFFFFFFFFu, u, 0);
+                    if (u >= units || s_evals >= kDangerEvalBudget) break;  // (budget: too ambiguous for CUDA cores)
+                    const int w = u / nchunks, e0 = (u - w * nchunks) * kDangerChunk;
                     const int4 c = s_work[w];  // (candidate, q, j, d0)
-                    const int2 r = danger[e];
-                    if (r.y <= c.w && r.x != c.y) {
-                        if (atomicAdd(&s_evals, 1) >= kDangerEvalBudget) break;  // too ambiguous for CUDA cores
-                        const int d = sqdist_u8_rows(sp.desc_arena + (pd.qry_off + r.x) * kDim, sp.desc_arena + (pd.ref_off + c.z) * kDim,
-                                                     ckey_to_norm(sp.ckeys[pd.qry_off + r.x]), ckey_to_norm(sp.ckeys[pd.ref_off + c.z]));
-                        // several rivals may kill the same candidate: they all set the same bit, the other bits are final
-                        if (d < c.w || (d == c.w && r.x < c.y)) sp.cand_good[pd.knn_off + c.x] |= kCandKilled;
+                    int n = 0;
+                    const int e1 = min(e0 + kDangerChunk, nd);
+                    for (int eb = e0; eb < e1; eb += 32) {  // warp-uniform trip count
+                        const int e = eb + lane;
+                        bool hit = false;
+                        int2 r = make_int2(0, 0);
+                        if (e < e1) {
+                            r = danger[e];
+                            hit = r.y <= c.w && r.x != c.y;
+                        }
+                        const unsigned hits = __ballot_sync(0xFFFFFFFFu, hit);
+                        if (hit) hitq[n + __popc(hits & ((1u << lane) - 1u))] = r.x;
+                        n += __popc(hits);
                     }
+                    if (n == 0) continue;
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(&s_evals, n);
+                    const uint4 y = __ldg(reinterpret_cast<const uint4 *>(sp.desc_arena + (pd.ref_off + c.z) * kDim) + part);
+                    const int nb = ckey_to_norm(sp.ckeys[pd.ref_off + c.z]);
+                    for (int base = 0; base < n; base += 4 * kDangerFlight) {
+                        int row[kDangerFlight];
+                        uint4 x[kDangerFlight];
+#pragma unroll
+                        for (int k2 = 0; k2 < kDangerFlight; ++k2) {
+                            const int idx = base + k2 * 4 + sub;
+                            row[k2] = idx < n ? hitq[idx] : -1;
+                            x[k2] = make_uint4(0, 0, 0, 0);
+                            if (row[k2] >= 0) x[k2] = __ldg(reinterpret_cast<const uint4 *>(sp.desc_arena + (pd.qry_off + row[k2]) * kDim) + part);
+                        }
+#pragma unroll
+                        for (int k2 = 0; k2 < kDangerFlight; ++k2) {
+                            // this lane's share of ||x||^2 - 2 x.y  (the row's norm comes from the row itself)
+                            uint32_t ab = __dp4a(x[k2].x, y.x, 0u), aa = __dp4a(x[k2].x, x[k2].x, 0u);
+                            ab = __dp4a(x[k2].y, y.y, ab); aa = __dp4a(x[k2].y, x[k2].y, aa);
+                            ab = __dp4a(x[k2].z, y.z, ab); aa = __dp4a(x[k2].z, x[k2].z, aa);
+                            ab = __dp4a(x[k2].w, y.w, ab); aa = __dp4a(x[k2].w, x[k2].w, aa);
+                            int pd2 = (int)aa - 2 * (int)ab;
+                            pd2 += __shfl_xor_sync(0xFFFFFFFFu, pd2, 1);  // over the 8 lanes of the group
+                            pd2 += __shfl_xor_sync(0xFFFFFFFFu, pd2, 2);
+                            pd2 += __shfl_xor_sync(0xFFFFFFFFu, pd2, 4);
+                            if (part == 0 && row[k2] >= 0) {
+                                const int d = pd2 + nb;
+                                // several rivals may kill the same candidate: they all set the same bit, the other bits are final
+                                if (d < c.w || (d == c.w && row[k2] < c.y)) sp.cand_good[pd.knn_off + c.x] |= kCandKilled;
+                            }
+                        }
+                    }
+                    __syncwarp();  // the queue is rewritten by the next unit
                 }
                 __syncthreads();
                 overflow = s_evals >= kDangerEvalBudget;

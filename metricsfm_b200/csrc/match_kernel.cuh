@@ -23,6 +23,12 @@
 //   over the B ring (immediate addresses) and they sleep between polls (see the comment at the role dispatch).
 // MODE 1 ("collect", float regime) replaces the top-2 merge by "append every element under the row's fixed threshold
 // to an event list"; everything else is shared.
+// Work distribution (template parameter DYN):
+//   DYN = false  static: CTA b takes items b, b + grid, ...; every role walks that list on its own.
+//   DYN = true   the loader draws items from a device counter (atomicAdd) and publishes each index in a small shared-memory
+//                ring (s_item / i_full barriers) as soon as it knows it, i.e. one to two items ahead of the MMAs; issuers and
+//                epilogue warps read it there (-1 ends the CTA).  Items go to whichever CTA is free: a CTA that cannot be
+//                placed at launch (a collective or a packer kernel occupies its SM) simply finds nothing left.
 // Pipelines (all mbarrier based):
 //   A ring (2 deep)     : query strips of a work item, STRIPS x [128 rows x 128 B]
 //   B ring (STAGES)     : reference tiles [TILE_N rows x 128 B]
@@ -93,7 +99,13 @@ struct MatchKernelParams {
     uint32_t event_cap;
     const unsigned int *gate;     // optional: the whole launch returns at once when *gate == 0 (mutual twin pass with no
                                   // pair left for the tensor path, see select_candidates_kernel)
+    unsigned int *next_item;      // work-item counter of this launch (zero at launch): CTAs draw items from it, so a CTA that
+                                  // starts late (another kernel sits on its SM) or meets cheap items does not hold the launch up
+    uint32_t prune_q8;            // "dead row" rule of the forward pass (see the epilogue): a row whose two nearest neighbours
+                                  // so far satisfy d0 > (prune_q8 / 256) * d1 only follows its NEAREST neighbour exactly.
+                                  // kNoPrune = off (exact 2-NN of every row: msfm_knn2, twin and collect passes)
 };
+constexpr uint32_t kNoPrune = 4096;  // ((d1 >> 8) + 1) * 4096 >= 16 * d1 > d0 for every row, and fits in 32 bits (d < 2^25)
 
 template <int STRIPS, int TILE_N, int STAGES, int CSPLIT, int TBUFS>
 struct MatchKernelCfg {
@@ -122,9 +134,11 @@ struct MatchKernelCfg {
     static constexpr int kSmemKey = kSmemB + STAGES * kBBytes;
     static constexpr int kSmemShare = kSmemKey + kKeySlots * TILE_N * 4;       // [STRIPS*128 rows][CSPLIT] int4
     static constexpr int kSmemBar = kSmemShare + STRIPS * kStripRows * CSPLIT * 16;
-    static constexpr int kNumBars = 2 + 2 + STAGES + STAGES + kKeySlots + 2 * TBUFS * STRIPS;
+    static constexpr int kItemSlots = 8;  // published work-item indices (the loader runs at most two items ahead of the MMAs)
+    static constexpr int kNumBars = 2 + 2 + STAGES + STAGES + kKeySlots + 2 * TBUFS * STRIPS + kItemSlots;
     static constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
-    static constexpr int kSmemBytes = kSmemTmemPtr + 16;
+    static constexpr int kSmemItems = kSmemTmemPtr + 16;
+    static constexpr int kSmemBytes = kSmemItems + kItemSlots * 4;
     static constexpr int kSmemAlloc = kSmemBytes + 1024;  // slack for manual 1024-byte alignment
     static_assert(kTmemCols == 32 || kTmemCols == 64 || kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512,
                   "TMEM allocation must be a power of two in [32, 512] columns");
@@ -160,7 +174,7 @@ __device__ __forceinline__ void merge_top2(int sa, int ja, int sb, int jb, int &
     J0 = t0 ? ja : J0;
 }
 
-template <int STRIPS, int TILE_N, int STAGES, int CSPLIT, int TBUFS, bool DEBUG, int MODE = 0>
+template <int STRIPS, int TILE_N, int STAGES, int CSPLIT, int TBUFS, bool DEBUG, int MODE = 0, bool DYN = false>
 __global__ void __launch_bounds__(MatchKernelCfg<STRIPS, TILE_N, STAGES, CSPLIT, TBUFS>::kThreads, 1)
 match_pairs_kernel(const MatchKernelParams p) {
     using Cfg = MatchKernelCfg<STRIPS, TILE_N, STAGES, CSPLIT, TBUFS>;
@@ -180,7 +194,9 @@ match_pairs_kernel(const MatchKernelParams p) {
     uint64_t *k_full = b_empty + STAGES;             // [kKeySlots]
     uint64_t *t_full = k_full + Cfg::kKeySlots;      // [TBUFS][STRIPS]
     uint64_t *t_empty = t_full + TBUFS * STRIPS;     // [TBUFS][STRIPS]
+    uint64_t *i_full = t_empty + TBUFS * STRIPS;     // [kItemSlots] (DYN) item index published
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
+    volatile int32_t *s_item = reinterpret_cast<volatile int32_t *>(smem + Cfg::kSmemItems);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -193,6 +209,7 @@ match_pairs_kernel(const MatchKernelParams p) {
         for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], STRIPS); }
         for (int i = 0; i < Cfg::kKeySlots; ++i) ptx::mbar_init(&k_full[i], 1);
         for (int i = 0; i < TBUFS * STRIPS; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 4 * CSPLIT); }
+        for (int i = 0; i < Cfg::kItemSlots; ++i) ptx::mbar_init(&i_full[i], 1);
         ptx::fence_mbar_init();
     }
     if (warp == Cfg::kEpiWarps + 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
@@ -223,17 +240,27 @@ match_pairs_kernel(const MatchKernelParams p) {
         // immediates); items are switched inside it.  Every instruction here is taken from the issue slots of the
         // epilogue warps on the same sub-partition (~1.4 cycles each per tile), hence the lean loop and the long sleeps.
         if (ptx::elect_one()) {
-            int item = (int)blockIdx.x - (int)gridDim.x, left = 0, t = 0;
+            int cur = (int)blockIdx.x - (int)gridDim.x, left = 0, t = 0;
             uint32_t a = 0, round = 0;  // items started, trips round the B ring
             const CUtensorMap *rmap = nullptr;
             const int32_t *keyp = nullptr;
             auto next_item = [&]() -> bool {  // next item with work; fetches its query strips
                 for (;;) {
-                    item += gridDim.x;
-                    if (item >= p.n_items) return false;
-                    const WorkItem wi = p.items[item];
+                    const int idx = DYN ? (int)atomicAdd(p.next_item, 1u) : (cur += (int)gridDim.x);
+                    if (idx >= p.n_items) {
+                        if (DYN) {  // end marker
+                            s_item[a % Cfg::kItemSlots] = -1;
+                            ptx::mbar_arrive(&i_full[a % Cfg::kItemSlots]);
+                        }
+                        return false;
+                    }
+                    const WorkItem wi = p.items[idx];
                     const PairDesc pd = p.pairs[wi.pair];
                     if (pd.cand_idx >= 0 && wi.row0 >= p.counts[pd.cand_idx]) continue;  // item past the candidate list
+                    if (DYN) {  // published before the strips are even requested: the other roles prefetch the descriptors
+                        s_item[a % Cfg::kItemSlots] = idx;
+                        ptx::mbar_arrive(&i_full[a % Cfg::kItemSlots]);
+                    }
                     const CUtensorMap *qmap = p.maps + pd.qry_img;
                     const uint32_t abuf = a & 1;
                     LOADER_WAIT(&a_empty[abuf], ((a >> 1) & 1) ^ 1);
@@ -283,15 +310,22 @@ match_pairs_kernel(const MatchKernelParams p) {
             const uint32_t a_lo0 = (ptx::smem_u32(sA) + s * kStripRows * kDim) >> 4;
             const uint32_t d_tmem0 = tmem_base + s * TILE_N;
             uint64_t *t_full_s = t_full + s, *t_empty_s = t_empty + s;
-            int item = (int)blockIdx.x - (int)gridDim.x, left = 0;
+            int cur = (int)blockIdx.x - (int)gridDim.x, left = 0;
             uint32_t a = 0, abuf = 0, a_lo = 0, round = 0;
             auto next_item = [&]() -> bool {  // next item with work; waits for its query strips
                 for (;;) {
-                    item += gridDim.x;
-                    if (item >= p.n_items) return false;
-                    const WorkItem wi = p.items[item];
+                    int idx;
+                    if (DYN) {
+                        ISSUER_WAIT(&i_full[a % Cfg::kItemSlots], (a / Cfg::kItemSlots) & 1);
+                        idx = s_item[a % Cfg::kItemSlots];
+                        if (idx < 0) return false;
+                    } else {
+                        idx = (cur += (int)gridDim.x);
+                        if (idx >= p.n_items) return false;
+                    }
+                    const WorkItem wi = p.items[idx];
                     const PairDesc pd = p.pairs[wi.pair];
-                    if (pd.cand_idx >= 0 && wi.row0 >= p.counts[pd.cand_idx]) continue;
+                    if (!DYN && pd.cand_idx >= 0 && wi.row0 >= p.counts[pd.cand_idx]) continue;
                     abuf = a & 1;
                     ISSUER_WAIT(&a_full[abuf], (a >> 1) & 1);
                     a_lo = a_lo0 + abuf * (Cfg::kABytes >> 4);
@@ -368,11 +402,20 @@ match_pairs_kernel(const MatchKernelParams p) {
         const uint32_t t_empty_base = ptx::smem_u32(t_empty + strip);
         // ring positions are carried incrementally (no divisions in the tile loop)
         uint32_t ks = 0, k_phase = 0, buf = 0, t_phase = 0, a = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const uint32_t i_full_base = ptx::smem_u32(i_full);
+        for (int cur = blockIdx.x;; cur += gridDim.x) {
+            int item = cur;
+            if (DYN) {  // published by the loader one to two items ahead of the MMAs
+                ptx::mbar_wait_a(i_full_base + (a % Cfg::kItemSlots) * 8, (a / Cfg::kItemSlots) & 1);
+                item = s_item[a % Cfg::kItemSlots];
+                if (item < 0) break;
+            } else if (item >= p.n_items) {
+                break;
+            }
             const WorkItem wi = p.items[item];
             const PairDesc pd = p.pairs[wi.pair];
             const int qry_rows = pd.cand_idx >= 0 ? p.counts[pd.cand_idx] : pd.qry_rows;
-            if (wi.row0 >= qry_rows) continue;
+            if (!DYN && wi.row0 >= qry_rows) continue;  // item past the candidate list (never published when DYN)
             const int q = wi.row0 + row_local;
             const bool valid = q < qry_rows;
             const int na = valid ? ckey_to_norm((pd.cand_idx >= 0 ? p.cand_ckeys : p.ckeys)[pd.qry_off + q]) : 0;
@@ -383,6 +426,16 @@ match_pairs_kernel(const MatchKernelParams p) {
             // close are ever scored exactly.  The placeholders carry id -1 and are dropped by the consumers.
             // Collect mode keeps that threshold for the whole row: every reference row at distance <= cand_d0 is listed.
             if (pd.cand_idx >= 0 && valid) S0 = S1 = na - p.cand_d0[pd.qry_off + q] - 1;
+            // "Dead row" rule (forward items of msfm_match_pairs only).  The caller keeps a row only if d0/d1 < ratio.  While
+            // the running pair violates that with a margin (d0 > rho * d1, rho just above every ratio the caller tests:
+            // the row is "dead"), only an element closer than d0 can change the verdict: it becomes the nearest neighbour and
+            // the old one — the exact minimum of everything before it, because elements under d0 are never skipped — the
+            // second, so the pair is exact again.  Elements between d0 and d1 would only push a dead row further from the
+            // threshold, so the pruning threshold of a dead row is its BEST score instead of its second best: about half of
+            // the running-top-2 records of such rows (most rows of an image pair) never reach the exact phase.  A row that
+            // ends dead reports d1 := d0: "rejected", and still a valid lower bound of its distance to every row but nn0,
+            // which is what the mutual check's dangerous-row bound needs (select_candidates_kernel).
+            const int rho8 = (MODE == 0 && CSPLIT == 1 && pd.cand_idx < 0) ? (int)p.prune_q8 : (int)kNoPrune;  // shares keep partial states
             const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
             long long acc_wait = 0, acc_load = 0, acc_p1 = 0, acc_p2 = 0, acc_hot = 0;
             int jtile = share * kCols;  // first column of this warp's share in the current tile
@@ -405,7 +458,10 @@ match_pairs_kernel(const MatchKernelParams p) {
 #pragma unroll
                 for (int k = 1; k < kCols / 32; ++k) ckmax = max(ckmax, ptx::lds_s32(ck + (lane + 32 * k) * 4));
                 const int nbmin = ckey_to_norm(__reduce_max_sync(0xFFFFFFFFu, ckmax));
-                int theta = S1;
+                // dead rows are pruned against their best score (d = na - S; placeholders never count as dead)
+                const int d1_now = (int)((uint32_t)na - (uint32_t)S1);
+                const bool dead = (S1 > kAbsent) && ((int)((uint32_t)na - (uint32_t)S0) > (d1_now >> 8) * rho8 + rho8);
+                int theta = dead ? S0 : S1;
                 if (CSPLIT > 1) {
                     // peer's {S0 - 1, S1 - 1, item tag}: the row's final second best is >= its own S1, >= the peer's S1
                     // and >= min(S0_own, S0_peer); peer scores count minus one (see above)
@@ -484,6 +540,8 @@ match_pairs_kernel(const MatchKernelParams p) {
                 atomicAdd(p.stats + 9 + 2 * quarter, (unsigned long long)(acc_load + acc_p1 + acc_p2));
             }
             if (valid && MODE == 0) {
+                const int d1_end = (int)((uint32_t)na - (uint32_t)S1);
+                if ((S1 > kAbsent) && ((int)((uint32_t)na - (uint32_t)S0) > (d1_end >> 8) * rho8 + rho8)) S1 = S0;  // ended dead: d1 := d0 (lower bound)
                 int4 out;
                 out.x = (S0 > kAbsent) ? J0 : -1;
                 out.y = (S1 > kAbsent) ? J1 : -1;

@@ -103,11 +103,23 @@ struct msfm_ctx {
 
     DeviceBuf dbg_stats;  // debug flag 8: per-phase cycle counters of the matching kernel, dumped at destroy
     DeviceBuf cand_q, cand_j, cand_d0, cand_good, cand_counts, cand_desc, cand_ckeys;  // one-way candidates + gathered rows
+    DeviceBuf item_counter;  // work-item counter of the matching launch in flight (zeroed before every launch)
     DeviceBuf colbest, twin_counts;  // mutual check: per-pair column table (nearest claimant per reference row); [n_pairs] + gate word
     DeviceBuf band_q, band_counts;  // float regime: query rows near a ratio threshold, per pair
     DeviceBuf band_thr, band_state, band_events, band_event_keys, band_event_count;  // ... and the collect pass over them
     int64_t band_event_cap_override = -1;  // msfm_test_set_band_event_cap (tests: 0 forces the brute-force fallback)
     bool force_twin = false;               // msfm_test_force_twin_pass
+#ifdef MSFM_DYNAMIC_ITEMS       // A/B builds only: work items drawn from a device counter instead of the static walk
+    bool dynamic_items = true;
+#else
+    bool dynamic_items = false;
+#endif
+#ifdef MSFM_NO_PRUNE_DEFAULT   // A/B builds only
+    bool no_prune = true;
+#else
+    bool no_prune = false;
+#endif
+    // ^ msfm_test_disable_pruning: the forward pass keeps exact 2-NN rows for every query row
     DeviceBuf staging, knn, matches, good, counts, offsets, pairdesc, items, tight_matches, tight_good;
     void *h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
@@ -301,6 +313,7 @@ struct BatchPlan {
     bool big_ref = false;            // some reference image's column table does not fit in shared memory
     int64_t ops = 0;
     bool mutual = false;
+    uint32_t prune_q8 = msfm::kNoPrune;  // forward pass: dead-row rule of the matching kernel (match_kernel.cuh); off = exact 2-NN rows
     bool has_empty = false;          // some pair has no work items: its kNN rows must read "absent"
     bool any_float = false;          // some pair has retained float rows on both sides (rescoring possible)
     int64_t knn_rows() const { return mutual ? 2 * query_rows : query_rows; }
@@ -308,7 +321,8 @@ struct BatchPlan {
 
 // collect = false: 2-NN of the items' query rows (forward pairs and mutual twins).  collect = true: the items are band
 // twins; every reference row within band_thr of a band row is appended to the event list instead.
-msfm_status launch_match_kernel(msfm_ctx *ctx, size_t first_item, size_t n_items, bool collect = false, uint32_t event_cap = 0, bool twin = false) {
+msfm_status launch_match_kernel(msfm_ctx *ctx, size_t first_item, size_t n_items, bool collect = false, uint32_t event_cap = 0, bool twin = false,
+                                uint32_t prune_q8 = msfm::kNoPrune) {
     msfm::MatchKernelParams kp;
     kp.maps = ctx->d_maps;
     kp.ckeys = ctx->norms;
@@ -326,11 +340,22 @@ msfm_status launch_match_kernel(msfm_ctx *ctx, size_t first_item, size_t n_items
     kp.stats = static_cast<unsigned long long *>(ctx->dbg_stats.ptr);  // null unless MSFM_DEBUG_FLAGS & 8
     kp.debug_flags = ctx->debug_flags;
     kp.knn = static_cast<int4 *>(ctx->knn.ptr);
+    kp.prune_q8 = (collect || twin || ctx->no_prune) ? msfm::kNoPrune : prune_q8;
     const int grid = std::max(1, std::min<int>(ctx->num_sms, kp.n_items));
+    const bool dyn = ctx->dynamic_items && !collect && !ctx->debug_flags;
+    kp.next_item = nullptr;
+    if (dyn) {  // the launch's work-item counter
+        msfm_status st = ensure(ctx, ctx->item_counter, 256);
+        if (st != MSFM_OK) return st;
+        MSFM_CUDA(ctx, cudaMemsetAsync(ctx->item_counter.ptr, 0, 4, ctx->stream));
+        kp.next_item = static_cast<unsigned int *>(ctx->item_counter.ptr);
+    }
     if (collect)
         msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, false, 1><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
     else if (ctx->debug_flags)
         msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, true><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
+    else if (dyn)
+        msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, false, 0, true><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
     else
         msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, false><<<grid, KCfg::kThreads, KCfg::kSmemAlloc, ctx->stream>>>(kp);
     MSFM_CUDA(ctx, cudaGetLastError());
@@ -455,7 +480,7 @@ msfm_status run_match_stage(msfm_ctx *ctx, const BatchPlan &plan) {
     }
     if (plan.has_empty) MSFM_CUDA(ctx, cudaMemsetAsync(ctx->knn.ptr, 0xFF, (size_t)plan.query_rows * kCsplit * sizeof(int4), ctx->stream));
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
-    if (!plan.items.empty() && (st = launch_match_kernel(ctx, 0, plan.items.size())) != MSFM_OK) return st;
+    if (!plan.items.empty() && (st = launch_match_kernel(ctx, 0, plan.items.size(), false, 0, false, plan.prune_q8)) != MSFM_OK) return st;
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
     ctx->timing.int8_ops += plan.ops;
     return MSFM_OK;
@@ -555,6 +580,15 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
     int64_t total = 0;
     if (!resident) out->offsets[0] = 0;
 
+    // Dead-row rule of the forward pass: rho = the largest ratio any consumer tests (+ the re-scoring band, whose rows need
+    // exact neighbours) rounded UP to 1/256 plus one step, so that "dead" (d0 > rho * d1) implies fl(d0/d1) > ratio under
+    // both ratio rules; thresholds near or above 1 switch the rule off.
+    uint32_t prune_q8 = msfm::kNoPrune;
+    {
+        float rmax = std::max(params->ratio, params->ratio_good);
+        if (params->rescore_band > 0.0f) rmax += params->rescore_band;
+        if (rmax > 0.0f && rmax < 0.97f) prune_q8 = (uint32_t)std::floor(rmax * 256.0f) + 2;
+    }
     // Batches are carved (host-only work: pair descriptors + work items) one ahead, while the previous batch runs on the GPU.
     struct Carved { BatchPlan plan; int64_t first = 0, last = 0; };
     int64_t next = 0;
@@ -562,6 +596,7 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
         c.plan = BatchPlan();
         c.plan.mutual = mutual;
         c.plan.rescoring = params->rescore_band > 0.0f && ctx->fdesc != nullptr;
+        c.plan.prune_q8 = prune_q8;
         c.first = next;
         while (next < n_pairs && (int64_t)c.plan.pairs.size() < kBatchMaxPairs) {
             const ImageSlot &r = ctx->images[pairs[next].ref], &q = ctx->images[pairs[next].query];
@@ -908,6 +943,8 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
                              cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::kSmemAlloc) != cudaSuccess ||
         cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, false, 1>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::kSmemAlloc) != cudaSuccess ||
+        cudaFuncSetAttribute(msfm::match_pairs_kernel<kStrips, kTileN, kStages, kCsplit, kTbufs, false, 0, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, KCfg::kSmemAlloc) != cudaSuccess ||
         cudaFuncSetAttribute(msfm::select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msfm::kSelectSmemBytes) != cudaSuccess)
         return bail(MSFM_ERR_CUDA);
     if (ctx->debug_flags & 8u) {
@@ -945,7 +982,7 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
         cudaFree(ctx->dbg_stats.ptr);
     }
     if (ctx->fdesc) cudaFree(ctx->fdesc);
-    DeviceBuf *bufs[] = {&ctx->band_q, &ctx->band_counts, &ctx->band_thr, &ctx->band_state, &ctx->band_events, &ctx->band_event_keys, &ctx->band_event_count, &ctx->cand_q, &ctx->cand_j, &ctx->cand_d0, &ctx->cand_good, &ctx->cand_counts, &ctx->cand_desc, &ctx->cand_ckeys, &ctx->colbest, &ctx->twin_counts,
+    DeviceBuf *bufs[] = {&ctx->band_q, &ctx->band_counts, &ctx->band_thr, &ctx->band_state, &ctx->band_events, &ctx->band_event_keys, &ctx->band_event_count, &ctx->cand_q, &ctx->cand_j, &ctx->cand_d0, &ctx->cand_good, &ctx->cand_counts, &ctx->cand_desc, &ctx->cand_ckeys, &ctx->colbest, &ctx->twin_counts, &ctx->item_counter,
                          &ctx->staging, &ctx->knn, &ctx->matches, &ctx->good, &ctx->counts, &ctx->offsets,
                          &ctx->pairdesc, &ctx->items, &ctx->tight_matches, &ctx->tight_good};
     for (DeviceBuf *b : bufs)
@@ -1488,6 +1525,13 @@ msfm_status msfm_wait_event(msfm_ctx *ctx, void *cuda_event) {
     std::lock_guard<std::mutex> lock(ctx->mu);
     MSFM_CUDA(ctx, cudaSetDevice(ctx->device));
     MSFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, static_cast<cudaEvent_t>(cuda_event), 0));
+    return MSFM_OK;
+}
+
+msfm_status msfm_test_disable_pruning(msfm_ctx *ctx, int32_t on) {
+    if (!ctx) return MSFM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->no_prune = on != 0;
     return MSFM_OK;
 }
 

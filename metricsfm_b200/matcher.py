@@ -346,6 +346,9 @@ class Matcher:
     def _test_force_twin_pass(self, on: bool) -> None:
         self._check(self._L.msfm_test_force_twin_pass(self._h, int(bool(on))))
 
+    def _test_disable_pruning(self, on: bool) -> None:
+        self._check(self._L.msfm_test_disable_pruning(self._h, int(bool(on))))
+
     def timing(self) -> dict:
         t = Timing()
         self._check(self._L.msfm_last_timing(self._h, C.byref(t)))

@@ -1010,3 +1010,48 @@ def test_failed_batch_upload_leaves_no_half_uploaded_image(matcher):
     matcher.upload(1, b)
     got, _ = matcher.download_packed(1)
     np.testing.assert_array_equal(got, b)
+
+
+@pytest.mark.parametrize("ratio,ratio_good,flags", [(0.85, 0.6, 0), (0.5, 0.0, 0), (0.8, 0.0, 1), (0.95, 0.6, 0)])
+def test_dead_row_rule_is_invisible(oracle_mod, native_lib, ratio, ratio_good, flags):
+    """Forward pass with the dead-row rule (rows that already violate every tested ratio follow only their nearest
+    neighbour exactly, match_kernel.cuh) against the same call with the rule switched off and against the oracle: one-way
+    and mutual lists and the 'good' flags must be identical — on SIFT-like images, on images whose rows sit in tight
+    clusters (ratios near 1 and exact ties, the mutual check's dangerous-row bound at work) and on rows engineered to
+    die early and be revived by a much closer neighbour in the LAST reference tile."""
+    from metricsfm_b200.matcher import Matcher
+    rng = np.random.default_rng(4242)
+    col = synth.Collection(3000, seed=5)
+    a, b = col.image_u8(0, 3000), col.image_u8(1, 2777)
+    centres = rng.integers(0, 120, size=(40, 128))
+    c = np.clip(centres[rng.integers(0, 40, 2500)] + rng.integers(-3, 4, size=(2500, 128)), 0, 255).astype(np.uint8)
+    d = np.clip(centres[rng.integers(0, 40, 2100)] + rng.integers(-3, 4, size=(2100, 128)), 0, 255).astype(np.uint8)
+    # revival: query rows of e copy rows of the last tile of f (+ tiny noise), so the true match arrives after ~3000 rivals
+    f = col.image_u8(2, 3001)
+    e = col.image_u8(3, 900)
+    e[:300] = np.clip(f[-300:].astype(np.int32) + rng.integers(-2, 3, size=(300, 128)), 0, 255).astype(np.uint8)
+    imgs = [np.ascontiguousarray(x) for x in (a, b, c, d, e, f)]
+    pairs = [(0, 1), (1, 0), (2, 3), (3, 2), (5, 4), (4, 5), (0, 3), (2, 1)]
+    with Matcher(device=0, max_images=8, arena_rows=1 << 16) as m:
+        for i, x in enumerate(imgs):
+            m.upload(i, x)
+        out = {}
+        for prune in (True, False):
+            m._test_disable_pruning(not prune)
+            for mutual in (False, True):
+                out[prune, mutual] = m.match_pairs(pairs, ratio, ratio_good=ratio_good, mutual=mutual, flags=flags)
+        m._test_disable_pruning(False)
+        ids, dists = m.knn2(5, 4)   # the S1/S2 seam always reports exact neighbours
+    oids, odists = oracle_mod.knn2_u8(imgs[5], imgs[4])
+    np.testing.assert_array_equal(ids, oids)
+    np.testing.assert_array_equal(dists, odists)
+    n = 0
+    for mutual in (False, True):
+        for p, (r, q) in enumerate(pairs):
+            exp = oracle_mod.match_pair_u8(imgs[r], imgs[q], ratio, mutual=mutual, ratio_good=ratio_good, reject_gt=bool(flags))
+            for prune in (True, False):
+                np.testing.assert_array_equal(out[prune, mutual].pair(p), exp["pairs"], err_msg=f"prune={prune} mutual={mutual} pair ({r},{q})")
+                if ratio_good > 0:
+                    np.testing.assert_array_equal(out[prune, mutual].pair_good(p), exp["good"], err_msg=f"good flags, prune={prune} mutual={mutual} pair ({r},{q})")
+            n += len(exp["pairs"])
+    assert n > 300

@@ -1,0 +1,114 @@
+"""Round-2 evidence: turn the raw outputs in gpurun_out/ into the committed summaries under profiles/.
+Run here (no GPU): `python tools/summarise_r2.py`.  Numbers printed under a profiler are never used as bench values."""
+import collections
+import csv
+import json
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+KEEP = re.compile(r"^(dram__bytes_(read|write)\.sum(\.per_second)?|gpu__dram_throughput\.avg\.pct_of_peak_sustained_elapsed|"
+                  r"gpu__time_duration\.sum|l1tex__data_pipe_(lsu|tc)_wavefronts_mem_shared\.sum\.pct_of_peak_sustained_elapsed|"
+                  r"launch__(block_size|grid_size|registers_per_thread)|sm__cycles_elapsed\.avg|"
+                  r"sm__inst_executed_pipe_alu\.avg\.pct_of_peak_sustained_active|sm__pipe_(alu|fma|tensor)_cycles_active\.avg\.pct_of_peak_sustained_active|"
+                  r"sm__pipe_tensor_subpipe_imma_cycles_active\.avg\.pct_of_peak_sustained_active|sm__throughput\.avg\.pct_of_peak_sustained_elapsed|"
+                  r"sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off\.(avg\.pct_of_peak_sustained_elapsed|sum|sum\.per_second|avg\.peak_sustained)|"
+                  r"sm__warps_active\.avg\.pct_of_peak_sustained_active|smsp__average_warps_issue_stalled_.*_per_issue_active\.ratio|"
+                  r"smsp__inst_executed\.sum|smsp__issue_active\.avg\.pct_of_peak_sustained_active)$")
+
+
+def copy_lines(pairs):
+    for src, dst in pairs:
+        p = os.path.join(OUT, src)
+        if os.path.exists(p):
+            lines = [x for x in open(p) if x.startswith("{")]
+            if lines:
+                open(os.path.join(PROF, dst), "w").write(lines[-1])
+
+
+def launch_list(src, dst_raw, dst_sum, cmd):
+    p = os.path.join(OUT, src)
+    if not os.path.exists(p):
+        return
+    rows = [r for r in csv.reader(open(p)) if r]
+    hdr = next(i for i, r in enumerate(rows) if r[0] == "ID")
+    H = rows[hdr]
+    ki, vi = H.index("Kernel Name"), H.index("Metric Value")
+    with open(os.path.join(PROF, dst_raw), "w") as f:
+        f.write("kernel,gpu__time_duration_ns\n")
+        for r in rows[hdr + 1:]:
+            if len(r) > vi:
+                f.write(f"\"{re.sub(r'[(].*$', '', r[ki])}\",{r[vi].replace(',', '')}\n")
+    tot, cnt = collections.Counter(), collections.Counter()
+    for r in rows[hdr + 1:]:
+        if len(r) > vi:
+            name = re.sub(r"\(.*$", "", r[ki])
+            tot[name] += float(r[vi].replace(",", "")) / 1e6
+            cnt[name] += 1
+    total = sum(tot.values())
+    with open(os.path.join(PROF, dst_sum), "w") as f:
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, `{cmd}` (cold-cache serialised times: compare shares)\n")
+        f.write("kernel,launches,total_ms,share_pct\n")
+        for k, v in tot.most_common():
+            f.write(f"\"{k}\",{cnt[k]},{v:.4f},{100 * v / total:.2f}\n")
+
+
+def full_capture(rep, dst, title):
+    p = os.path.join(OUT, rep)
+    if not os.path.exists(p):
+        return None
+    raw = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    names, units, launches = rows[0], rows[1], rows[2:]
+    out = {}
+    with open(os.path.join(PROF, dst), "w") as f:
+        f.write(f"# {title}; raw report: gpurun_out/{rep}\n")
+        for li, vals in enumerate(launches):
+            f.write(f"== launch {li}\n")
+            for n, u, v in zip(names, units, vals):
+                if n == "Kernel Name" or KEEP.match(n):
+                    f.write(f"{n},{u},{v}\n")
+                    out[(li, n)] = (u, v)
+    return out
+
+
+def to_bytes(u, v):
+    x = float(v.replace(",", ""))
+    return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+
+
+def main():
+    copy_lines([("r2_bench_headline.json", "r2_bench_headline_1gpu.json"), ("r2_bench_mutual0.json", "r2_bench_mutual0_1gpu.json"),
+                ("r2_bench_reference.json", "r2_bench_reference_arm.json")] +
+               [(f"r2_scale_w{w}_{n}gpu.json", f"r2_scale_w{w}_{n}gpu.json") for w in (2, 3, 4, 5) for n in (1, 2, 4, 8)] +
+               [(f"r2_scale_w2_{n}gpu_single.json", f"r2_scale_w2_{n}gpu_single_process.json") for n in (2, 8)])
+    launch_list("r2_launches_headline.csv", "r2_launch_list_raw.csv", "r2_launch_list_summary.csv",
+                "python bench.py --no-cpu-baseline --no-e2e --no-int8-peak --parity-pairs 0 --steps 2 --warmup 1 (100 images x 8192, mutual)")
+    cap = full_capture("r2_match_headline.ncu-rep", "r2_match_kernel_ncu_headline_summary.csv",
+                       "ncu --set full --clock-control none --import-source on -k regex:match_pairs_kernel -s 4 -c 1, "
+                       "`python bench.py --no-cpu-baseline --no-e2e --no-int8-peak --parity-pairs 0 --steps 1 --warmup 1`: the HEADLINE workload "
+                       "(100 images x 8192 rows, 4,950 pairs, mutual); the captured launch is the forward pass of the step's third batch (854 pairs)")
+    caps = []
+    if cap:
+        rd, wr = to_bytes(*cap[(0, "dram__bytes_read.sum")]), to_bytes(*cap[(0, "dram__bytes_write.sum")])
+        pairs = 854
+        caps.append({"workload": 2, "rows": 8192, "images_per_gpu": 100, "n_gpus": 1, "launch": "forward pass of the third batch of a step", "pairs_in_launch": pairs,
+                     "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr, "dram_bytes_per_pair": (rd + wr) / pairs,
+                     "algorithmic_bytes_per_pair": 2 * 8192 * 132 + 8192 * 16,
+                     "source": "profiles/r2_match_kernel_ncu_headline_summary.csv (ncu --set full on the headline workload)"})
+    cap3 = full_capture("r2_match_w3.ncu-rep", "r2_match_kernel_ncu_config3_summary.csv",
+                        "ncu --set full, one forward launch of BASELINE config #3 (1,000 images x 20,000 rows, GPS-guided pairs), 1 GPU")
+    if cap3:
+        rd, wr = to_bytes(*cap3[(0, "dram__bytes_read.sum")]), to_bytes(*cap3[(0, "dram__bytes_write.sum")])
+        caps.append({"workload": 3, "rows": 20000, "images_per_gpu": 1000, "n_gpus": 1, "launch": "first forward launch of a step (batch of <= 16 Mi query rows)",
+                     "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
+                     "source": "profiles/r2_match_kernel_ncu_config3_summary.csv"})
+    if caps:
+        json.dump({"captures": caps, "note": "algorithmic bytes per pair = both images read once (128 B row + 4 B key) + 16 B kNN row per query row written; "
+                                             "the N x M distance matrix never leaves the SM"}, open(os.path.join(PROF, "r2_match_kernel_traffic.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
