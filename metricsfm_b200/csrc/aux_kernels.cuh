@@ -445,9 +445,9 @@ __global__ void __launch_bounds__(256) rescore_band_kernel(const BandParams bp, 
 constexpr int kDangerWorkCap = 2048;     // candidates per pair that have to look at the dangerous rows (shared memory)
 constexpr int kDangerEvalBudget = 65536;  // exact 128-byte distances per pair on CUDA cores
 constexpr int kSmemTableRows = 20480;    // reference rows whose column table fits in shared memory (160 KiB)
-constexpr int kDangerChunk = 256;        // list rows per work unit of the exact evaluation (= entries of a warp's hit queue)
-constexpr int kDangerFlight = 8;         // row loads in flight per lane while scoring hits (4 x this many hits per warp and round)
-constexpr size_t kSelectSmemBytes = (size_t)kDangerWorkCap * 16 + 32 * kDangerChunk * 4 + (size_t)kSmemTableRows * 8;  // 224 KiB
+constexpr int kDangerChunk = 128;        // list rows per work unit of the exact evaluation (= entries of a warp's hit queue)
+constexpr int kDangerFlight = 2;         // hits per lane group and round while scoring (8 groups of 4 lanes, 2 row loads per lane and hit)
+constexpr size_t kSelectSmemBytes = (size_t)kDangerWorkCap * 16 + 32 * kDangerChunk * 4 + (size_t)kSmemTableRows * 8;  // 208 KiB
 constexpr int kCandGood = 1, kCandKilled = 2;  // bits of cand_good[]
 
 struct SelectParams {
@@ -525,6 +525,9 @@ __device__ __forceinline__ int block_scan_excl(int v, int &running, int *warp_ex
     return excl;
 }
 
+// Bucket of a dangerous row's bound d in [d1min, d0max]: monotone in d, 0..255.
+__device__ __forceinline__ int danger_bucket(int d, int d1min, float inv) { return min(255, max(0, (int)((float)(d - d1min) * inv))); }
+
 constexpr int kSelRows = 8;  // query rows per thread and chunk: their kNN records are loaded together (one L2 round trip)
 
 __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectParams sp) {
@@ -537,6 +540,7 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
     __shared__ int warp_excl[32];
     __shared__ int chunk_total;
     __shared__ int s_d0max, s_d1min, s_nd, s_nwork, s_evals, s_unit;
+    __shared__ int s_hist[257], s_cursor[256];  // counting sort of the dangerous-row list
     const PairDesc pd = sp.pairs[blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     int2 *danger = sp.danger + pd.knn_off;  // this pair's dangerous rows (row, d1), unordered; at most one per query row
@@ -634,33 +638,66 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
             __syncthreads();
             const int nwork = s_nwork;
             overflow = nwork > kDangerWorkCap;
+            bool sorted = false;
             if (!overflow && nwork > 0 && nd <= sp.smem_table_rows) {
-                // the column table has done its job (verdicts above): its shared memory now holds the dangerous-row list, so
-                // that the bound tests below are shared-memory reads instead of dependent L2 round trips
+                // The column table has done its job (verdicts above): its shared memory now holds the dangerous-row list,
+                // counting-sorted into 256 buckets of the bound (d1min .. d0max).  A candidate then only looks at the list
+                // prefix up to its own bucket — rows in lower buckets are hits by construction (the bucket function is
+                // monotone), rows in higher ones cannot be — instead of testing every listed row.
                 int2 *s_danger = reinterpret_cast<int2 *>(s_table);
-                for (int e = threadIdx.x; e < nd; e += blockDim.x) s_danger[e] = danger[e];
+                const float inv = 256.0f / (float)(s_d0max - d1min + 1);
+                for (int b = threadIdx.x; b < 257; b += blockDim.x) s_hist[b] = 0;
+                __syncthreads();
+                for (int e = threadIdx.x; e < nd; e += blockDim.x) atomicAdd(&s_hist[danger_bucket(danger[e].y, d1min, inv) + 1], 1);
+                __syncthreads();
+                if (warp == 0) {  // inclusive scan of the 256 counts -> s_hist[b] = first list position of bucket b
+                    int v[8], sum = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { v[i] = s_hist[1 + lane * 8 + i]; sum += v[i]; }
+                    int incl = sum;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    int run = incl - sum;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { run += v[i]; s_hist[1 + lane * 8 + i] = run; }
+                }
+                __syncthreads();
+                for (int b = threadIdx.x; b < 256; b += blockDim.x) s_cursor[b] = s_hist[b];
+                __syncthreads();
+                for (int e = threadIdx.x; e < nd; e += blockDim.x) {
+                    const int2 r = danger[e];
+                    s_danger[atomicAdd(&s_cursor[danger_bucket(r.y, d1min, inv)], 1)] = r;
+                }
                 __syncthreads();
                 danger = s_danger;
+                sorted = true;
             }
             if (!overflow && nwork > 0) {
                 // (listed candidate) x (dangerous row).  The bound test is one compare per combination; the few that pass
-                // ("hits", ~1e4 per 8192 x 8192 pair) cost an exact 128-byte distance each and are latency-bound L2 reads.
-                // Work unit = (candidate, chunk of kDangerChunk list rows), dealt round-robin to the warps: the warp keeps
-                // its 16-byte share of the candidate's reference row in registers, queues the chunk's hits in shared memory
-                // and scores them 16 at a time — eight lanes per distance, four independent row loads in flight per lane.
+                // ("hits", ~1e4 per 8192 x 8192 pair) cost an exact 128-byte distance each.  Work unit = (candidate, chunk of
+                // kDangerChunk list rows), dealt to the warps on demand: the warp keeps its 32-byte share of the candidate's
+                // reference row in registers, queues the chunk's hits in shared memory and scores them 16 at a time —
+                // four lanes per distance, four independent row loads in flight per lane.
                 const int nchunks = (nd + kDangerChunk - 1) / kDangerChunk;
                 const int units = nwork * nchunks;
-                const int sub = lane >> 3, part = lane & 7;  // which of the warp's 4 concurrent distances, which 16 bytes
+                const int sub = lane >> 2, part = lane & 3;  // which of the warp's 8 concurrent distances, which 32 bytes
                 int *hitq = s_hitq + warp * kDangerChunk;
+                const float inv = 256.0f / (float)(s_d0max - d1min + 1);
                 for (;;) {
                     int u = 0;
-                    if (lane == 0) u = atomicAdd(&s_unit, 1);  // units differ widely in hits: dealt on demand
+                    if (lane == 0) u = atomicAdd(&s_unit, 1);  // units differ widely in hits
                     u = __shfl_sync(0xFFFFFFFFu, u, 0);
                     if (u >= units || s_evals >= kDangerEvalBudget) break;  // (budget: too ambiguous for CUDA cores)
                     const int w = u / nchunks, e0 = (u - w * nchunks) * kDangerChunk;
                     const int4 c = s_work[w];  // (candidate, q, j, d0)
+                    // list prefix this candidate has to look at (d1min <= c.w <= d0max holds for every listed candidate)
+                    const int prefix = sorted ? s_hist[danger_bucket(c.w, d1min, inv) + 1] : nd;
+                    if (e0 >= prefix) continue;
                     int n = 0;
-                    const int e1 = min(e0 + kDangerChunk, nd);
+                    const int e1 = min(e0 + kDangerChunk, prefix);
                     for (int eb = e0; eb < e1; eb += 32) {  // warp-uniform trip count
                         const int e = eb + lane;
                         bool hit = false;
@@ -676,29 +713,38 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
                     if (n == 0) continue;
                     __syncwarp();
                     if (lane == 0) atomicAdd(&s_evals, n);
-                    const uint4 y = __ldg(reinterpret_cast<const uint4 *>(sp.desc_arena + (pd.ref_off + c.z) * kDim) + part);
+                    const uint4 *yp = reinterpret_cast<const uint4 *>(sp.desc_arena + (pd.ref_off + c.z) * kDim) + part * 2;
+                    const uint4 y0 = __ldg(yp), y1 = __ldg(yp + 1);
                     const int nb = ckey_to_norm(sp.ckeys[pd.ref_off + c.z]);
-                    for (int base = 0; base < n; base += 4 * kDangerFlight) {
+                    for (int base = 0; base < n; base += 8 * kDangerFlight) {
                         int row[kDangerFlight];
-                        uint4 x[kDangerFlight];
+                        uint4 x0[kDangerFlight], x1[kDangerFlight];
 #pragma unroll
                         for (int k2 = 0; k2 < kDangerFlight; ++k2) {
-                            const int idx = base + k2 * 4 + sub;
+                            const int idx = base + k2 * 8 + sub;
                             row[k2] = idx < n ? hitq[idx] : -1;
-                            x[k2] = make_uint4(0, 0, 0, 0);
-                            if (row[k2] >= 0) x[k2] = __ldg(reinterpret_cast<const uint4 *>(sp.desc_arena + (pd.qry_off + row[k2]) * kDim) + part);
+                            x0[k2] = x1[k2] = make_uint4(0, 0, 0, 0);
+                            if (row[k2] >= 0) {
+                                const uint4 *xp = reinterpret_cast<const uint4 *>(sp.desc_arena + (pd.qry_off + row[k2]) * kDim) + part * 2;
+                                x0[k2] = __ldg(xp);
+                                x1[k2] = __ldg(xp + 1);
+                            }
                         }
 #pragma unroll
                         for (int k2 = 0; k2 < kDangerFlight; ++k2) {
                             // this lane's share of ||x||^2 - 2 x.y  (the row's norm comes from the row itself)
-                            uint32_t ab = __dp4a(x[k2].x, y.x, 0u), aa = __dp4a(x[k2].x, x[k2].x, 0u);
-                            ab = __dp4a(x[k2].y, y.y, ab); aa = __dp4a(x[k2].y, x[k2].y, aa);
-                            ab = __dp4a(x[k2].z, y.z, ab); aa = __dp4a(x[k2].z, x[k2].z, aa);
-                            ab = __dp4a(x[k2].w, y.w, ab); aa = __dp4a(x[k2].w, x[k2].w, aa);
+                            const uint4 a = x0[k2], b = x1[k2];
+                            uint32_t ab = __dp4a(a.x, y0.x, 0u), aa = __dp4a(a.x, a.x, 0u);
+                            ab = __dp4a(a.y, y0.y, ab); aa = __dp4a(a.y, a.y, aa);
+                            ab = __dp4a(a.z, y0.z, ab); aa = __dp4a(a.z, a.z, aa);
+                            ab = __dp4a(a.w, y0.w, ab); aa = __dp4a(a.w, a.w, aa);
+                            ab = __dp4a(b.x, y1.x, ab); aa = __dp4a(b.x, b.x, aa);
+                            ab = __dp4a(b.y, y1.y, ab); aa = __dp4a(b.y, b.y, aa);
+                            ab = __dp4a(b.z, y1.z, ab); aa = __dp4a(b.z, b.z, aa);
+                            ab = __dp4a(b.w, y1.w, ab); aa = __dp4a(b.w, b.w, aa);
                             int pd2 = (int)aa - 2 * (int)ab;
-                            pd2 += __shfl_xor_sync(0xFFFFFFFFu, pd2, 1);  // over the 8 lanes of the group
+                            pd2 += __shfl_xor_sync(0xFFFFFFFFu, pd2, 1);  // over the 4 lanes of the group
                             pd2 += __shfl_xor_sync(0xFFFFFFFFu, pd2, 2);
-                            pd2 += __shfl_xor_sync(0xFFFFFFFFu, pd2, 4);
                             if (part == 0 && row[k2] >= 0) {
                                 const int d = pd2 + nb;
                                 // several rivals may kill the same candidate: they all set the same bit, the other bits are final
