@@ -174,6 +174,15 @@ __device__ __forceinline__ void merge_top2(int sa, int ja, int sb, int jb, int &
     J0 = t0 ? ja : J0;
 }
 
+// The score a row prunes against: its second best, or — "dead row" rule, see the epilogue — its best when the running pair
+// already violates d0 <= rho * d1 (rho = rho8 / 256, rounded so that the test errs on the live side; d = na - S).
+// Placeholder states (nothing or one neighbour seen, pad rows) never count as dead.
+__device__ __forceinline__ int prune_score(int S0, int S1, int na, int rho8, int absent) {
+    const int d0 = (int)((uint32_t)na - (uint32_t)S0), d1 = (int)((uint32_t)na - (uint32_t)S1);
+    const bool dead = (S1 > absent) && (d0 > (d1 >> 8) * rho8 + rho8);
+    return dead ? S0 : S1;
+}
+
 template <int STRIPS, int TILE_N, int STAGES, int CSPLIT, int TBUFS, bool DEBUG, int MODE = 0, bool DYN = false>
 __global__ void __launch_bounds__(MatchKernelCfg<STRIPS, TILE_N, STAGES, CSPLIT, TBUFS>::kThreads, 1)
 match_pairs_kernel(const MatchKernelParams p) {
@@ -230,7 +239,13 @@ match_pairs_kernel(const MatchKernelParams p) {
       // latency is hidden anyway (the loader runs STAGES tiles ahead, the issuers have a spare accumulator buffer), and
       // tile loops that walk the B ring unrolled, so that stage / barrier / key-slot addresses are immediates.
       // Spreading the loads over four loader warps was measured too: more total service work, slower.
-      constexpr unsigned kLoaderSleepNs = 1000, kIssuerSleepNs = 200;
+#ifndef MSFM_LOADER_SLEEP
+#define MSFM_LOADER_SLEEP 1000
+#endif
+#ifndef MSFM_ISSUER_SLEEP
+#define MSFM_ISSUER_SLEEP 200
+#endif
+      constexpr unsigned kLoaderSleepNs = MSFM_LOADER_SLEEP, kIssuerSleepNs = MSFM_ISSUER_SLEEP;
 #define LOADER_WAIT(bar, par) ptx::mbar_wait_backoff<kLoaderSleepNs>(bar, par)
 #define ISSUER_WAIT(bar, par) ptx::mbar_wait_backoff<kIssuerSleepNs>(bar, par)
       const int x = warp - Cfg::kEpiWarps;
@@ -438,6 +453,7 @@ match_pairs_kernel(const MatchKernelParams p) {
             const int rho8 = (MODE == 0 && CSPLIT == 1 && pd.cand_idx < 0) ? (int)p.prune_q8 : (int)kNoPrune;  // shares keep partial states
             const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
             long long acc_wait = 0, acc_load = 0, acc_p1 = 0, acc_p2 = 0, acc_hot = 0;
+            int theta = prune_score(S0, S1, na, rho8, kAbsent);  // pruning score of the row, refreshed after every hot tile
             int jtile = share * kCols;  // first column of this warp's share in the current tile
             for (int t = 0; t < ntiles; ++t, jtile += TILE_N) {
                 // ---- pull this warp's whole share of the accumulator tile into registers and release TMEM at once
@@ -448,9 +464,16 @@ match_pairs_kernel(const MatchKernelParams p) {
                 ptx::tc_fence_after();
                 if (prof) c1 = clock64();
                 const uint32_t tile_taddr = warp_taddr + buf * (STRIPS * TILE_N);
+#ifdef MSFM_LD_X32
+                uint32_t acc32[kCols / 32][32];
+#pragma unroll
+                for (int c = 0; c < kCols / 32; ++c) ptx::tmem_ld_32x32b_x32(tile_taddr + c * 32, acc32[c]);
+                uint32_t (*acc)[16] = reinterpret_cast<uint32_t (*)[16]>(acc32);
+#else
                 uint32_t acc[kCols / 16][16];
 #pragma unroll
                 for (int c = 0; c < kCols / 16; ++c) ptx::tmem_ld_32x32b_x16(tile_taddr + c * 16, acc[c]);
+#endif
                 // ---- while the loads fly: column keys of the tile, smallest reference norm, pruning threshold
                 ptx::mbar_wait_a(k_full_base + ks * 8, k_phase);
                 const uint32_t ck = key_base + ks * (TILE_N * 4);
@@ -458,17 +481,14 @@ match_pairs_kernel(const MatchKernelParams p) {
 #pragma unroll
                 for (int k = 1; k < kCols / 32; ++k) ckmax = max(ckmax, ptx::lds_s32(ck + (lane + 32 * k) * 4));
                 const int nbmin = ckey_to_norm(__reduce_max_sync(0xFFFFFFFFu, ckmax));
-                // dead rows are pruned against their best score (d = na - S; placeholders never count as dead)
-                const int d1_now = (int)((uint32_t)na - (uint32_t)S1);
-                const bool dead = (S1 > kAbsent) && ((int)((uint32_t)na - (uint32_t)S0) > (d1_now >> 8) * rho8 + rho8);
-                int theta = dead ? S0 : S1;
+                int th = theta;  // dead rows are pruned against their best score, the others against their second best
                 if (CSPLIT > 1) {
                     // peer's {S0 - 1, S1 - 1, item tag}: the row's final second best is >= its own S1, >= the peer's S1
                     // and >= min(S0_own, S0_peer); peer scores count minus one (see above)
                     const int4 peer = ptx::lds_v4_volatile(peer_slot);
-                    if ((uint32_t)peer.z == a) theta = __vimax3_s32(theta, peer.y, min(S0, peer.x));
+                    if ((uint32_t)peer.z == a) th = __vimax3_s32(th, peer.y, min(S0, peer.x));
                 }
-                const int T = (theta + nbmin) >> 1;
+                const int T = (th + nbmin) >> 1;
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -477,44 +497,58 @@ match_pairs_kernel(const MatchKernelParams p) {
                 if (DEBUG && (p.debug_flags & 6u)) {  // experiments: 2/4 = TMEM loads + hand-back only
                     if (acc[0][0] == 0x7fffffffu) S1 = 0;
                 } else {
-                    // ---- phase 1: which groups of 8 columns can still matter to some lane?
-                    bool hot[kCols / 8];
+                    // ---- phase 1: can any column of this tile still matter to some lane?  (maximum of the raw accumulators
+                    //      per group of 8 columns, then of the tile: one vote; most tiles late in an item end here)
+                    int gm[kCols / 8];
 #pragma unroll
                     for (int gq = 0; gq < kCols / 8; ++gq) {
                         const uint32_t *v = &acc[gq / 2][8 * (gq & 1)];
                         const int m1 = __vimax3_s32((int)v[0], (int)v[1], (int)v[2]);
                         const int m2 = __vimax3_s32((int)v[3], (int)v[4], (int)v[5]);
                         const int m3 = __vimax3_s32((int)v[6], (int)v[7], m1);
-                        hot[gq] = __any_sync(0xFFFFFFFFu, max(m2, m3) > T);
+                        gm[gq] = max(m2, m3);
                     }
+                    int tm = gm[0];
+#pragma unroll
+                    for (int gq = 1; gq + 1 < kCols / 8; gq += 2) tm = __vimax3_s32(tm, gm[gq], gm[gq + 1]);
+                    tm = max(tm, gm[kCols / 8 - 1]);
+                    const bool tile_hot = __any_sync(0xFFFFFFFFu, tm > T);
                     if (prof) c3 = clock64();
-                    // ---- phase 2: exact scoring of the hot groups straight from the registers
                     bool touched = false;
+                    if (tile_hot) {
+                        // ---- which groups?  (one vote and one branch per group: only paid by tiles that have one)
+                        bool hot[kCols / 8];
 #pragma unroll
-                    for (int gq = 0; gq < kCols / 8; ++gq) {
-                        if (hot[gq] && !(DEBUG && (p.debug_flags & 1u))) {
-                            const uint32_t *v = &acc[gq / 2][8 * (gq & 1)];
-                            const int4 c0 = ptx::lds_v4(ck + gq * 32);
-                            const int4 c1 = ptx::lds_v4(ck + gq * 32 + 16);
-                            const int key[8] = {16 * (int)v[0] + c0.x, 16 * (int)v[1] + c0.y, 16 * (int)v[2] + c0.z,
-                                                16 * (int)v[3] + c0.w, 16 * (int)v[4] + c1.x, 16 * (int)v[5] + c1.y,
-                                                16 * (int)v[6] + c1.z, 16 * (int)v[7] + c1.w};
-                            const int jb8 = jtile + gq * 8;
-                            if (MODE == 1) {
+                        for (int gq = 0; gq < kCols / 8; ++gq) hot[gq] = __any_sync(0xFFFFFFFFu, gm[gq] > T);
+                        // ---- phase 2: exact scoring of the hot groups straight from the registers
 #pragma unroll
-                                for (int i = 0; i < 8; ++i)
-                                    if ((key[i] >> 3) > S1) {
-                                        const unsigned slot = atomicAdd(p.event_count, 1u);
-                                        if (slot < p.event_cap) p.events[slot] = make_int4((int)(pd.qry_off + q), jb8 + i, pd.cand_idx, 0);
-                                    }
-                            } else {
-                                int g0, g1;
-                                top2_of8(key, g0, g1);
-                                merge_top2(g0 >> 3, jb8 + ((g0 & 7) ^ 7), g1 >> 3, jb8 + ((g1 & 7) ^ 7), S0, J0, S1, J1);
+                        for (int gq = 0; gq < kCols / 8; ++gq) {
+                            if (hot[gq] && !(DEBUG && (p.debug_flags & 1u))) {
+                                const uint32_t *v = &acc[gq / 2][8 * (gq & 1)];
+                                const int4 c0 = ptx::lds_v4(ck + gq * 32);
+                                const int4 c1 = ptx::lds_v4(ck + gq * 32 + 16);
+                                const int key[8] = {16 * (int)v[0] + c0.x, 16 * (int)v[1] + c0.y, 16 * (int)v[2] + c0.z,
+                                                    16 * (int)v[3] + c0.w, 16 * (int)v[4] + c1.x, 16 * (int)v[5] + c1.y,
+                                                    16 * (int)v[6] + c1.z, 16 * (int)v[7] + c1.w};
+                                const int jb8 = jtile + gq * 8;
+                                if (MODE == 1) {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i)
+                                        if ((key[i] >> 3) > S1) {
+                                            const unsigned slot = atomicAdd(p.event_count, 1u);
+                                            if (slot < p.event_cap) p.events[slot] = make_int4((int)(pd.qry_off + q), jb8 + i, pd.cand_idx, 0);
+                                        }
+                                } else {
+                                    int g0, g1;
+                                    top2_of8(key, g0, g1);
+                                    merge_top2(g0 >> 3, jb8 + ((g0 & 7) ^ 7), g1 >> 3, jb8 + ((g1 & 7) ^ 7), S0, J0, S1, J1);
+                                }
+                                touched = true;
+                                if (prof) ++acc_hot;
                             }
-                            touched = true;
-                            if (prof) ++acc_hot;
                         }
+                        // the row's pruning score for the next tiles (only a hot tile can change it)
+                        theta = prune_score(S0, S1, na, rho8, kAbsent);
                     }
                     if (CSPLIT > 1 && touched)
                         ptx::sts_v4_volatile(my_slot, max(S0, INT_MIN + 1) - 1, max(S1, INT_MIN + 1) - 1, (int)a, 0);
@@ -540,8 +574,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                 atomicAdd(p.stats + 9 + 2 * quarter, (unsigned long long)(acc_load + acc_p1 + acc_p2));
             }
             if (valid && MODE == 0) {
-                const int d1_end = (int)((uint32_t)na - (uint32_t)S1);
-                if ((S1 > kAbsent) && ((int)((uint32_t)na - (uint32_t)S0) > (d1_end >> 8) * rho8 + rho8)) S1 = S0;  // ended dead: d1 := d0 (lower bound)
+                if (prune_score(S0, S1, na, rho8, kAbsent) != S1) S1 = S0;  // ended dead: d1 := d0 (lower bound)
                 int4 out;
                 out.x = (S0 > kAbsent) ? J0 : -1;
                 out.y = (S1 > kAbsent) ? J1 : -1;

@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 cp metricsfm_b200/csrc/libmsfm_match.so /tmp/orig.so
 for f in exp_libs/*.so; do
     n=$(basename $f .so); cp $f metricsfm_b200/csrc/libmsfm_match.so
-    for m in 1 0; do
+    for m in ${AB_MODES:-1 0}; do
         timeout 300 python bench.py --no-cpu-baseline --no-int8-peak --mutual $m --steps 5 --warmup 3 "$@" > gpurun_out/ab_${n}_m$m.json 2> gpurun_out/ab_${n}_m$m.err
         python - gpurun_out/ab_${n}_m$m.json $n $m <<'PY'
 import json,sys
