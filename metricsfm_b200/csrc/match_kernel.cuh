@@ -207,7 +207,8 @@ match_pairs_kernel(const MatchKernelParams p) {
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
     volatile int32_t *s_item = reinterpret_cast<volatile int32_t *>(smem + Cfg::kSmemItems);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);  // warp-uniform by construction: lets the compiler keep
+                                                                            // everything derived from it in uniform registers
     const int lane = threadIdx.x & 31;
     if (p.gate != nullptr && *p.gate == 0u) return;  // uniform over the grid: nothing was routed to this pass
     if (threadIdx.x == 0 && (ptx::smem_u32(smem) & 1023u) != 0) __trap();
