@@ -77,6 +77,22 @@ __global__ void init_pad_kernel(int rows, int rows_padded, uint8_t *__restrict__
 // The per-batch plan (pair descriptors + work items, a few hundred KB in page-locked host memory) is PULLED by the SMs over
 // PCIe instead of being copied by the host->device copy engine: that engine is a FIFO, and a plan copy queued behind the
 // bulk descriptor uploads of later image groups would hold back the matching launch until all of them had finished.
+// Per reference tile (kKeyTileRows rows of the arena) the smallest squared norm of its rows, for the matching kernel's pruning
+// threshold (one shared-memory read per tile instead of a reduction over the tile's keys in each of the 16 epilogue warps).
+// One warp per tile; recomputed per batch over the arena range the batch's images span (the column keys are written by
+// the packers, by NCCL during replication, or by the caller: only at launch time is everything the batch needs in place).
+__global__ void tile_min_kernel(const int32_t *__restrict__ ckeys, int4 *__restrict__ tilemin, int64_t tile0, int64_t ntiles) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= ntiles) return;
+    const int32_t *k = ckeys + (tile0 + i) * kKeyTileRows;
+    int m = k[lane];
+#pragma unroll
+    for (int r = 32; r < kKeyTileRows; r += 32) m = max(m, k[lane + r]);
+    m = __reduce_max_sync(0xFFFFFFFFu, m);  // largest key = smallest norm
+    if (lane == 0) tilemin[tile0 + i] = make_int4(ckey_to_norm(m), 0, 0, 0);
+}
+
 __global__ void pull_plan_kernel(const uint4 *__restrict__ host_src, uint4 *__restrict__ dst0, size_t n0, uint4 *__restrict__ dst1, size_t n1) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += (size_t)gridDim.x * blockDim.x) {
         const uint4 v = host_src[i];

@@ -50,6 +50,7 @@ constexpr int kDim = 128;        // bytes per packed descriptor row
 constexpr int kStripRows = 128;  // MMA M
 constexpr int kAlignRows = 256;  // every image starts on / is padded to a multiple of this many rows
 constexpr int kBoxRows = 64;     // rows per TMA box (strips and reference tiles are loaded as 64-row boxes)
+constexpr int kKeyTileRows = 64; // granularity of the per-tile minimum-norm table (MatchKernelParams::tilemin) = TILE_N
 
 // Per-row side table ("column keys").  For row j with squared norm nb:  ckey = -8*nb + (7 - j%8).
 //   * exact packed score key of element (q, j):  16*acc + ckey = 8*(2*acc - nb) + (7 - j%8)
@@ -81,6 +82,8 @@ struct WorkItem {
 struct MatchKernelParams {
     const CUtensorMap *maps;      // [max_images] one 2-D map per image: {128 B, rows}, box {128 B, kBoxRows rows}, SW128
     const int32_t *ckeys;         // arena of column keys (see make_ckey)
+    const int4 *tilemin;          // [arena rows / kKeyTileRows] {smallest squared norm of the tile's rows, -, -, -}: refreshed per batch
+                                  // by tile_min_kernel; images start on multiples of kAlignRows, so tiles never straddle images
     const int32_t *cand_ckeys;    // column keys of the gathered candidate rows (query side of cand_idx >= 0 pairs)
     const int32_t *cand_d0;       // squared distance of each candidate to the query row that proposed it
     const int32_t *counts;        // per-pair candidate counts
@@ -132,7 +135,8 @@ struct MatchKernelCfg {
     static constexpr int kSmemA = 0;
     static constexpr int kSmemB = kSmemA + 2 * kABytes;
     static constexpr int kSmemKey = kSmemB + STAGES * kBBytes;
-    static constexpr int kSmemShare = kSmemKey + kKeySlots * TILE_N * 4;       // [STRIPS*128 rows][CSPLIT] int4
+    static constexpr int kSmemTmin = kSmemKey + kKeySlots * TILE_N * 4;        // [kKeySlots] int4: the tile's smallest reference norm
+    static constexpr int kSmemShare = kSmemTmin + kKeySlots * 16;              // [STRIPS*128 rows][CSPLIT] int4
     static constexpr int kSmemBar = kSmemShare + STRIPS * kStripRows * CSPLIT * 16;
     static constexpr int kItemSlots = 8;  // published work-item indices (the loader runs at most two items ahead of the MMAs)
     static constexpr int kNumBars = 2 + 2 + STAGES + STAGES + kKeySlots + 2 * TBUFS * STRIPS + kItemSlots;
@@ -144,6 +148,7 @@ struct MatchKernelCfg {
                   "TMEM allocation must be a power of two in [32, 512] columns");
     static_assert(TILE_N % kBoxRows == 0 && TILE_N <= 256, "reference tile is loaded as 64-row TMA boxes; UMMA N <= 256");
     static_assert(kAlignRows % TILE_N == 0, "image padding must cover whole reference tiles");
+    static_assert(TILE_N == kKeyTileRows, "the minimum-norm table is kept per reference tile");
     static_assert(CSPLIT == 1 || CSPLIT == 2, "one or two warps per (strip, quarter)");
     static_assert(kColsPerWarp % 16 == 0 && kColsPerWarp / 8 <= 32, "one flag bit per group of 8 columns");
     static_assert(kThreads <= 1024, "too many warps");
@@ -194,6 +199,7 @@ match_pairs_kernel(const MatchKernelParams p) {
     uint8_t *sA = smem + Cfg::kSmemA;
     uint8_t *sB = smem + Cfg::kSmemB;
     int32_t *sKey = reinterpret_cast<int32_t *>(smem + Cfg::kSmemKey);
+    int4 *sTmin = reinterpret_cast<int4 *>(smem + Cfg::kSmemTmin);
     int4 *sShare = reinterpret_cast<int4 *>(smem + Cfg::kSmemShare);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
     uint64_t *a_full = bars;                         // [2]
@@ -260,6 +266,7 @@ match_pairs_kernel(const MatchKernelParams p) {
             uint32_t a = 0, round = 0;  // items started, trips round the B ring
             const CUtensorMap *rmap = nullptr;
             const int32_t *keyp = nullptr;
+            const int4 *tminp = nullptr;
             auto next_item = [&]() -> bool {  // next item with work; fetches its query strips
                 for (;;) {
                     const int idx = DYN ? (int)atomicAdd(p.next_item, 1u) : (cur += (int)gridDim.x);
@@ -287,6 +294,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                                          pd.qry_row_base + wi.row0 + s * kBoxRows);
                     rmap = p.maps + pd.ref_img;
                     keyp = p.ckeys + pd.ref_off;
+                    tminp = p.tilemin + pd.ref_off / kKeyTileRows;
                     left = (pd.ref_rows + TILE_N - 1) / TILE_N;
                     t = 0;
                     ++a;
@@ -304,8 +312,9 @@ match_pairs_kernel(const MatchKernelParams p) {
                     for (int h = 0; h < TILE_N / kBoxRows; ++h)
                         ptx::tma_load_2d(sB + st * Cfg::kBBytes + h * kBoxRows * kDim, rmap, &b_full[st], 0, t + h * kBoxRows);
                     const uint32_t ks = st + STAGES * (round & 1);
-                    ptx::mbar_arrive_expect_tx(&k_full[ks], TILE_N * 4);
+                    ptx::mbar_arrive_expect_tx(&k_full[ks], TILE_N * 4 + 16);
                     ptx::bulk_load_1d(sKey + ks * TILE_N, keyp + t, TILE_N * 4, &k_full[ks]);
+                    ptx::bulk_load_1d(sTmin + ks, tminp++, 16, &k_full[ks]);
                     t += TILE_N;  // first reference row of the next tile
                     if (--left == 0) more = next_item();
                 }
@@ -414,10 +423,13 @@ match_pairs_kernel(const MatchKernelParams p) {
         const uint32_t peer_slot = ptx::smem_u32(sShare + row_local * CSPLIT + (share ^ (CSPLIT - 1)));
         const uint32_t key_base = ptx::smem_u32(sKey) + share * kCols * 4;
         const uint32_t k_full_base = ptx::smem_u32(k_full);
+        const uint32_t tmin_base = ptx::smem_u32(sTmin);
         const uint32_t t_full_base = ptx::smem_u32(t_full + strip);
         const uint32_t t_empty_base = ptx::smem_u32(t_empty + strip);
         // ring positions are carried incrementally (no divisions in the tile loop)
-        uint32_t ks = 0, k_phase = 0, buf = 0, t_phase = 0, a = 0;
+        // ring positions all derive from ONE running tile counter g (TBUFS and kKeySlots are powers of two)
+        static_assert((TBUFS & (TBUFS - 1)) == 0 && (Cfg::kKeySlots & (Cfg::kKeySlots - 1)) == 0, "ring sizes must be powers of two");
+        uint32_t g = 0, a = 0;
         const uint32_t i_full_base = ptx::smem_u32(i_full);
         for (int cur = blockIdx.x;; cur += gridDim.x) {
             int item = cur;
@@ -461,6 +473,8 @@ match_pairs_kernel(const MatchKernelParams p) {
                 long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
                 const bool prof = DEBUG && (p.debug_flags & 8u) && p.stats != nullptr;
                 if (prof) c0 = clock64();
+                const uint32_t buf = g % TBUFS, t_phase = (g / TBUFS) & 1;
+                const uint32_t ks = g % Cfg::kKeySlots, k_phase = (g / Cfg::kKeySlots) & 1;
                 ptx::mbar_wait_a(t_full_base + buf * (STRIPS * 8), t_phase);
                 ptx::tc_fence_after();
                 if (prof) c1 = clock64();
@@ -478,10 +492,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                 // ---- while the loads fly: column keys of the tile, smallest reference norm, pruning threshold
                 ptx::mbar_wait_a(k_full_base + ks * 8, k_phase);
                 const uint32_t ck = key_base + ks * (TILE_N * 4);
-                int ckmax = ptx::lds_s32(ck + lane * 4);
-#pragma unroll
-                for (int k = 1; k < kCols / 32; ++k) ckmax = max(ckmax, ptx::lds_s32(ck + (lane + 32 * k) * 4));
-                const int nbmin = ckey_to_norm(__reduce_max_sync(0xFFFFFFFFu, ckmax));
+                const int nbmin = ptx::lds_s32(tmin_base + ks * 16);  // smallest reference norm of the tile (tile_min_kernel)
                 int th = theta;  // dead rows are pruned against their best score, the others against their second best
                 if (CSPLIT > 1) {
                     // peer's {S0 - 1, S1 - 1, item tag}: the row's final second best is >= its own S1, >= the peer's S1
@@ -542,7 +553,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                                 } else {
                                     int g0, g1;
                                     top2_of8(key, g0, g1);
-                                    merge_top2(g0 >> 3, jb8 + ((g0 & 7) ^ 7), g1 >> 3, jb8 + ((g1 & 7) ^ 7), S0, J0, S1, J1);
+                                    merge_top2(g0 >> 3, jb8 | (g0 & 7), g1 >> 3, jb8 | (g1 & 7), S0, J0, S1, J1);  // columns stay packed: see the item's end
                                 }
                                 touched = true;
                                 if (prof) ++acc_hot;
@@ -561,8 +572,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                     acc_p1 += c3 - c2;    // phase 1
                     acc_p2 += c4 - c3;    // phase 2 + publish
                 }
-                if (++ks == Cfg::kKeySlots) { ks = 0; k_phase ^= 1; }
-                if (++buf == TBUFS) { buf = 0; t_phase ^= 1; }
+                ++g;
             }
             if (DEBUG && (p.debug_flags & 8u) && p.stats != nullptr && lane == 0) {
                 atomicAdd(p.stats + 0, (unsigned long long)acc_hot);
@@ -577,8 +587,9 @@ match_pairs_kernel(const MatchKernelParams p) {
             if (valid && MODE == 0) {
                 if (prune_score(S0, S1, na, rho8, kAbsent) != S1) S1 = S0;  // ended dead: d1 := d0 (lower bound)
                 int4 out;
-                out.x = (S0 > kAbsent) ? J0 : -1;
-                out.y = (S1 > kAbsent) ? J1 : -1;
+                out.x = (S0 > kAbsent && J0 >= 0) ? (J0 ^ 7) : -1;  // low three bits hold 7 - (column mod 8), as in the packed keys;
+                                                                   // seeded placeholders (mutual twin items) keep id -1
+                out.y = (S1 > kAbsent && J1 >= 0) ? (J1 ^ 7) : -1;
                 out.z = (S0 > kAbsent) ? na - S0 : INT_MAX;
                 out.w = (S1 > kAbsent) ? na - S1 : INT_MAX;
                 p.knn[(pd.knn_off + q) * CSPLIT + share] = out;

@@ -103,6 +103,7 @@ struct msfm_ctx {
 
     DeviceBuf dbg_stats;  // debug flag 8: per-phase cycle counters of the matching kernel, dumped at destroy
     DeviceBuf cand_q, cand_j, cand_d0, cand_good, cand_counts, cand_desc, cand_ckeys;  // one-way candidates + gathered rows
+    DeviceBuf tilemin;       // per reference tile: smallest squared norm (tile_min_kernel, refreshed per batch)
     DeviceBuf item_counter;  // work-item counter of the matching launch in flight (zeroed before every launch)
     DeviceBuf colbest, twin_counts;  // mutual check: per-pair column table (nearest claimant per reference row); [n_pairs] + gate word
     DeviceBuf band_q, band_counts;  // float regime: query rows near a ratio threshold, per pair
@@ -309,6 +310,7 @@ struct BatchPlan {
     bool rescoring = false;          // the caller asked for fp32 re-scoring and the context keeps float rows
     int64_t query_rows = 0;          // forward kNN rows (= candidate / match scratch rows)
     int64_t ref_rows = 0;            // sum of reference rows (= entries of the mutual check's column table)
+    int64_t row_lo = INT64_MAX, row_hi = 0;  // arena rows spanned by the batch's images (tile_min_kernel's range)
     uint64_t need_seq = 0;           // newest upload mark among the batch's images
     bool big_ref = false;            // some reference image's column table does not fit in shared memory
     int64_t ops = 0;
@@ -326,6 +328,7 @@ msfm_status launch_match_kernel(msfm_ctx *ctx, size_t first_item, size_t n_items
     msfm::MatchKernelParams kp;
     kp.maps = ctx->d_maps;
     kp.ckeys = ctx->norms;
+    kp.tilemin = static_cast<const int4 *>(ctx->tilemin.ptr);
     kp.cand_ckeys = static_cast<const int32_t *>(ctx->cand_ckeys.ptr);
     kp.cand_d0 = static_cast<const int32_t *>(collect ? ctx->band_thr.ptr : ctx->cand_d0.ptr);
     kp.counts = static_cast<const int32_t *>(collect ? ctx->band_counts.ptr : ctx->twin_counts.ptr);
@@ -479,6 +482,13 @@ msfm_status run_match_stage(msfm_ctx *ctx, const BatchPlan &plan) {
         ctx->timing.total_launches += 1;
     }
     if (plan.has_empty) MSFM_CUDA(ctx, cudaMemsetAsync(ctx->knn.ptr, 0xFF, (size_t)plan.query_rows * kCsplit * sizeof(int4), ctx->stream));
+    if (plan.row_hi > plan.row_lo) {  // smallest norm per reference tile, over the arena rows this batch can touch
+        if ((st = ensure(ctx, ctx->tilemin, (size_t)(ctx->arena_rows / msfm::kKeyTileRows + 1) * sizeof(int4))) != MSFM_OK) return st;
+        const int64_t tile0 = plan.row_lo / msfm::kKeyTileRows, tile1 = (plan.row_hi + msfm::kKeyTileRows - 1) / msfm::kKeyTileRows;
+        msfm::tile_min_kernel<<<(unsigned)((tile1 - tile0 + 7) / 8), 256, 0, ctx->stream>>>(ctx->norms, static_cast<int4 *>(ctx->tilemin.ptr), tile0, tile1 - tile0);
+        MSFM_CUDA(ctx, cudaGetLastError());
+        ctx->timing.total_launches += 1;
+    }
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
     if (!plan.items.empty() && (st = launch_match_kernel(ctx, 0, plan.items.size(), false, 0, false, plan.prune_q8)) != MSFM_OK) return st;
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
@@ -503,6 +513,8 @@ void plan_add_pair(msfm_ctx *ctx, BatchPlan &plan, int64_t src, int32_t ref, int
     pd.col_off = plan.ref_rows;
     if (r.rows > msfm::kSmemTableRows) plan.big_ref = true;
     plan.need_seq = std::max(plan.need_seq, std::max(r.ready_seq, q.ready_seq));
+    plan.row_lo = std::min(plan.row_lo, std::min<int64_t>(r.off, q.off));
+    plan.row_hi = std::max(plan.row_hi, std::max<int64_t>(r.off + r.rows, q.off + q.rows));
     if (pd.fscale2 > 0.0f) plan.any_float = true;
     const int32_t pidx = (int32_t)plan.pairs.size();
     plan.pairs.push_back(pd);
@@ -982,7 +994,7 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
         cudaFree(ctx->dbg_stats.ptr);
     }
     if (ctx->fdesc) cudaFree(ctx->fdesc);
-    DeviceBuf *bufs[] = {&ctx->band_q, &ctx->band_counts, &ctx->band_thr, &ctx->band_state, &ctx->band_events, &ctx->band_event_keys, &ctx->band_event_count, &ctx->cand_q, &ctx->cand_j, &ctx->cand_d0, &ctx->cand_good, &ctx->cand_counts, &ctx->cand_desc, &ctx->cand_ckeys, &ctx->colbest, &ctx->twin_counts, &ctx->item_counter,
+    DeviceBuf *bufs[] = {&ctx->band_q, &ctx->band_counts, &ctx->band_thr, &ctx->band_state, &ctx->band_events, &ctx->band_event_keys, &ctx->band_event_count, &ctx->cand_q, &ctx->cand_j, &ctx->cand_d0, &ctx->cand_good, &ctx->cand_counts, &ctx->cand_desc, &ctx->cand_ckeys, &ctx->colbest, &ctx->twin_counts, &ctx->item_counter, &ctx->tilemin,
                          &ctx->staging, &ctx->knn, &ctx->matches, &ctx->good, &ctx->counts, &ctx->offsets,
                          &ctx->pairdesc, &ctx->items, &ctx->tight_matches, &ctx->tight_good};
     for (DeviceBuf *b : bufs)
