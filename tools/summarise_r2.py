@@ -87,22 +87,23 @@ def main():
     launch_list("r2_launches_headline.csv", "r2_launch_list_raw.csv", "r2_launch_list_summary.csv",
                 "python bench.py --no-cpu-baseline --no-e2e --no-int8-peak --parity-pairs 0 --steps 2 --warmup 1 (100 images x 8192, mutual)")
     cap = full_capture("r2_match_headline.ncu-rep", "r2_match_kernel_ncu_headline_summary.csv",
-                       "ncu --set full --clock-control none --import-source on -k regex:match_pairs_kernel -s 4 -c 1, "
+                       "ncu --set full --clock-control none --import-source on -k regex:match_pairs_kernel -s 6 -c 1, "
                        "`python bench.py --no-cpu-baseline --no-e2e --no-int8-peak --parity-pairs 0 --steps 1 --warmup 1`: the HEADLINE workload "
-                       "(100 images x 8192 rows, 4,950 pairs, mutual); the captured launch is the forward pass of the step's third batch (854 pairs)")
+                       "(100 images x 8192 rows, 4,950 pairs, mutual); the captured launch is the forward pass of the timed step's first batch (2,048 pairs)")
     caps = []
     if cap:
         rd, wr = to_bytes(*cap[(0, "dram__bytes_read.sum")]), to_bytes(*cap[(0, "dram__bytes_write.sum")])
-        pairs = 854
-        caps.append({"workload": 2, "rows": 8192, "images_per_gpu": 100, "n_gpus": 1, "launch": "forward pass of the third batch of a step", "pairs_in_launch": pairs,
+        pairs = 2048
+        caps.append({"workload": 2, "rows": 8192, "images_per_gpu": 100, "n_gpus": 1, "launch": "forward pass of the first batch (2,048 pairs) of the timed step", "pairs_in_launch": pairs,
                      "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr, "dram_bytes_per_pair": (rd + wr) / pairs,
                      "algorithmic_bytes_per_pair": 2 * 8192 * 132 + 8192 * 16,
                      "source": "profiles/r2_match_kernel_ncu_headline_summary.csv (ncu --set full on the headline workload)"})
     cap3 = full_capture("r2_match_w3.ncu-rep", "r2_match_kernel_ncu_config3_summary.csv",
-                        "ncu --set full, one forward launch of BASELINE config #3 (1,000 images x 20,000 rows, GPS-guided pairs), 1 GPU")
+                        "ncu --set full --clock-control none -k regex:match_pairs_kernel -s 8 -c 1, `python bench.py --workload 3 --no-cpu-baseline --no-e2e --no-int8-peak --parity-pairs 0 --steps 1 --warmup 1`: "
+                        "one forward launch (a batch of <= 16 Mi query rows = 838 pairs) of BASELINE config #3 (1,000 images x 20,000 rows, GPS-guided pairs), 1 GPU")
     if cap3:
         rd, wr = to_bytes(*cap3[(0, "dram__bytes_read.sum")]), to_bytes(*cap3[(0, "dram__bytes_write.sum")])
-        caps.append({"workload": 3, "rows": 20000, "images_per_gpu": 1000, "n_gpus": 1, "launch": "first forward launch of a step (batch of <= 16 Mi query rows)",
+        caps.append({"workload": 3, "rows": 20000, "images_per_gpu": 1000, "n_gpus": 1, "launch": "fifth forward launch of a step (batch of <= 16 Mi query rows)",
                      "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
                      "source": "profiles/r2_match_kernel_ncu_config3_summary.csv"})
     if caps:
