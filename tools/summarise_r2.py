@@ -79,11 +79,36 @@ def to_bytes(u, v):
     return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
 
 
+def scaling_table():
+    """profiles/r2_scaling_summary.csv: one row per (workload, N) from the committed bench lines."""
+    rows = []
+    for w in (2, 3, 4, 5):
+        base = None
+        for n in (1, 2, 4, 8):
+            p = os.path.join(PROF, f"r2_scale_w{w}_{n}gpu.json")
+            if not os.path.exists(p):
+                continue
+            d = json.loads(open(p).read())
+            e = d.get("e2e") or {}
+            if n == 1:
+                base = (d["value"], e.get("value"))
+            rows.append((w, n, d["config"]["pairs_per_step_all_gpus"], d["scaling"], d["value"], d["ms_per_step"], d["roofline"]["frac"], e.get("value"),
+                         e.get("host_rows", ""), (e.get("uint8_rows") or {}).get("value"), d["value"] / base[0] if base else None,
+                         e.get("value") / base[1] if base and base[1] else None, d.get("parity_checked"), d.get("parity_ok"),
+                         d["clocks"].get("sm_mhz"), "+".join(d["clocks"].get("reasons") or [])))
+    with open(os.path.join(PROF, "r2_scaling_summary.csv"), "w") as f:
+        f.write("# one process per GPU (torch.distributed/NCCL); value = device-resident, e2e = host rows -> match lists in host memory; speed-ups vs N = 1 of the same workload\n")
+        f.write("workload,n_gpus,pairs_per_step,scaling,value_pairs_s,ms_per_step,frac_of_int8_spec,e2e_pairs_s,e2e_host_rows,e2e_uint8_rows_pairs_s,value_speedup,e2e_speedup,parity_checked,parity_ok,sm_mhz,throttle\n")
+        for r in rows:
+            f.write(",".join("" if x is None else (f"{x:.4g}" if isinstance(x, float) else str(x)) for x in r) + "\n")
+
+
 def main():
     copy_lines([("r2_bench_headline.json", "r2_bench_headline_1gpu.json"), ("r2_bench_mutual0.json", "r2_bench_mutual0_1gpu.json"),
                 ("r2_bench_reference.json", "r2_bench_reference_arm.json")] +
                [(f"r2_scale_w{w}_{n}gpu.json", f"r2_scale_w{w}_{n}gpu.json") for w in (2, 3, 4, 5) for n in (1, 2, 4, 8)] +
                [(f"r2_scale_w2_{n}gpu_single.json", f"r2_scale_w2_{n}gpu_single_process.json") for n in (2, 8)])
+    scaling_table()
     launch_list("r2_launches_headline.csv", "r2_launch_list_raw.csv", "r2_launch_list_summary.csv",
                 "python bench.py --no-cpu-baseline --no-e2e --no-int8-peak --parity-pairs 0 --steps 2 --warmup 1 (100 images x 8192, mutual)")
     cap = full_capture("r2_match_headline.ncu-rep", "r2_match_kernel_ncu_headline_summary.csv",
