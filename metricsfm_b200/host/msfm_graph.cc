@@ -124,6 +124,7 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
             if (st != MSFM_OK) return fail(err, err_cap, -4, "msfm_create: %s", msfm_status_string(st));
         }
     }
+    clk.lap("create context(s)");
     void *stage[2] = {nullptr, nullptr};
     auto bail = [&](int code, const std::string &msg) {
         if (mm) msfm_multi_destroy(mm);
@@ -141,11 +142,14 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
         const size_t cap = std::max(kStageBytes, largest + 16);
         for (void *&p : stage)
             if (msfm_host_alloc(cap, &p) != MSFM_OK) return bail(-4, "cannot allocate page-locked staging memory");
+        clk.lap("page-locked staging buffers");
+        double read_ms = 0.0, wait_ms = 0.0;
         int which = 0;
         int32_t i = 0;
         while (i < num_imgs) {
             // fill one staging buffer with as many consecutive needed images of one descriptor type as fit
             char *base = static_cast<char *>(stage[which]);
+            const auto t_read0 = std::chrono::steady_clock::now();
             size_t used = 0;
             std::vector<int32_t> ids, nrows;
             std::vector<const void *> ptrs;
@@ -167,6 +171,7 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
                 ++i;
             }
             if (ids.empty()) break;
+            read_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_read0).count();
             msfm_status st;
             const int32_t n = (int32_t)ids.size();
             if (type == 0)
@@ -178,14 +183,17 @@ extern "C" int msfm_build_match_graph(const char *fold, int32_t num_imgs, const 
             if (st != MSFM_OK) return bail(-4, std::string("upload: ") + (mm ? msfm_multi_last_error(mm) : msfm_last_error(ctx)));
             which ^= 1;
             // the other buffer is filled next: its copies (queued one round ago) must have left it
+            const auto t_wait0 = std::chrono::steady_clock::now();
             if (sync_uploads() != MSFM_OK) return bail(-4, "upload synchronisation failed");
+            wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wait0).count();
         }
         if (sync_uploads() != MSFM_OK) return bail(-4, "upload synchronisation failed");
+        if (clk.on) fprintf(stderr, "[msfm graph]   of which: reading feature files %.1f ms, waiting for uploads %.1f ms\n", read_ms, wait_ms);
         msfm_host_free(stage[0]);
         msfm_host_free(stage[1]);
         stage[0] = stage[1] = nullptr;
     }
-    clk.lap("create + read + upload");
+    clk.lap("read + upload");
 
     // ---- the missing images in chunks of consecutive idx1 (host match buffers stay bounded; match_index.txt advances
     //      chunk by chunk, so an interrupted run resumes where it stopped)
