@@ -74,6 +74,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-dtype", default="", choices=["", "f32", "u8"])
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-e2e-prefetch", action="store_true", help="single GPU: do not stage step k+1's table under step k's matching")
     ap.add_argument("--parity-pairs", type=int, default=-1, help="pairs checked against the CPU oracle after the timed regions")
     ap.add_argument("--mutual", type=int, default=1, help="1 = ratio + mutual cross-check (headline), 0 = ratio only")
     ap.add_argument("--no-int8-peak", action="store_true", help="skip the cuBLAS int8 GEMM peak measurement (rank 0, N = 1)")
@@ -411,7 +412,7 @@ def run_native_ranks(args):
     lib_stream = torch.cuda.ExternalStream(m.cuda_stream(), device=dev)
     up_stream = torch.cuda.ExternalStream(m.upload_stream(), device=dev)
 
-    def stage_table(use_f32: bool):
+    def stage_table(use_f32: bool, m=m):
         """Queue the staging of the whole table, group by group: H2D + pack of this rank's slice on the library's upload
         streams, the other ranks' slices reserved.  Nothing waits on the host.  Returns, per group, what replicate_group()
         needs (the event after the group's uploads and its arena range), and the H2D bytes."""
@@ -528,22 +529,36 @@ def run_native_ranks(args):
 
     trace = os.environ.get("BENCH_TRACE") is not None
 
-    def e2e_step(use_f32: bool):
+    # Single GPU: two contexts (two copies of the table in HBM) alternate, so that the NEXT step's table is copied and packed
+    # (upload stream / copy engine of the other context) while the current step is matched.  Every step's host->device copy
+    # and its device->host read of the match lists still happen inside the timed region; only their overlap changes.
+    m_alt, alt_keep = None, None
+    if world == 1 and not args.no_e2e and not args.no_e2e_prefetch:
+        alt_keep = (torch.empty((arena_rows, 128), dtype=torch.uint8, device=dev), torch.empty((arena_rows,), dtype=torch.int32, device=dev))
+        m_alt = Matcher(device=local_rank, max_images=n_images, arena_rows=arena_rows, external_desc_arena=alt_keep[0].data_ptr(),
+                        external_norm_arena=alt_keep[1].data_ptr())
+    staged = {}   # matcher -> (metas, h2d) of a table already queued for it by the previous step
+
+    def e2e_step(use_f32: bool, step: int = 0, last: bool = True):
         t_begin = time.perf_counter()
-        metas, h2d = stage_table(use_f32)
+        cur = m if (m_alt is None or step % 2 == 0) else m_alt
+        metas, h2d = staged.pop(cur, None) or stage_table(use_f32, cur)
+        if m_alt is not None and not last:
+            nxt = m_alt if cur is m else m
+            staged[nxt] = stage_table(use_f32, nxt)          # queued now, runs under this step's matching
         stamps = [time.perf_counter() - t_begin]
         done, d2h = 0, 0
         if world == 1:
             # ONE call over the whole list (ordered by staging group): the library cuts its batches where the next pair's
             # images have not landed yet, so matching starts on group 0 while the later groups are still being copied
             sub = MatchResult(offsets=out.offsets[:len(my_pairs) + 1], ok=out.ok[:len(my_pairs)], matches=out.matches, good=out.good)
-            res = m.match_pairs(my_pairs, RATIO_ALL, out=sub, **kw)
+            res = cur.match_pairs(my_pairs, RATIO_ALL, out=sub, **kw)
             list_off[:] = sub.offsets[:len(my_pairs) + 1]
             stamps.append(time.perf_counter() - t_begin)
             if trace:
                 print(f"[trace rank {rank}] f32={use_f32} staging enqueued at {1e3 * stamps[0]:.2f} ms, done at {1e3 * stamps[1]:.2f} ms, "
-                      f"{m.timing()['match_launches']} matching launches", file=sys.stderr, flush=True)
-            return h2d + my_pairs.nbytes, m.timing()["d2h_bytes"], len(res.matches)
+                      f"{cur.timing()['match_launches']} matching launches", file=sys.stderr, flush=True)
+            return h2d + my_pairs.nbytes, cur.timing()["d2h_bytes"], len(res.matches)
         for g in range(n_groups):
             a, b = sub_bounds[g], sub_bounds[g + 1]
             replicate_group(g, metas[g])                 # queued on the main stream: runs before sub-list g's launches
@@ -562,11 +577,13 @@ def run_native_ranks(args):
 
     if not args.no_e2e:
         e2e_steps = max(1, args.e2e_steps)
-        e2e_step(e2e_f32)                                   # warm-up (allocations, NCCL channels)
+        e2e_step(e2e_f32, 0, m_alt is None)                 # warm-up (allocations, NCCL channels) ...
+        if m_alt is not None:
+            e2e_step(e2e_f32, 1, True)                      # ... of both contexts
         barrier()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            h2d, d2h, n_e2e = e2e_step(e2e_f32)
+        for k in range(e2e_steps):
+            h2d, d2h, n_e2e = e2e_step(e2e_f32, k, k == e2e_steps - 1)
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -578,15 +595,18 @@ def run_native_ranks(args):
                "pipeline": f"{n_groups} staging groups on the upload streams" + (" + one NCCL all-gather per group between matching launches; one "
                                                                                       "msfm_match_pairs call per group" if world > 1 else
                                                                                       "; ONE msfm_match_pairs call, batches cut where uploads have not landed")
-                           + "; the pairs of groups <= g are matched while group g+1 is copied",
+                           + "; the pairs of groups <= g are matched while group g+1 is copied"
+                           + ("; two contexts alternate: step k+1's table is copied + packed while step k is matched" if m_alt is not None else ""),
                "timer": "host wall clock between barriers + cuda synchronize, max over ranks", "matches_per_step_this_rank": int(n_e2e),
                "match_lists": "page-locked host buffers of the rank that matched the pair"}
         if e2e_f32:                                         # the same pipeline fed with pre-quantised uint8 rows, for comparison
-            e2e_step(False)
+            e2e_step(False, 0, m_alt is None)
+            if m_alt is not None:
+                e2e_step(False, 1, True)
             barrier()
             t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                h2d_u8, _, _ = e2e_step(False)
+            for k in range(e2e_steps):
+                h2d_u8, _, _ = e2e_step(False, k, k == e2e_steps - 1)
             barrier()
             dt8 = time.perf_counter() - t0
             if world > 1:
@@ -644,6 +664,9 @@ def run_native_ranks(args):
             forest["extrapolated_pairs_per_s_one_query_per_core"] = cores / forest["kd_forest_query_s_per_pair"]
             cpu["production_kd_forest"] = forest
 
+    if m_alt is not None:
+        m_alt.close()
+        m_alt, alt_keep = None, None
     int8_peak = None
     if rank == 0 and world == 1 and not args.no_int8_peak:
         m.close()                      # the library's scratch is not needed any more

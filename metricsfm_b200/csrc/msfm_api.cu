@@ -83,6 +83,9 @@ struct msfm_ctx {
     cudaStream_t copy_stream = nullptr;    // host->device copies of the asynchronous batch uploads: they never queue behind a
                                            // packer launch that is waiting for an SM (the matching kernel is persistent)
     cudaEvent_t ev_copy = nullptr;
+    cudaStream_t d2h_stream = nullptr;     // match lists of batch k go back to the host under batch k+1's kernels
+    cudaEvent_t ev_d2h0 = nullptr, ev_d2h1 = nullptr;  // brackets of the list copy in flight (timed)
+    bool d2h_in_flight = false;
     struct StageBuf { void *ptr; size_t bytes; cudaEvent_t done; bool used; };
     std::vector<StageBuf> stage_pool;      // float staging of msfm_upload_f32_batch_async calls still in flight
     std::vector<UploadMark> marks;         // asynchronous uploads still to be ordered before matching launches
@@ -122,6 +125,7 @@ struct msfm_ctx {
 #endif
     // ^ msfm_test_disable_pruning: the forward pass keeps exact 2-NN rows for every query row
     DeviceBuf staging, knn, matches, good, counts, offsets, pairdesc, items, tight_matches, tight_good;
+    DeviceBuf tight_matches_b, tight_good_b;  // second set: a batch's lists are copied out while the next batch is gathered
     void *h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_k2 = nullptr, ev_k3 = nullptr,
@@ -528,6 +532,17 @@ void plan_add_pair(msfm_ctx *ctx, BatchPlan &plan, int64_t src, int32_t ref, int
     plan.ops += 2ll * r.rows * q.rows * kDim;
 }
 
+// Host wait for the list copy in flight (if any); its duration goes to timing.d2h_ms.
+msfm_status wait_list_copy(msfm_ctx *ctx) {
+    if (!ctx->d2h_in_flight) return MSFM_OK;
+    ctx->d2h_in_flight = false;
+    MSFM_CUDA(ctx, cudaEventSynchronize(ctx->ev_d2h1));
+    float ms = 0.f;
+    MSFM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_d2h0, ctx->ev_d2h1));
+    ctx->timing.d2h_ms += ms;
+    return MSFM_OK;
+}
+
 msfm_status accumulate_kernel_time(msfm_ctx *ctx, cudaEvent_t e0, cudaEvent_t e1) {
     float ms = 0.f;
     MSFM_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
@@ -630,6 +645,7 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
     Carved cur, ahead;
     bool have = next < n_pairs;
     if (have) carve(cur);
+    int64_t batch_no = 0;  // picks the set of tight list buffers (the other set may still be on its way to the host)
     while (have) {
         BatchPlan &plan = cur.plan;
         const int64_t first = cur.first, last = cur.last;
@@ -648,8 +664,10 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             if (want_good && (st = ensure(ctx, ctx->good, rows)) != MSFM_OK) return st;
             if ((st = ensure(ctx, ctx->counts, (size_t)nb * 4)) != MSFM_OK) return st;
             if ((st = ensure(ctx, ctx->offsets, (size_t)(nb + 1) * 8)) != MSFM_OK) return st;
-            if ((st = ensure(ctx, ctx->tight_matches, rows * sizeof(int2))) != MSFM_OK) return st;
-            if (want_good && (st = ensure(ctx, ctx->tight_good, rows)) != MSFM_OK) return st;
+            // (a buffer that has to grow is not the one a list copy is still reading: see wait_list_copy below)
+            DeviceBuf &tm = batch_no & 1 ? ctx->tight_matches_b : ctx->tight_matches, &tg = batch_no & 1 ? ctx->tight_good_b : ctx->tight_good;
+            if ((st = ensure(ctx, tm, rows * sizeof(int2))) != MSFM_OK) return st;
+            if (want_good && (st = ensure(ctx, tg, rows)) != MSFM_OK) return st;
             // ---- forward 2-NN
             if ((st = run_match_stage(ctx, plan)) != MSFM_OK) return st;
             // ---- float regime: rows near a ratio threshold are decided on exact fp32 distances
@@ -765,7 +783,7 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             msfm::scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(ep.counts, nb, static_cast<int64_t *>(ctx->offsets.ptr));
             msfm::gather_matches_kernel<<<nb, 256, 0, ctx->stream>>>(
                 ep.pairs, ep.counts, static_cast<const int64_t *>(ctx->offsets.ptr), ep.matches, ep.good,
-                static_cast<int2 *>(ctx->tight_matches.ptr), want_good ? static_cast<uint8_t *>(ctx->tight_good.ptr) : nullptr);
+                static_cast<int2 *>(tm.ptr), want_good ? static_cast<uint8_t *>(tg.ptr) : nullptr);
             MSFM_CUDA(ctx, cudaGetLastError());
             MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_f1, ctx->stream));
             ctx->timing.total_launches += 3;
@@ -792,23 +810,24 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
             }
             const int64_t bt = batch_offsets[nb];
             total += bt;
+            if ((st = wait_list_copy(ctx)) != MSFM_OK) return st;  // the previous batch's lists (copied under this batch's kernels)
             if (!resident && bt > 0) {
                 int32_t (*dst_m)[2] = nullptr;
                 uint8_t *dst_g = nullptr;
                 if (out->sink(out->user, written, bt, &dst_m, &dst_g) != 0 || !dst_m)
                     return fail(ctx, MSFM_ERR_CAPACITY, "match buffer too small: need at least %lld entries", (long long)(written + bt));
-                cudaEvent_t d0 = ctx->ev_k0, d1 = ctx->ev_k1;  // reuse as D2H brackets (kernel time already read)
-                MSFM_CUDA(ctx, cudaEventRecord(d0, ctx->stream));
-                MSFM_CUDA(ctx, cudaMemcpyAsync(dst_m, ctx->tight_matches.ptr, (size_t)bt * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
+                // The lists leave on their own stream, ordered behind this batch's gather (ev_f1); the next batch's kernels
+                // start right away on the main stream and write the OTHER set of tight buffers.  At most one list copy is
+                // in flight: the previous one was waited for above, before the sink could move the host buffers.
+                MSFM_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_f1, 0));
+                MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_d2h0, ctx->d2h_stream));
+                MSFM_CUDA(ctx, cudaMemcpyAsync(dst_m, tm.ptr, (size_t)bt * sizeof(int2), cudaMemcpyDeviceToHost, ctx->d2h_stream));
                 if (dst_g) {
-                    if (want_good) MSFM_CUDA(ctx, cudaMemcpyAsync(dst_g, ctx->tight_good.ptr, (size_t)bt, cudaMemcpyDeviceToHost, ctx->stream));
+                    if (want_good) MSFM_CUDA(ctx, cudaMemcpyAsync(dst_g, tg.ptr, (size_t)bt, cudaMemcpyDeviceToHost, ctx->d2h_stream));
                     else memset(dst_g, 0, (size_t)bt);
                 }
-                MSFM_CUDA(ctx, cudaEventRecord(d1, ctx->stream));
-                MSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                float ms = 0.f;
-                MSFM_CUDA(ctx, cudaEventElapsedTime(&ms, d0, d1));
-                ctx->timing.d2h_ms += ms;
+                MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_d2h1, ctx->d2h_stream));
+                ctx->d2h_in_flight = true;
                 ctx->timing.d2h_bytes += bt * (int64_t)(sizeof(int2) + (dst_g && want_good ? 1 : 0));
             }
         }
@@ -834,7 +853,9 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
         }
         std::swap(cur, ahead);
         have = have_next;
+        ++batch_no;
     }
+    if ((st = wait_list_copy(ctx)) != MSFM_OK) return st;
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
     MSFM_CUDA(ctx, cudaEventSynchronize(ctx->ev_end));
     MSFM_CUDA(ctx, cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev_begin, ctx->ev_end));
@@ -929,6 +950,8 @@ msfm_status msfm_create(const msfm_config *cfg, msfm_ctx **out) {
     if (cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MSFM_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MSFM_ERR_CUDA);
     if (cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming) != cudaSuccess) return bail(MSFM_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MSFM_ERR_CUDA);
+    if (cudaEventCreate(&ctx->ev_d2h0) != cudaSuccess || cudaEventCreate(&ctx->ev_d2h1) != cudaSuccess) return bail(MSFM_ERR_CUDA);
     cudaEvent_t *evs[] = {&ctx->ev_begin, &ctx->ev_end, &ctx->ev_k0, &ctx->ev_k1, &ctx->ev_k2, &ctx->ev_k3, &ctx->ev_f1};
     for (cudaEvent_t *e : evs)
         if (cudaEventCreate(e) != cudaSuccess) return bail(MSFM_ERR_CUDA);
@@ -972,6 +995,7 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
     if (!ctx) return MSFM_OK;
     cudaSetDevice(ctx->device);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
     if (ctx->upload_stream) cudaStreamSynchronize(ctx->upload_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (const msfm_ctx::StageBuf &b : ctx->stage_pool) {
@@ -979,6 +1003,8 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
         cudaEventDestroy(b.done);
     }
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    if (ctx->ev_d2h0) cudaEventDestroy(ctx->ev_d2h0);
+    if (ctx->ev_d2h1) cudaEventDestroy(ctx->ev_d2h1);
     if (ctx->dbg_stats.ptr) {
         unsigned long long h[64] = {0};
         cudaMemcpy(h, ctx->dbg_stats.ptr, 512, cudaMemcpyDeviceToHost);
@@ -996,7 +1022,7 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
     if (ctx->fdesc) cudaFree(ctx->fdesc);
     DeviceBuf *bufs[] = {&ctx->band_q, &ctx->band_counts, &ctx->band_thr, &ctx->band_state, &ctx->band_events, &ctx->band_event_keys, &ctx->band_event_count, &ctx->cand_q, &ctx->cand_j, &ctx->cand_d0, &ctx->cand_good, &ctx->cand_counts, &ctx->cand_desc, &ctx->cand_ckeys, &ctx->colbest, &ctx->twin_counts, &ctx->item_counter, &ctx->tilemin,
                          &ctx->staging, &ctx->knn, &ctx->matches, &ctx->good, &ctx->counts, &ctx->offsets,
-                         &ctx->pairdesc, &ctx->items, &ctx->tight_matches, &ctx->tight_good};
+                         &ctx->pairdesc, &ctx->items, &ctx->tight_matches, &ctx->tight_good, &ctx->tight_matches_b, &ctx->tight_good_b};
     for (DeviceBuf *b : bufs)
         if (b->ptr) cudaFree(b->ptr);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -1013,6 +1039,7 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MSFM_OK;
