@@ -479,16 +479,9 @@ match_pairs_kernel(const MatchKernelParams p) {
                 ptx::tc_fence_after();
                 if (prof) c1 = clock64();
                 const uint32_t tile_taddr = warp_taddr + buf * (STRIPS * TILE_N);
-#ifdef MSFM_LD_X32
-                uint32_t acc32[kCols / 32][32];
-#pragma unroll
-                for (int c = 0; c < kCols / 32; ++c) ptx::tmem_ld_32x32b_x32(tile_taddr + c * 32, acc32[c]);
-                uint32_t (*acc)[16] = reinterpret_cast<uint32_t (*)[16]>(acc32);
-#else
                 uint32_t acc[kCols / 16][16];
 #pragma unroll
                 for (int c = 0; c < kCols / 16; ++c) ptx::tmem_ld_32x32b_x16(tile_taddr + c * 16, acc[c]);
-#endif
                 // ---- while the loads fly: column keys of the tile, smallest reference norm, pruning threshold
                 ptx::mbar_wait_a(k_full_base + ks * 8, k_phase);
                 const uint32_t ck = key_base + ks * (TILE_N * 4);

@@ -110,3 +110,87 @@ def test_numa_pinning_helper_never_raises():
     if not info["pinned"]:
         assert os.sched_getaffinity(0) == before
     os.sched_setaffinity(0, before)
+
+
+def _dead_row_stream(Q, R, rho8, tile=64, group=8, warp=32):
+    """numpy restatement of the matching kernel's epilogue with the dead-row rule (metricsfm_b200/csrc/match_kernel.cuh):
+    tiles of `tile` reference rows, a group of `group` columns is scored exactly (by every row of the warp) iff some row of
+    the warp has a raw accumulator above T = (theta + min norm of the tile) >> 1; theta = best score of a dead row
+    (d0 > ((d1 >> 8) + 1) * rho8), second best otherwise; refreshed after a tile that scored something.
+    Returns per row (d0, j0, d1_reported, j1, dead_at_end)."""
+    N, M = Q.shape[0], R.shape[0]
+    acc = Q.astype(np.int64) @ R.astype(np.int64).T
+    nb = (R.astype(np.int64) ** 2).sum(1)
+    na = (Q.astype(np.int64) ** 2).sum(1)
+    score = 2 * acc - nb[None, :]
+    NEG = -(1 << 40)
+    S0 = np.full(N, NEG); S1 = np.full(N, NEG); J0 = np.full(N, -1); J1 = np.full(N, -1)
+
+    def prune_score():
+        d0, d1 = na - S0, na - S1
+        dead = (S1 > NEG) & (d0 > ((d1 >> 8) * rho8 + rho8))
+        return np.where(dead, S0, S1), dead
+
+    theta, _ = prune_score()
+    for t0 in range(0, M, tile):
+        cols = np.arange(t0, min(t0 + tile, M))
+        T = np.where(theta > NEG, (theta + nb[cols].min()) >> 1, NEG)
+        touched = False
+        for g0 in range(0, len(cols), group):
+            gc = cols[g0:g0 + group]
+            flag = acc[:, gc].max(1) > T
+            hot = flag.reshape(-1, warp).any(1).repeat(warp)          # warp-wide decision
+            if not hot.any():
+                continue
+            touched = True
+            for j in gc:                                              # ascending columns, strict > (lowest index on ties)
+                s = score[:, j]
+                b0 = hot & (s > S0)
+                b1 = hot & ~b0 & (s > S1)
+                S1 = np.where(b0, S0, np.where(b1, s, S1)); J1 = np.where(b0, J0, np.where(b1, j, J1))
+                S0 = np.where(b0, s, S0); J0 = np.where(b0, j, J0)
+        if touched:
+            theta, _ = prune_score()
+    _, dead = prune_score()
+    d1 = np.where(dead, na - S0, na - S1)                             # a row that ends dead reports d1 := d0
+    return na - S0, J0, d1, J1, dead
+
+
+@pytest.mark.parametrize("kind", ["sift", "clusters", "late_match"])
+@pytest.mark.parametrize("ratio", [0.5, 0.85])
+def test_dead_row_rule_restatement_keeps_every_verdict(kind, ratio):
+    """The rule the forward pass uses to skip second-best updates of rows that already fail the ratio test: against the
+    exact 2-NN it must keep d0 / nn0 of EVERY row, the exact (d1, nn1) of every row that passes the ratio test, reject
+    exactly the rows the exact test rejects, and report for the others a d1 that is a lower bound of the row's distance to
+    every reference row but nn0 (what the mutual check's dangerous-row bound relies on, aux_kernels.cuh)."""
+    from metricsfm_b200 import synth
+    rng = np.random.default_rng(7)
+    if kind == "sift":
+        col = synth.Collection(768, seed=3)
+        R, Q = col.image_u8(0, 768), col.image_u8(1, 512)
+    elif kind == "clusters":
+        c = rng.integers(0, 100, size=(12, 128))
+        R = np.clip(c[rng.integers(0, 12, 640)] + rng.integers(-3, 4, size=(640, 128)), 0, 255).astype(np.uint8)
+        Q = np.clip(c[rng.integers(0, 12, 512)] + rng.integers(-3, 4, size=(512, 128)), 0, 255).astype(np.uint8)
+    else:
+        col = synth.Collection(768, seed=4)
+        R, Q = col.image_u8(2, 704), col.image_u8(3, 512)
+        Q[:200] = np.clip(R[-200:].astype(np.int32) + rng.integers(-2, 3, size=(200, 128)), 0, 255).astype(np.uint8)  # match in the last tiles
+    rho8 = int(np.floor(ratio * 256.0)) + 2                          # msfm_api.cu: ratio rounded up to 1/256 plus one step
+    d0, j0, d1, j1, dead = _dead_row_stream(Q, R, rho8)
+    D = ((Q.astype(np.int64)[:, None, :] - R.astype(np.int64)[None, :, :]) ** 2).sum(2)
+    order = np.argsort(D, axis=1, kind="stable")                     # stable: lowest index on ties
+    e0, e1 = order[:, 0], order[:, 1]
+    x0, x1 = D[np.arange(len(Q)), e0], D[np.arange(len(Q)), e1]
+    np.testing.assert_array_equal(d0, x0)
+    np.testing.assert_array_equal(j0, e0)
+    accept = (x0.astype(np.float32) / np.maximum(x1, 1).astype(np.float32) < np.float32(ratio)) & (x1 > 0)
+    got = (d0.astype(np.float32) / np.maximum(d1, 1).astype(np.float32) < np.float32(ratio)) & (d1 > 0)
+    np.testing.assert_array_equal(got, accept)
+    np.testing.assert_array_equal(d1[accept], x1[accept])
+    np.testing.assert_array_equal(j1[accept], e1[accept])
+    assert not (dead & accept).any()
+    assert dead.sum() > (len(Q) // 2 if kind == "sift" else 0)          # the rule is at work (on most rows of SIFT-like images)
+    Dm = D.copy()
+    Dm[np.arange(len(Q)), e0] = np.iinfo(np.int64).max
+    assert (d1 <= Dm.min(1)).all()                                    # reported d1 bounds every other distance from below
