@@ -32,8 +32,9 @@
 // Pipelines (all mbarrier based):
 //   A ring (2 deep)     : query strips of a work item, STRIPS x [128 rows x 128 B]
 //   B ring (STAGES)     : reference tiles [TILE_N rows x 128 B]
-//   column-key ring     : ckey_j = -8*||r_j||^2 + (7 - j%8) of the tile's reference rows (no empty barrier needed,
-//                         see MatchKernelCfg::kKeySlots)
+//   column-key ring     : ckey_j = -8*||r_j||^2 + (7 - j%8) of the tile's reference rows + the tile's smallest norm; they
+//                         complete the B stage's "full" barrier together with the tile (no barriers of their own: the
+//                         epilogue reads them behind the tile's MMAs; for the slot count see MatchKernelCfg::kKeySlots)
 //   TMEM                : TBUFS x STRIPS accumulator blocks of TILE_N int32 columns, each with its own full/empty
 //                         barrier pair, so the MMA of tile t+1 runs under the epilogue of tile t
 #pragma once
@@ -139,7 +140,7 @@ struct MatchKernelCfg {
     static constexpr int kSmemShare = kSmemTmin + kKeySlots * 16;              // [STRIPS*128 rows][CSPLIT] int4
     static constexpr int kSmemBar = kSmemShare + STRIPS * kStripRows * CSPLIT * 16;
     static constexpr int kItemSlots = 8;  // published work-item indices (the loader runs at most two items ahead of the MMAs)
-    static constexpr int kNumBars = 2 + 2 + STAGES + STAGES + kKeySlots + 2 * TBUFS * STRIPS + kItemSlots;
+    static constexpr int kNumBars = 2 + 2 + STAGES + STAGES + 2 * TBUFS * STRIPS + kItemSlots;
     static constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
     static constexpr int kSmemItems = kSmemTmemPtr + 16;
     static constexpr int kSmemBytes = kSmemItems + kItemSlots * 4;
@@ -206,8 +207,7 @@ match_pairs_kernel(const MatchKernelParams p) {
     uint64_t *a_empty = a_full + 2;                  // [2]
     uint64_t *b_full = a_empty + 2;                  // [STAGES]
     uint64_t *b_empty = b_full + STAGES;             // [STAGES]
-    uint64_t *k_full = b_empty + STAGES;             // [kKeySlots]
-    uint64_t *t_full = k_full + Cfg::kKeySlots;      // [TBUFS][STRIPS]
+    uint64_t *t_full = b_empty + STAGES;             // [TBUFS][STRIPS]
     uint64_t *t_empty = t_full + TBUFS * STRIPS;     // [TBUFS][STRIPS]
     uint64_t *i_full = t_empty + TBUFS * STRIPS;     // [kItemSlots] (DYN) item index published
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
@@ -223,7 +223,6 @@ match_pairs_kernel(const MatchKernelParams p) {
         // A buffers and B stages are released by the commits of all STRIPS MMA issuers
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], STRIPS); }
         for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], STRIPS); }
-        for (int i = 0; i < Cfg::kKeySlots; ++i) ptx::mbar_init(&k_full[i], 1);
         for (int i = 0; i < TBUFS * STRIPS; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 4 * CSPLIT); }
         for (int i = 0; i < Cfg::kItemSlots; ++i) ptx::mbar_init(&i_full[i], 1);
         ptx::fence_mbar_init();
@@ -307,14 +306,15 @@ match_pairs_kernel(const MatchKernelParams p) {
                 for (int st = 0; st < STAGES; ++st) {
                     if (!more) break;
                     LOADER_WAIT(&b_empty[st], (round & 1) ^ 1);
-                    ptx::mbar_arrive_expect_tx(&b_full[st], Cfg::kBBytes);
+                    // one barrier for the tile, its column keys and its minimum norm: the MMAs are issued behind it and the
+                    // epilogue reads the keys behind the MMAs, so it needs no barrier of its own for them
+                    ptx::mbar_arrive_expect_tx(&b_full[st], Cfg::kBBytes + TILE_N * 4 + 16);
 #pragma unroll
                     for (int h = 0; h < TILE_N / kBoxRows; ++h)
                         ptx::tma_load_2d(sB + st * Cfg::kBBytes + h * kBoxRows * kDim, rmap, &b_full[st], 0, t + h * kBoxRows);
                     const uint32_t ks = st + STAGES * (round & 1);
-                    ptx::mbar_arrive_expect_tx(&k_full[ks], TILE_N * 4 + 16);
-                    ptx::bulk_load_1d(sKey + ks * TILE_N, keyp + t, TILE_N * 4, &k_full[ks]);
-                    ptx::bulk_load_1d(sTmin + ks, tminp++, 16, &k_full[ks]);
+                    ptx::bulk_load_1d(sKey + ks * TILE_N, keyp + t, TILE_N * 4, &b_full[st]);
+                    ptx::bulk_load_1d(sTmin + ks, tminp++, 16, &b_full[st]);
                     t += TILE_N;  // first reference row of the next tile
                     if (--left == 0) more = next_item();
                 }
@@ -422,7 +422,6 @@ match_pairs_kernel(const MatchKernelParams p) {
         const uint32_t my_slot = ptx::smem_u32(sShare + row_local * CSPLIT + share);
         const uint32_t peer_slot = ptx::smem_u32(sShare + row_local * CSPLIT + (share ^ (CSPLIT - 1)));
         const uint32_t key_base = ptx::smem_u32(sKey) + share * kCols * 4;
-        const uint32_t k_full_base = ptx::smem_u32(k_full);
         const uint32_t tmin_base = ptx::smem_u32(sTmin);
         const uint32_t t_full_base = ptx::smem_u32(t_full + strip);
         const uint32_t t_empty_base = ptx::smem_u32(t_empty + strip);
@@ -474,7 +473,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                 const bool prof = DEBUG && (p.debug_flags & 8u) && p.stats != nullptr;
                 if (prof) c0 = clock64();
                 const uint32_t buf = g % TBUFS, t_phase = (g / TBUFS) & 1;
-                const uint32_t ks = g % Cfg::kKeySlots, k_phase = (g / Cfg::kKeySlots) & 1;
+                const uint32_t ks = g % Cfg::kKeySlots;
                 ptx::mbar_wait_a(t_full_base + buf * (STRIPS * 8), t_phase);
                 ptx::tc_fence_after();
                 if (prof) c1 = clock64();
@@ -483,7 +482,7 @@ match_pairs_kernel(const MatchKernelParams p) {
 #pragma unroll
                 for (int c = 0; c < kCols / 16; ++c) ptx::tmem_ld_32x32b_x16(tile_taddr + c * 16, acc[c]);
                 // ---- while the loads fly: column keys of the tile, smallest reference norm, pruning threshold
-                ptx::mbar_wait_a(k_full_base + ks * 8, k_phase);
+                // (the tile's keys and minimum norm landed before its MMAs were issued: they share the B stage's barrier)
                 const uint32_t ck = key_base + ks * (TILE_N * 4);
                 const int nbmin = ptx::lds_s32(tmin_base + ks * 16);  // smallest reference norm of the tile (tile_min_kernel)
                 int th = theta;  // dead rows are pruned against their best score, the others against their second best
