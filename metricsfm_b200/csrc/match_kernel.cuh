@@ -464,7 +464,7 @@ match_pairs_kernel(const MatchKernelParams p) {
             // which is what the mutual check's dangerous-row bound needs (select_candidates_kernel).
             const int rho8 = (MODE == 0 && CSPLIT == 1 && pd.cand_idx < 0) ? (int)p.prune_q8 : (int)kNoPrune;  // shares keep partial states
             const int ntiles = (pd.ref_rows + TILE_N - 1) / TILE_N;
-            long long acc_wait = 0, acc_load = 0, acc_p1 = 0, acc_p2 = 0, acc_hot = 0;
+            long long acc_wait = 0, acc_load = 0, acc_p1 = 0, acc_p2 = 0, acc_hot = 0, acc_first = 0;
             int theta = prune_score(S0, S1, na, rho8, kAbsent);  // pruning score of the row, refreshed after every hot tile
             int jtile = share * kCols;  // first column of this warp's share in the current tile
             for (int t = 0; t < ntiles; ++t, jtile += TILE_N) {
@@ -560,6 +560,7 @@ match_pairs_kernel(const MatchKernelParams p) {
                 if (prof) {  // per-warp cycle accounting of the tile loop (debug flag 8)
                     const long long c4 = clock64();
                     acc_wait += c1 - c0;  // waiting for the accumulator
+                    if (t == 0) acc_first = c1 - c0;  // ... of the item's first tile (the item-switch bubble)
                     acc_load += c2 - c1;  // TMEM loads + keys + threshold + hand-back
                     acc_p1 += c3 - c2;    // phase 1
                     acc_p2 += c4 - c3;    // phase 2 + publish
@@ -568,6 +569,8 @@ match_pairs_kernel(const MatchKernelParams p) {
             }
             if (DEBUG && (p.debug_flags & 8u) && p.stats != nullptr && lane == 0) {
                 atomicAdd(p.stats + 0, (unsigned long long)acc_hot);
+                atomicAdd(p.stats + 6, (unsigned long long)acc_first);
+                atomicAdd(p.stats + 7, 1ull);  // warp-items
                 atomicAdd(p.stats + 1, (unsigned long long)acc_wait);
                 atomicAdd(p.stats + 2, (unsigned long long)acc_load);
                 atomicAdd(p.stats + 3, (unsigned long long)acc_p1);

@@ -1011,6 +1011,7 @@ msfm_status msfm_destroy(msfm_ctx *ctx) {
         const double wt = h[5] ? (double)h[5] : 1.0;
         fprintf(stderr, "[msfm debug] warp-tiles %llu | hot groups/warp-tile %.3f | cycles/warp-tile: wait-acc %.1f load+thresh %.1f "
                         "phase1 %.1f phase2 %.1f\n", h[5], h[0] / wt, h[1] / wt, h[2] / wt, h[3] / wt, h[4] / wt);
+        fprintf(stderr, "[msfm debug] accumulator wait of an item's first tile: %.0f cycles per warp and item (%llu warp-items)\n", h[7] ? (double)h[6] / (double)h[7] : 0.0, h[7]);
         fprintf(stderr, "[msfm debug] epilogue warps by sub-partition, cycles per warp-tile (wait | work):");
         for (int qd = 0; qd < 4; ++qd) fprintf(stderr, " q%d %.0f|%.0f", qd, h[8 + 2 * qd] / (wt / 4.0), h[9 + 2 * qd] / (wt / 4.0));
         fprintf(stderr, "\n");
