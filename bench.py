@@ -562,9 +562,30 @@ def run_native_ranks(args):
         cx = cx_main if (cx_alt is None or step % 2 == 0) else cx_alt
         cur = cx[0]
         metas, h2d = staged.pop(cur, None) or stage_table(use_f32, cx)
+        stager = None
         if cx_alt is not None and not last:
+            # the next step's staging is queued by a helper thread while this thread sits in the (GIL-free) matching call:
+            # the ~1 ms of host work it takes would otherwise leave the GPU idle between two steps
             nxt = cx_alt if cx is cx_main else cx_main
-            staged[nxt[0]] = stage_table(use_f32, nxt)       # queued now, runs under this step's matching
+            box = {}
+
+            def stage_next():
+                try:
+                    torch.cuda.set_device(dev)
+                    box["staged"] = stage_table(use_f32, nxt)
+                except BaseException as exc:                 # noqa: BLE001  (re-raised by the joining thread)
+                    box["error"] = exc
+
+            stager = threading.Thread(target=stage_next)
+            stager.start()
+
+        def join_stager():
+            if stager is not None:
+                stager.join()
+                if "error" in box:
+                    raise box["error"]
+                staged[nxt[0]] = box["staged"]
+
         stamps = [time.perf_counter() - t_begin]
         done, d2h = 0, 0
         if world == 1:
@@ -573,6 +594,7 @@ def run_native_ranks(args):
             sub = MatchResult(offsets=out.offsets[:len(my_pairs) + 1], ok=out.ok[:len(my_pairs)], matches=out.matches, good=out.good)
             res = cur.match_pairs(my_pairs, RATIO_ALL, out=sub, **kw)
             list_off[:] = sub.offsets[:len(my_pairs) + 1]
+            join_stager()
             stamps.append(time.perf_counter() - t_begin)
             if trace:
                 print(f"[trace rank {rank}] f32={use_f32} staging enqueued at {1e3 * stamps[0]:.2f} ms, done at {1e3 * stamps[1]:.2f} ms, "
@@ -589,6 +611,7 @@ def run_native_ranks(args):
             done += len(res.matches)
             d2h += cur.timing()["d2h_bytes"]
             stamps.append(time.perf_counter() - t_begin)
+        join_stager()
         if trace:
             print(f"[trace rank {rank}] f32={use_f32} staging enqueued at {1e3 * stamps[0]:.2f} ms, sub-lists done at "
                   + ", ".join(f"{1e3 * t:.2f}" for t in stamps[1:]) + " ms", file=sys.stderr, flush=True)
