@@ -698,7 +698,9 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
                 // reference row in registers, queues the chunk's hits in shared memory and scores them 16 at a time —
                 // four lanes per distance, four independent row loads in flight per lane.
                 const int nchunks = (nd + kDangerChunk - 1) / kDangerChunk;
-                const int units = nwork * nchunks;
+                int cshift = 0;  // units are numbered candidate * 2^cshift + chunk: no division per unit
+                while ((1 << cshift) < nchunks) ++cshift;
+                const int units = nwork << cshift;
                 const int sub = lane >> 2, part = lane & 3;  // which of the warp's 8 concurrent distances, which 32 bytes
                 int *hitq = s_hitq + warp * kDangerChunk;
                 const float inv = 256.0f / (float)(s_d0max - d1min + 1);
@@ -707,7 +709,7 @@ __global__ void __launch_bounds__(1024) select_candidates_kernel(const SelectPar
                     if (lane == 0) u = atomicAdd(&s_unit, 1);  // units differ widely in hits
                     u = __shfl_sync(0xFFFFFFFFu, u, 0);
                     if (u >= units || s_evals >= kDangerEvalBudget) break;  // (budget: too ambiguous for CUDA cores)
-                    const int w = u / nchunks, e0 = (u - w * nchunks) * kDangerChunk;
+                    const int w = u >> cshift, e0 = (u & ((1 << cshift) - 1)) * kDangerChunk;
                     const int4 c = s_work[w];  // (candidate, q, j, d0)
                     // list prefix this candidate has to look at (d1min <= c.w <= d0max holds for every listed candidate)
                     const int prefix = sorted ? s_hist[danger_bucket(c.w, d1min, inv) + 1] : nd;
