@@ -194,3 +194,54 @@ def test_dead_row_rule_restatement_keeps_every_verdict(kind, ratio):
     Dm = D.copy()
     Dm[np.arange(len(Q)), e0] = np.iinfo(np.int64).max
     assert (d1 <= Dm.min(1)).all()                                    # reported d1 bounds every other distance from below
+
+
+@pytest.mark.parametrize("kind", ["sift", "clusters"])
+def test_mutual_check_from_forward_results_restatement(kind):
+    """select_candidates_kernel's mutual cross-check (aux_kernels.cuh) restated in numpy on the rows the dead-row stream
+    reports: (A) a per-column table of the nearest claimant among the rows whose nn0 is that column, (B) exact distances
+    only for 'dangerous' rows, i.e. rows whose reported d1 (a lower bound of their distance to every column but nn0) does
+    not exceed the candidate's d0.  The survivors must be exactly the brute-force mutual matches (lowest index on ties)."""
+    from metricsfm_b200 import synth
+    rng = np.random.default_rng(11)
+    ratio = 0.85
+    if kind == "sift":
+        col = synth.Collection(768, seed=6)
+        R, Q = col.image_u8(0, 640), col.image_u8(1, 512)
+    else:
+        c = rng.integers(0, 100, size=(10, 128))
+        R = np.clip(c[rng.integers(0, 10, 576)] + rng.integers(-3, 4, size=(576, 128)), 0, 255).astype(np.uint8)
+        Q = np.clip(c[rng.integers(0, 10, 512)] + rng.integers(-3, 4, size=(512, 128)), 0, 255).astype(np.uint8)
+        Q[:40] = R[:40]                                              # exact duplicates: distance ties between query rows
+        Q[40:80] = R[:40]
+    d0, j0, d1, _, _ = _dead_row_stream(Q, R, int(np.floor(ratio * 256.0)) + 2)
+    D = ((Q.astype(np.int64)[:, None, :] - R.astype(np.int64)[None, :, :]) ** 2).sum(2)
+    n = len(Q)
+    accept = (d0.astype(np.float32) / np.maximum(d1, 1).astype(np.float32) < np.float32(ratio)) & (d1 > 0)
+    cand = np.nonzero(accept)[0]
+    # (A) column table: (d0, q) minimum over ALL rows, keyed by nn0
+    table = {}
+    for q in range(n):
+        key = (int(d0[q]), q)
+        if j0[q] not in table or key < table[j0[q]]:
+            table[int(j0[q])] = key
+    d0max = int(d0[cand].max()) if len(cand) else -1
+    danger = [q for q in range(n) if d1[q] <= d0max]                 # (B) rows that could interfere with some candidate
+    survivors, exact_evals = [], 0
+    for q in cand:
+        j = int(j0[q])
+        if table[j] != (int(d0[q]), int(q)):
+            continue                                                 # a kind-(A) rival is closer (or ties with a lower index)
+        killed = False
+        for r in danger:
+            if r != q and d1[r] <= d0[q]:
+                exact_evals += 1
+                d = int(D[r, j])
+                if d < d0[q] or (d == d0[q] and r < q):
+                    killed = True
+        if not killed:
+            survivors.append((j, int(q)))
+    best_q = np.argmin(D, axis=0)                                     # numpy argmin: lowest index on ties
+    expect = [(int(j0[q]), int(q)) for q in cand if best_q[j0[q]] == q]
+    assert survivors == expect and len(expect) > 20
+    assert exact_evals < n * len(cand) // 4                           # the bound prunes most (row, candidate) combinations
