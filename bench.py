@@ -142,8 +142,42 @@ class ClockSampler:
         self.index, self.lines, self.proc, self.enabled = index, [], None, enabled
         self.t0 = self.t1 = None   # timed window (perf_counter)
 
+    def _start_nvml(self) -> bool:
+        """Preferred sampler: NVML polled every 5 ms from a thread (a 0.2 s timed region then holds ~40 samples instead of the
+        1-2 that nvidia-smi's 100 ms loop gives).  Same quantities as the nvidia-smi query below."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            get_reasons(h)
+        except Exception:
+            return False
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        self.nvml_stop = threading.Event()
+
+        def poll():
+            while not self.nvml_stop.is_set():
+                try:
+                    sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                    pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    r = int(get_reasons(h))
+                    flags = ",".join("Active" if r & b else "Not Active" for _, b in bits)
+                    self.lines.append((time.perf_counter(), f"{self.index},{sm},{mx},{pw},{r},{flags}"))
+                except Exception:
+                    pass
+                time.sleep(0.005)
+
+        self.thread = threading.Thread(target=poll, daemon=True)
+        self.thread.start()
+        self.proc = "nvml"
+        return True
+
     def start(self):
         if not self.enabled:
+            return
+        if self._start_nvml():
             return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -168,11 +202,15 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampled on rank 0 only"]}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        if self.proc == "nvml":
+            self.nvml_stop.set()
+            self.thread.join(timeout=2)
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         # samples inside the timed window; nvidia-smi needs ~1 s to come up, so it is started before the warm-up steps and
         # a window shorter than its period falls back to the warm-up + timed span (same kernels, same load)
         t0 = self.t0 if self.t0 is not None else 0.0
@@ -196,7 +234,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)), "samples": len(sm),
-                "window": window, "reasons": sorted(reasons)}
+                "window": window, "reasons": sorted(reasons), "sampler": "NVML, 5 ms" if self.proc == "nvml" else "nvidia-smi -lms 100"}
 
 
 # ====================================================================================================== reference arm
