@@ -599,6 +599,17 @@ msfm_status match_pairs_impl(msfm_ctx *ctx, const msfm_pair *pairs, int64_t n_pa
         if ((st = check_image_id(ctx, pairs[i].query, true)) != MSFM_OK) return st;
     }
     ctx->timing = msfm_timing{};
+    // A list copy still in flight when the call fails half-way must not outlive the call: the caller may free the
+    // destination buffers as soon as it sees the error.  (On success wait_list_copy has already cleared the flag.)
+    struct DrainListCopy {
+        msfm_ctx *c;
+        ~DrainListCopy() {
+            if (c->d2h_in_flight) {
+                cudaStreamSynchronize(c->d2h_stream);
+                c->d2h_in_flight = false;
+            }
+        }
+    } drain_list_copy{ctx};
     MSFM_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
     const bool mutual = params->mutual != 0;
     const bool want_good = params->ratio_good > 0.0f && (resident || out->has_good);
